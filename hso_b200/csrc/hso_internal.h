@@ -1,0 +1,115 @@
+// Internal structures shared between the C-ABI layer (capi.cu) and the kernels. Product code: never includes oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hso_b200.h"
+#include "common.cuh"
+
+namespace hso {
+
+constexpr int kMaxLevels = 5;     // max(Config::nPyrLevels, kltMaxLevel+1) = 5 (src/frame.cpp:92)
+constexpr int kMaxPatternN = 25;  // largest pattern actually reachable (idx 6, include/hso/CoarseTracker.h:100-109)
+constexpr int kMaxCluster = 8;    // portable thread-block-cluster size
+constexpr int kPadRows = 3;       // zero rows kept below every pyramid level (gradient taps may touch row == rows)
+
+// Device layout of one frame's pyramid. All frames of a context share the camera, hence the geometry.
+// Level l lives at byte offset off[l] with `pitch[l]` bytes per row (multiple of 16, > w[l]). The bytes [w, pitch) of
+// row y repeat the first bytes of row y+1 ("wrap padding"): with the reference's stride == cols a tap at column == cols
+// reads the next row's first pixel (src/CoarseTracker.cpp:368-371 at the right border), and so do we. kPadRows zero rows
+// follow each level (the reference reads one row past the image there, which is undefined; zeros are our definition).
+struct PyrGeom {
+  int n_levels;
+  int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
+  size_t off[kMaxLevels];   // 128-byte aligned
+  size_t bytes;             // total bytes per frame
+  int half_path;            // 1: halfSample chain (W%16==0 && H%16==0, src/frame.cpp:303), 0: cv::resize chain
+  int sse_rounding[kMaxLevels];  // level l>=1 is produced with SSE2 double rounding iff w[l-1]%16==0 (src/vikit/vision.cpp:82)
+};
+
+// ---- pyramid ------------------------------------------------------------------------------------------------------------
+struct PyrJobDev {
+  const uint8_t* src;  // raw level-0 image on the device, row stride = src_stride
+  uint8_t* pyr;        // destination pyramid buffer (PyrGeom layout)
+  int16_t* sobel;      // nullptr, or [level 0..2][gx plane | gy plane], tightly packed w*h each
+  double* sums;        // [2] scratch: sum I, sum |grad| over the level-0 interior (zeroed by the launcher)
+  float* stats;        // [2] out: Frame::integralImage_, Frame::gradMean_
+};
+cudaError_t launch_pyramid(const PyrGeom& g, const PyrJobDev* jobs_dev, int B, int src_stride, int n_sobel_levels, int store_sobel,
+                           cudaStream_t stream, uint64_t* launches);
+
+// ---- CoarseTracker ------------------------------------------------------------------------------------------------------
+// Per-problem persistent state, lives in device memory across the per-level launches.
+struct TrackState {
+  Se3d T;        // accepted T_cur_ref
+  float a;       // accepted exposure ratio
+  int n_iters, n_evals;
+  int iters_per_level[8];
+  int last_total_terms, last_N;
+  unsigned long long patch_evals[8];  // per level: sum over evaluations of patches that produced terms
+  int trace_len;
+  int pad_;
+};
+
+struct TrackJobDev {
+  const uint8_t* ref_pyr;
+  const uint8_t* cur_pyr;
+  int F;                 // features with a valid depth (compacted on the host; see capi.cu)
+  int Fpad;              // row length of the SoA scratch arrays (multiple of 32)
+  const double* px;      // [2][Fpad]  level-0 pixel of the reference feature
+  const double* xyz;     // [3][Fpad]  f * dist
+  float* ref_cache;      // [25][Fpad] reference intensities, pattern-major => coalesced for lane == patch
+  float* ref_gx;         // [25][Fpad] inverse-compositional reference gradients (nullptr in forward mode)
+  float* ref_gy;
+  float* absres;         // [25][Fpad] |r| scratch of the robust threshold selection (-1 = not in view)
+  uint8_t* vis;          // [Fpad]
+  TrackState* state;
+  hso_trace* trace;      // [trace_cap] or nullptr
+};
+
+
+struct TrackLevelParams {
+  int ic, max_level, level, n_iter;
+  int trace_cap;
+  int w, h, pitch;          // geometry of this level
+  size_t level_off;         // byte offset of this level in a pyramid buffer
+  int stage_smem;           // 1: the current level image is staged in shared memory
+  uint32_t img_bytes;       // bytes staged (pitch * (h + kPadRows)), multiple of 16
+  CamDev cam;
+};
+
+size_t track_level_smem_bytes(const TrackLevelParams& p, int threads);
+cudaError_t launch_track_level(const TrackLevelParams& p, const TrackJobDev* jobs_dev, int B, int cluster, int threads, cudaStream_t stream,
+                               uint64_t* launches);
+cudaError_t launch_track_init(const TrackJobDev* jobs_dev, const double* T0 /*[B][12]*/, const float* a0, int B, cudaStream_t stream,
+                              uint64_t* launches);
+cudaError_t launch_track_finish(const TrackJobDev* jobs_dev, hso_track_result* out_dev, int B, cudaStream_t stream, uint64_t* launches);
+
+// ---- align --------------------------------------------------------------------------------------------------------------
+struct AlignJobDev {
+  hso_align_job job;
+  const uint8_t* ref_pyr;
+};
+cudaError_t launch_align(const PyrGeom& g, const uint8_t* cur_pyr, const int16_t* cur_sobel, const AlignJobDev* jobs_dev, int M, int max_iter,
+                         hso_align_result* out_dev, cudaStream_t stream, uint64_t* launches);
+
+// ---- pose optimiser -----------------------------------------------------------------------------------------------------
+struct PoseJobDev {
+  int F, K, n_fts_total, pad_;
+  const double* f;          // 3F
+  const double* p_host;     // 3F
+  const int32_t* host_idx;  // F
+  const double* T_host_w;   // K x 12
+  const double* grad;       // 2F
+  const int8_t* level;
+  const int8_t* ftype;
+  const int8_t* ptype;
+  double T_f_w_in[12];
+  uint8_t* outlier;         // F
+  float* scratch;           // 2F floats for the order statistics
+  hso_pose_result* out;
+};
+cudaError_t launch_pose(const PoseJobDev* jobs_dev, int B, double reproj_thresh, int n_iter, double err_mult2, cudaStream_t stream,
+                        uint64_t* launches);
+
+}  // namespace hso

@@ -1,0 +1,184 @@
+/* hso_b200 — C-ABI of the B200-native (sm_100a CUDA) implementation of HSO's per-frame tracking hot path.
+ *
+ * The reference (luodongting/HSO) has no plugin/FFI surface: its hot path is reached through concrete C++
+ * classes with Eigen/Sophus/cv::Mat types. This header is the boundary a replacement sits
+ * under. Each entry point names the reference interface it replaces (paths relative to the reference root).
+ * The C++ host shim in hso_b200/host/ keeps the reference's class/function names on top of these calls;
+ * INTEGRATION.md shows the glue a maintainer adds inside the reference tree.
+ *
+ * Conventions: POD only, caller-owned host buffers, row-major; poses are 12 doubles = 3x4 [R | t];
+ * every call returns HSO_OK (0) or a negative hso_status; no exceptions/aborts cross the boundary;
+ * one hso_ctx per host thread (a ctx owns one CUDA stream; calls on one ctx are not thread-safe,
+ * distinct contexts are independent). There is NO CPU fallback: without a CUDA device hso_create fails.
+ */
+#ifndef HSO_B200_H
+#define HSO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  HSO_OK = 0,
+  HSO_ERR_INVALID = -1,     /* bad argument (mirrors the reference's size/type check, src/frame.cpp:85-86) */
+  HSO_ERR_CUDA = -2,        /* CUDA runtime error; see hso_last_error */
+  HSO_ERR_NO_DEVICE = -3,   /* no usable sm_100 device */
+  HSO_ERR_CAPACITY = -4,    /* frame table / feature capacity exceeded */
+  HSO_ERR_BAD_FRAME = -5    /* unknown or released frame id */
+} hso_status;
+
+typedef struct hso_ctx hso_ctx;
+typedef int32_t hso_frame_id;
+
+/* Camera models of src/camera.cpp. model 0 = PinholeCamera (radial-tangential distortion applied inside world2cam
+ * when |d[0]| > 1e-7, camera.cpp:36,99-125), 1 = FOVCamera (omega in d[0]; undistort != 0 => plain pinhole,
+ * camera.cpp:199-221), 2 = EquidistantCamera (image undistorted up-front => plain pinhole, camera.cpp:307-315). */
+typedef struct {
+  int32_t model, width, height, undistort;
+  double fx, fy, cx, cy;
+  double d[5];
+} hso_cam;
+
+/* Subset of hso::Config that the path reads (src/config.cpp:28-64). Zero-initialise then call hso_cfg_default. */
+typedef struct {
+  int32_t n_pyr_levels;      /* Config::nPyrLevels = 3 : levels that get Sobel images / are searched by the matcher */
+  int32_t klt_max_level;     /* Config::kltMaxLevel = 4 : pyramid has max(n_pyr_levels, klt_max_level+1) levels */
+  int32_t max_frames;        /* frames resident on the device per context (ring; default 16) */
+  int32_t max_features;      /* per-job feature capacity (default 8192) */
+  int32_t materialize_sobel; /* 1: keep the int16 Sobel L0..L2 images on device (src/frame.cpp:216-220) */
+  int32_t reserved[3];
+} hso_cfg;
+void hso_cfg_default(hso_cfg* cfg);
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+int hso_create(int device, const hso_cam* cam, const hso_cfg* cfg, hso_ctx** out);
+void hso_destroy(hso_ctx* ctx);
+const char* hso_last_error(const hso_ctx* ctx);
+/* Use an existing CUDA stream (cudaStream_t as void*) for all work of this context; NULL restores the ctx's own. */
+int hso_set_stream(hso_ctx* ctx, void* cuda_stream);
+void* hso_get_stream(hso_ctx* ctx);
+int hso_synchronize(hso_ctx* ctx);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+uint64_t hso_kernel_launches(const hso_ctx* ctx);
+
+/* ---- F1: Frame construction — replaces hso::Frame::Frame / initFrame (include/hso/frame.h:131, src/frame.cpp:82-96):
+ * frame_utils::createImgPyramid (src/frame.cpp:296-314, halfSample src/vikit/vision.cpp:19-108) and
+ * Frame::prepareForFeatureDetect (src/frame.cpp:205-246). The pyramid stays on the device. -------------------------- */
+/* img: CV_8UC1 W x H with `stride` bytes per row. W,H must equal the camera's (else HSO_ERR_INVALID, as frame.cpp:85).
+ * integral/grad_mean receive Frame::integralImage_ / Frame::gradMean_ (may be NULL to skip the read-back). */
+int hso_frame_upload(hso_ctx* ctx, const uint8_t* img, int W, int H, int stride, hso_frame_id* out, float* integral, float* grad_mean);
+/* Batched form: B images -> B frames with one synchronisation. imgs[i] are host pointers (pinned or pageable). */
+int hso_frame_upload_batch(hso_ctx* ctx, int B, const uint8_t* const* imgs, int W, int H, int stride, hso_frame_id* out,
+                           float* integral, float* grad_mean);
+/* Device-resident variant for benchmarking: raw level-0 images already live in device memory (dev_imgs = B device ptrs). */
+int hso_frame_build_batch_device(hso_ctx* ctx, int B, const void* const* dev_imgs, int W, int H, int stride, hso_frame_id* out);
+int hso_frame_stats(hso_ctx* ctx, hso_frame_id id, float* integral, float* grad_mean);
+int hso_frame_level_size(hso_ctx* ctx, hso_frame_id id, int level, int* w, int* h);
+/* Host mirrors for consumers that stay on the CPU (mapping thread, feature detection). */
+int hso_frame_download_level(hso_ctx* ctx, hso_frame_id id, int level, uint8_t* dst);
+int hso_frame_download_sobel(hso_ctx* ctx, hso_frame_id id, int level, int16_t* gx, int16_t* gy);
+int hso_frame_release(hso_ctx* ctx, hso_frame_id id);
+
+/* ---- F2: sparse direct image alignment — replaces size_t hso::CoarseTracker::run(FramePtr ref, FramePtr cur)
+ * (include/hso/CoarseTracker.h:134,141 ; src/CoarseTracker.cpp:51-208). ------------------------------------------------ */
+typedef struct {
+  int32_t inverse_comp;  /* ctor arg inverse_composition (frame_handler_mono.cpp:184-203) */
+  int32_t max_level;     /* Config::kltMaxLevel() = 4 */
+  int32_t min_level;     /* Config::kltMinLevel()+1 = 1 ; 0 when relocalising */
+  int32_t n_iter;        /* 50 ; 15 when relocalising */
+} hso_track_params;
+
+typedef struct {
+  hso_frame_id ref, cur;
+  int32_t n_features;    /* ref_frame->fts_.size() */
+  int32_t reserved;
+  const double* px;      /* 2F: Feature::px (level-0 pixels) */
+  const double* f;       /* 3F: Feature::f (unit bearing) */
+  const double* dist;    /* F : makeDepthRef output, <0 = no point / behind camera (CoarseTracker.cpp:210-240) */
+  double T_cur_ref[12];  /* in: cur.T_f_w * ref.T_f_w^-1 (CoarseTracker.cpp:63) */
+  float exposure_rat;    /* in: cur.integralImage_/ref.integralImage_ (CoarseTracker.cpp:60) */
+  float reserved2;
+} hso_track_job;
+
+typedef struct {
+  double T_cur_ref[12];        /* out: m_T_cur_ref */
+  float exposure_rat;          /* out: m_exposure_rat */
+  int32_t n_iters;             /* LM trials executed over all levels */
+  int32_t n_evals;             /* residual evaluations = n_iters + number of levels */
+  int32_t iters_per_level[8];
+  uint64_t n_tracked;          /* return value of run(): size_t(float(total_terms)/PATCH_AREA) (CoarseTracker.cpp:207) */
+  uint64_t visible_patch_evals[8]; /* per level: sum over evaluations of patches that produced terms (roofline accounting) */
+} hso_track_result;
+
+/* Per-evaluation trace for parity checking; same fields as the oracle's orc_trace. */
+typedef struct {
+  int32_t level, iter;
+  double T_eval[12];
+  float a_eval, lambda;
+  double H[49], b[7], step[7];
+  double energy;
+  int32_t total_terms, saturated_terms, accepted;
+  float huber, outlier;
+} hso_trace;
+
+/* makeDepthRef helper on the host side of the boundary is hso::host::makeDepthRef (hso_b200/host); here dist is an input. */
+int hso_coarse_track(hso_ctx* ctx, const hso_track_params* prm, const hso_track_job* job, hso_track_result* out,
+                     hso_trace* trace, int trace_cap, int* trace_len);
+/* Many independent (ref,cur) problems in one launch (the many-sequence mode). trace is [B][trace_cap] or NULL. */
+int hso_coarse_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_track_job* jobs, hso_track_result* out,
+                           hso_trace* trace, int trace_cap, int* trace_len);
+/* The same call split in three so a caller can keep inputs resident and time the device part alone:
+ * stage = H2D of the feature arrays, run = kernel launches only (asynchronous on the ctx stream), collect = sync + D2H. */
+int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_track_job* jobs, int trace_cap);
+int hso_track_restage_frames(hso_ctx* ctx, int B, const hso_frame_id* ref, const hso_frame_id* cur);
+int hso_track_run(hso_ctx* ctx);
+int hso_track_collect(hso_ctx* ctx, hso_track_result* out, hso_trace* trace, int* trace_len);
+/* Tuning knob: CTAs cooperating on one problem through a thread-block cluster (1,2,4,8; 0 = auto). */
+int hso_track_set_cluster(hso_ctx* ctx, int ctas_per_problem, int threads_per_cta);
+
+/* ---- F3-inner: direct patch matching — replaces the body of bool hso::Matcher::findMatchDirect(const Point&, Frame&,
+ * Vector2d&) after the host-side getCloseViewObs/getWarpMatrixAffine (include/hso/matcher.h:153 ; src/matcher.cpp:310-375),
+ * i.e. warp::warpAffine (:120-155), feature_alignment::align1D / align2D float overloads
+ * (include/hso/feature_alignment.h:47-55,66-73 ; src/feature_alignment.cpp:164-308,464-605), checkNormal (:406-440),
+ * checkNCC (:379-404) and the 20 px displacement gate. ------------------------------------------------------------------ */
+typedef struct {
+  int32_t ref_level, search_level, type /* Feature::FeatureType: 0 corner, 1 edgelet, 2 gradient */, scale_patch;
+  double px_ref[2], A_cur_ref[4], grad[2], px_cur[2];
+  float exposure_rat, pad_;
+} hso_align_job;
+typedef struct {
+  int32_t ok, align_converged;
+  double px_cur[2];
+  double h_inv;
+} hso_align_result;
+/* jobs may reference different reference frames: ref_frames[m] is the frame id of job m's reference observation. */
+int hso_align_batch(hso_ctx* ctx, hso_frame_id cur, int M, const hso_align_job* jobs, const hso_frame_id* ref_frames,
+                    int align_max_iter, hso_align_result* out);
+
+/* ---- F4: pose refinement — replaces void pose_optimizer::optimizeLevenbergMarquardt3rd(double reproj_thresh, size_t n_iter,
+ * bool verbose, FramePtr&, double& scale, double& err_init, double& err_final, size_t& num_obs)
+ * (include/hso/pose_optimizer.h:61-64 ; src/pose_optimizer.cpp:399-771). ------------------------------------------------- */
+typedef struct {
+  double T_f_w[12], cov[36];
+  double estimated_scale, error_init, error_final;
+  uint64_t num_obs;
+  float error_in_px;
+  int32_t n_trials_total, early_return;
+} hso_pose_result;
+int hso_pose_optimize(hso_ctx* ctx, double reproj_thresh, int n_iter, int n_fts_total, int F, const double* f, const double* p_host,
+                      const int32_t* host_idx, int K, const double* T_host_w, const double* grad, const int8_t* level, const int8_t* ftype,
+                      const int8_t* ptype, const double T_f_w_in[12], uint8_t* outlier_out, hso_pose_result* out);
+/* Many independent frames in one launch. Arrays are concatenated; offs[B+1] indexes features, hoffs[B+1] indexes host poses. */
+int hso_pose_optimize_batch(hso_ctx* ctx, double reproj_thresh, int n_iter, int B, const int32_t* n_fts_total, const int32_t* offs,
+                            const double* f, const double* p_host, const int32_t* host_idx, const int32_t* hoffs, const double* T_host_w,
+                            const double* grad, const int8_t* level, const int8_t* ftype, const int8_t* ptype, const double* T_f_w_in,
+                            uint8_t* outlier_out, hso_pose_result* out);
+
+/* ---- stage timers, named like the reference's HSO_START_TIMER sites (src/frame_handler_base.cpp:57-66) ------------------- */
+/* Accumulated device time in ms of: 0 "pyramid_creation", 1 "sparse_img_align", 2 "feature_align", 3 "pose_optimizer". */
+int hso_stage_time_ms(hso_ctx* ctx, int stage, double* ms, uint64_t* calls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
