@@ -1,0 +1,199 @@
+"""Host-side (numpy) mirror of the reference interfaces of the tracking hot path, on top of the C-ABI.
+
+Names follow the reference: Frame (include/hso/frame.h:131), CoarseTracker(inverse_composition, max_level, min_level, n_iter).run
+(include/hso/CoarseTracker.h:134,141), pose_optimizer.optimizeLevenbergMarquardt3rd (include/hso/pose_optimizer.h:61-64),
+Matcher.findMatchDirect's inner part as align_batch (include/hso/matcher.h:153). All compute runs in libhso_b200.so on the GPU;
+this module only flattens arguments. No oracle/, no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as K
+
+PINHOLE, FOV, EQUIDISTANT = 0, 1, 2
+
+
+class HsoError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"hso_b200 error {code}: {msg}")
+        self.code = code
+
+
+def make_cam(width, height, fx, fy, cx, cy, d=(0, 0, 0, 0, 0), model=PINHOLE, undistort=0):
+    c = K.hso_cam()
+    c.model, c.width, c.height, c.undistort = model, width, height, undistort
+    c.fx, c.fy, c.cx, c.cy = fx, fy, cx, cy
+    for i in range(5):
+        c.d[i] = float(d[i]) if i < len(d) else 0.0
+    return c
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Context:
+    """One hso_ctx: one CUDA stream, one camera model, a table of device-resident frames."""
+
+    def __init__(self, cam, device=0, max_frames=16, max_features=8192, materialize_sobel=False, n_pyr_levels=3, klt_max_level=4):
+        self.lib = K.load()
+        cfg = K.hso_cfg()
+        self.lib.hso_cfg_default(C.byref(cfg))
+        cfg.max_frames, cfg.max_features = max_frames, max_features
+        cfg.materialize_sobel = 1 if materialize_sobel else 0
+        cfg.n_pyr_levels, cfg.klt_max_level = n_pyr_levels, klt_max_level
+        self.cam = cam
+        self.h = C.c_void_p()
+        rc = self.lib.hso_create(device, C.byref(cam), C.byref(cfg), C.byref(self.h))
+        if rc != K.HSO_OK:
+            self.h = None
+            raise HsoError(rc, "hso_create failed (no sm_100 CUDA device? hso_b200 has no CPU fallback)")
+        self.n_levels = max(n_pyr_levels, klt_max_level + 1)
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.hso_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != K.HSO_OK:
+            raise HsoError(rc, self.lib.hso_last_error(self.h).decode())
+
+    # ---- F1: Frame ------------------------------------------------------------------------------------------------------------
+    def upload_frames(self, imgs):
+        """imgs: list of HxW uint8 arrays (C-contiguous rows; arbitrary row stride allowed). Returns (ids, integral, grad_mean)."""
+        B = len(imgs)
+        H, W = imgs[0].shape
+        stride = imgs[0].strides[0]
+        ptrs = (C.c_void_p * B)(*[im.ctypes.data for im in imgs])
+        ids = (C.c_int32 * B)()
+        integral = np.zeros(B, np.float32)
+        gm = np.zeros(B, np.float32)
+        self._chk(self.lib.hso_frame_upload_batch(self.h, B, ptrs, W, H, stride, ids,
+                                                  integral.ctypes.data_as(C.POINTER(C.c_float)), gm.ctypes.data_as(C.POINTER(C.c_float))))
+        return list(ids), integral, gm
+
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        self._chk(self.lib.hso_frame_level_size(self.h, 0, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def download_level(self, fid, level):
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        self._chk(self.lib.hso_frame_download_level(self.h, fid, level, out.ctypes.data))
+        return out
+
+    def download_sobel(self, fid, level):
+        w, h = self.level_size(level)
+        gx = np.empty((h, w), np.int16)
+        gy = np.empty((h, w), np.int16)
+        self._chk(self.lib.hso_frame_download_sobel(self.h, fid, level, gx.ctypes.data, gy.ctypes.data))
+        return gx, gy
+
+    def release(self, fid):
+        self._chk(self.lib.hso_frame_release(self.h, fid))
+
+    # ---- F2: CoarseTracker ----------------------------------------------------------------------------------------------------
+    def _track_jobs(self, jobs):
+        B = len(jobs)
+        arr = (K.hso_track_job * B)()
+        keep = []
+        for b, j in enumerate(jobs):
+            px = np.ascontiguousarray(j["px"], np.float64).reshape(-1)
+            f = np.ascontiguousarray(j["f"], np.float64).reshape(-1)
+            dist = np.ascontiguousarray(j["dist"], np.float64).reshape(-1)
+            keep += [px, f, dist]
+            a = arr[b]
+            a.ref, a.cur, a.n_features = int(j["ref"]), int(j["cur"]), dist.shape[0]
+            a.px, a.f, a.dist = _dp(px), _dp(f), _dp(dist)
+            T = np.ascontiguousarray(j["T_cur_ref"], np.float64).reshape(12)
+            for k in range(12):
+                a.T_cur_ref[k] = T[k]
+            a.exposure_rat = float(j["exposure_rat"])
+        return arr, keep
+
+    def coarse_track_batch(self, jobs, inverse_comp=False, max_level=4, min_level=1, n_iter=50, trace_cap=0):
+        """jobs: list of dicts {ref, cur, px (F,2), f (F,3), dist (F,), T_cur_ref (3,4), exposure_rat}. Returns (results, traces)."""
+        B = len(jobs)
+        prm = K.hso_track_params(int(bool(inverse_comp)), max_level, min_level, n_iter)
+        arr, keep = self._track_jobs(jobs)
+        out = (K.hso_track_result * B)()
+        trace = (K.hso_trace * (B * trace_cap))() if trace_cap else None
+        tlen = (C.c_int * B)()
+        self._chk(self.lib.hso_coarse_track_batch(self.h, C.byref(prm), B, arr, out, trace, trace_cap, tlen))
+        res = []
+        for b in range(B):
+            o = out[b]
+            res.append(dict(T_cur_ref=np.array(o.T_cur_ref[:]).reshape(3, 4), exposure_rat=float(o.exposure_rat), n_iters=o.n_iters,
+                            n_evals=o.n_evals, iters_per_level=list(o.iters_per_level), n_tracked=int(o.n_tracked),
+                            visible_patch_evals=list(o.visible_patch_evals)))
+        traces = []
+        for b in range(B):
+            traces.append([trace[b * trace_cap + i] for i in range(tlen[b])] if trace_cap else [])
+        return res, traces
+
+    def track_stage(self, jobs, inverse_comp=False, max_level=4, min_level=1, n_iter=50):
+        prm = K.hso_track_params(int(bool(inverse_comp)), max_level, min_level, n_iter)
+        arr, keep = self._track_jobs(jobs)
+        self._chk(self.lib.hso_track_stage(self.h, C.byref(prm), len(jobs), arr, 0))
+        self._tB = len(jobs)
+
+    def track_run(self):
+        self._chk(self.lib.hso_track_run(self.h))
+
+    def track_collect(self):
+        out = (K.hso_track_result * self._tB)()
+        self._chk(self.lib.hso_track_collect(self.h, out, None, None))
+        return out
+
+    def set_cluster(self, ctas=0, threads=0):
+        self._chk(self.lib.hso_track_set_cluster(self.h, ctas, threads))
+
+    def synchronize(self):
+        self._chk(self.lib.hso_synchronize(self.h))
+
+    def kernel_launches(self):
+        return int(self.lib.hso_kernel_launches(self.h))
+
+    def stream(self):
+        return self.lib.hso_get_stream(self.h)
+
+
+class CoarseTracker:
+    """Mirror of hso::CoarseTracker (include/hso/CoarseTracker.h:134-143): ctor(inverse_composition, max_level, min_level, n_iter),
+    run(ref, cur) -> number of tracked patches; updates cur['T_f_w'] and cur['exposure_time'] like src/CoarseTracker.cpp:198-202.
+
+    Frames are dicts: {id, T_f_w (3x4), integral, exposure_time, px (F,2), f (F,3), dist (F,)} where dist is makeDepthRef's output
+    (src/CoarseTracker.cpp:210-240; < 0 for features without point)."""
+
+    def __init__(self, ctx, inverse_composition, max_level, min_level, n_iter, verbose=False):
+        self.ctx, self.ic, self.max_level, self.min_level, self.n_iter = ctx, inverse_composition, max_level, min_level, n_iter
+
+    def run(self, ref, cur):
+        if len(ref["dist"]) == 0:
+            return 0  # src/CoarseTracker.cpp:53
+        T_ref, T_cur = _rt44(ref["T_f_w"]), _rt44(cur["T_f_w"])
+        T_cur_ref = (T_cur @ np.linalg.inv(T_ref))[:3]
+        job = dict(ref=ref["id"], cur=cur["id"], px=ref["px"], f=ref["f"], dist=ref["dist"], T_cur_ref=T_cur_ref,
+                   exposure_rat=np.float32(cur["integral"]) / np.float32(ref["integral"]))
+        res, _ = self.ctx.coarse_track_batch([job], self.ic, self.max_level, self.min_level, self.n_iter)
+        r = res[0]
+        cur["T_f_w"] = (_rt44(r["T_cur_ref"]) @ T_ref)[:3]
+        a = r["exposure_rat"]
+        cur["exposure_time"] = ref["exposure_time"] if 0.99 < a < 1.01 else a * ref["exposure_time"]
+        return r["n_tracked"]
+
+
+def _rt44(T):
+    M = np.eye(4)
+    M[:3] = np.asarray(T, np.float64).reshape(3, 4)
+    return M

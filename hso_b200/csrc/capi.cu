@@ -1,0 +1,650 @@
+// C-ABI of hso_b200 (include/hso_b200.h): context, device-resident frame table, staging of flattened feature arrays,
+// kernel sequencing. Host-side only; all arithmetic of the path lives in the kernels. There is no CPU fallback.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hso_internal.h"
+
+using namespace hso;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct FrameSlot {
+  bool used = false;
+  uint8_t* pyr = nullptr;
+  int16_t* sobel = nullptr;
+  double* sums = nullptr;
+  float* stats = nullptr;  // device [2]
+};
+
+}  // namespace
+
+struct hso_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  hso_cam cam;
+  CamDev camdev;
+  hso_cfg cfg;
+  PyrGeom geom;
+  size_t sobel_elems = 0;
+  int n_tiles = 0;
+  std::string err;
+  uint64_t launches = 0;
+  std::vector<FrameSlot> frames;
+  // pyramid
+  DevBuf pyr_jobs_dev, pyr_counters, resize_tab_dev;
+  PinBuf pyr_jobs_host, stats_host;
+  std::vector<ResizeTabDev> resize_tabs;
+  // tracker
+  hso_track_params tprm;
+  int tB = 0, t_trace_cap = 0;
+  int t_cluster = 0, t_threads = 0;  // 0 = auto
+  DevBuf t_arena, t_jobs_dev, t_T0, t_a0, t_out_dev;
+  PinBuf t_stage_host, t_jobs_host, t_out_host;
+  std::vector<size_t> t_trace_off;  // byte offset of each job's trace in the arena
+  size_t t_arena_bytes = 0;
+  int t_maxF = 0;
+  // align / pose scratch
+  DevBuf a_jobs_dev, a_out_dev, p_arena, p_jobs_dev, p_out_dev;
+  PinBuf a_jobs_host, a_out_host, p_stage_host, p_out_host;
+  // stage timers
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double stage_ms[4] = {0, 0, 0, 0};
+  uint64_t stage_calls[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(hso_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    c->err = what;
+    if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+  }
+  return code;
+}
+#define CU(call)                                                              \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) return fail(ctx, HSO_ERR_CUDA, #call, e__);       \
+  } while (0)
+
+inline int cv_round(double v) { return (int)std::nearbyint(v); }
+inline short sat_short(int v) { return (short)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
+
+// frame_utils::createImgPyramid level sizes (src/frame.cpp:296-314).
+void build_geom(const hso_cam& cam, const hso_cfg& cfg, PyrGeom& g) {
+  memset(&g, 0, sizeof g);
+  g.n_levels = std::max(cfg.n_pyr_levels, cfg.klt_max_level + 1);
+  if (g.n_levels > kMaxLevels) g.n_levels = kMaxLevels;
+  const int W = cam.width, H = cam.height;
+  g.half_path = (W % 16 == 0) && (H % 16 == 0);
+  g.w[0] = W; g.h[0] = H;
+  for (int i = 1; i < g.n_levels; ++i) {
+    if (g.half_path) {
+      g.w[i] = g.w[i - 1] / 2; g.h[i] = g.h[i - 1] / 2;
+      g.sse_rounding[i] = (g.w[i - 1] % 16) == 0;
+    } else {
+      const float scale = (float)(1.0 / (1 << i));
+      g.w[i] = cv_round((float)W * scale);
+      g.h[i] = cv_round((float)H * scale);
+    }
+  }
+  size_t off = 0;
+  for (int i = 0; i < g.n_levels; ++i) {
+    g.off[i] = off;
+    const size_t bytes = (size_t)g.w[i] * g.h[i] + (size_t)kPadRows * g.w[i] + 16;
+    g.stage_bytes[i] = (uint32_t)((bytes + 15) / 16 * 16);
+    off += (g.stage_bytes[i] + 127) / 128 * 128;
+  }
+  g.bytes = off;
+}
+
+// Coefficient tables of cv::resize(INTER_LINEAR, 8UC1) for one level (OpenCV resize.cpp; fixed point, 11 bits).
+int build_resize_tab(hso_ctx* ctx, int sw, int sh, int dw, int dh, std::vector<char>& blob, ResizeTabDev& tab_offsets) {
+  const double inv_fx = (double)sw / dw, inv_fy = (double)sh / dh;
+  const int isx = (int)std::lrint(inv_fx), isy = (int)std::lrint(inv_fy);
+  const bool area = std::fabs(inv_fx - isx) < 2.220446049250313e-16 && std::fabs(inv_fy - isy) < 2.220446049250313e-16;
+  tab_offsets.area_fast = (area && isx == 2 && isy == 2) ? 1 : 0;
+  std::vector<int> xofs(dw), yofs(dh);
+  std::vector<short> ialpha(2 * dw), ibeta(2 * dh);
+  for (int dx = 0; dx < dw; ++dx) {
+    float fx = (float)((dx + 0.5) * inv_fx - 0.5);
+    int sx = (int)std::floor(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+    xofs[dx] = sx;
+    ialpha[2 * dx] = sat_short(cv_round((1.f - fx) * 2048));
+    ialpha[2 * dx + 1] = sat_short(cv_round(fx * 2048));
+  }
+  for (int dy = 0; dy < dh; ++dy) {
+    float fy = (float)((dy + 0.5) * inv_fy - 0.5);
+    int sy = (int)std::floor(fy);
+    fy -= sy;
+    yofs[dy] = sy;
+    ibeta[2 * dy] = sat_short(cv_round((1.f - fy) * 2048));
+    ibeta[2 * dy + 1] = sat_short(cv_round(fy * 2048));
+  }
+  auto put = [&](const void* p, size_t n) {
+    size_t o = (blob.size() + 15) / 16 * 16;
+    blob.resize(o + n);
+    memcpy(blob.data() + o, p, n);
+    return o;
+  };
+  tab_offsets.xofs = (const int*)put(xofs.data(), xofs.size() * 4);
+  tab_offsets.ialpha = (const short*)put(ialpha.data(), ialpha.size() * 2);
+  tab_offsets.yofs = (const int*)put(yofs.data(), yofs.size() * 4);
+  tab_offsets.ibeta = (const short*)put(ibeta.data(), ibeta.size() * 2);
+  (void)ctx;
+  return 0;
+}
+
+int alloc_frame(hso_ctx* ctx, hso_frame_id* out) {
+  for (size_t i = 0; i < ctx->frames.size(); ++i) {
+    FrameSlot& s = ctx->frames[i];
+    if (s.used) continue;
+    if (!s.pyr) {
+      CU(cudaMalloc((void**)&s.pyr, ctx->geom.bytes));
+      CU(cudaMemsetAsync(s.pyr, 0, ctx->geom.bytes, ctx->stream));
+      CU(cudaMalloc((void**)&s.sums, sizeof(double) * 2 * ctx->n_tiles));
+      CU(cudaMalloc((void**)&s.stats, sizeof(float) * 2));
+      if (ctx->cfg.materialize_sobel) CU(cudaMalloc((void**)&s.sobel, sizeof(int16_t) * ctx->sobel_elems));
+    }
+    s.used = true;
+    *out = (hso_frame_id)i;
+    return HSO_OK;
+  }
+  return fail(ctx, HSO_ERR_CAPACITY, "frame table full (hso_cfg.max_frames)");
+}
+
+FrameSlot* get_frame(hso_ctx* ctx, hso_frame_id id) {
+  if (id < 0 || (size_t)id >= ctx->frames.size() || !ctx->frames[id].used) return nullptr;
+  return &ctx->frames[id];
+}
+
+int run_pyramid(hso_ctx* ctx, int B, const hso_frame_id* ids, const uint8_t* const* srcs, int src_stride, int aligned) {
+  CU(ctx->pyr_jobs_host.reserve(sizeof(PyrJobDev) * B));
+  CU(ctx->pyr_jobs_dev.reserve(sizeof(PyrJobDev) * B));
+  if (ctx->pyr_counters.cap < sizeof(unsigned) * (size_t)B) {
+    CU(ctx->pyr_counters.reserve(sizeof(unsigned) * B));
+    CU(cudaMemsetAsync(ctx->pyr_counters.p, 0, ctx->pyr_counters.cap, ctx->stream));
+  }
+  PyrJobDev* jobs = (PyrJobDev*)ctx->pyr_jobs_host.p;
+  for (int i = 0; i < B; ++i) {
+    FrameSlot* s = get_frame(ctx, ids[i]);
+    jobs[i].src = srcs[i];
+    jobs[i].pyr = s->pyr;
+    jobs[i].sobel = s->sobel;
+    jobs[i].sums = s->sums;
+    jobs[i].stats = s->stats;
+  }
+  CU(cudaMemcpyAsync(ctx->pyr_jobs_dev.p, jobs, sizeof(PyrJobDev) * B, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_pyramid(ctx->geom, (const PyrJobDev*)ctx->pyr_jobs_dev.p, B, src_stride, (const ResizeTabDev*)ctx->resize_tab_dev.p,
+                    ctx->cfg.materialize_sobel, (unsigned*)ctx->pyr_counters.p, aligned, ctx->stream, &ctx->launches));
+  return HSO_OK;
+}
+
+int read_stats(hso_ctx* ctx, int B, const hso_frame_id* ids, float* integral, float* grad_mean) {
+  if (!integral && !grad_mean) return HSO_OK;
+  CU(ctx->stats_host.reserve(sizeof(float) * 2 * B));
+  float* h = (float*)ctx->stats_host.p;
+  for (int i = 0; i < B; ++i) CU(cudaMemcpyAsync(h + 2 * i, get_frame(ctx, ids[i])->stats, sizeof(float) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < B; ++i) {
+    if (integral) integral[i] = h[2 * i];
+    if (grad_mean) grad_mean[i] = h[2 * i + 1];
+  }
+  return HSO_OK;
+}
+
+struct StageTimer {
+  hso_ctx* c; int stage;
+  StageTimer(hso_ctx* ctx, int s) : c(ctx), stage(s) { cudaEventRecord(c->ev0, c->stream); }
+  void stop_after_sync() {
+    cudaEventRecord(c->ev1, c->stream);
+    cudaEventSynchronize(c->ev1);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) { c->stage_ms[stage] += ms; c->stage_calls[stage]++; }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void hso_cfg_default(hso_cfg* cfg) {
+  memset(cfg, 0, sizeof *cfg);
+  cfg->n_pyr_levels = 3;   // src/config.cpp:32
+  cfg->klt_max_level = 4;  // src/config.cpp:40
+  cfg->max_frames = 16;
+  cfg->max_features = 8192;
+  cfg->materialize_sobel = 0;
+}
+
+int hso_create(int device, const hso_cam* cam, const hso_cfg* cfg_in, hso_ctx** out) {
+  if (!cam || !out) return HSO_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return HSO_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return HSO_ERR_NO_DEVICE;
+  if (prop.major != 10) return HSO_ERR_NO_DEVICE;  // the kernels are sm_100a only
+  if (cam->width <= 32 || cam->height <= 32) return HSO_ERR_INVALID;
+  hso_ctx* ctx = new hso_ctx();
+  ctx->device = device;
+  ctx->cam = *cam;
+  if (cfg_in) ctx->cfg = *cfg_in; else hso_cfg_default(&ctx->cfg);
+  if (ctx->cfg.max_frames <= 0) ctx->cfg.max_frames = 16;
+  if (ctx->cfg.max_features <= 0) ctx->cfg.max_features = 8192;
+  if (ctx->cfg.n_pyr_levels <= 0) ctx->cfg.n_pyr_levels = 3;
+  if (ctx->cfg.klt_max_level <= 0) ctx->cfg.klt_max_level = 4;
+  CamDev& cd = ctx->camdev;
+  cd.model = cam->model; cd.width = cam->width; cd.height = cam->height; cd.undistort = cam->undistort;
+  cd.fx = cam->fx; cd.fy = cam->fy; cd.cx = cam->cx; cd.cy = cam->cy;
+  for (int i = 0; i < 5; ++i) cd.d[i] = cam->d[i];
+  cd.distortion = (cam->model == 0 && std::fabs(cam->d[0]) > 0.0000001) ? 1 : 0;  // src/camera.cpp:36
+  build_geom(ctx->cam, ctx->cfg, ctx->geom);
+  ctx->n_tiles = pyramid_tiles(ctx->geom);
+  ctx->sobel_elems = 0;
+  for (int l = 0; l < 3 && l < ctx->geom.n_levels; ++l) ctx->sobel_elems += (size_t)2 * ctx->geom.w[l] * ctx->geom.h[l];
+  ctx->frames.resize(ctx->cfg.max_frames);
+  auto bail = [&](const char* what) { fprintf(stderr, "hso_create: %s\n", what); hso_destroy(ctx); return HSO_ERR_CUDA; };
+  if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice");
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
+  ctx->stream = ctx->own_stream;
+  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) return bail("cudaEventCreate");
+  if (!ctx->geom.half_path) {
+    std::vector<char> blob;
+    ctx->resize_tabs.assign(ctx->geom.n_levels, ResizeTabDev{});
+    for (int l = 1; l < ctx->geom.n_levels; ++l)
+      build_resize_tab(ctx, ctx->geom.w[l - 1], ctx->geom.h[l - 1], ctx->geom.w[l], ctx->geom.h[l], blob, ctx->resize_tabs[l]);
+    const size_t tab_bytes = sizeof(ResizeTabDev) * ctx->geom.n_levels;
+    const size_t blob_off = (tab_bytes + 255) / 256 * 256;
+    if (ctx->resize_tab_dev.reserve(blob_off + blob.size()) != cudaSuccess) return bail("cudaMalloc resize tables");
+    char* base = (char*)ctx->resize_tab_dev.p + blob_off;
+    for (int l = 1; l < ctx->geom.n_levels; ++l) {
+      ResizeTabDev& t = ctx->resize_tabs[l];
+      t.xofs = (const int*)(base + (size_t)t.xofs);
+      t.ialpha = (const short*)(base + (size_t)t.ialpha);
+      t.yofs = (const int*)(base + (size_t)t.yofs);
+      t.ibeta = (const short*)(base + (size_t)t.ibeta);
+    }
+    if (cudaMemcpy(base, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) return bail("cudaMemcpy resize tables");
+  }
+  ctx->tprm.inverse_comp = 0; ctx->tprm.max_level = 4; ctx->tprm.min_level = 1; ctx->tprm.n_iter = 50;
+  *out = ctx;
+  return HSO_OK;
+}
+
+void hso_destroy(hso_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  for (FrameSlot& s : ctx->frames) {
+    if (s.pyr) cudaFree(s.pyr);
+    if (s.sobel) cudaFree(s.sobel);
+    if (s.sums) cudaFree(s.sums);
+    if (s.stats) cudaFree(s.stats);
+  }
+  DevBuf* db[] = {&ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
+                  &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
+  for (DevBuf* b : db) b->release();
+  PinBuf* pb[] = {&ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
+                  &ctx->a_jobs_host, &ctx->a_out_host, &ctx->p_stage_host, &ctx->p_out_host};
+  for (PinBuf* b : pb) b->release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* hso_last_error(const hso_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int hso_set_stream(hso_ctx* ctx, void* s) {
+  if (!ctx) return HSO_ERR_INVALID;
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return HSO_OK;
+}
+void* hso_get_stream(hso_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int hso_synchronize(hso_ctx* ctx) {
+  if (!ctx) return HSO_ERR_INVALID;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HSO_OK;
+}
+uint64_t hso_kernel_launches(const hso_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- F1 ---------------------------------------------------------------------------------------------------------------------
+int hso_frame_upload_batch(hso_ctx* ctx, int B, const uint8_t* const* imgs, int W, int H, int stride, hso_frame_id* out, float* integral,
+                           float* grad_mean) {
+  if (!ctx || B <= 0 || !imgs || !out) return HSO_ERR_INVALID;
+  // Frame::initFrame: "image must be CV_8UC1 of the camera's size" else throws (src/frame.cpp:85-86)
+  if (W != ctx->cam.width || H != ctx->cam.height || stride < W) return fail(ctx, HSO_ERR_INVALID, "image size does not match the camera model");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<const uint8_t*> srcs(B);
+  for (int i = 0; i < B; ++i) {
+    if (!imgs[i]) return fail(ctx, HSO_ERR_INVALID, "null image");
+    int rc = alloc_frame(ctx, &out[i]);
+    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) ctx->frames[out[j]].used = false; return rc; }
+  }
+  StageTimer tm(ctx, 0);
+  for (int i = 0; i < B; ++i) {
+    FrameSlot* s = get_frame(ctx, out[i]);
+    // straight into the level-0 slot of the pyramid (row stride == W); the kernel then builds in place
+    CU(cudaMemcpy2DAsync(s->pyr + ctx->geom.off[0], W, imgs[i], stride, W, H, cudaMemcpyHostToDevice, ctx->stream));
+    srcs[i] = s->pyr + ctx->geom.off[0];
+  }
+  int rc = run_pyramid(ctx, B, out, srcs.data(), W, 1);
+  if (rc != HSO_OK) return rc;
+  rc = read_stats(ctx, B, out, integral, grad_mean);
+  if (rc != HSO_OK) return rc;
+  tm.stop_after_sync();
+  return HSO_OK;
+}
+
+int hso_frame_upload(hso_ctx* ctx, const uint8_t* img, int W, int H, int stride, hso_frame_id* out, float* integral, float* grad_mean) {
+  return hso_frame_upload_batch(ctx, 1, &img, W, H, stride, out, integral, grad_mean);
+}
+
+int hso_frame_build_batch_device(hso_ctx* ctx, int B, const void* const* dev_imgs, int W, int H, int stride, hso_frame_id* out) {
+  if (!ctx || B <= 0 || !dev_imgs || !out) return HSO_ERR_INVALID;
+  if (W != ctx->cam.width || H != ctx->cam.height || stride < W) return fail(ctx, HSO_ERR_INVALID, "image size does not match the camera model");
+  CU(cudaSetDevice(ctx->device));
+  int aligned = 1;
+  for (int i = 0; i < B; ++i) {
+    if (((uintptr_t)dev_imgs[i] & 15) != 0) aligned = 0;
+    int rc = alloc_frame(ctx, &out[i]);
+    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) ctx->frames[out[j]].used = false; return rc; }
+  }
+  return run_pyramid(ctx, B, out, (const uint8_t* const*)dev_imgs, stride, aligned);
+}
+
+// Rebuild existing frames from device-resident images (benchmark loop: no allocation, asynchronous).
+int hso_frame_rebuild_batch_device(hso_ctx* ctx, int B, const void* const* dev_imgs, int W, int H, int stride, const hso_frame_id* ids) {
+  if (!ctx || B <= 0 || !dev_imgs || !ids) return HSO_ERR_INVALID;
+  if (W != ctx->cam.width || H != ctx->cam.height || stride < W) return fail(ctx, HSO_ERR_INVALID, "image size does not match the camera model");
+  int aligned = 1;
+  for (int i = 0; i < B; ++i) {
+    if (!get_frame(ctx, ids[i])) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
+    if (((uintptr_t)dev_imgs[i] & 15) != 0) aligned = 0;
+  }
+  return run_pyramid(ctx, B, ids, (const uint8_t* const*)dev_imgs, stride, aligned);
+}
+
+int hso_frame_stats(hso_ctx* ctx, hso_frame_id id, float* integral, float* grad_mean) {
+  if (!ctx) return HSO_ERR_INVALID;
+  if (!get_frame(ctx, id)) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
+  return read_stats(ctx, 1, &id, integral, grad_mean);
+}
+
+int hso_frame_level_size(hso_ctx* ctx, hso_frame_id id, int level, int* w, int* h) {
+  if (!ctx || level < 0 || level >= ctx->geom.n_levels) return HSO_ERR_INVALID;
+  (void)id;
+  if (w) *w = ctx->geom.w[level];
+  if (h) *h = ctx->geom.h[level];
+  return HSO_OK;
+}
+
+int hso_frame_download_level(hso_ctx* ctx, hso_frame_id id, int level, uint8_t* dst) {
+  if (!ctx || !dst || level < 0 || level >= ctx->geom.n_levels) return HSO_ERR_INVALID;
+  FrameSlot* s = get_frame(ctx, id);
+  if (!s) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
+  CU(cudaMemcpyAsync(dst, s->pyr + ctx->geom.off[level], (size_t)ctx->geom.w[level] * ctx->geom.h[level], cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HSO_OK;
+}
+
+int hso_frame_download_sobel(hso_ctx* ctx, hso_frame_id id, int level, int16_t* gx, int16_t* gy) {
+  if (!ctx || level < 0 || level >= 3 || level >= ctx->geom.n_levels) return HSO_ERR_INVALID;
+  FrameSlot* s = get_frame(ctx, id);
+  if (!s) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
+  if (!s->sobel) return fail(ctx, HSO_ERR_INVALID, "context was created without materialize_sobel");
+  size_t so = 0;
+  for (int l = 0; l < level; ++l) so += (size_t)2 * ctx->geom.w[l] * ctx->geom.h[l];
+  const size_t n = (size_t)ctx->geom.w[level] * ctx->geom.h[level];
+  if (gx) CU(cudaMemcpyAsync(gx, s->sobel + so, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  if (gy) CU(cudaMemcpyAsync(gy, s->sobel + so + n, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HSO_OK;
+}
+
+int hso_frame_release(hso_ctx* ctx, hso_frame_id id) {
+  if (!ctx) return HSO_ERR_INVALID;
+  FrameSlot* s = get_frame(ctx, id);
+  if (!s) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
+  s->used = false;  // buffers are kept for reuse; stream order protects in-flight work on this context
+  return HSO_OK;
+}
+
+// ---- F2 ---------------------------------------------------------------------------------------------------------------------
+int hso_track_set_cluster(hso_ctx* ctx, int ctas, int threads) {
+  if (!ctx) return HSO_ERR_INVALID;
+  if (!(ctas == 0 || ctas == 1 || ctas == 2 || ctas == 4 || ctas == 8)) return fail(ctx, HSO_ERR_INVALID, "cluster size must be 0,1,2,4,8");
+  if (threads != 0 && (threads < 64 || threads > 512 || threads % 32)) return fail(ctx, HSO_ERR_INVALID, "threads must be a multiple of 32 in [64,512]");
+  ctx->t_cluster = ctas;
+  ctx->t_threads = threads;
+  return HSO_OK;
+}
+
+int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_track_job* jobs, int trace_cap) {
+  if (!ctx || !prm || B <= 0 || !jobs) return HSO_ERR_INVALID;
+  if (prm->max_level >= ctx->geom.n_levels || prm->min_level < 0 || prm->min_level > prm->max_level || prm->max_level - prm->min_level > 5 ||
+      prm->n_iter < 0)
+    return fail(ctx, HSO_ERR_INVALID, "bad track params");
+  CU(cudaSetDevice(ctx->device));
+  ctx->tprm = *prm;
+  ctx->tB = B;
+  ctx->t_trace_cap = trace_cap > 0 ? trace_cap : 0;
+  // compact features with a valid depth (dist >= 0): the reference skips the others in every stage
+  // (src/CoarseTracker.cpp:290,433,455,557), so dropping them only changes the summation order.
+  std::vector<int> nvalid(B);
+  size_t host_bytes = 0, arena = 0;
+  int maxF = 0;
+  for (int b = 0; b < B; ++b) {
+    const hso_track_job& j = jobs[b];
+    if (j.n_features < 0 || j.n_features > ctx->cfg.max_features) return fail(ctx, HSO_ERR_CAPACITY, "n_features exceeds hso_cfg.max_features");
+    if (!get_frame(ctx, j.ref) || !get_frame(ctx, j.cur)) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id in track job");
+    if (j.n_features > 0 && (!j.px || !j.f || !j.dist)) return fail(ctx, HSO_ERR_INVALID, "null feature arrays");
+    int n = 0;
+    for (int i = 0; i < j.n_features; ++i) n += (j.dist[i] >= 0) ? 1 : 0;
+    nvalid[b] = n;
+    maxF = std::max(maxF, n);
+    const int Fpad = std::max(32, (n + 31) / 32 * 32);
+    host_bytes += sizeof(double) * 5 * Fpad;
+    arena += sizeof(double) * 5 * Fpad;
+  }
+  ctx->t_maxF = maxF;
+  const size_t geo_bytes = arena;
+  // per-job scratch behind the geometry block
+  std::vector<size_t> off_cache(B), off_gx(B), off_gy(B), off_abs(B), off_vis(B), off_state(B), off_trace(B);
+  for (int b = 0; b < B; ++b) {
+    const int Fpad = std::max(32, (nvalid[b] + 31) / 32 * 32);
+    auto take = [&](size_t bytes) { size_t o = (arena + 127) / 128 * 128; arena = o + bytes; return o; };
+    off_cache[b] = take(sizeof(float) * kMaxPatternN * Fpad);
+    if (prm->inverse_comp) { off_gx[b] = take(sizeof(float) * kMaxPatternN * Fpad); off_gy[b] = take(sizeof(float) * kMaxPatternN * Fpad); }
+    off_abs[b] = take(sizeof(float) * kMaxPatternN * Fpad);
+    off_vis[b] = take(Fpad);
+    off_state[b] = take(sizeof(TrackState));
+    off_trace[b] = ctx->t_trace_cap ? take(sizeof(hso_trace) * ctx->t_trace_cap) : 0;
+  }
+  CU(ctx->t_arena.reserve(arena));
+  ctx->t_arena_bytes = arena;
+  ctx->t_trace_off = off_trace;
+  CU(ctx->t_stage_host.reserve(host_bytes + sizeof(double) * 12 * B + sizeof(float) * B));
+  CU(ctx->t_jobs_host.reserve(sizeof(TrackJobDev) * B));
+  CU(ctx->t_jobs_dev.reserve(sizeof(TrackJobDev) * B));
+  CU(ctx->t_T0.reserve(sizeof(double) * 12 * B));
+  CU(ctx->t_a0.reserve(sizeof(float) * B));
+  CU(ctx->t_out_dev.reserve(sizeof(hso_track_result) * B));
+  CU(ctx->t_out_host.reserve(sizeof(hso_track_result) * B));
+  char* hbase = (char*)ctx->t_stage_host.p;
+  char* dbase = (char*)ctx->t_arena.p;
+  TrackJobDev* hj = (TrackJobDev*)ctx->t_jobs_host.p;
+  size_t go = 0;
+  for (int b = 0; b < B; ++b) {
+    const hso_track_job& j = jobs[b];
+    const int Fpad = std::max(32, (nvalid[b] + 31) / 32 * 32);
+    double* px = (double*)(hbase + go);
+    double* xyz = px + 2 * Fpad;
+    int k = 0;
+    for (int i = 0; i < j.n_features; ++i) {
+      const double d = j.dist[i];
+      if (!(d >= 0)) continue;
+      px[k] = j.px[2 * i]; px[Fpad + k] = j.px[2 * i + 1];
+      // Vector3d xyz_ref((*it_ft)->f*dist)  (src/CoarseTracker.cpp:292)
+      xyz[k] = j.f[3 * i] * d; xyz[Fpad + k] = j.f[3 * i + 1] * d; xyz[2 * Fpad + k] = j.f[3 * i + 2] * d;
+      ++k;
+    }
+    for (; k < Fpad; ++k) { px[k] = px[Fpad + k] = 0; xyz[k] = xyz[Fpad + k] = 0; xyz[2 * Fpad + k] = 1; }
+    TrackJobDev& d = hj[b];
+    d.ref_pyr = get_frame(ctx, j.ref)->pyr;
+    d.cur_pyr = get_frame(ctx, j.cur)->pyr;
+    d.F = nvalid[b];
+    d.Fpad = Fpad;
+    d.px = (const double*)(dbase + go);
+    d.xyz = d.px + 2 * Fpad;
+    d.ref_cache = (float*)(dbase + off_cache[b]);
+    d.ref_gx = prm->inverse_comp ? (float*)(dbase + off_gx[b]) : nullptr;
+    d.ref_gy = prm->inverse_comp ? (float*)(dbase + off_gy[b]) : nullptr;
+    d.absres = (float*)(dbase + off_abs[b]);
+    d.vis = (uint8_t*)(dbase + off_vis[b]);
+    d.state = (TrackState*)(dbase + off_state[b]);
+    d.trace = ctx->t_trace_cap ? (hso_trace*)(dbase + off_trace[b]) : nullptr;
+    go += sizeof(double) * 5 * Fpad;
+  }
+  double* T0 = (double*)(hbase + host_bytes);
+  float* a0 = (float*)(T0 + 12 * B);
+  for (int b = 0; b < B; ++b) {
+    memcpy(T0 + 12 * b, jobs[b].T_cur_ref, sizeof(double) * 12);
+    a0[b] = jobs[b].exposure_rat;
+  }
+  CU(cudaMemcpyAsync(dbase, hbase, geo_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->t_T0.p, T0, sizeof(double) * 12 * B, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->t_a0.p, a0, sizeof(float) * B, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->t_jobs_dev.p, hj, sizeof(TrackJobDev) * B, cudaMemcpyHostToDevice, ctx->stream));
+  return HSO_OK;
+}
+
+int hso_track_restage_frames(hso_ctx* ctx, int B, const hso_frame_id* ref, const hso_frame_id* cur) {
+  if (!ctx || B != ctx->tB || !ref || !cur) return HSO_ERR_INVALID;
+  TrackJobDev* hj = (TrackJobDev*)ctx->t_jobs_host.p;
+  for (int b = 0; b < B; ++b) {
+    if (!get_frame(ctx, ref[b]) || !get_frame(ctx, cur[b])) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
+    hj[b].ref_pyr = get_frame(ctx, ref[b])->pyr;
+    hj[b].cur_pyr = get_frame(ctx, cur[b])->pyr;
+  }
+  CU(cudaMemcpyAsync(ctx->t_jobs_dev.p, hj, sizeof(TrackJobDev) * B, cudaMemcpyHostToDevice, ctx->stream));
+  return HSO_OK;
+}
+
+int hso_track_run(hso_ctx* ctx) {
+  if (!ctx || ctx->tB <= 0) return HSO_ERR_INVALID;
+  const int B = ctx->tB;
+  const hso_track_params& prm = ctx->tprm;
+  int cluster = ctx->t_cluster;
+  if (cluster == 0) cluster = B >= 64 ? 1 : (B >= 32 ? 2 : (B >= 16 ? 4 : 8));
+  int threads = ctx->t_threads;
+  if (threads == 0) {
+    const int per = (ctx->t_maxF + cluster - 1) / cluster;
+    threads = std::min(512, std::max(64, (per + 31) / 32 * 32));
+    if (B >= 64) threads = std::min(threads, 256);
+  }
+  const TrackJobDev* jd = (const TrackJobDev*)ctx->t_jobs_dev.p;
+  CU(launch_track_init(jd, (const double*)ctx->t_T0.p, (const float*)ctx->t_a0.p, B, ctx->stream, &ctx->launches));
+  for (int level = prm.max_level; level >= prm.min_level; --level) {
+    TrackLevelParams p;
+    memset(&p, 0, sizeof p);
+    p.ic = prm.inverse_comp; p.max_level = prm.max_level; p.level = level; p.n_iter = prm.n_iter;
+    p.trace_cap = ctx->t_trace_cap;
+    p.w = ctx->geom.w[level]; p.h = ctx->geom.h[level];
+    p.level_off = ctx->geom.off[level];
+    p.img_bytes = ctx->geom.stage_bytes[level];
+    p.cam = ctx->camdev;
+    p.stage_smem = 1;
+    if (track_level_smem_bytes(p, threads) > 227 * 1024) p.stage_smem = 0;
+    CU(launch_track_level(p, jd, B, cluster, threads, ctx->stream, &ctx->launches));
+  }
+  CU(launch_track_finish(jd, (hso_track_result*)ctx->t_out_dev.p, B, ctx->stream, &ctx->launches));
+  return HSO_OK;
+}
+
+int hso_track_collect(hso_ctx* ctx, hso_track_result* out, hso_trace* trace, int* trace_len) {
+  if (!ctx || ctx->tB <= 0 || !out) return HSO_ERR_INVALID;
+  const int B = ctx->tB;
+  CU(cudaMemcpyAsync(ctx->t_out_host.p, ctx->t_out_dev.p, sizeof(hso_track_result) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (trace && ctx->t_trace_cap) {
+    for (int b = 0; b < B; ++b)
+      CU(cudaMemcpyAsync(trace + (size_t)b * ctx->t_trace_cap, (char*)ctx->t_arena.p + ctx->t_trace_off[b], sizeof(hso_trace) * ctx->t_trace_cap,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->t_out_host.p, sizeof(hso_track_result) * B);
+  if (trace_len) for (int b = 0; b < B; ++b) trace_len[b] = out[b].trace_len;
+  return HSO_OK;
+}
+
+int hso_coarse_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_track_job* jobs, hso_track_result* out, hso_trace* trace,
+                           int trace_cap, int* trace_len) {
+  if (!ctx) return HSO_ERR_INVALID;
+  int rc = hso_track_stage(ctx, prm, B, jobs, trace ? trace_cap : 0);
+  if (rc != HSO_OK) return rc;
+  StageTimer tm(ctx, 1);
+  rc = hso_track_run(ctx);
+  if (rc != HSO_OK) return rc;
+  rc = hso_track_collect(ctx, out, trace, trace_len);
+  if (rc != HSO_OK) return rc;
+  tm.stop_after_sync();
+  // CoarseTracker::run returns 0 and leaves the pose untouched when the reference frame has no features (:53)
+  for (int b = 0; b < B; ++b)
+    if (jobs[b].n_features == 0) {
+      memcpy(out[b].T_cur_ref, jobs[b].T_cur_ref, sizeof(double) * 12);
+      out[b].exposure_rat = jobs[b].exposure_rat;
+      out[b].n_tracked = 0;
+    }
+  return HSO_OK;
+}
+
+int hso_coarse_track(hso_ctx* ctx, const hso_track_params* prm, const hso_track_job* job, hso_track_result* out, hso_trace* trace, int trace_cap,
+                     int* trace_len) {
+  return hso_coarse_track_batch(ctx, prm, 1, job, out, trace, trace_cap, trace_len);
+}
+
+int hso_stage_time_ms(hso_ctx* ctx, int stage, double* ms, uint64_t* calls) {
+  if (!ctx || stage < 0 || stage > 3) return HSO_ERR_INVALID;
+  if (ms) *ms = ctx->stage_ms[stage];
+  if (calls) *calls = ctx->stage_calls[stage];
+  return HSO_OK;
+}
+
+}  // extern "C"

@@ -9,21 +9,21 @@
 namespace hso {
 
 constexpr int kMaxLevels = 5;     // max(Config::nPyrLevels, kltMaxLevel+1) = 5 (src/frame.cpp:92)
-constexpr int kMaxPatternN = 25;  // largest pattern actually reachable (idx 6, include/hso/CoarseTracker.h:100-109)
+constexpr int kMaxPatternN = 25;  // largest pattern (include/hso/CoarseTracker.h:100-109)
 constexpr int kMaxCluster = 8;    // portable thread-block-cluster size
 constexpr int kPadRows = 3;       // zero rows kept below every pyramid level (gradient taps may touch row == rows)
 
 // Device layout of one frame's pyramid. All frames of a context share the camera, hence the geometry.
-// Level l lives at byte offset off[l] with `pitch[l]` bytes per row (multiple of 16, > w[l]). The bytes [w, pitch) of
-// row y repeat the first bytes of row y+1 ("wrap padding"): with the reference's stride == cols a tap at column == cols
-// reads the next row's first pixel (src/CoarseTracker.cpp:368-371 at the right border), and so do we. kPadRows zero rows
-// follow each level (the reference reads one row past the image there, which is undefined; zeros are our definition).
+// Level l is tightly packed (row stride == w[l], exactly the reference's `stride = img.cols`, src/CoarseTracker.cpp:248),
+// starts at the 128-byte aligned offset off[l], and is followed by kPadRows zero rows + 16 zero bytes: the reference's
+// forward-mode gradient taps can read row == rows (undefined there; zero here, see DESIGN.md "quirks").
 struct PyrGeom {
   int n_levels;
-  int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
-  size_t off[kMaxLevels];   // 128-byte aligned
-  size_t bytes;             // total bytes per frame
-  int half_path;            // 1: halfSample chain (W%16==0 && H%16==0, src/frame.cpp:303), 0: cv::resize chain
+  int w[kMaxLevels], h[kMaxLevels];
+  size_t off[kMaxLevels];        // 128-byte aligned
+  uint32_t stage_bytes[kMaxLevels];  // bytes a kernel stages in shared memory for level l (image + pad, multiple of 16)
+  size_t bytes;                  // total bytes per frame
+  int half_path;                 // 1: halfSample chain (W%16==0 && H%16==0, src/frame.cpp:303), 0: cv::resize chain
   int sse_rounding[kMaxLevels];  // level l>=1 is produced with SSE2 double rounding iff w[l-1]%16==0 (src/vikit/vision.cpp:82)
 };
 
@@ -32,11 +32,22 @@ struct PyrJobDev {
   const uint8_t* src;  // raw level-0 image on the device, row stride = src_stride
   uint8_t* pyr;        // destination pyramid buffer (PyrGeom layout)
   int16_t* sobel;      // nullptr, or [level 0..2][gx plane | gy plane], tightly packed w*h each
-  double* sums;        // [2] scratch: sum I, sum |grad| over the level-0 interior (zeroed by the launcher)
+  double* sums;        // [2 * pyramid_tiles] scratch: per-tile sum |grad|, sum I over the level-0 interior
   float* stats;        // [2] out: Frame::integralImage_, Frame::gradMean_
 };
-cudaError_t launch_pyramid(const PyrGeom& g, const PyrJobDev* jobs_dev, int B, int src_stride, int n_sobel_levels, int store_sobel,
-                           cudaStream_t stream, uint64_t* launches);
+// cv::resize(INTER_LINEAR) coefficient tables for the non-%16 pyramid path, built on the host once per context.
+struct ResizeTabDev {
+  const int* xofs;     // [dw]
+  const short* ialpha; // [2*dw]
+  const int* yofs;     // [dh]
+  const short* ibeta;  // [2*dh]
+  int area_fast;       // exact 2x decimation => (a+b+c+d+2)>>2
+};
+// counters_dev: [B] zero-initialised uints (tile arrival counters, reset by the kernel). src_aligned16: every job's src pointer
+// is 16-byte aligned (enables the TMA row copies). A job whose src equals pyr + off[0] is built in place (no level-0 copy).
+cudaError_t launch_pyramid(const PyrGeom& g, const PyrJobDev* jobs_dev, int B, int src_stride, const ResizeTabDev* tabs /*[n_levels]*/,
+                           int store_sobel, unsigned int* counters_dev, int src_aligned16, cudaStream_t stream, uint64_t* launches);
+int pyramid_tiles(const PyrGeom& g);  // number of level-0 tiles per frame (size of PyrJobDev::sums / 2)
 
 // ---- CoarseTracker ------------------------------------------------------------------------------------------------------
 // Per-problem persistent state, lives in device memory across the per-level launches.
@@ -67,14 +78,13 @@ struct TrackJobDev {
   hso_trace* trace;      // [trace_cap] or nullptr
 };
 
-
 struct TrackLevelParams {
   int ic, max_level, level, n_iter;
   int trace_cap;
-  int w, h, pitch;          // geometry of this level
+  int w, h;                 // geometry of this level
   size_t level_off;         // byte offset of this level in a pyramid buffer
   int stage_smem;           // 1: the current level image is staged in shared memory
-  uint32_t img_bytes;       // bytes staged (pitch * (h + kPadRows)), multiple of 16
+  uint32_t img_bytes;       // bytes staged (multiple of 16)
   CamDev cam;
 };
 

@@ -1,0 +1,710 @@
+// CoarseTracker on sm_100a: sparse direct image alignment, one thread-block cluster per (ref, cur) problem, the whole
+// Levenberg-Marquardt loop of a pyramid level resident on the device (no host round trips between trials).
+//
+// Replaces hso::CoarseTracker::{precomputeReferencePatches, selectRobustFunctionLevel, computeResiduals, computeGS} and the
+// level loop of run() — src/CoarseTracker.cpp:74-195,242-644 — for a batch of independent problems.
+//
+// Mapping (see DESIGN.md "k_track_level"):
+//   * lane == patch. A thread owns patches i = t, t+NT, ... for the whole launch, so the reference-intensity cache it
+//     writes in phase 1 is only ever read back by itself (no barrier), and all scratch arrays are [pattern px][patch]
+//     so that a warp's accesses are coalesced.
+//   * the current-level image is staged once per launch into shared memory with a TMA bulk copy (cp.async.bulk +
+//     mbarrier; SASS UBLKCP); every residual evaluation of the level then gathers its taps from shared memory.
+//   * the 7x7 normal equations are not accumulated term by term. Every Jacobian row of a patch has the form
+//     J = [-c, gx*A + gy*B] with A,B in R^6 constant over the patch (src/CoarseTracker.cpp:372), so per term only the nine
+//     moments  sum w*{gx^2, gx gy, gy^2, c gx, c gy, c^2, r gx, r gy, r c}  are accumulated and the 28+7 entries are
+//     expanded once per patch — mathematically identical to computeGS (src/CoarseTracker.cpp:499-525), 4x fewer FMAs.
+//   * fp32 inside a patch (as the reference), fp32 tree inside a warp, fp64 across warps / CTAs in a fixed order
+//     (run-to-run deterministic); the reference accumulates H in fp32 over all terms (MatrixAccumulator.h:65-140).
+//   * the robust thresholds (median / MAD, src/CoarseTracker.cpp:608-630) are exact order statistics obtained with a
+//     3-pass radix select on the float bit patterns — the k-th element is order independent, so they match nth_element.
+//   * cluster of C CTAs per problem: partial sums and histograms are exchanged through distributed shared memory;
+//     every CTA then runs the (tiny, fp64) damped solve + SE3 update redundantly, so one cluster barrier per trial suffices.
+#include <cooperative_groups.h>
+
+#include "hso_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace hso {
+
+// include/hso/CoarseTracker.h:58-120 — first staticPatternNum[idx] entries of every pattern (idx 2 repeats {-1,0}: quirk kept).
+__constant__ int8_t c_pat[8][25][2] = {
+    {{0, 0}},
+    {{0, -1}, {-1, 0}, {0, 0}, {1, 0}, {0, 1}},
+    {{-1, -1}, {-1, 0}, {-1, 1}, {-1, 0}, {0, 0}, {0, 1}, {1, -1}, {1, 0}, {1, 1}},
+    {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {1, 1}, {0, 2}, {0, -1}, {-1, 0}, {1, 0}, {0, 1}},
+    {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {1, 1}, {0, 2}, {-2, -2}, {-2, 2}, {2, -2}, {2, 2}},
+    {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {1, 1}, {0, 2}, {-2, -2}, {-2, 2},
+     {2, -2}, {2, 2}, {-3, -1}, {-3, 1}, {3, -1}, {3, 1}, {1, -3}, {-1, -3}, {1, 3}, {-1, 3}},
+    {{-2, -2}, {-2, -1}, {-2, 0}, {-2, 1}, {-2, 2}, {-1, -2}, {-1, -1}, {-1, 0}, {-1, 1}, {-1, 2}, {0, -2}, {0, -1}, {0, 0},
+     {0, 1}, {0, 2}, {1, -2}, {1, -1}, {1, 0}, {1, 1}, {1, 2}, {2, -2}, {2, -1}, {2, 0}, {2, 1}, {2, 2}},
+    {{-4, -4}, {-4, -2}, {-4, 0}, {-4, 2}, {-4, 4}, {-2, -4}, {-2, -2}, {-2, 0}, {-2, 2}, {-2, 4}, {0, -4}, {0, -2}, {0, 0},
+     {0, 2}, {0, 4}, {2, -4}, {2, -2}, {2, 0}, {2, 2}, {2, 4}, {4, -4}, {4, -2}, {4, 0}, {4, 2}, {4, 4}},
+};
+static const int h_pat_num[8] = {1, 5, 9, 13, 13, 21, 25, 25};
+static const int h_pat_pad[8] = {1, 1, 1, 2, 2, 3, 2, 4};
+
+constexpr int NRED = 40;       // 28 H + 7 b + E + terms + saturated + patches (+1 pad)
+constexpr int NHIST = 2048;    // radix-select bins per pass (11 + 11 + 10 bits)
+
+struct TrackCtrl {
+  double Rt[12];       // pose used by the evaluation in flight
+  Se3d T_acc, T_try;
+  float a_acc, a_try, a_eval;
+  float lambda, huber, outlier;
+  double H[28], b[7];  // accepted system (upper triangle, row-major)
+  double step[7];
+  double E_old;
+  int done, iter, n_err;
+  uint32_t sel_prefix, sel_k, sel_n;
+};
+
+struct Smem {
+  uint8_t* img;
+  double* warp_part;   // [nwarps][NRED]
+  double* cta_part;    // [2][NRED]
+  double* tot;         // [NRED]
+  uint32_t* hist;      // [2][NHIST]
+  uint32_t* ghist;     // [NHIST]
+  TrackCtrl* ctrl;
+  uint64_t* mbar;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline size_t smem_layout(uint32_t img_bytes, int nwarps, size_t* o_warp, size_t* o_cta, size_t* o_tot, size_t* o_hist,
+                                              size_t* o_ghist, size_t* o_ctrl, size_t* o_mbar) {
+  size_t o = align_up(img_bytes, 128);
+  *o_warp = o; o += sizeof(double) * nwarps * NRED;
+  *o_cta = o; o += sizeof(double) * 2 * NRED;
+  *o_tot = o; o += sizeof(double) * NRED;
+  *o_hist = o; o += sizeof(uint32_t) * 2 * NHIST;
+  *o_ghist = o; o += sizeof(uint32_t) * NHIST;
+  *o_ctrl = o; o += align_up(sizeof(TrackCtrl), 16);
+  *o_mbar = o; o += 16;
+  return o;
+}
+
+size_t track_level_smem_bytes(const TrackLevelParams& p, int threads) {
+  size_t a, b, c, d, e, f, g;
+  return smem_layout(p.stage_smem ? p.img_bytes : 0, threads / 32, &a, &b, &c, &d, &e, &f, &g);
+}
+
+// ---- unaligned 4-byte window from a byte image: two aligned words + funnel shift -----------------------------------------
+template <bool STAGE>
+HSO_DEV uint32_t ld4(const uint8_t* img, int byte_addr) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(img) + (byte_addr >> 2);
+  uint32_t lo, hi;
+  if (STAGE) { lo = w[0]; hi = w[1]; }
+  else { lo = __ldg(w); hi = __ldg(w + 1); }
+  return __funnelshift_r(lo, hi, (byte_addr & 3) << 3);
+}
+HSO_DEV float b0(uint32_t w) { return (float)(w & 0xffu); }
+HSO_DEV float b1(uint32_t w) { return (float)((w >> 8) & 0xffu); }
+HSO_DEV float b2(uint32_t w) { return (float)((w >> 16) & 0xffu); }
+HSO_DEV float b3(uint32_t w) { return (float)(w >> 24); }
+
+struct Acc {
+  float h[28], b[7], E;
+  int terms, sat, patches;
+};
+
+HSO_DEV void acc_zero(Acc& a) {
+#pragma unroll
+  for (int i = 0; i < 28; ++i) a.h[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) a.b[i] = 0.f;
+  a.E = 0.f; a.terms = 0; a.sat = 0; a.patches = 0;
+}
+
+// Projection head shared by computeResiduals / selectRobustFunctionLevel (src/CoarseTracker.cpp:290-323, :557-583).
+struct Proj {
+  bool ok;
+  int base;  // byte index of (u_i, v_i) in the level image
+  float wtl, wtr, wbl, wbr;
+  double x, y, z;
+};
+
+HSO_DEV Proj project_patch(const double* Rt, const CamDev& cam, double X, double Y, double Z, float scale, int border, int w, int h) {
+  Proj p;
+  p.ok = false;
+  p.x = Rt[0] * X + Rt[1] * Y + Rt[2] * Z + Rt[3];
+  p.y = Rt[4] * X + Rt[5] * Y + Rt[6] * Z + Rt[7];
+  p.z = Rt[8] * X + Rt[9] * Y + Rt[10] * Z + Rt[11];
+  if (p.z < 0) return p;
+  double pu, pv;
+  world2cam(cam, p.x, p.y, p.z, pu, pv);
+  const float u = (float)pu * scale, v = (float)pv * scale;
+  const float uf = floorf(u), vf = floorf(v);
+  // floorf + saturating conversion: NaN/inf projections (z == 0) fail the bounds test instead of being undefined
+  const int ui = __float2int_rd(u), vi = __float2int_rd(v);
+  if (!(ui >= border && vi >= border && ui < w - border && vi < h - border)) return p;  // overflow-safe form of :310
+  const float su = u - uf, sv = v - vf;
+  p.wtl = (float)((1.0 - su) * (1.0 - sv));
+  p.wtr = (float)(su * (1.0 - sv));
+  p.wbl = (float)((1.0 - su) * sv);
+  p.wbr = su * sv;
+  p.base = vi * w + ui;
+  p.ok = true;
+  return p;
+}
+
+// Frame::jacobian_xyz2uv (include/hso/frame.h:192-212), rows pre-multiplied by fx*scale / fy*scale (CoarseTracker.cpp:372).
+HSO_DEV void patch_jacobian(double x, double y, double z, float fxl, float fyl, float* A, float* B) {
+  const float zi = (float)(1.0 / z);
+  const float xf = (float)x, yf = (float)y;
+  const float zi2 = zi * zi;
+  const float j02 = xf * zi2, j12 = yf * zi2;
+  const float j03 = yf * j02;
+  A[0] = -zi * fxl; A[1] = 0.f; A[2] = j02 * fxl; A[3] = j03 * fxl; A[4] = -(1.0f + xf * j02) * fxl; A[5] = yf * zi * fxl;
+  B[0] = 0.f; B[1] = -zi * fyl; B[2] = j12 * fyl; B[3] = (1.0f + yf * j12) * fyl; B[4] = -j03 * fyl; B[5] = -xf * zi * fyl;
+}
+
+struct Moments { float xx, xy, yy, cx, cy, cc, rx, ry, rc; };
+
+HSO_DEV void expand_patch(Acc& a, const Moments& m, const float* A, const float* B) {
+  a.h[0] += m.cc;
+  float P[6], Q[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    a.h[1 + k] -= m.cx * A[k] + m.cy * B[k];
+    P[k] = m.xx * A[k] + m.xy * B[k];
+    Q[k] = m.xy * A[k] + m.yy * B[k];
+    a.b[1 + k] -= m.rx * A[k] + m.ry * B[k];
+  }
+  a.b[0] += m.rc;
+  int idx = 7;
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int k = j; k < 6; ++k) a.h[idx++] += A[j] * P[k] + B[j] * Q[k];
+}
+
+struct LevelCtx {
+  const uint8_t* cur;  // shared-memory copy or global level image
+  int w, h, N, border;
+  float scale, fxl, fyl;
+  bool top;
+};
+
+// One residual evaluation over the calling thread's patches: computeResiduals + computeGS fused
+// (src/CoarseTracker.cpp:242-414, :499-525).
+template <int PIDX, bool IC, bool STAGE>
+HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const CamDev& cam, const double* Rt, float a, float huber, float cutoff,
+                          int t0, int nt, Acc& acc) {
+  constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
+  const int Fp = job.Fpad;
+  // max_energy = 2*huber*cutoff - huber^2, evaluated in double like the reference (cutoff_error is a double there)
+  const float max_energy = (float)(2.0 * (double)huber * (double)cutoff - (double)(huber * huber));
+  double R[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) R[k] = Rt[k];
+  for (int i = t0; i < job.F; i += nt) {
+    if (!job.vis[i]) continue;
+    const double X = job.xyz[i], Y = job.xyz[Fp + i], Z = job.xyz[2 * Fp + i];
+    const Proj p = project_patch(R, cam, X, Y, Z, L.scale, L.border, L.w, L.h);
+    if (!p.ok) continue;
+    float A[6], B[6];
+    if (!IC) {
+      patch_jacobian(p.x, p.y, p.z, L.fxl, L.fyl, A, B);
+    } else {
+      patch_jacobian(X, Y, Z, L.fxl, L.fyl, A, B);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { A[k] *= a; B[k] *= a; }  // m_jacobian_cache_true = exposure_rat * raw (:244-245)
+    }
+    Moments m = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float Ep = 0.f;
+    int terms = 0, sat = 0;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const int addr = p.base + (int)c_pat[PIDX][n][1] * L.w + (int)c_pat[PIDX][n][0];
+      const float c = job.ref_cache[n * Fp + i];
+      float color, gx, gy;
+      if (!IC) {
+        const uint32_t rm = ld4<STAGE>(L.cur, addr - L.w - 1);
+        const uint32_t r0 = ld4<STAGE>(L.cur, addr - 1);
+        const uint32_t r1 = ld4<STAGE>(L.cur, addr + L.w - 1);
+        const uint32_t r2 = ld4<STAGE>(L.cur, addr + 2 * L.w - 1);
+        color = p.wtl * b1(r0) + p.wtr * b2(r0) + p.wbl * b1(r1) + p.wbr * b2(r1);
+        gx = 0.5f * ((p.wtl * b2(r0) + p.wtr * b3(r0) + p.wbl * b2(r1) + p.wbr * b3(r1)) -
+                     (p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1)));
+        gy = 0.5f * ((p.wtl * b1(r1) + p.wtr * b2(r1) + p.wbl * b1(r2) + p.wbr * b2(r2)) -
+                     (p.wtl * b1(rm) + p.wtr * b2(rm) + p.wbl * b1(r0) + p.wbr * b2(r0)));
+      } else {
+        const uint32_t r0 = ld4<STAGE>(L.cur, addr);
+        const uint32_t r1 = ld4<STAGE>(L.cur, addr + L.w);
+        color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
+        gx = job.ref_gx[n * Fp + i];
+        gy = job.ref_gy[n * Fp + i];
+      }
+      const float r = color - (a * c + 0.f);
+      const float ar = fabsf(r);
+      const float hw = ar < huber ? 1.f : huber / ar;
+      ++terms;
+      if (ar > cutoff && !L.top) {
+        Ep += max_energy;
+        ++sat;
+      } else {
+        Ep += L.top ? hw * r * r : hw * r * r * (2.f - hw);
+        const float wgx = hw * gx, wgy = hw * gy, wc = hw * c;
+        m.xx += wgx * gx; m.xy += wgx * gy; m.yy += wgy * gy;
+        m.cx += wc * gx;  m.cy += wc * gy;  m.cc += wc * c;
+        m.rx += wgx * r;  m.ry += wgy * r;  m.rc += wc * r;
+      }
+    }
+    expand_patch(acc, m, A, B);
+    acc.E += Ep;
+    acc.terms += terms;
+    acc.sat += sat;
+    acc.patches += 1;
+  }
+}
+
+// CTA + cluster reduction of the per-thread partial sums into s.tot[0..NRED) (identical in every CTA of the cluster).
+HSO_DEV void reduce_acc(const Acc& acc, const Smem& s, int slot, int csize, int nwarps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* wp = s.warp_part + warp * NRED;
+#pragma unroll
+  for (int k = 0; k < 28; ++k) { float v = warp_sum(acc.h[k]); if (lane == 0) wp[k] = (double)v; }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { float v = warp_sum(acc.b[k]); if (lane == 0) wp[28 + k] = (double)v; }
+  { float v = warp_sum(acc.E); if (lane == 0) wp[35] = (double)v; }
+  { int v = warp_sum(acc.terms); if (lane == 0) wp[36] = (double)v; }
+  { int v = warp_sum(acc.sat); if (lane == 0) wp[37] = (double)v; }
+  { int v = warp_sum(acc.patches); if (lane == 0) wp[38] = (double)v; }
+  __syncthreads();
+  if (threadIdx.x < NRED - 1) {
+    double sum = 0;
+    for (int w = 0; w < nwarps; ++w) sum += s.warp_part[w * NRED + threadIdx.x];
+    if (csize == 1) s.tot[threadIdx.x] = sum;
+    else s.cta_part[slot * NRED + threadIdx.x] = sum;
+  }
+  if (csize == 1) {
+    __syncthreads();
+    return;
+  }
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();
+  if (threadIdx.x < NRED - 1) {
+    double sum = 0;
+    for (int r = 0; r < csize; ++r) {
+      const double* peer = cluster.map_shared_rank(s.cta_part, r);
+      sum += peer[slot * NRED + threadIdx.x];
+    }
+    s.tot[threadIdx.x] = sum;
+  }
+  __syncthreads();
+}
+
+// Exact k-th smallest (k = n/2, hso::getMedian, include/hso/vikit/math_utils.h:119-126) of the non-negative floats
+// { f(absres) : absres >= 0 } owned by the cluster; MAD = true selects over fabsf(v - center). Result in ctrl->sel_prefix.
+template <int N>
+HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, int t0, int nt, bool mad, float center, int csize, int& hist_phase) {
+  const int Fp = job.Fpad;
+  uint32_t prefix = 0, mask = 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+    const uint32_t dmask = pass == 2 ? 0x3ffu : 0x7ffu;
+    uint32_t* hist = s.hist + (hist_phase & 1) * NHIST;
+    for (int j = threadIdx.x; j < NHIST; j += blockDim.x) hist[j] = 0;
+    __syncthreads();
+    for (int i = t0; i < job.F; i += nt) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        float v = job.absres[n * Fp + i];
+        if (v < 0.f) continue;
+        if (mad) v = fabsf(v - center);
+        const uint32_t key = __float_as_uint(v);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
+      }
+    }
+    if (csize == 1) {
+      __syncthreads();
+      for (int j = threadIdx.x; j < NHIST; j += blockDim.x) s.ghist[j] = hist[j];
+    } else {
+      cg::cluster_group cluster = cg::this_cluster();
+      cluster.sync();
+      for (int j = threadIdx.x; j < NHIST; j += blockDim.x) {
+        uint32_t sum = 0;
+        for (int r = 0; r < csize; ++r) sum += cluster.map_shared_rank(hist, r)[j];
+        s.ghist[j] = sum;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      uint32_t local = 0;
+      for (int j = 0; j < NHIST / 32; ++j) local += s.ghist[lane * (NHIST / 32) + j];
+      uint32_t incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      uint32_t k;
+      if (pass == 0) {
+        k = total / 2;
+        if (lane == 0) { s.ctrl->sel_n = total; }
+      } else {
+        k = s.ctrl->sel_k;
+      }
+      const uint32_t excl = incl - local;
+      const bool mine = total > 0 && k >= excl && k < incl;
+      if (mine) {
+        uint32_t cum = excl;
+        int d = lane * (NHIST / 32);
+        for (int j = 0; j < NHIST / 32; ++j) {
+          const uint32_t c = s.ghist[lane * (NHIST / 32) + j];
+          if (k < cum + c) { d = lane * (NHIST / 32) + j; break; }
+          cum += c;
+        }
+        s.ctrl->sel_k = k - cum;
+        s.ctrl->sel_prefix = prefix | ((uint32_t)d << shift);
+      }
+      if (total == 0 && lane == 0) { s.ctrl->sel_k = 0; s.ctrl->sel_prefix = 0; }
+    }
+    __syncthreads();
+    prefix = s.ctrl->sel_prefix;
+    mask |= dmask << shift;
+    ++hist_phase;
+  }
+}
+
+// Thread-0 control step after a residual evaluation: accept/reject, damping update, convergence test, damped 7x7 solve and
+// SE3 update for the next trial (src/CoarseTracker.cpp:108-194). Every CTA of a cluster runs it redundantly on identical totals.
+__device__ __noinline__ void lm_control(TrackCtrl* c, const double* tot, const TrackJobDev& job, int iter, int n_iter, int level, int trace_cap,
+                                        bool ic, bool rank0, float a_eval, float huber, float cutoff, int N) {
+  const int terms = (int)tot[36];
+  const double E = (double)((float)tot[35] / (float)terms);  // return E/m_total_terms (float / int), :413
+  const bool accepted = iter < 0 ? true : (E < c->E_old);
+  if (job.trace != nullptr && rank0) {
+    const int tl = job.state->trace_len;
+    if (tl < trace_cap) {
+      hso_trace* e = job.trace + tl;
+      e->level = level; e->iter = iter;
+      for (int k = 0; k < 12; ++k) e->T_eval[k] = c->Rt[k];
+      e->a_eval = a_eval; e->lambda = iter < 0 ? 0.f : c->lambda;
+      int idx = 0;
+      for (int r = 0; r < 7; ++r)
+        for (int q = r; q < 7; ++q) { e->H[r * 7 + q] = e->H[q * 7 + r] = tot[idx]; ++idx; }
+      for (int k = 0; k < 7; ++k) { e->b[k] = tot[28 + k]; e->step[k] = iter < 0 ? 0.0 : c->step[k]; }
+      e->energy = E; e->total_terms = terms; e->saturated_terms = (int)tot[37];
+      e->accepted = accepted ? 1 : 0; e->huber = huber; e->outlier = cutoff;
+      job.state->trace_len = tl + 1;
+    }
+  }
+  if (iter < 0) c->lambda = 0.1f;
+  if (accepted) {
+    for (int k = 0; k < 28; ++k) c->H[k] = tot[k];
+    for (int k = 0; k < 7; ++k) c->b[k] = tot[28 + k];
+    c->E_old = E;
+    if (iter >= 0) {
+      c->a_acc = c->a_try;
+      c->T_acc = c->T_try;
+      c->lambda *= 0.5f;
+    }
+  } else {
+    c->lambda *= 4.f;
+    if (c->lambda < 0.001f) c->lambda = 0.001f;
+  }
+  bool done = false;
+  if (iter >= 0) {
+    double nrm = 0;
+    for (int k = 0; k < 7; ++k) nrm += c->step[k] * c->step[k];
+    if (!(sqrt(nrm) > 1e-4)) done = true;  // :188
+  }
+  if (iter + 1 >= n_iter) done = true;
+  if (rank0) { job.state->last_total_terms = terms; job.state->last_N = N; }
+  if (!done) {
+    // damped solve, extrapolation, NaN guard (:112-124)
+    double Hl[49], step[7];
+    int idx = 0;
+    for (int r = 0; r < 7; ++r)
+      for (int q = r; q < 7; ++q) { Hl[r * 7 + q] = Hl[q * 7 + r] = c->H[idx]; ++idx; }
+    const float lambda = c->lambda;
+    for (int k = 0; k < 7; ++k) Hl[k * 7 + k] *= (double)(1.f + lambda);
+    ldlt_solve<7>(Hl, c->b, step);
+    float extrap = 1.f;
+    if (lambda < 0.001f) extrap = (float)sqrt(sqrt(0.001 / (double)lambda));
+    double sum = 0;
+    for (int k = 0; k < 7; ++k) { step[k] *= (double)extrap; sum += step[k]; }
+    if (!isfinite(sum) || isnan(step[0])) for (int k = 0; k < 7; ++k) step[k] = 0.0;
+    for (int k = 0; k < 7; ++k) c->step[k] = step[k];
+    c->a_try = (float)((double)c->a_acc + step[0]);
+    double neg[6];
+    for (int k = 0; k < 6; ++k) neg[k] = -step[1 + k];
+    const Se3d dT = se3_exp(neg);
+    c->T_try = ic ? se3_mul(c->T_acc, dT) : se3_mul(dT, c->T_acc);
+    se3_to_rt(c->T_try, c->Rt);
+  }
+  c->done = done ? 1 : 0;
+}
+
+template <int PIDX, bool IC, bool STAGE>
+__global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams prm, const TrackJobDev* __restrict__ jobs) {
+  constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
+  constexpr int PAD = (PIDX == 5) ? 3 : (PIDX == 7) ? 4 : (PIDX <= 2) ? 1 : 2;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csize = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const int problem = blockIdx.x / csize;
+  const TrackJobDev job = jobs[problem];
+  const int nwarps = blockDim.x >> 5;
+
+  Smem s;
+  {
+    size_t ow, oc, ot, oh, og, ox, om;
+    smem_layout(STAGE ? prm.img_bytes : 0, nwarps, &ow, &oc, &ot, &oh, &og, &ox, &om);
+    s.img = smem_raw;
+    s.warp_part = reinterpret_cast<double*>(smem_raw + ow);
+    s.cta_part = reinterpret_cast<double*>(smem_raw + oc);
+    s.tot = reinterpret_cast<double*>(smem_raw + ot);
+    s.hist = reinterpret_cast<uint32_t*>(smem_raw + oh);
+    s.ghist = reinterpret_cast<uint32_t*>(smem_raw + og);
+    s.ctrl = reinterpret_cast<TrackCtrl*>(smem_raw + ox);
+    s.mbar = reinterpret_cast<uint64_t*>(smem_raw + om);
+  }
+  TrackCtrl* c = s.ctrl;
+  const int t0 = crank * blockDim.x + threadIdx.x;
+  const int nt = csize * blockDim.x;
+  const int Fp = job.Fpad;
+
+  // ---- phase 0: stage the current level image (TMA bulk copy), read the accepted state ---------------------------------
+  const uint8_t* cur_g = job.cur_pyr + prm.level_off;
+  const uint8_t* ref_g = job.ref_pyr + prm.level_off;
+  if (threadIdx.x == 0) {
+    if (STAGE) {
+      mbar_init(s.mbar, 1);
+      mbar_fence_init();
+      fence_proxy_async();
+      mbar_expect_tx(s.mbar, prm.img_bytes);
+      uint32_t done = 0;
+      while (done < prm.img_bytes) {
+        uint32_t chunk = prm.img_bytes - done;
+        if (chunk > 32768u) chunk = 32768u;
+        tma_bulk_g2s(s.img + done, cur_g + done, chunk, s.mbar);
+        done += chunk;
+      }
+    }
+    c->T_acc = job.state->T;
+    c->a_acc = job.state->a;
+    c->done = 0;
+    c->iter = -1;
+  }
+
+  LevelCtx L;
+  L.cur = STAGE ? s.img : cur_g;
+  L.w = prm.w; L.h = prm.h; L.N = N; L.border = PAD + 1;
+  L.scale = 1.0f / (float)(1 << prm.level);
+  L.fxl = (float)(prm.cam.fx * (double)L.scale);
+  L.fyl = (float)(prm.cam.fy * (double)L.scale);
+  L.top = prm.level == prm.max_level;
+
+  // ---- phase 1: precomputeReferencePatches (src/CoarseTracker.cpp:416-497); overlaps the bulk copy ------------------------
+  for (int i = t0; i < job.F; i += nt) {
+    const float u = (float)(job.px[i] * (double)L.scale), v = (float)(job.px[Fp + i] * (double)L.scale);
+    const float uf = floorf(u), vf = floorf(v);
+    const int ui = __float2int_rd(u), vi = __float2int_rd(v);
+    const bool in = ui >= L.border && vi >= L.border && ui < L.w - L.border && vi < L.h - L.border;  // :441
+    job.vis[i] = in ? 1 : 0;
+    if (!in) continue;
+    const float su = u - uf, sv = v - vf;
+    const float wtl = (float)((1.0 - su) * (1.0 - sv));
+    const float wtr = (float)(su * (1.0 - sv));
+    const float wbl = (float)((1.0 - su) * sv);
+    const float wbr = (float)(1.0 - (double)(wtl + wtr + wbl));  // quirk: differs from the current-image weights (:467 vs :323)
+    const int base = vi * L.w + ui;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const int addr = base + (int)c_pat[PIDX][n][1] * L.w + (int)c_pat[PIDX][n][0];
+      if (!IC) {
+        const uint32_t r0 = ld4<false>(ref_g, addr);
+        const uint32_t r1 = ld4<false>(ref_g, addr + L.w);
+        job.ref_cache[n * Fp + i] = wtl * b0(r0) + wtr * b1(r0) + wbl * b0(r1) + wbr * b1(r1);
+      } else {
+        const uint32_t rm = ld4<false>(ref_g, addr - L.w - 1);
+        const uint32_t r0 = ld4<false>(ref_g, addr - 1);
+        const uint32_t r1 = ld4<false>(ref_g, addr + L.w - 1);
+        const uint32_t r2 = ld4<false>(ref_g, addr + 2 * L.w - 1);
+        job.ref_cache[n * Fp + i] = wtl * b1(r0) + wtr * b2(r0) + wbl * b1(r1) + wbr * b2(r1);
+        job.ref_gx[n * Fp + i] = 0.5f * ((wtl * b2(r0) + wtr * b3(r0) + wbl * b2(r1) + wbr * b3(r1)) -
+                                         (wtl * b0(r0) + wtr * b1(r0) + wbl * b0(r1) + wbr * b1(r1)));
+        job.ref_gy[n * Fp + i] = 0.5f * ((wtl * b1(r1) + wtr * b2(r1) + wbl * b1(r2) + wbr * b2(r2)) -
+                                         (wtl * b1(rm) + wtr * b2(rm) + wbl * b1(r0) + wbr * b2(r0)));
+      }
+    }
+  }
+  __syncthreads();
+  if (STAGE) mbar_wait(s.mbar, 0);
+  if (threadIdx.x == 0) se3_to_rt(c->T_acc, c->Rt);
+  __syncthreads();
+
+  // ---- phase 2: selectRobustFunctionLevel (src/CoarseTracker.cpp:530-644) ------------------------------------------------
+  {
+    const float a = c->a_acc;
+    double R[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) R[k] = c->Rt[k];
+    for (int i = t0; i < job.F; i += nt) {
+      bool ok = job.vis[i] != 0;
+      Proj p;
+      if (ok) {
+        p = project_patch(R, prm.cam, job.xyz[i], job.xyz[Fp + i], job.xyz[2 * Fp + i], L.scale, L.border, L.w, L.h);
+        ok = p.ok;
+      }
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        float out = -1.f;
+        if (ok) {
+          const int addr = p.base + (int)c_pat[PIDX][n][1] * L.w + (int)c_pat[PIDX][n][0];
+          const uint32_t r0 = ld4<STAGE>(L.cur, addr);
+          const uint32_t r1 = ld4<STAGE>(L.cur, addr + L.w);
+          const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
+          out = fabsf(color - (a * job.ref_cache[n * Fp + i] + 0.f));
+        }
+        job.absres[n * Fp + i] = out;
+      }
+    }
+    int hist_phase = 0;
+    radix_select<N>(job, s, t0, nt, false, 0.f, csize, hist_phase);
+    const uint32_t n_err = c->sel_n;
+    float huber = 5.2f, outlier = 100.f;
+    if (n_err >= 30) {
+      const float median = __uint_as_float(c->sel_prefix);
+      __syncthreads();
+      radix_select<N>(job, s, t0, nt, true, median, csize, hist_phase);
+      const float mad = __uint_as_float(c->sel_prefix);
+      const float sd = (float)(1.4826 * (double)mad);
+      huber = median + sd;
+      outlier = 3.f * huber;
+      if (outlier < 10.f) outlier = 10.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { c->huber = huber; c->outlier = outlier; c->n_err = (int)n_err; }
+    __syncthreads();
+  }
+
+  // ---- phase 3: the LM loop of the level (src/CoarseTracker.cpp:100-194) -------------------------------------------------
+  const float huber = c->huber, cutoff = c->outlier;
+  int slot = 0;
+  int level_iters = 0, level_evals = 0;
+  unsigned long long patch_evals = 0;
+  for (int iter = -1; iter < prm.n_iter; ++iter) {
+    const float a_eval = iter < 0 ? c->a_acc : c->a_try;
+    Acc acc;
+    acc_zero(acc);
+    eval_patches<PIDX, IC, STAGE>(L, job, prm.cam, c->Rt, a_eval, huber, cutoff, t0, nt, acc);
+    reduce_acc(acc, s, slot, csize, nwarps);
+    slot ^= 1;
+    ++level_evals;
+    if (iter >= 0) ++level_iters;
+    patch_evals += (unsigned long long)s.tot[38];
+    if (threadIdx.x == 0)
+      lm_control(c, s.tot, job, iter, prm.n_iter, prm.level, prm.trace_cap, IC, crank == 0, a_eval, huber, cutoff, N);
+    __syncthreads();
+    if (c->done) break;
+  }
+
+  // ---- write the accepted state back -------------------------------------------------------------------------------------
+  if (threadIdx.x == 0 && crank == 0) {
+    TrackState* st = job.state;
+    st->T = c->T_acc;
+    st->a = c->a_acc;
+    st->n_iters += level_iters;
+    st->n_evals += level_evals;
+    st->iters_per_level[prm.level & 7] = level_iters;
+    st->patch_evals[prm.level & 7] = patch_evals;
+  }
+  if (csize > 1) cluster.sync();  // peers may still be reading this CTA's shared memory
+}
+
+__global__ void k_track_init(const TrackJobDev* __restrict__ jobs, const double* __restrict__ T0, const float* __restrict__ a0, int B) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B) return;
+  TrackState* st = jobs[p].state;
+  st->T = se3_from_rt(T0 + 12 * p);
+  st->a = a0[p];
+  st->n_iters = 0; st->n_evals = 0;
+  for (int k = 0; k < 8; ++k) { st->iters_per_level[k] = 0; st->patch_evals[k] = 0; }
+  st->last_total_terms = 0; st->last_N = 1; st->trace_len = 0;
+}
+
+__global__ void k_track_finish(const TrackJobDev* __restrict__ jobs, hso_track_result* __restrict__ out, int B) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B) return;
+  const TrackState* st = jobs[p].state;
+  hso_track_result* o = out + p;
+  se3_to_rt(st->T, o->T_cur_ref);
+  o->exposure_rat = st->a;
+  o->n_iters = st->n_iters;
+  o->n_evals = st->n_evals;
+  for (int k = 0; k < 8; ++k) { o->iters_per_level[k] = st->iters_per_level[k]; o->visible_patch_evals[k] = st->patch_evals[k]; }
+  // return float(m_total_terms) / PATCH_AREA  (src/CoarseTracker.cpp:207)
+  o->n_tracked = (uint64_t)((float)st->last_total_terms / (float)st->last_N);
+  o->trace_len = st->trace_len;
+}
+
+cudaError_t launch_track_init(const TrackJobDev* jobs_dev, const double* T0, const float* a0, int B, cudaStream_t stream, uint64_t* launches) {
+  k_track_init<<<(B + 127) / 128, 128, 0, stream>>>(jobs_dev, T0, a0, B);
+  ++*launches;
+  return cudaGetLastError();
+}
+cudaError_t launch_track_finish(const TrackJobDev* jobs_dev, hso_track_result* out_dev, int B, cudaStream_t stream, uint64_t* launches) {
+  k_track_finish<<<(B + 127) / 128, 128, 0, stream>>>(jobs_dev, out_dev, B);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+template <int PIDX, bool IC, bool STAGE>
+static cudaError_t launch_one(const TrackLevelParams& p, const TrackJobDev* jobs_dev, int B, int cluster, int threads, size_t smem,
+                              cudaStream_t stream) {
+  auto kern = k_track_level<PIDX, IC, STAGE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * cluster), 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p, jobs_dev);
+}
+
+template <int PIDX>
+static cudaError_t launch_pidx(const TrackLevelParams& p, const TrackJobDev* jobs_dev, int B, int cluster, int threads, size_t smem,
+                               cudaStream_t stream) {
+  if (p.ic) {
+    return p.stage_smem ? launch_one<PIDX, true, true>(p, jobs_dev, B, cluster, threads, smem, stream)
+                        : launch_one<PIDX, true, false>(p, jobs_dev, B, cluster, threads, smem, stream);
+  }
+  return p.stage_smem ? launch_one<PIDX, false, true>(p, jobs_dev, B, cluster, threads, smem, stream)
+                      : launch_one<PIDX, false, false>(p, jobs_dev, B, cluster, threads, smem, stream);
+}
+
+cudaError_t launch_track_level(const TrackLevelParams& p, const TrackJobDev* jobs_dev, int B, int cluster, int threads, cudaStream_t stream,
+                               uint64_t* launches) {
+  const int pidx = p.max_level - p.level + 2;  // m_offset_all (src/CoarseTracker.cpp:80, CoarseTracker.h:122)
+  if (pidx < 2 || pidx > 7) return cudaErrorInvalidValue;
+  (void)h_pat_num; (void)h_pat_pad;
+  const size_t smem = track_level_smem_bytes(p, threads);
+  ++*launches;
+  switch (pidx) {
+    case 2: return launch_pidx<2>(p, jobs_dev, B, cluster, threads, smem, stream);
+    case 3: return launch_pidx<3>(p, jobs_dev, B, cluster, threads, smem, stream);
+    case 4: return launch_pidx<4>(p, jobs_dev, B, cluster, threads, smem, stream);
+    case 5: return launch_pidx<5>(p, jobs_dev, B, cluster, threads, smem, stream);
+    case 6: return launch_pidx<6>(p, jobs_dev, B, cluster, threads, smem, stream);
+    default: return launch_pidx<7>(p, jobs_dev, B, cluster, threads, smem, stream);
+  }
+}
+
+}  // namespace hso

@@ -108,17 +108,21 @@ typedef struct {
   int32_t iters_per_level[8];
   uint64_t n_tracked;          /* return value of run(): size_t(float(total_terms)/PATCH_AREA) (CoarseTracker.cpp:207) */
   uint64_t visible_patch_evals[8]; /* per level: sum over evaluations of patches that produced terms (roofline accounting) */
+  int32_t trace_len;           /* trace entries written for this problem */
+  int32_t reserved;
 } hso_track_result;
 
-/* Per-evaluation trace for parity checking; same fields as the oracle's orc_trace. */
+/* Per-evaluation trace for parity checking (one entry per computeResiduals call, CoarseTracker.cpp:102,141).
+ * iter = -1: evaluation at level entry; iter >= 0: LM trial `iter`. */
 typedef struct {
   int32_t level, iter;
-  double T_eval[12];
-  float a_eval, lambda;
-  double H[49], b[7], step[7];
-  double energy;
+  double T_eval[12];           /* pose the residuals were evaluated at */
+  float a_eval, lambda;        /* exposure ratio evaluated; damping used to solve for this trial (0 for iter = -1) */
+  double H[49], b[7];          /* normal equations built AT this evaluation (computeGS of this state, whether or not accepted) */
+  double step[7];              /* extrapolated, NaN-guarded step that led to T_eval (zeros for iter = -1) */
+  double energy;               /* E / total_terms of this evaluation */
   int32_t total_terms, saturated_terms, accepted;
-  float huber, outlier;
+  float huber, outlier;        /* thresholds of the level (selectRobustFunctionLevel) */
 } hso_trace;
 
 /* makeDepthRef helper on the host side of the boundary is hso::host::makeDepthRef (hso_b200/host); here dist is an input. */

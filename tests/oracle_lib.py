@@ -1,0 +1,178 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle_hso.so) — test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle_hso.so")
+
+
+class orc_cam(C.Structure):
+    _fields_ = [("model", C.c_int), ("width", C.c_int), ("height", C.c_int), ("undistort", C.c_int),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("d", C.c_double * 5)]
+
+
+class orc_trace(C.Structure):
+    _fields_ = [("level", C.c_int), ("iter", C.c_int), ("T_eval", C.c_double * 12), ("a_eval", C.c_float), ("lambda_", C.c_float),
+                ("H", C.c_double * 49), ("b", C.c_double * 7), ("step", C.c_double * 7), ("energy", C.c_double),
+                ("total_terms", C.c_int), ("saturated_terms", C.c_int), ("accepted", C.c_int), ("huber", C.c_float), ("outlier", C.c_float)]
+
+
+class orc_track_params(C.Structure):
+    _fields_ = [("inverse_comp", C.c_int), ("max_level", C.c_int), ("min_level", C.c_int), ("n_iter", C.c_int)]
+
+
+class orc_align_job(C.Structure):
+    _fields_ = [("ref_level", C.c_int32), ("search_level", C.c_int32), ("type", C.c_int32), ("scale_patch", C.c_int32),
+                ("px_ref", C.c_double * 2), ("A_cur_ref", C.c_double * 4), ("grad", C.c_double * 2), ("px_cur", C.c_double * 2),
+                ("exposure_rat", C.c_float), ("pad_", C.c_float)]
+
+
+class orc_align_result(C.Structure):
+    _fields_ = [("ok", C.c_int32), ("align_converged", C.c_int32), ("px_cur", C.c_double * 2), ("h_inv", C.c_double)]
+
+
+class orc_pose_result(C.Structure):
+    _fields_ = [("T_f_w", C.c_double * 12), ("cov", C.c_double * 36), ("estimated_scale", C.c_double), ("error_init", C.c_double),
+                ("error_final", C.c_double), ("num_obs", C.c_uint64), ("error_in_px", C.c_float), ("n_trials_total", C.c_int),
+                ("early_return", C.c_int)]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        _lib = C.CDLL(LIB)
+        _lib.orc_coarse_track.restype = C.c_uint64
+        for n in ("orc_align2d", "orc_align1d", "orc_get_best_search_level", "orc_check_ncc", "orc_check_normal", "orc_create_pyramid"):
+            getattr(_lib, n).restype = C.c_int
+    return _lib
+
+
+def cam_of(c):
+    o = orc_cam()
+    o.model, o.width, o.height, o.undistort = c.get("model", 0), c["width"], c["height"], c.get("undistort", 0)
+    o.fx, o.fy, o.cx, o.cy = c["fx"], c["fy"], c["cx"], c["cy"]
+    for i in range(5):
+        o.d[i] = float(c["d"][i])
+    return o
+
+
+def dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def pad_level(img, pad_rows=3):
+    """Level image followed by zero rows: the reference's forward-mode gradient taps may read row == rows (undefined there);
+    both the oracle harness and the CUDA path define those bytes as zero."""
+    h, w = img.shape
+    buf = np.zeros((h + pad_rows) * w + 64, np.uint8)
+    buf[: h * w] = img.reshape(-1)
+    return buf
+
+
+def create_pyramid(img, n_levels=5):
+    lib = load()
+    H, W = img.shape
+    out = np.zeros(W * H, np.uint8)
+    lw = (C.c_int * n_levels)()
+    lh = (C.c_int * n_levels)()
+    img = np.ascontiguousarray(img)
+    path = lib.orc_create_pyramid(img.ctypes.data_as(C.c_void_p), W, H, n_levels, out.ctypes.data_as(C.c_void_p), lw, lh)
+    levels = [img]
+    o = 0
+    for i in range(1, n_levels):
+        n = lw[i] * lh[i]
+        levels.append(out[o:o + n].reshape(lh[i], lw[i]).copy())
+        o += n
+    return levels, path
+
+
+def sobel5(img):
+    lib = load()
+    h, w = img.shape
+    gx = np.zeros((h, w), np.int16)
+    gy = np.zeros((h, w), np.int16)
+    img = np.ascontiguousarray(img)
+    lib.orc_sobel5(img.ctypes.data_as(C.c_void_p), w, h, gx.ctypes.data_as(C.c_void_p), gy.ctypes.data_as(C.c_void_p))
+    return gx, gy
+
+
+def frame_stats(img):
+    lib = load()
+    gx, gy = sobel5(img)
+    h, w = img.shape
+    a, b = C.c_float(), C.c_float()
+    img = np.ascontiguousarray(img)
+    lib.orc_frame_stats(img.ctypes.data_as(C.c_void_p), gx.ctypes.data_as(C.c_void_p), gy.ctypes.data_as(C.c_void_p), w, h, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+class TrackProblem:
+    """Flattened CoarseTracker inputs for the oracle: padded level buffers + feature arrays."""
+
+    def __init__(self, cam, ref_levels, cur_levels, px, f, dist):
+        self.cam = cam_of(cam)
+        self.n = len(ref_levels)
+        self.ref_bufs = [pad_level(l) for l in ref_levels]
+        self.cur_bufs = [pad_level(l) for l in cur_levels]
+        self.refp = (C.c_void_p * self.n)(*[b.ctypes.data for b in self.ref_bufs])
+        self.curp = (C.c_void_p * self.n)(*[b.ctypes.data for b in self.cur_bufs])
+        self.lw = (C.c_int * self.n)(*[l.shape[1] for l in ref_levels])
+        self.lh = (C.c_int * self.n)(*[l.shape[0] for l in ref_levels])
+        self.px = np.ascontiguousarray(px, np.float64).reshape(-1)
+        self.f = np.ascontiguousarray(f, np.float64).reshape(-1)
+        self.dist = np.ascontiguousarray(dist, np.float64).reshape(-1)
+        self.F = self.dist.shape[0]
+
+    def run(self, T0, a0, inverse_comp=False, max_level=4, min_level=1, n_iter=50, trace_cap=512):
+        lib = load()
+        prm = orc_track_params(int(inverse_comp), max_level, min_level, n_iter)
+        T = np.ascontiguousarray(T0, np.float64).reshape(12).copy()
+        a = C.c_float(a0)
+        trace = (orc_trace * trace_cap)()
+        tl, ne = C.c_int(), C.c_int()
+        n = lib.orc_coarse_track(C.byref(self.cam), C.byref(prm), self.n, self.refp, self.curp, self.lw, self.lh, self.F, dp(self.px),
+                                 dp(self.f), dp(self.dist), dp(T), C.byref(a), trace, trace_cap, C.byref(tl), C.byref(ne))
+        return dict(T_cur_ref=T.reshape(3, 4), exposure_rat=a.value, n_tracked=int(n), n_evals=ne.value, trace=[trace[i] for i in range(tl.value)])
+
+    def eval(self, level, max_level, T, a, huber, outlier, inverse_comp=False):
+        lib = load()
+        H = np.zeros(49)
+        b = np.zeros(7)
+        E = C.c_double()
+        tt, st = C.c_int(), C.c_int()
+        T = np.ascontiguousarray(T, np.float64).reshape(12)
+        lib.orc_track_eval(C.byref(self.cam), int(inverse_comp), level, max_level, self.refp[level], self.curp[level], self.lw[level],
+                           self.lh[level], self.F, dp(self.px), dp(self.f), dp(self.dist), dp(T), C.c_float(a), C.c_float(huber),
+                           C.c_float(outlier), dp(H), dp(b), C.byref(E), C.byref(tt), C.byref(st))
+        return H.reshape(7, 7), b, E.value, tt.value, st.value
+
+    def select_robust(self, level, max_level, T, a):
+        lib = load()
+        hu, ou = C.c_float(), C.c_float()
+        n = C.c_int()
+        T = np.ascontiguousarray(T, np.float64).reshape(12)
+        lib.orc_track_select_robust(C.byref(self.cam), level, max_level, self.refp[level], self.curp[level], self.lw[level], self.lh[level],
+                                    self.F, dp(self.px), dp(self.f), dp(self.dist), dp(T), C.c_float(a), C.byref(hu), C.byref(ou), C.byref(n))
+        return hu.value, ou.value, n.value
+
+
+def track_solve(H, b, lam):
+    lib = load()
+    H = np.ascontiguousarray(H, np.float64).reshape(49)
+    b = np.ascontiguousarray(b, np.float64).reshape(7)
+    step = np.zeros(7)
+    lib.orc_track_solve(dp(H), dp(b), C.c_float(lam), dp(step))
+    return step

@@ -1,0 +1,100 @@
+"""GPU parity: Frame construction (a1, a2) through the C-ABI vs the CPU oracle — pyramid / Sobel bytes bit-exact.
+
+Statistics tolerance: the reference accumulates ~2.7e5 pixel values into one float in raster order (src/frame.cpp:223-245);
+past 2^24 that running sum rounds every addend to a multiple of 2 or 4, so the reference's own integralImage_ is off the
+true mean by ~1e-5 relative (measured: 125.93458 vs exact 125.93305). The CUDA path sums exactly (integers) / in fp64, so
+parity is checked to 5e-5 relative."""
+STAT_REL = 5e-5
+import numpy as np
+import pytest
+
+from hso_b200 import Context, make_cam, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(cam, **kw):
+    c = synth.CAMS[cam] if isinstance(cam, str) else cam
+    return Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), **kw)
+
+
+@pytest.mark.parametrize("cam", ["icl", "euroc", "tum_fov"])
+def test_pyramid_bit_exact_and_stats(oracle, cam):
+    c = synth.CAMS[cam]
+    rng = np.random.default_rng(7)
+    imgs = [synth.texture(rng, c["width"], c["height"]), rng.integers(0, 256, (c["height"], c["width"]), dtype=np.uint8)]
+    ctx = _ctx(cam)
+    ids, integral, gm = ctx.upload_frames(imgs)
+    for k, img in enumerate(imgs):
+        levels, path = oracle.create_pyramid(img, 5)
+        assert path == (0 if (c["width"] % 16 == 0 and c["height"] % 16 == 0) else 1)
+        for l in range(5):
+            got = ctx.download_level(ids[k], l)
+            assert got.shape == levels[l].shape
+            assert np.array_equal(got, levels[l]), f"level {l} differs ({np.count_nonzero(got != levels[l])} px)"
+        oi, og = oracle.frame_stats(img)
+        assert abs(integral[k] - oi) <= STAT_REL * abs(oi)
+        assert abs(gm[k] - og) <= STAT_REL * abs(og)
+    ctx.close()
+
+
+def test_gradmean_unclamped(oracle):
+    # low-contrast image so that gradMean_ is not clamped to [7, 20]
+    c = synth.CAMS["icl"]
+    rng = np.random.default_rng(3)
+    img = synth.texture(rng, c["width"], c["height"], contrast=6.0)
+    ctx = _ctx("icl")
+    ids, integral, gm = ctx.upload_frames([img])
+    oi, og = oracle.frame_stats(img)
+    assert 7.0 < og < 20.0
+    assert abs(gm[0] - og) <= STAT_REL * og and abs(integral[0] - oi) <= STAT_REL * oi
+    ctx.close()
+
+
+def test_strided_input_and_batch(oracle):
+    c = synth.CAMS["icl"]
+    rng = np.random.default_rng(11)
+    big = rng.integers(0, 256, (c["height"], c["width"] + 48), dtype=np.uint8)
+    view = big[:, 8:8 + c["width"]]  # non-contiguous rows, unaligned start
+    ctx = _ctx("icl")
+    ids, _, _ = ctx.upload_frames([view] * 3)
+    levels, _ = oracle.create_pyramid(np.ascontiguousarray(view), 5)
+    for fid in ids:
+        for l in range(5):
+            assert np.array_equal(ctx.download_level(fid, l), levels[l])
+    ctx.close()
+
+
+def test_sobel_materialised(oracle):
+    c = synth.CAMS["euroc"]
+    rng = np.random.default_rng(5)
+    img = synth.texture(rng, c["width"], c["height"])
+    ctx = _ctx("euroc", materialize_sobel=True)
+    ids, _, _ = ctx.upload_frames([img])
+    levels, _ = oracle.create_pyramid(img, 5)
+    for l in range(3):
+        gx, gy = ctx.download_sobel(ids[0], l)
+        ox, oy = oracle.sobel5(levels[l])
+        assert np.array_equal(gx, ox) and np.array_equal(gy, oy)
+    ctx.close()
+
+
+def test_size_mismatch_is_rejected():
+    from hso_b200 import HsoError
+    ctx = _ctx("icl")
+    with pytest.raises(HsoError):
+        ctx.upload_frames([np.zeros((480, 752), np.uint8)])  # Frame ctor throws on a wrong size (src/frame.cpp:85-86)
+    ctx.close()
+
+
+def test_frame_table_capacity_and_reuse():
+    from hso_b200 import HsoError
+    ctx = _ctx("icl", max_frames=2)
+    img = np.zeros((480, 640), np.uint8)
+    ids, _, _ = ctx.upload_frames([img, img])
+    with pytest.raises(HsoError):
+        ctx.upload_frames([img])
+    ctx.release(ids[0])
+    ids2, _, _ = ctx.upload_frames([img])
+    assert ids2[0] == ids[0]
+    ctx.close()
