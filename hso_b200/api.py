@@ -155,6 +155,63 @@ class Context:
         self._chk(self.lib.hso_track_collect(self.h, out, None, None))
         return out
 
+    # ---- F3-inner: Matcher::findMatchDirect after getWarpMatrixAffine ------------------------------------------------------
+    def align_batch(self, cur, jobs, ref_frames, align_max_iter=10):
+        """jobs: ctypes array of hso_align_job (or list of dicts with its field names); ref_frames: frame id per job.
+        Returns a ctypes array of hso_align_result."""
+        M = len(jobs)
+        if M and not isinstance(jobs, C.Array):
+            arr = (K.hso_align_job * M)()
+            for m, j in enumerate(jobs):
+                a = arr[m]
+                a.ref_level, a.search_level, a.type, a.scale_patch = j["ref_level"], j["search_level"], j["type"], j.get("scale_patch", 0)
+                for k in range(2):
+                    a.px_ref[k], a.grad[k], a.px_cur[k] = j["px_ref"][k], j["grad"][k], j["px_cur"][k]
+                for k in range(4):
+                    a.A_cur_ref[k] = float(np.asarray(j["A_cur_ref"]).reshape(4)[k])
+                a.exposure_rat = j.get("exposure_rat", 1.0)
+            jobs = arr
+        refs = (C.c_int32 * max(M, 1))(*[int(r) for r in ref_frames])
+        out = (K.hso_align_result * max(M, 1))()
+        self._chk(self.lib.hso_align_batch(self.h, int(cur), M, jobs, refs, align_max_iter, out))
+        return out
+
+    # ---- F4: pose_optimizer::optimizeLevenbergMarquardt3rd -----------------------------------------------------------------
+    def pose_optimize_batch(self, problems, reproj_thresh=2.0, n_iter=12):
+        """problems: list of dicts {f (F,3), p_host (F,3), host_idx (F,), T_host_w (K,3,4), grad (F,2), level, ftype, ptype (F,),
+        T_f_w (3,4), n_fts_total}. Returns list of dicts with the reference's outputs + outlier mask."""
+        B = len(problems)
+        cat = lambda key, dt, w: np.ascontiguousarray(np.concatenate([np.asarray(p[key], dt).reshape(-1, w) for p in problems]) if B else np.zeros((0, w), dt))
+        f, ph, g = cat("f", np.float64, 3), cat("p_host", np.float64, 3), cat("grad", np.float64, 2)
+        hi = cat("host_idx", np.int32, 1)
+        lv, ft, pt = cat("level", np.int8, 1), cat("ftype", np.int8, 1), cat("ptype", np.int8, 1)
+        Th = np.ascontiguousarray(np.concatenate([np.asarray(p["T_host_w"], np.float64).reshape(-1, 12) for p in problems]))
+        T0 = np.ascontiguousarray(np.stack([np.asarray(p["T_f_w"], np.float64).reshape(12) for p in problems]))
+        offs = np.zeros(B + 1, np.int32)
+        hoffs = np.zeros(B + 1, np.int32)
+        for b, p in enumerate(problems):
+            offs[b + 1] = offs[b] + np.asarray(p["f"]).reshape(-1, 3).shape[0]
+            hoffs[b + 1] = hoffs[b] + np.asarray(p["T_host_w"]).reshape(-1, 12).shape[0]
+        nf = np.array([int(p.get("n_fts_total", np.asarray(p["f"]).reshape(-1, 3).shape[0])) for p in problems], np.int32)
+        outl = np.zeros(max(int(offs[B]), 1), np.uint8)
+        out = (K.hso_pose_result * B)()
+        i32, i8, u8 = C.POINTER(C.c_int32), C.POINTER(C.c_int8), C.POINTER(C.c_uint8)
+        self._chk(self.lib.hso_pose_optimize_batch(self.h, reproj_thresh, n_iter, B, nf.ctypes.data_as(i32), offs.ctypes.data_as(i32), _dp(f), _dp(ph),
+                                                   hi.ctypes.data_as(i32), hoffs.ctypes.data_as(i32), _dp(Th), _dp(g), lv.ctypes.data_as(i8),
+                                                   ft.ctypes.data_as(i8), pt.ctypes.data_as(i8), _dp(T0), outl.ctypes.data_as(u8), out))
+        res = []
+        for b in range(B):
+            o = out[b]
+            res.append(dict(T_f_w=np.array(o.T_f_w[:]).reshape(3, 4), cov=np.array(o.cov[:]).reshape(6, 6), estimated_scale=o.estimated_scale,
+                            error_init=o.error_init, error_final=o.error_final, num_obs=int(o.num_obs), error_in_px=float(o.error_in_px),
+                            n_trials_total=o.n_trials_total, early_return=o.early_return, outlier=outl[offs[b]:offs[b + 1]].copy()))
+        return res
+
+    def stage_time_ms(self, stage):
+        ms, calls = C.c_double(), C.c_uint64()
+        self._chk(self.lib.hso_stage_time_ms(self.h, stage, C.byref(ms), C.byref(calls)))
+        return ms.value, calls.value
+
     def set_cluster(self, ctas=0, threads=0):
         self._chk(self.lib.hso_track_set_cluster(self.h, ctas, threads))
 

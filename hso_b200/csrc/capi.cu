@@ -195,6 +195,7 @@ FrameSlot* get_frame(hso_ctx* ctx, hso_frame_id id) {
 }
 
 int run_pyramid(hso_ctx* ctx, int B, const hso_frame_id* ids, const uint8_t* const* srcs, int src_stride, int aligned) {
+  if (ctx->pyr_jobs_host.cap < sizeof(PyrJobDev) * (size_t)B) CU(cudaStreamSynchronize(ctx->stream));  // before re-allocating staging
   CU(ctx->pyr_jobs_host.reserve(sizeof(PyrJobDev) * B));
   CU(ctx->pyr_jobs_dev.reserve(sizeof(PyrJobDev) * B));
   if (ctx->pyr_counters.cap < sizeof(unsigned) * (size_t)B) {
@@ -211,7 +212,7 @@ int run_pyramid(hso_ctx* ctx, int B, const hso_frame_id* ids, const uint8_t* con
     jobs[i].stats = s->stats;
   }
   CU(cudaMemcpyAsync(ctx->pyr_jobs_dev.p, jobs, sizeof(PyrJobDev) * B, cudaMemcpyHostToDevice, ctx->stream));
-  CU(launch_pyramid(ctx->geom, (const PyrJobDev*)ctx->pyr_jobs_dev.p, B, src_stride, (const ResizeTabDev*)ctx->resize_tab_dev.p,
+  CU(launch_pyramid(ctx->geom, (const PyrJobDev*)ctx->pyr_jobs_dev.p, B, src_stride, ctx->resize_tabs.data() /* host array; passed by value */,
                     ctx->cfg.materialize_sobel, (unsigned*)ctx->pyr_counters.p, aligned, ctx->stream, &ctx->launches));
   return HSO_OK;
 }
@@ -463,6 +464,7 @@ int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_
       prm->n_iter < 0)
     return fail(ctx, HSO_ERR_INVALID, "bad track params");
   CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));  // the pinned staging below is reused between calls
   ctx->tprm = *prm;
   ctx->tB = B;
   ctx->t_trace_cap = trace_cap > 0 ? trace_cap : 0;
@@ -638,6 +640,122 @@ int hso_coarse_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B, con
 int hso_coarse_track(hso_ctx* ctx, const hso_track_params* prm, const hso_track_job* job, hso_track_result* out, hso_trace* trace, int trace_cap,
                      int* trace_len) {
   return hso_coarse_track_batch(ctx, prm, 1, job, out, trace, trace_cap, trace_len);
+}
+
+// ---- F3-inner ---------------------------------------------------------------------------------------------------------------
+int hso_align_batch(hso_ctx* ctx, hso_frame_id cur, int M, const hso_align_job* jobs, const hso_frame_id* ref_frames, int align_max_iter,
+                    hso_align_result* out) {
+  if (!ctx || M < 0 || (M > 0 && (!jobs || !ref_frames || !out))) return HSO_ERR_INVALID;
+  if (M == 0) return HSO_OK;
+  FrameSlot* fc = get_frame(ctx, cur);
+  if (!fc) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown current frame id");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));  // the pinned staging below is reused between calls
+  CU(ctx->a_jobs_host.reserve(sizeof(AlignJobDev) * M));
+  CU(ctx->a_jobs_dev.reserve(sizeof(AlignJobDev) * M));
+  CU(ctx->a_out_dev.reserve(sizeof(hso_align_result) * M));
+  CU(ctx->a_out_host.reserve(sizeof(hso_align_result) * M));
+  AlignJobDev* hj = (AlignJobDev*)ctx->a_jobs_host.p;
+  const int max_search = std::min(ctx->cfg.n_pyr_levels, ctx->geom.n_levels) - 1;  // getBestSearchLevel(A, nPyrLevels-1)
+  for (int m = 0; m < M; ++m) {
+    const hso_align_job& j = jobs[m];
+    FrameSlot* fr = get_frame(ctx, ref_frames[m]);
+    if (!fr) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown reference frame id in align job");
+    if (j.ref_level < 0 || j.ref_level >= ctx->geom.n_levels || j.search_level < 0 || j.search_level > max_search)
+      return fail(ctx, HSO_ERR_INVALID, "align job level out of range");
+    if (j.type == 1 && !fc->sobel) return fail(ctx, HSO_ERR_INVALID, "edgelet jobs need hso_cfg.materialize_sobel (checkNormal reads sobelX_/Y_)");
+    hj[m].job = j;
+    hj[m].ref_pyr = fr->pyr;
+  }
+  StageTimer tm(ctx, 2);
+  CU(cudaMemcpyAsync(ctx->a_jobs_dev.p, hj, sizeof(AlignJobDev) * M, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_align(ctx->geom, fc->pyr, fc->sobel, (const AlignJobDev*)ctx->a_jobs_dev.p, M, align_max_iter, (hso_align_result*)ctx->a_out_dev.p,
+                  ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(ctx->a_out_host.p, ctx->a_out_dev.p, sizeof(hso_align_result) * M, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->a_out_host.p, sizeof(hso_align_result) * M);
+  tm.stop_after_sync();
+  return HSO_OK;
+}
+
+// ---- F4 ---------------------------------------------------------------------------------------------------------------------
+int hso_pose_optimize_batch(hso_ctx* ctx, double reproj_thresh, int n_iter, int B, const int32_t* n_fts_total, const int32_t* offs,
+                            const double* f, const double* p_host, const int32_t* host_idx, const int32_t* hoffs, const double* T_host_w,
+                            const double* grad, const int8_t* level, const int8_t* ftype, const int8_t* ptype, const double* T_f_w_in,
+                            uint8_t* outlier_out, hso_pose_result* out) {
+  if (!ctx || B <= 0 || !n_fts_total || !offs || !hoffs || !T_f_w_in || !out || n_iter < 0) return HSO_ERR_INVALID;
+  const int Ftot = offs[B], Ktot = hoffs[B];
+  if (Ftot < 0 || Ktot < 0) return HSO_ERR_INVALID;
+  if (Ftot > 0 && (!f || !p_host || !host_idx || !T_host_w || !grad || !level || !ftype || !ptype || !outlier_out)) return HSO_ERR_INVALID;
+  for (int b = 0; b < B; ++b) {
+    const int F = offs[b + 1] - offs[b], K = hoffs[b + 1] - hoffs[b];
+    if (F < 0 || K < 0) return HSO_ERR_INVALID;
+    for (int i = offs[b]; i < offs[b + 1]; ++i)
+      if (host_idx[i] < 0 || host_idx[i] >= K) return fail(ctx, HSO_ERR_INVALID, "host_idx out of range");
+  }
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  // one staging blob: [f | p_host | grad | T_host_w | host_idx | level | ftype | ptype] then device-only scratch
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = (o + 63) / 64 * 64; o = r + bytes; return r; };
+  const size_t o_f = take(sizeof(double) * 3 * Ftot), o_ph = take(sizeof(double) * 3 * Ftot), o_g = take(sizeof(double) * 2 * Ftot);
+  const size_t o_th = take(sizeof(double) * 12 * Ktot), o_hi = take(sizeof(int32_t) * Ftot);
+  const size_t o_lv = take(Ftot), o_ft = take(Ftot), o_pt = take(Ftot);
+  const size_t o_jobs = take(sizeof(PoseJobDev) * B), o_scr = take(sizeof(PoseScratch) * B);
+  const size_t staged = o;
+  const size_t o_inv = take(sizeof(Se3d) * Ktot), o_tth = take(sizeof(double) * 12 * Ktot), o_keys = take(sizeof(unsigned long long) * Ftot);
+  const size_t o_cls = take(Ftot), o_outl = take(Ftot), o_res = take(sizeof(hso_pose_result) * B);
+  CU(ctx->p_arena.reserve(o));
+  CU(ctx->p_stage_host.reserve(staged));
+  CU(ctx->p_out_host.reserve(sizeof(hso_pose_result) * B + Ftot));
+  char* h = (char*)ctx->p_stage_host.p;
+  char* d = (char*)ctx->p_arena.p;
+  if (Ftot > 0) {
+    memcpy(h + o_f, f, sizeof(double) * 3 * Ftot); memcpy(h + o_ph, p_host, sizeof(double) * 3 * Ftot);
+    memcpy(h + o_g, grad, sizeof(double) * 2 * Ftot); memcpy(h + o_hi, host_idx, sizeof(int32_t) * Ftot);
+    memcpy(h + o_lv, level, Ftot); memcpy(h + o_ft, ftype, Ftot); memcpy(h + o_pt, ptype, Ftot);
+  }
+  if (Ktot > 0) memcpy(h + o_th, T_host_w, sizeof(double) * 12 * Ktot);
+  PoseJobDev* hj = (PoseJobDev*)(h + o_jobs);
+  PoseScratch* hs = (PoseScratch*)(h + o_scr);
+  for (int b = 0; b < B; ++b) {
+    const int F0 = offs[b], K0 = hoffs[b];
+    PoseJobDev& j = hj[b];
+    j.F = offs[b + 1] - F0; j.K = hoffs[b + 1] - K0; j.n_fts_total = n_fts_total[b]; j.pad_ = 0;
+    j.f = (const double*)(d + o_f) + 3 * F0; j.p_host = (const double*)(d + o_ph) + 3 * F0;
+    j.host_idx = (const int32_t*)(d + o_hi) + F0; j.T_host_w = (const double*)(d + o_th) + 12 * K0;
+    j.grad = (const double*)(d + o_g) + 2 * F0;
+    j.level = (const int8_t*)(d + o_lv) + F0; j.ftype = (const int8_t*)(d + o_ft) + F0; j.ptype = (const int8_t*)(d + o_pt) + F0;
+    memcpy(j.T_f_w_in, T_f_w_in + 12 * b, sizeof(double) * 12);
+    j.outlier = (uint8_t*)(d + o_outl) + F0;
+    j.scratch = nullptr;
+    j.out = (hso_pose_result*)(d + o_res) + b;
+    hs[b].T_host_inv = (Se3d*)(d + o_inv) + K0; hs[b].Tth = (double*)(d + o_tth) + 12 * K0;
+    hs[b].keys = (unsigned long long*)(d + o_keys) + F0; hs[b].cls = (int8_t*)(d + o_cls) + F0;
+  }
+  // AbstractCamera::errorMultiplier2() = fxy_mean_ (src/camera.cpp:59,161,287)
+  const double fx = ctx->cam.fx, fy = ctx->cam.fy;
+  const double err_mult2 = (fx * fy < 0) ? std::fabs(fx) : std::fabs((fx + fy) * 0.5);
+  StageTimer tm(ctx, 3);
+  CU(cudaMemcpyAsync(d, h, staged, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_pose((const PoseJobDev*)(d + o_jobs), (const PoseScratch*)(d + o_scr), B, reproj_thresh, n_iter, err_mult2, ctx->stream,
+                 &ctx->launches));
+  char* ho = (char*)ctx->p_out_host.p;
+  CU(cudaMemcpyAsync(ho, d + o_res, sizeof(hso_pose_result) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (Ftot > 0) CU(cudaMemcpyAsync(ho + sizeof(hso_pose_result) * B, d + o_outl, Ftot, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ho, sizeof(hso_pose_result) * B);
+  if (Ftot > 0) memcpy(outlier_out, ho + sizeof(hso_pose_result) * B, Ftot);
+  tm.stop_after_sync();
+  return HSO_OK;
+}
+
+int hso_pose_optimize(hso_ctx* ctx, double reproj_thresh, int n_iter, int n_fts_total, int F, const double* f, const double* p_host,
+                      const int32_t* host_idx, int K, const double* T_host_w, const double* grad, const int8_t* level, const int8_t* ftype,
+                      const int8_t* ptype, const double T_f_w_in[12], uint8_t* outlier_out, hso_pose_result* out) {
+  const int32_t offs[2] = {0, F}, hoffs[2] = {0, K}, nf[1] = {n_fts_total};
+  return hso_pose_optimize_batch(ctx, reproj_thresh, n_iter, 1, nf, offs, f, p_host, host_idx, hoffs, T_host_w, grad, level, ftype, ptype,
+                                 T_f_w_in, outlier_out, out);
 }
 
 int hso_stage_time_ms(hso_ctx* ctx, int stage, double* ms, uint64_t* calls) {

@@ -119,7 +119,13 @@ struct PoseJobDev {
   float* scratch;           // 2F floats for the order statistics
   hso_pose_result* out;
 };
-cudaError_t launch_pose(const PoseJobDev* jobs_dev, int B, double reproj_thresh, int n_iter, double err_mult2, cudaStream_t stream,
-                        uint64_t* launches);
+struct PoseScratch {  // per problem, device memory
+  Se3d* T_host_inv;           // [K]
+  double* Tth;                // [K][12]  T_f_w * T_host^-1 for the pose of the pass in flight
+  unsigned long long* keys;   // [F] radix-select keys
+  int8_t* cls;                // [F] 0 = point-like, 1 = edgelet
+};
+cudaError_t launch_pose(const PoseJobDev* jobs_dev, const PoseScratch* scratch_dev, int B, double reproj_thresh, int n_iter, double err_mult2,
+                        cudaStream_t stream, uint64_t* launches);
 
 }  // namespace hso

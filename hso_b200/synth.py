@@ -80,3 +80,68 @@ def make_pair(seed, cam="icl", F=500, motion_scale=1.0, gain=1.05, depth=4.0, fr
     dist = depth / f[:, 2]
     dist[rng.uniform(size=F) < frac_no_point] = -1.0  # features without a point (Feature::point == NULL)
     return dict(ref_img=ref, cur_img=cur, px=px, f=f, dist=dist, T_true=T, gain=gain, cam=c)
+
+
+def homography(K, T_cur_ref, depth):
+    R, t = T_cur_ref[:3, :3], T_cur_ref[:3, 3]
+    return K @ (R + np.outer(t, np.array([0, 0, 1.0])) / depth) @ np.linalg.inv(K)
+
+
+def make_align_jobs(seed, pair, M=500, frac_edgelet=0.3, noise_px=1.5, depth=4.0):
+    """Candidate matches for Matcher::findMatchDirect's inner part on a make_pair() scene: the affine warp is the local Jacobian of
+    the plane homography (what warp::getWarpMatrixAffine measures by finite differences, src/matcher.cpp:46-72)."""
+    rng = np.random.default_rng(seed)
+    c = pair["cam"]
+    W, H = c["width"], c["height"]
+    Kc = np.array([[c["fx"], 0, c["cx"]], [0, c["fy"], c["cy"]], [0, 0, 1.0]])
+    Hm = homography(Kc, pair["T_true"], depth)
+
+    def warp(p):
+        q = Hm @ np.array([p[0], p[1], 1.0])
+        return q[:2] / q[2]
+
+    jobs = []
+    for m in range(M):
+        lvl = int(rng.integers(0, 3))
+        px_ref = np.array([rng.uniform(40, W - 40), rng.uniform(40, H - 40)])
+        s = 5.0 * (1 << lvl)
+        pc = warp(px_ref)
+        A = np.stack([(warp(px_ref + [s, 0]) - pc) / 5.0, (warp(px_ref + [0, s]) - pc) / 5.0], axis=1)
+        if m % 7 == 3:
+            A = A * 2.3  # exercise search levels > 0
+        D, sl = np.linalg.det(A), 0
+        while D > 3.0 and sl < 2:
+            sl += 1
+            D *= 0.25
+        ang = rng.uniform(0, 2 * np.pi)
+        jobs.append(dict(ref_level=lvl, search_level=sl, type=1 if rng.uniform() < frac_edgelet else 0, scale_patch=int(m % 5 == 0),
+                         px_ref=px_ref, A_cur_ref=A, grad=np.array([np.cos(ang), np.sin(ang)]), px_cur=pc + rng.normal(0, noise_px, 2),
+                         exposure_rat=float(pair["gain"])))
+    return jobs
+
+
+def make_pose_problem(seed, cam="icl", F=400, K=8, noise_px=0.5, frac_outlier=0.1, frac_edgelet=0.3, pose_err=1.0):
+    """Inputs of pose_optimizer::optimizeLevenbergMarquardt3rd: F observed bearings of points hosted in K keyframes."""
+    rng = np.random.default_rng(seed)
+    c = CAMS[cam] if isinstance(cam, str) else cam
+    fbar = abs((c["fx"] + c["fy"]) * 0.5)
+    T_fw = se3_exp(np.concatenate([rng.normal(0, 0.2, 3), rng.normal(0, 0.05, 3)]))
+    T_hosts = [se3_exp(np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 0.08, 3)])) for _ in range(K)]
+    uv = np.stack([rng.uniform(-0.6, 0.6, F), rng.uniform(-0.45, 0.45, F)], axis=1)
+    z = rng.uniform(1.0, 8.0, F)
+    Pf = np.stack([uv[:, 0] * z, uv[:, 1] * z, z], axis=1)
+    Pw = (np.linalg.inv(T_fw) @ np.concatenate([Pf, np.ones((F, 1))], axis=1).T).T
+    host_idx = rng.integers(0, K, F).astype(np.int32)
+    p_host = np.stack([(T_hosts[h] @ Pw[i])[:3] for i, h in enumerate(host_idx)]) if F else np.zeros((0, 3))
+    noise = rng.normal(0, noise_px / fbar, (F, 2))
+    out = rng.uniform(size=F) < frac_outlier
+    noise[out] += rng.normal(0, 10.0 / fbar, (int(out.sum()), 2))
+    fobs = np.stack([uv[:, 0] + noise[:, 0], uv[:, 1] + noise[:, 1], np.ones(F)], axis=1)
+    fobs /= np.linalg.norm(fobs, axis=1, keepdims=True)
+    ang = rng.uniform(0, 2 * np.pi, F)
+    T0 = se3_exp(np.concatenate([rng.normal(0, 0.01, 3), rng.normal(0, 0.003, 3)]) * pose_err) @ T_fw
+    return dict(f=fobs, p_host=p_host, host_idx=host_idx, T_host_w=np.stack([T[:3] for T in T_hosts]),
+                grad=np.stack([np.cos(ang), np.sin(ang)], axis=1), level=rng.integers(0, 3, F).astype(np.int8),
+                ftype=(rng.uniform(size=F) < frac_edgelet).astype(np.int8),
+                ptype=np.where(rng.uniform(size=F) < 0.1, 1, 4).astype(np.int8), T_f_w=T0[:3], T_true=T_fw[:3], n_fts_total=F + 7,
+                err_mult2=fbar)

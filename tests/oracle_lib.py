@@ -176,3 +176,54 @@ def track_solve(H, b, lam):
     step = np.zeros(7)
     lib.orc_track_solve(dp(H), dp(b), C.c_float(lam), dp(step))
     return step
+
+
+def match_direct_batch(jobs, ref_levels, cur_levels, cur_sobel, align_max_iter=10):
+    """jobs: list of dicts (hso_b200.synth.make_align_jobs). ref/cur_levels: lists of u8 level images; cur_sobel: [(gx, gy)] x3."""
+    lib = load()
+    M = len(jobs)
+    arr = (orc_align_job * M)()
+    for m, j in enumerate(jobs):
+        a = arr[m]
+        a.ref_level, a.search_level, a.type, a.scale_patch = j["ref_level"], j["search_level"], j["type"], j.get("scale_patch", 0)
+        for k in range(2):
+            a.px_ref[k], a.grad[k], a.px_cur[k] = j["px_ref"][k], j["grad"][k], j["px_cur"][k]
+        A = np.asarray(j["A_cur_ref"], np.float64).reshape(4)
+        for k in range(4):
+            a.A_cur_ref[k] = A[k]
+        a.exposure_rat = j.get("exposure_rat", 1.0)
+    n = len(ref_levels)
+    rb = [pad_level(l) for l in ref_levels]
+    cb = [pad_level(l) for l in cur_levels]
+    refp = (C.c_void_p * n)(*[b.ctypes.data for b in rb])
+    curp = (C.c_void_p * n)(*[b.ctypes.data for b in cb])
+    lw = (C.c_int * n)(*[l.shape[1] for l in ref_levels])
+    lh = (C.c_int * n)(*[l.shape[0] for l in ref_levels])
+    sx = [np.ascontiguousarray(g[0]) for g in cur_sobel]
+    sy = [np.ascontiguousarray(g[1]) for g in cur_sobel]
+    sxp = (C.c_void_p * 3)(*[a.ctypes.data for a in sx])
+    syp = (C.c_void_p * 3)(*[a.ctypes.data for a in sy])
+    out = (orc_align_result * M)()
+    lib.orc_match_direct_batch(M, arr, refp, curp, lw, lh, sxp, syp, align_max_iter, out)
+    return out
+
+
+def pose_optimize(p, reproj_thresh=2.0, n_iter=12):
+    lib = load()
+    f = np.ascontiguousarray(p["f"], np.float64).reshape(-1)
+    ph = np.ascontiguousarray(p["p_host"], np.float64).reshape(-1)
+    hi = np.ascontiguousarray(p["host_idx"], np.int32)
+    Th = np.ascontiguousarray(p["T_host_w"], np.float64).reshape(-1)
+    g = np.ascontiguousarray(p["grad"], np.float64).reshape(-1)
+    lv, ft, pt = (np.ascontiguousarray(p[k], np.int8) for k in ("level", "ftype", "ptype"))
+    T0 = np.ascontiguousarray(p["T_f_w"], np.float64).reshape(12)
+    F = hi.shape[0]
+    outl = np.zeros(max(F, 1), np.uint8)
+    out = orc_pose_result()
+    i8 = C.POINTER(C.c_int8)
+    lib.orc_pose_optimize(C.c_double(reproj_thresh), n_iter, C.c_double(p["err_mult2"]), int(p["n_fts_total"]), F, dp(f), dp(ph),
+                          hi.ctypes.data_as(C.POINTER(C.c_int32)), dp(Th), dp(g), lv.ctypes.data_as(i8), ft.ctypes.data_as(i8),
+                          pt.ctypes.data_as(i8), dp(T0), outl.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(out))
+    return dict(T_f_w=np.array(out.T_f_w[:]).reshape(3, 4), cov=np.array(out.cov[:]).reshape(6, 6), estimated_scale=out.estimated_scale,
+                error_init=out.error_init, error_final=out.error_final, num_obs=int(out.num_obs), error_in_px=float(out.error_in_px),
+                n_trials_total=out.n_trials_total, early_return=out.early_return, outlier=outl[:F].copy())
