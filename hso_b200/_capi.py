@@ -94,6 +94,8 @@ SYMBOLS = {
     "hso_track_restage_frames": (C.c_int, [_vp, C.c_int, _P(C.c_int32), _P(C.c_int32)]),
     "hso_track_run": (C.c_int, [_vp]),
     "hso_track_collect": (C.c_int, [_vp, _P(hso_track_result), _P(hso_trace), _P(C.c_int)]),
+    "hso_track_set_profile": (C.c_int, [_vp, C.c_int]),
+    "hso_track_level_profile": (C.c_int, [_vp, C.c_int, _P(C.c_double), _P(C.c_uint64)]),
     "hso_track_set_cluster": (C.c_int, [_vp, C.c_int, C.c_int]),
     "hso_align_batch": (C.c_int, [_vp, C.c_int32, C.c_int, _P(hso_align_job), _P(C.c_int32), C.c_int, _P(hso_align_result)]),
     "hso_pose_optimize": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_int32), C.c_int,

@@ -160,7 +160,10 @@ class Context:
         """jobs: ctypes array of hso_align_job (or list of dicts with its field names); ref_frames: frame id per job.
         Returns a ctypes array of hso_align_result."""
         M = len(jobs)
-        if M and not isinstance(jobs, C.Array):
+        if M == 0:
+            self._chk(self.lib.hso_align_batch(self.h, int(cur), 0, None, None, align_max_iter, None))
+            return []
+        if not isinstance(jobs, C.Array):
             arr = (K.hso_align_job * M)()
             for m, j in enumerate(jobs):
                 a = arr[m]

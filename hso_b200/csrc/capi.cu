@@ -76,6 +76,10 @@ struct hso_ctx {
   std::vector<size_t> t_trace_off;  // byte offset of each job's trace in the arena
   size_t t_arena_bytes = 0;
   int t_maxF = 0;
+  int t_profile = 0, t_prof_pending = 0;
+  cudaEvent_t t_ev[kMaxLevels + 1] = {nullptr};
+  double t_level_ms[kMaxLevels] = {0};
+  uint64_t t_level_launches[kMaxLevels] = {0};
   // align / pose scratch
   DevBuf a_jobs_dev, a_out_dev, p_arena, p_jobs_dev, p_out_dev;
   PinBuf a_jobs_host, a_out_host, p_stage_host, p_out_host;
@@ -325,6 +329,7 @@ void hso_destroy(hso_ctx* ctx) {
   PinBuf* pb[] = {&ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
                   &ctx->a_jobs_host, &ctx->a_out_host, &ctx->p_stage_host, &ctx->p_out_host};
   for (PinBuf* b : pb) b->release();
+  for (cudaEvent_t e : ctx->t_ev) if (e) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -570,6 +575,44 @@ int hso_track_restage_frames(hso_ctx* ctx, int B, const hso_frame_id* ref, const
   return HSO_OK;
 }
 
+// Per-level kernel timing (CUDA events on the launching stream) for bench.py's roofline: events bracket each k_track_level launch.
+static int track_profile_flush(hso_ctx* ctx) {
+  if (!ctx->t_prof_pending) return HSO_OK;
+  const hso_track_params& prm = ctx->tprm;
+  const int n = prm.max_level - prm.min_level + 1;
+  CU(cudaEventSynchronize(ctx->t_ev[n]));
+  int slot = 0;
+  for (int level = prm.max_level; level >= prm.min_level; --level, ++slot) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->t_ev[slot], ctx->t_ev[slot + 1]));
+    ctx->t_level_ms[level] += ms;
+    ctx->t_level_launches[level] += 1;
+  }
+  ctx->t_prof_pending = 0;
+  return HSO_OK;
+}
+
+int hso_track_set_profile(hso_ctx* ctx, int on) {
+  if (!ctx) return HSO_ERR_INVALID;
+  if (on) {
+    for (int i = 0; i <= kMaxLevels; ++i)
+      if (!ctx->t_ev[i]) CU(cudaEventCreate(&ctx->t_ev[i]));
+    for (int l = 0; l < kMaxLevels; ++l) { ctx->t_level_ms[l] = 0; ctx->t_level_launches[l] = 0; }
+    ctx->t_prof_pending = 0;
+  }
+  ctx->t_profile = on ? 1 : 0;
+  return HSO_OK;
+}
+
+int hso_track_level_profile(hso_ctx* ctx, int level, double* ms_total, uint64_t* launches) {
+  if (!ctx || level < 0 || level >= kMaxLevels) return HSO_ERR_INVALID;
+  int rc = track_profile_flush(ctx);
+  if (rc != HSO_OK) return rc;
+  if (ms_total) *ms_total = ctx->t_level_ms[level];
+  if (launches) *launches = ctx->t_level_launches[level];
+  return HSO_OK;
+}
+
 int hso_track_run(hso_ctx* ctx) {
   if (!ctx || ctx->tB <= 0) return HSO_ERR_INVALID;
   const int B = ctx->tB;
@@ -583,8 +626,14 @@ int hso_track_run(hso_ctx* ctx) {
     if (B >= 64) threads = std::min(threads, 256);
   }
   const TrackJobDev* jd = (const TrackJobDev*)ctx->t_jobs_dev.p;
+  if (ctx->t_profile) {
+    int rc = track_profile_flush(ctx);
+    if (rc != HSO_OK) return rc;
+  }
   CU(launch_track_init(jd, (const double*)ctx->t_T0.p, (const float*)ctx->t_a0.p, B, ctx->stream, &ctx->launches));
+  int slot = 0;
   for (int level = prm.max_level; level >= prm.min_level; --level) {
+    if (ctx->t_profile) CU(cudaEventRecord(ctx->t_ev[slot++], ctx->stream));
     TrackLevelParams p;
     memset(&p, 0, sizeof p);
     p.ic = prm.inverse_comp; p.max_level = prm.max_level; p.level = level; p.n_iter = prm.n_iter;
@@ -596,6 +645,10 @@ int hso_track_run(hso_ctx* ctx) {
     p.stage_smem = 1;
     if (track_level_smem_bytes(p, threads) > 227 * 1024) p.stage_smem = 0;
     CU(launch_track_level(p, jd, B, cluster, threads, ctx->stream, &ctx->launches));
+  }
+  if (ctx->t_profile) {
+    CU(cudaEventRecord(ctx->t_ev[slot], ctx->stream));
+    ctx->t_prof_pending = 1;
   }
   CU(launch_track_finish(jd, (hso_track_result*)ctx->t_out_dev.p, B, ctx->stream, &ctx->launches));
   return HSO_OK;

@@ -105,8 +105,11 @@ HSO_DEV float b1(uint32_t w) { return (float)((w >> 8) & 0xffu); }
 HSO_DEV float b2(uint32_t w) { return (float)((w >> 16) & 0xffu); }
 HSO_DEV float b3(uint32_t w) { return (float)(w >> 24); }
 
+// H and E are sums of (mostly) same-sign terms: fp32 is enough. b = -sum J r w is a gradient that cancels towards zero at the
+// optimum, so it is kept in fp64 end to end (the reference also builds b in double, src/CoarseTracker.cpp:520).
 struct Acc {
-  float h[28], b[7], E;
+  float h[28], E;
+  double b[7];
   int terms, sat, patches;
 };
 
@@ -114,7 +117,7 @@ HSO_DEV void acc_zero(Acc& a) {
 #pragma unroll
   for (int i = 0; i < 28; ++i) a.h[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < 7; ++i) a.b[i] = 0.f;
+  for (int i = 0; i < 7; ++i) a.b[i] = 0.0;
   a.E = 0.f; a.terms = 0; a.sat = 0; a.patches = 0;
 }
 
@@ -161,7 +164,7 @@ HSO_DEV void patch_jacobian(double x, double y, double z, float fxl, float fyl, 
   B[0] = 0.f; B[1] = -zi * fyl; B[2] = j12 * fyl; B[3] = (1.0f + yf * j12) * fyl; B[4] = -j03 * fyl; B[5] = -xf * zi * fyl;
 }
 
-struct Moments { float xx, xy, yy, cx, cy, cc, rx, ry, rc; };
+struct Moments { float xx, xy, yy, cx, cy, cc; double rx, ry, rc; };
 
 HSO_DEV void expand_patch(Acc& a, const Moments& m, const float* A, const float* B) {
   a.h[0] += m.cc;
@@ -171,7 +174,7 @@ HSO_DEV void expand_patch(Acc& a, const Moments& m, const float* A, const float*
     a.h[1 + k] -= m.cx * A[k] + m.cy * B[k];
     P[k] = m.xx * A[k] + m.xy * B[k];
     Q[k] = m.xy * A[k] + m.yy * B[k];
-    a.b[1 + k] -= m.rx * A[k] + m.ry * B[k];
+    a.b[1 + k] -= m.rx * (double)A[k] + m.ry * (double)B[k];
   }
   a.b[0] += m.rc;
   int idx = 7;
@@ -250,7 +253,7 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const CamDe
         const float wgx = hw * gx, wgy = hw * gy, wc = hw * c;
         m.xx += wgx * gx; m.xy += wgx * gy; m.yy += wgy * gy;
         m.cx += wc * gx;  m.cy += wc * gy;  m.cc += wc * c;
-        m.rx += wgx * r;  m.ry += wgy * r;  m.rc += wc * r;
+        m.rx += (double)wgx * (double)r; m.ry += (double)wgy * (double)r; m.rc += (double)wc * (double)r;
       }
     }
     expand_patch(acc, m, A, B);
@@ -268,7 +271,7 @@ HSO_DEV void reduce_acc(const Acc& acc, const Smem& s, int slot, int csize, int 
 #pragma unroll
   for (int k = 0; k < 28; ++k) { float v = warp_sum(acc.h[k]); if (lane == 0) wp[k] = (double)v; }
 #pragma unroll
-  for (int k = 0; k < 7; ++k) { float v = warp_sum(acc.b[k]); if (lane == 0) wp[28 + k] = (double)v; }
+  for (int k = 0; k < 7; ++k) { double v = warp_sum(acc.b[k]); if (lane == 0) wp[28 + k] = v; }
   { float v = warp_sum(acc.E); if (lane == 0) wp[35] = (double)v; }
   { int v = warp_sum(acc.terms); if (lane == 0) wp[36] = (double)v; }
   { int v = warp_sum(acc.sat); if (lane == 0) wp[37] = (double)v; }

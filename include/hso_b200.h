@@ -72,6 +72,8 @@ int hso_frame_upload_batch(hso_ctx* ctx, int B, const uint8_t* const* imgs, int 
                            float* integral, float* grad_mean);
 /* Device-resident variant for benchmarking: raw level-0 images already live in device memory (dev_imgs = B device ptrs). */
 int hso_frame_build_batch_device(hso_ctx* ctx, int B, const void* const* dev_imgs, int W, int H, int stride, hso_frame_id* out);
+/* Rebuild existing frames `ids` from device-resident images (asynchronous on the ctx stream, no allocation). */
+int hso_frame_rebuild_batch_device(hso_ctx* ctx, int B, const void* const* dev_imgs, int W, int H, int stride, const hso_frame_id* ids);
 int hso_frame_stats(hso_ctx* ctx, hso_frame_id id, float* integral, float* grad_mean);
 int hso_frame_level_size(hso_ctx* ctx, hso_frame_id id, int level, int* w, int* h);
 /* Host mirrors for consumers that stay on the CPU (mapping thread, feature detection). */
@@ -137,6 +139,10 @@ int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_
 int hso_track_restage_frames(hso_ctx* ctx, int B, const hso_frame_id* ref, const hso_frame_id* cur);
 int hso_track_run(hso_ctx* ctx);
 int hso_track_collect(hso_ctx* ctx, hso_track_result* out, hso_trace* trace, int* trace_len);
+/* Kernel timing for the roofline report: when on, CUDA events on the ctx stream bracket every per-level tracker launch;
+ * hso_track_level_profile returns the accumulated device time and launch count of the level's kernel since profiling was enabled. */
+int hso_track_set_profile(hso_ctx* ctx, int on);
+int hso_track_level_profile(hso_ctx* ctx, int level, double* ms_total, uint64_t* launches);
 /* Tuning knob: CTAs cooperating on one problem through a thread-block cluster (1,2,4,8; 0 = auto). */
 int hso_track_set_cluster(hso_ctx* ctx, int ctas_per_problem, int threads_per_cta);
 

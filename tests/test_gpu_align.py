@@ -67,10 +67,13 @@ def test_edge_cases(oracle):
     exp = oracle.match_direct_batch(jobs, rl, cl, sob)
     for m in range(len(jobs)):
         assert got[m].ok == exp[m].ok and got[m].align_converged == exp[m].align_converged, m
+        if np.isnan(exp[m].px_cur[0]):  # singular warp: the reference's update is NaN and it writes NaN back (feature_alignment.cpp:603)
+            assert np.isnan(got[m].px_cur[0])
+            continue
         assert np.hypot(got[m].px_cur[0] - exp[m].px_cur[0], got[m].px_cur[1] - exp[m].px_cur[1]) < 5e-2, m
     assert got[0].ok == 0 and abs(got[0].px_cur[0] - 1.0) < 1e-6
     # empty batch is a no-op
-    assert len(ctx.align_batch(ids[1], [], [])) >= 0
+    assert len(ctx.align_batch(ids[1], [], [])) == 0
     # edgelets without Sobel images are refused loudly
     from hso_b200 import HsoError
     ctx2 = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]))

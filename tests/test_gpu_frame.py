@@ -42,7 +42,7 @@ def test_gradmean_unclamped(oracle):
     # low-contrast image so that gradMean_ is not clamped to [7, 20]
     c = synth.CAMS["icl"]
     rng = np.random.default_rng(3)
-    img = synth.texture(rng, c["width"], c["height"], contrast=6.0)
+    img = synth.texture(rng, c["width"], c["height"], contrast=14.0)
     ctx = _ctx("icl")
     ids, integral, gm = ctx.upload_frames([img])
     oi, og = oracle.frame_stats(img)
