@@ -7,9 +7,12 @@
 // Mapping (see DESIGN.md "k_track_level"):
 //   * lane == patch. A thread owns patches i = t, t+NT, ... for the whole launch, so the reference-intensity cache it
 //     writes in phase 1 is only ever read back by itself (no barrier), and all scratch arrays are [pattern px][patch]
-//     so that a warp's accesses are coalesced.
-//   * the current-level image is staged once per launch into shared memory with a TMA bulk copy (cp.async.bulk +
-//     mbarrier; SASS UBLKCP); every residual evaluation of the level then gathers its taps from shared memory.
+//     so that a warp's accesses are coalesced / bank-conflict free.
+//   * FAST path: the current-level image is staged once per launch into shared memory with a TMA bulk copy (cp.async.bulk +
+//     mbarrier; SASS UBLKCP) and the reference-patch cache of the CTA's patches lives in shared memory too, so a residual
+//     evaluation touches global memory only for 24 B of geometry per patch (prefetched one patch ahead). The host picks the
+//     smallest cluster size whose per-CTA share fits the 227 KB of an SM. SLOW path (level 0 / oversized problems): same code
+//     reading the image and the caches from global memory through L1/L2.
 //   * the 7x7 normal equations are not accumulated term by term. Every Jacobian row of a patch has the form
 //     J = [-c, gx*A + gy*B] with A,B in R^6 constant over the patch (src/CoarseTracker.cpp:372), so per term only the nine
 //     moments  sum w*{gx^2, gx gy, gy^2, c gx, c gy, c^2, r gx, r gy, r c}  are accumulated and the 28+7 entries are
@@ -46,7 +49,7 @@ static const int h_pat_num[8] = {1, 5, 9, 13, 13, 21, 25, 25};
 static const int h_pat_pad[8] = {1, 1, 1, 2, 2, 3, 2, 4};
 
 constexpr int NRED = 40;       // 28 H + 7 b + E + terms + saturated + patches (+1 pad)
-constexpr int NHIST = 2048;    // radix-select bins per pass (11 + 11 + 10 bits)
+constexpr int NHIST = 256;     // radix-select bins per pass (4 passes of 8 bits)
 
 struct TrackCtrl {
   double Rt[12];       // pose used by the evaluation in flight
@@ -62,6 +65,8 @@ struct TrackCtrl {
 
 struct Smem {
   uint8_t* img;
+  float* cache;        // FAST: [N (x3 in IC mode)][pc] reference intensities (+ gradients) of this CTA's patches
+  uint8_t* vis;        // FAST: [pc]
   double* warp_part;   // [nwarps][NRED]
   double* cta_part;    // [2][NRED]
   double* tot;         // [NRED]
@@ -73,9 +78,12 @@ struct Smem {
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline size_t smem_layout(uint32_t img_bytes, int nwarps, size_t* o_warp, size_t* o_cta, size_t* o_tot, size_t* o_hist,
-                                              size_t* o_ghist, size_t* o_ctrl, size_t* o_mbar) {
+__host__ __device__ inline size_t smem_layout(uint32_t img_bytes, size_t cache_bytes, size_t vis_bytes, int nwarps, size_t* o_cache, size_t* o_vis,
+                                              size_t* o_warp, size_t* o_cta, size_t* o_tot, size_t* o_hist, size_t* o_ghist, size_t* o_ctrl,
+                                              size_t* o_mbar) {
   size_t o = align_up(img_bytes, 128);
+  *o_cache = o; o += align_up(cache_bytes, 16);
+  *o_vis = o; o += align_up(vis_bytes, 16);
   *o_warp = o; o += sizeof(double) * nwarps * NRED;
   *o_cta = o; o += sizeof(double) * 2 * NRED;
   *o_tot = o; o += sizeof(double) * NRED;
@@ -86,9 +94,14 @@ __host__ __device__ inline size_t smem_layout(uint32_t img_bytes, int nwarps, si
   return o;
 }
 
+static __host__ __device__ inline int pattern_n(int pidx) { return pidx <= 0 ? 1 : pidx == 1 ? 5 : pidx == 2 ? 9 : pidx <= 4 ? 13 : pidx == 5 ? 21 : 25; }
+
+// Shared memory of one CTA. fast: image + patch caches resident; pc = patch slots per CTA (patches-per-thread * threads).
 size_t track_level_smem_bytes(const TrackLevelParams& p, int threads) {
-  size_t a, b, c, d, e, f, g;
-  return smem_layout(p.stage_smem ? p.img_bytes : 0, threads / 32, &a, &b, &c, &d, &e, &f, &g);
+  size_t a, b, c, d, e, f, g, h, i;
+  const int N = pattern_n(p.max_level - p.level + 2);
+  const size_t cache = p.fast ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : 0;
+  return smem_layout(p.fast ? p.img_bytes : 0, cache, p.fast ? (size_t)p.pc : 0, threads / 32, &a, &b, &c, &d, &e, &f, &g, &h, &i);
 }
 
 // ---- unaligned 4-byte window from a byte image: two aligned words + funnel shift -----------------------------------------

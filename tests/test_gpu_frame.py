@@ -2,9 +2,11 @@
 
 Statistics tolerance: the reference accumulates ~2.7e5 pixel values into one float in raster order (src/frame.cpp:223-245);
 past 2^24 that running sum rounds every addend to a multiple of 2 or 4, so the reference's own integralImage_ is off the
-true mean by ~1e-5 relative (measured: 125.93458 vs exact 125.93305). The CUDA path sums exactly (integers) / in fp64, so
-parity is checked to 5e-5 relative."""
+true mean by ~1e-5 relative (measured: 125.93458 vs exact 125.93305), and its gradient-magnitude sum (~1e8, ulp 8) by up to
+~1e-4 relative (measured on the B200 box: reference-order float sum 7.296347 vs exact 7.295590 vs CUDA 7.295591). The CUDA path
+sums exactly (integers) / in fp64 and lands on the exact value, so parity is checked to 5e-5 (intensity) and 2.5e-4 (gradient)."""
 STAT_REL = 5e-5
+GRAD_REL = 2.5e-4
 import numpy as np
 import pytest
 
@@ -34,7 +36,7 @@ def test_pyramid_bit_exact_and_stats(oracle, cam):
             assert np.array_equal(got, levels[l]), f"level {l} differs ({np.count_nonzero(got != levels[l])} px)"
         oi, og = oracle.frame_stats(img)
         assert abs(integral[k] - oi) <= STAT_REL * abs(oi)
-        assert abs(gm[k] - og) <= STAT_REL * abs(og)
+        assert abs(gm[k] - og) <= GRAD_REL * abs(og)
     ctx.close()
 
 
@@ -47,7 +49,7 @@ def test_gradmean_unclamped(oracle):
     ids, integral, gm = ctx.upload_frames([img])
     oi, og = oracle.frame_stats(img)
     assert 7.0 < og < 20.0
-    assert abs(gm[0] - og) <= STAT_REL * og and abs(integral[0] - oi) <= STAT_REL * oi
+    assert abs(gm[0] - og) <= GRAD_REL * og and abs(integral[0] - oi) <= STAT_REL * oi
     ctx.close()
 
 
