@@ -40,7 +40,7 @@ class hso_track_job(C.Structure):
 class hso_track_result(C.Structure):
     _fields_ = [("T_cur_ref", C.c_double * 12), ("exposure_rat", C.c_float), ("n_iters", C.c_int32), ("n_evals", C.c_int32),
                 ("iters_per_level", C.c_int32 * 8), ("n_tracked", C.c_uint64), ("visible_patch_evals", C.c_uint64 * 8),
-                ("trace_len", C.c_int32), ("reserved", C.c_int32)]
+                ("trace_len", C.c_int32), ("reserved", C.c_int32), ("cycles", C.c_uint64 * 8)]
 
 
 class hso_trace(C.Structure):

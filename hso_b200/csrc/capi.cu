@@ -64,7 +64,7 @@ struct hso_ctx {
   uint64_t launches = 0;
   std::vector<FrameSlot> frames;
   // pyramid
-  DevBuf pyr_jobs_dev, pyr_counters, resize_tab_dev;
+  DevBuf pyr_jobs_dev, pyr_counters, resize_tab_dev, stats_table;  // stats_table: [max_frames][2] floats, one D2H per read
   PinBuf pyr_jobs_host, stats_host;
   std::vector<ResizeTabDev> resize_tabs;
   // tracker
@@ -183,7 +183,7 @@ int alloc_frame(hso_ctx* ctx, hso_frame_id* out) {
       CU(cudaMalloc((void**)&s.pyr, ctx->geom.bytes));
       CU(cudaMemsetAsync(s.pyr, 0, ctx->geom.bytes, ctx->stream));
       CU(cudaMalloc((void**)&s.sums, sizeof(double) * 2 * ctx->n_tiles));
-      CU(cudaMalloc((void**)&s.stats, sizeof(float) * 2));
+      s.stats = (float*)ctx->stats_table.p + 2 * i;
       if (ctx->cfg.materialize_sobel) CU(cudaMalloc((void**)&s.sobel, sizeof(int16_t) * ctx->sobel_elems));
     }
     s.used = true;
@@ -223,13 +223,16 @@ int run_pyramid(hso_ctx* ctx, int B, const hso_frame_id* ids, const uint8_t* con
 
 int read_stats(hso_ctx* ctx, int B, const hso_frame_id* ids, float* integral, float* grad_mean) {
   if (!integral && !grad_mean) return HSO_OK;
-  CU(ctx->stats_host.reserve(sizeof(float) * 2 * B));
+  // one copy of the id range instead of one tiny copy per frame
+  int lo = ids[0], hi = ids[0];
+  for (int i = 1; i < B; ++i) { lo = std::min(lo, (int)ids[i]); hi = std::max(hi, (int)ids[i]); }
+  CU(ctx->stats_host.reserve(sizeof(float) * 2 * (hi - lo + 1)));
   float* h = (float*)ctx->stats_host.p;
-  for (int i = 0; i < B; ++i) CU(cudaMemcpyAsync(h + 2 * i, get_frame(ctx, ids[i])->stats, sizeof(float) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h, (float*)ctx->stats_table.p + 2 * lo, sizeof(float) * 2 * (hi - lo + 1), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < B; ++i) {
-    if (integral) integral[i] = h[2 * i];
-    if (grad_mean) grad_mean[i] = h[2 * i + 1];
+    if (integral) integral[i] = h[2 * (ids[i] - lo)];
+    if (grad_mean) grad_mean[i] = h[2 * (ids[i] - lo) + 1];
   }
   return HSO_OK;
 }
@@ -290,6 +293,7 @@ int hso_create(int device, const hso_cam* cam, const hso_cfg* cfg_in, hso_ctx** 
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
   ctx->stream = ctx->own_stream;
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) return bail("cudaEventCreate");
+  if (ctx->stats_table.reserve(sizeof(float) * 2 * ctx->cfg.max_frames) != cudaSuccess) return bail("cudaMalloc stats table");
   if (!ctx->geom.half_path) {
     std::vector<char> blob;
     ctx->resize_tabs.assign(ctx->geom.n_levels, ResizeTabDev{});
@@ -321,9 +325,8 @@ void hso_destroy(hso_ctx* ctx) {
     if (s.pyr) cudaFree(s.pyr);
     if (s.sobel) cudaFree(s.sobel);
     if (s.sums) cudaFree(s.sums);
-    if (s.stats) cudaFree(s.stats);
   }
-  DevBuf* db[] = {&ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
+  DevBuf* db[] = {&ctx->stats_table, &ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
                   &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
@@ -617,14 +620,6 @@ int hso_track_run(hso_ctx* ctx) {
   if (!ctx || ctx->tB <= 0) return HSO_ERR_INVALID;
   const int B = ctx->tB;
   const hso_track_params& prm = ctx->tprm;
-  int cluster = ctx->t_cluster;
-  if (cluster == 0) cluster = B >= 64 ? 1 : (B >= 32 ? 2 : (B >= 16 ? 4 : 8));
-  int threads = ctx->t_threads;
-  if (threads == 0) {
-    const int per = (ctx->t_maxF + cluster - 1) / cluster;
-    threads = std::min(512, std::max(64, (per + 31) / 32 * 32));
-    if (B >= 64) threads = std::min(threads, 256);
-  }
   const TrackJobDev* jd = (const TrackJobDev*)ctx->t_jobs_dev.p;
   if (ctx->t_profile) {
     int rc = track_profile_flush(ctx);
@@ -642,8 +637,28 @@ int hso_track_run(hso_ctx* ctx) {
     p.level_off = ctx->geom.off[level];
     p.img_bytes = ctx->geom.stage_bytes[level];
     p.cam = ctx->camdev;
-    p.stage_smem = 1;
-    if (track_level_smem_bytes(p, threads) > 227 * 1024) p.stage_smem = 0;
+    // Launch shape of this level. FAST keeps the level image and the CTA's reference-patch cache in shared memory: take the
+    // smallest cluster size whose per-CTA share fits 227 KB, but never fewer CTAs than it takes to cover the 148 SMs when the
+    // batch is small (single-problem latency mode). Otherwise fall back to the global-memory path.
+    const int maxF = std::max(ctx->t_maxF, 1);
+    int c_min = ctx->t_cluster;
+    if (c_min == 0) c_min = B >= 148 ? 1 : (B >= 74 ? 2 : (B >= 37 ? 4 : 8));
+    int cluster = 0, threads = 0;
+    for (int cc = c_min; cc <= 8; cc *= 2) {
+      int th = ctx->t_threads ? ctx->t_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
+      const int kpt = (maxF + cc * th - 1) / (cc * th);
+      p.fast = 1; p.pc = kpt * th; p.cluster = cc;
+      p.hist_bits = 11;
+      if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
+      p.hist_bits = 8;
+      if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
+      if (ctx->t_cluster) break;  // the caller fixed the cluster size
+    }
+    if (!cluster) {
+      cluster = c_min;
+      threads = ctx->t_threads ? ctx->t_threads : std::min(512, std::max(64, ((maxF + cluster - 1) / cluster + 31) / 32 * 32));
+      p.fast = 0; p.pc = 0; p.hist_bits = 11; p.cluster = cluster;
+    }
     CU(launch_track_level(p, jd, B, cluster, threads, ctx->stream, &ctx->launches));
   }
   if (ctx->t_profile) {

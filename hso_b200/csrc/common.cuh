@@ -183,6 +183,57 @@ HSO_DEV void ldlt_solve(const double* A /*NxN row-major symmetric*/, const doubl
   for (int i = 0; i < N; ++i) x[i] = y[i];
 }
 
+// Unpivoted LDL^T of a small SPD system entirely in registers (compile-time indices). Returns false when a pivot is not safely
+// positive — the caller then takes the pivoted path above, which reproduces Eigen::LDLT's handling of semi-definite systems.
+// On SPD input both give the same solution up to rounding (order cond(A) * 1e-16).
+template <int N>
+HSO_DEV bool ldlt_solve_spd_fast(const double* A /*NxN row-major symmetric*/, const double* b, double* x) {
+  double L[N][N], d[N];
+  double maxdiag = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) maxdiag = fmax(maxdiag, fabs(A[i * N + i]));
+  const double tiny = 1e-11 * maxdiag;
+  bool ok = isfinite(maxdiag) && maxdiag > 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double dk = A[k * N + k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) dk -= L[k][j] * L[k][j] * d[j];
+    d[k] = dk;
+    ok = ok && (dk > tiny);
+    const double inv = 1.0 / dk;
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      double v = A[i * N + k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) v -= L[i][j] * L[k][j] * d[j];
+      L[i][k] = v * inv;
+    }
+  }
+  if (!ok) return false;
+  double y[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double v = b[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) v -= L[i][j] * y[j];
+    y[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] /= d[i];
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double v = y[i];
+#pragma unroll
+    for (int j = i + 1; j < N; ++j) v -= L[j][i] * y[j];
+    y[i] = v;
+  }
+  bool fin = true;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { x[i] = y[i]; fin = fin && isfinite(y[i]); }
+  return fin;
+}
+
 // ---- camera projection, double (src/camera.cpp:94-125,199-221,307-315) -------------------------------------------------
 struct CamDev {
   int model, width, height, undistort;

@@ -60,6 +60,7 @@ struct TrackState {
   unsigned long long patch_evals[8];  // per level: sum over evaluations of patches that produced terms
   int trace_len;
   int pad_;
+  unsigned long long cycles[8];       // diagnostics (CTA rank 0, thread 0): launch, setup, control
 };
 
 struct TrackJobDev {
@@ -83,7 +84,10 @@ struct TrackLevelParams {
   int trace_cap;
   int w, h;                 // geometry of this level
   size_t level_off;         // byte offset of this level in a pyramid buffer
-  int stage_smem;           // 1: the current level image is staged in shared memory
+  int fast;                 // 1: level image + reference-patch caches of the CTA live in shared memory
+  int pc;                   // FAST: patch slots per CTA = patches-per-thread * threads
+  int hist_bits;            // radix-select digit width: 11 when the histogram fits next to the caches, else 8
+  int cluster;              // CTAs per problem (shared-memory layout depends on it)
   uint32_t img_bytes;       // bytes staged (multiple of 16)
   CamDev cam;
 };

@@ -45,11 +45,30 @@ __constant__ int8_t c_pat[8][25][2] = {
     {{-4, -4}, {-4, -2}, {-4, 0}, {-4, 2}, {-4, 4}, {-2, -4}, {-2, -2}, {-2, 0}, {-2, 2}, {-2, 4}, {0, -4}, {0, -2}, {0, 0},
      {0, 2}, {0, 4}, {2, -4}, {2, -2}, {2, 0}, {2, 2}, {2, 4}, {4, -4}, {4, -2}, {4, 0}, {4, 2}, {4, 4}},
 };
+// The same table as compile-time constants: 8 bits per pattern pixel, (dx + 8) | (dy + 8) << 4, eight pixels per 64-bit word. With the
+// term loop fully unrolled the offsets fold into immediates (no constant-memory loads in the inner loop).
+template <int PIDX> struct PatBits;
+template <> struct PatBits<0> { static constexpr unsigned long long w0 = 0x0000000000000088ull, w1 = 0x0000000000000000ull, w2 = 0x0000000000000000ull, w3 = 0x0000000000000000ull; };
+template <> struct PatBits<1> { static constexpr unsigned long long w0 = 0x0000009889888778ull, w1 = 0x0000000000000000ull, w2 = 0x0000000000000000ull, w3 = 0x0000000000000000ull; };
+template <> struct PatBits<2> { static constexpr unsigned long long w0 = 0x8979988887978777ull, w1 = 0x0000000000000099ull, w2 = 0x0000000000000000ull, w3 = 0x0000000000000000ull; };
+template <> struct PatBits<3> { static constexpr unsigned long long w0 = 0x99978a8886797768ull, w1 = 0x00000098898778a8ull, w2 = 0x0000000000000000ull, w3 = 0x0000000000000000ull; };
+template <> struct PatBits<4> { static constexpr unsigned long long w0 = 0x99978a8886797768ull, w1 = 0x000000aa6aa666a8ull, w2 = 0x0000000000000000ull, w3 = 0x0000000000000000ull; };
+template <> struct PatBits<5> { static constexpr unsigned long long w0 = 0x99978a8886797768ull, w1 = 0x7b9575aa6aa666a8ull, w2 = 0x000000b7b957599bull, w3 = 0x0000000000000000ull; };
+template <> struct PatBits<6> { static constexpr unsigned long long w0 = 0x877767a696867666ull, w1 = 0x69a898887868a797ull, w2 = 0x9a8a7a6aa9998979ull, w3 = 0x00000000000000aaull; };
+template <> struct PatBits<7> { static constexpr unsigned long long w0 = 0x866646c4a4846444ull, w1 = 0x4ac8a8886848c6a6ull, w2 = 0xac8c6c4ccaaa8a6aull, w3 = 0x00000000000000ccull; };
+template <int PIDX>
+HSO_DEV constexpr int pat_dx(int n) {
+  return (int)(((n < 8 ? PatBits<PIDX>::w0 : n < 16 ? PatBits<PIDX>::w1 : n < 24 ? PatBits<PIDX>::w2 : PatBits<PIDX>::w3) >> ((n & 7) * 8)) & 0xfull) - 8;
+}
+template <int PIDX>
+HSO_DEV constexpr int pat_dy(int n) {
+  return (int)(((n < 8 ? PatBits<PIDX>::w0 : n < 16 ? PatBits<PIDX>::w1 : n < 24 ? PatBits<PIDX>::w2 : PatBits<PIDX>::w3) >> ((n & 7) * 8 + 4)) & 0xfull) - 8;
+}
 static const int h_pat_num[8] = {1, 5, 9, 13, 13, 21, 25, 25};
 static const int h_pat_pad[8] = {1, 1, 1, 2, 2, 3, 2, 4};
 
 constexpr int NRED = 40;       // 28 H + 7 b + E + terms + saturated + patches (+1 pad)
-constexpr int NHIST = 256;     // radix-select bins per pass (4 passes of 8 bits)
+// radix-select digit width: 11 bits (2048 bins; passes 11+11+10) when shared memory allows, else 8 bits (256 bins; 4 passes)
 
 struct TrackCtrl {
   double Rt[12];       // pose used by the evaluation in flight
@@ -70,25 +89,26 @@ struct Smem {
   double* warp_part;   // [nwarps][NRED]
   double* cta_part;    // [2][NRED]
   double* tot;         // [NRED]
-  uint32_t* hist;      // [2][NHIST]
-  uint32_t* ghist;     // [NHIST]
+  uint32_t* hist;      // [1 << hist_bits]
+  uint32_t* ghist;     // [1 << hist_bits] cluster-wide sum (aliases hist when the cluster is a single CTA)
   TrackCtrl* ctrl;
   uint64_t* mbar;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline size_t smem_layout(uint32_t img_bytes, size_t cache_bytes, size_t vis_bytes, int nwarps, size_t* o_cache, size_t* o_vis,
-                                              size_t* o_warp, size_t* o_cta, size_t* o_tot, size_t* o_hist, size_t* o_ghist, size_t* o_ctrl,
-                                              size_t* o_mbar) {
+__host__ __device__ inline size_t smem_layout(uint32_t img_bytes, size_t cache_bytes, size_t vis_bytes, int nwarps, int hist_bits, int csize,
+                                              size_t* o_cache, size_t* o_vis, size_t* o_warp, size_t* o_cta, size_t* o_tot, size_t* o_hist,
+                                              size_t* o_ghist, size_t* o_ctrl, size_t* o_mbar) {
   size_t o = align_up(img_bytes, 128);
   *o_cache = o; o += align_up(cache_bytes, 16);
   *o_vis = o; o += align_up(vis_bytes, 16);
   *o_warp = o; o += sizeof(double) * nwarps * NRED;
   *o_cta = o; o += sizeof(double) * 2 * NRED;
   *o_tot = o; o += sizeof(double) * NRED;
-  *o_hist = o; o += sizeof(uint32_t) * 2 * NHIST;
-  *o_ghist = o; o += sizeof(uint32_t) * NHIST;
+  *o_hist = o; o += sizeof(uint32_t) << hist_bits;
+  *o_ghist = csize > 1 ? o : *o_hist;
+  if (csize > 1) o += sizeof(uint32_t) << hist_bits;
   *o_ctrl = o; o += align_up(sizeof(TrackCtrl), 16);
   *o_mbar = o; o += 16;
   return o;
@@ -101,7 +121,7 @@ size_t track_level_smem_bytes(const TrackLevelParams& p, int threads) {
   size_t a, b, c, d, e, f, g, h, i;
   const int N = pattern_n(p.max_level - p.level + 2);
   const size_t cache = p.fast ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : 0;
-  return smem_layout(p.fast ? p.img_bytes : 0, cache, p.fast ? (size_t)p.pc : 0, threads / 32, &a, &b, &c, &d, &e, &f, &g, &h, &i);
+  return smem_layout(p.fast ? p.img_bytes : 0, cache, p.fast ? (size_t)p.pc : 0, threads / 32, p.hist_bits, p.cluster, &a, &b, &c, &d, &e, &f, &g, &h, &i);
 }
 
 // ---- unaligned 4-byte window from a byte image: two aligned words + funnel shift -----------------------------------------
@@ -113,10 +133,14 @@ HSO_DEV uint32_t ld4(const uint8_t* img, int byte_addr) {
   else { lo = __ldg(w); hi = __ldg(w + 1); }
   return __funnelshift_r(lo, hi, (byte_addr & 3) << 3);
 }
-HSO_DEV float b0(uint32_t w) { return (float)(w & 0xffu); }
-HSO_DEV float b1(uint32_t w) { return (float)((w >> 8) & 0xffu); }
-HSO_DEV float b2(uint32_t w) { return (float)((w >> 16) & 0xffu); }
-HSO_DEV float b3(uint32_t w) { return (float)(w >> 24); }
+// byte k of w as float, exact, without the conversion (XU) pipe: PRMT builds the bit pattern of 2^23 + byte, FADD removes 2^23.
+// (I2F.U8 is quarter rate; the first profile showed it as the top stall reason of the term loop.)
+template <int K>
+HSO_DEV float byte_to_float(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | K)) - 8388608.0f; }
+HSO_DEV float b0(uint32_t w) { return byte_to_float<0>(w); }
+HSO_DEV float b1(uint32_t w) { return byte_to_float<1>(w); }
+HSO_DEV float b2(uint32_t w) { return byte_to_float<2>(w); }
+HSO_DEV float b3(uint32_t w) { return byte_to_float<3>(w); }
 
 // H and E are sums of (mostly) same-sign terms: fp32 is enough. b = -sum J r w is a gradient that cancels towards zero at the
 // optimum, so it is kept in fp64 end to end (the reference also builds b in double, src/CoarseTracker.cpp:520).
@@ -177,7 +201,7 @@ HSO_DEV void patch_jacobian(double x, double y, double z, float fxl, float fyl, 
   B[0] = 0.f; B[1] = -zi * fyl; B[2] = j12 * fyl; B[3] = (1.0f + yf * j12) * fyl; B[4] = -j03 * fyl; B[5] = -xf * zi * fyl;
 }
 
-struct Moments { float xx, xy, yy, cx, cy, cc; double rx, ry, rc; };
+struct Moments { float xx, xy, yy, cx, cy, cc, rx, ry, rc; };  // fp32 over the <= 25 terms of one patch
 
 HSO_DEV void expand_patch(Acc& a, const Moments& m, const float* A, const float* B) {
   a.h[0] += m.cc;
@@ -187,9 +211,9 @@ HSO_DEV void expand_patch(Acc& a, const Moments& m, const float* A, const float*
     a.h[1 + k] -= m.cx * A[k] + m.cy * B[k];
     P[k] = m.xx * A[k] + m.xy * B[k];
     Q[k] = m.xy * A[k] + m.yy * B[k];
-    a.b[1 + k] -= m.rx * (double)A[k] + m.ry * (double)B[k];
+    a.b[1 + k] -= (double)m.rx * (double)A[k] + (double)m.ry * (double)B[k];
   }
-  a.b[0] += m.rc;
+  a.b[0] += (double)m.rc;
   int idx = 7;
 #pragma unroll
   for (int j = 0; j < 6; ++j)
@@ -198,82 +222,104 @@ HSO_DEV void expand_patch(Acc& a, const Moments& m, const float* A, const float*
 }
 
 struct LevelCtx {
-  const uint8_t* cur;  // shared-memory copy or global level image
-  int w, h, N, border;
+  const uint8_t* cur;  // shared-memory copy (FAST) or global level image
+  int w, h, border;
   float scale, fxl, fyl;
   bool top;
 };
 
+// Where the per-patch caches of the calling thread live. FAST: shared memory, slot = k * blockDim + tid (conflict free);
+// SLOW: global scratch, slot = patch index (coalesced). Layout [pattern px][stride].
+struct PatchStore {
+  float* cache;    // reference intensities
+  float* gx;       // inverse-compositional reference gradients
+  float* gy;
+  uint8_t* vis;
+  int stride;
+};
+
+template <bool FAST>
+HSO_DEV int slot_of(int i, int k) { return FAST ? (k * (int)blockDim.x + (int)threadIdx.x) : i; }
+
 // One residual evaluation over the calling thread's patches: computeResiduals + computeGS fused
 // (src/CoarseTracker.cpp:242-414, :499-525).
-template <int PIDX, bool IC, bool STAGE>
-HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const CamDev& cam, const double* Rt, float a, float huber, float cutoff,
-                          int t0, int nt, Acc& acc) {
+template <int PIDX, bool IC, bool FAST>
+HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const PatchStore& ps, const CamDev& cam, const double* Rt, float a, float huber,
+                          float cutoff, int t0, int nt, Acc& acc) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
-  const int Fp = job.Fpad;
+  const int Fp = job.Fpad, S = ps.stride;
   // max_energy = 2*huber*cutoff - huber^2, evaluated in double like the reference (cutoff_error is a double there)
   const float max_energy = (float)(2.0 * (double)huber * (double)cutoff - (double)(huber * huber));
-  double R[12];
+  // geometry of the next patch is fetched while the current one is processed (the only global loads of the FAST path)
+  int i = t0, k = 0;
+  bool have = i < job.F && ps.vis[slot_of<FAST>(i, k)] != 0;
+  double X = 0, Y = 0, Z = 1;
+  if (have) { X = job.xyz[i]; Y = job.xyz[Fp + i]; Z = job.xyz[2 * Fp + i]; }
+  while (i < job.F) {
+    const int in = i + nt, kn = k + 1;
+    const bool have_n = in < job.F && ps.vis[slot_of<FAST>(in, kn)] != 0;
+    double Xn = 0, Yn = 0, Zn = 1;
+    if (have_n) { Xn = job.xyz[in]; Yn = job.xyz[Fp + in]; Zn = job.xyz[2 * Fp + in]; }
+    if (have) {
+      const Proj p = project_patch(Rt, cam, X, Y, Z, L.scale, L.border, L.w, L.h);
+      if (p.ok) {
+        const int sl = slot_of<FAST>(i, k);
+        float A[6], B[6];
+        if (!IC) {
+          patch_jacobian(p.x, p.y, p.z, L.fxl, L.fyl, A, B);
+        } else {
+          patch_jacobian(X, Y, Z, L.fxl, L.fyl, A, B);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) R[k] = Rt[k];
-  for (int i = t0; i < job.F; i += nt) {
-    if (!job.vis[i]) continue;
-    const double X = job.xyz[i], Y = job.xyz[Fp + i], Z = job.xyz[2 * Fp + i];
-    const Proj p = project_patch(R, cam, X, Y, Z, L.scale, L.border, L.w, L.h);
-    if (!p.ok) continue;
-    float A[6], B[6];
-    if (!IC) {
-      patch_jacobian(p.x, p.y, p.z, L.fxl, L.fyl, A, B);
-    } else {
-      patch_jacobian(X, Y, Z, L.fxl, L.fyl, A, B);
+          for (int q = 0; q < 6; ++q) { A[q] *= a; B[q] *= a; }  // m_jacobian_cache_true = exposure_rat * raw (:244-245)
+        }
+        Moments m = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float Ep = 0.f;
+        int sat = 0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { A[k] *= a; B[k] *= a; }  // m_jacobian_cache_true = exposure_rat * raw (:244-245)
-    }
-    Moments m = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    float Ep = 0.f;
-    int terms = 0, sat = 0;
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-      const int addr = p.base + (int)c_pat[PIDX][n][1] * L.w + (int)c_pat[PIDX][n][0];
-      const float c = job.ref_cache[n * Fp + i];
-      float color, gx, gy;
-      if (!IC) {
-        const uint32_t rm = ld4<STAGE>(L.cur, addr - L.w - 1);
-        const uint32_t r0 = ld4<STAGE>(L.cur, addr - 1);
-        const uint32_t r1 = ld4<STAGE>(L.cur, addr + L.w - 1);
-        const uint32_t r2 = ld4<STAGE>(L.cur, addr + 2 * L.w - 1);
-        color = p.wtl * b1(r0) + p.wtr * b2(r0) + p.wbl * b1(r1) + p.wbr * b2(r1);
-        gx = 0.5f * ((p.wtl * b2(r0) + p.wtr * b3(r0) + p.wbl * b2(r1) + p.wbr * b3(r1)) -
-                     (p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1)));
-        gy = 0.5f * ((p.wtl * b1(r1) + p.wtr * b2(r1) + p.wbl * b1(r2) + p.wbr * b2(r2)) -
-                     (p.wtl * b1(rm) + p.wtr * b2(rm) + p.wbl * b1(r0) + p.wbr * b2(r0)));
-      } else {
-        const uint32_t r0 = ld4<STAGE>(L.cur, addr);
-        const uint32_t r1 = ld4<STAGE>(L.cur, addr + L.w);
-        color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-        gx = job.ref_gx[n * Fp + i];
-        gy = job.ref_gy[n * Fp + i];
+        for (int n = 0; n < N; ++n) {
+          const int addr = p.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
+          const float c = ps.cache[n * S + sl];
+          float color, gx, gy;
+          if (!IC) {
+            const uint32_t rm = ld4<FAST>(L.cur, addr - L.w - 1);
+            const uint32_t r0 = ld4<FAST>(L.cur, addr - 1);
+            const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w - 1);
+            const uint32_t r2 = ld4<FAST>(L.cur, addr + 2 * L.w - 1);
+            color = p.wtl * b1(r0) + p.wtr * b2(r0) + p.wbl * b1(r1) + p.wbr * b2(r1);
+            gx = 0.5f * ((p.wtl * b2(r0) + p.wtr * b3(r0) + p.wbl * b2(r1) + p.wbr * b3(r1)) -
+                         (p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1)));
+            gy = 0.5f * ((p.wtl * b1(r1) + p.wtr * b2(r1) + p.wbl * b1(r2) + p.wbr * b2(r2)) -
+                         (p.wtl * b1(rm) + p.wtr * b2(rm) + p.wbl * b1(r0) + p.wbr * b2(r0)));
+          } else {
+            const uint32_t r0 = ld4<FAST>(L.cur, addr);
+            const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
+            color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
+            gx = ps.gx[n * S + sl];
+            gy = ps.gy[n * S + sl];
+          }
+          const float r = color - (a * c + 0.f);
+          const float ar = fabsf(r);
+          // Huber weight hw = huber / |r| (src/CoarseTracker.cpp:348) with the fast reciprocal (<= 2 ulp): hw only scales terms
+          const float hw = ar < huber ? 1.f : __fdividef(huber, ar);
+          // branch-free form of :350-361: a saturated term adds max_energy and contributes nothing to H, b
+          const bool saturated = ar > cutoff && !L.top;
+          const float e_in = L.top ? hw * r * r : hw * r * r * (2.f - hw);
+          Ep += saturated ? max_energy : e_in;
+          sat += saturated ? 1 : 0;
+          const float w = saturated ? 0.f : hw;
+          const float wgx = w * gx, wgy = w * gy, wc = w * c;
+          m.xx += wgx * gx; m.xy += wgx * gy; m.yy += wgy * gy;
+          m.cx += wc * gx;  m.cy += wc * gy;  m.cc += wc * c;
+          m.rx += wgx * r;  m.ry += wgy * r;  m.rc += wc * r;
+        }
+        expand_patch(acc, m, A, B);
+        acc.E += Ep;
+        acc.terms += N;
+        acc.sat += sat;
+        acc.patches += 1;
       }
-      const float r = color - (a * c + 0.f);
-      const float ar = fabsf(r);
-      const float hw = ar < huber ? 1.f : huber / ar;
-      ++terms;
-      if (ar > cutoff && !L.top) {
-        Ep += max_energy;
-        ++sat;
-      } else {
-        Ep += L.top ? hw * r * r : hw * r * r * (2.f - hw);
-        const float wgx = hw * gx, wgy = hw * gy, wc = hw * c;
-        m.xx += wgx * gx; m.xy += wgx * gy; m.yy += wgy * gy;
-        m.cx += wc * gx;  m.cy += wc * gy;  m.cc += wc * c;
-        m.rx += (double)wgx * (double)r; m.ry += (double)wgy * (double)r; m.rc += (double)wc * (double)r;
-      }
     }
-    expand_patch(acc, m, A, B);
-    acc.E += Ep;
-    acc.terms += terms;
-    acc.sat += sat;
-    acc.patches += 1;
+    i = in; k = kn; have = have_n; X = Xn; Y = Yn; Z = Zn;
   }
 }
 
@@ -313,45 +359,66 @@ HSO_DEV void reduce_acc(const Acc& acc, const Smem& s, int slot, int csize, int 
   __syncthreads();
 }
 
+// Warp-aggregated histogram increment: lanes of the warp that hit the same bin elect one leader which adds their count.
+// The top digit of |r| takes only a few dozen distinct values, so plain shared-memory atomics would serialise 32-way.
+HSO_DEV void hist_add_aggregated(uint32_t* hist, uint32_t bin) {
+  const unsigned act = __activemask();
+  const unsigned peers = __match_any_sync(act, bin);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+}
+
 // Exact k-th smallest (k = n/2, hso::getMedian, include/hso/vikit/math_utils.h:119-126) of the non-negative floats
 // { f(absres) : absres >= 0 } owned by the cluster; MAD = true selects over fabsf(v - center). Result in ctrl->sel_prefix.
+// Radix select over the IEEE bit pattern (monotone for non-negative floats), digits of `bits` bits from the top; histograms of the
+// CTAs of a cluster are merged through DSMEM. prefilled: the histogram of the first digit was already accumulated by the caller
+// (fused with the residual computation), so that pass does not re-read the residuals.
 template <int N>
-HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, int t0, int nt, bool mad, float center, int csize, int& hist_phase) {
+HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, int t0, int nt, bool mad, float center, int csize, int bits, bool prefilled) {
   const int Fp = job.Fpad;
+  const int nbins = 1 << bits;
   uint32_t prefix = 0, mask = 0;
-  for (int pass = 0; pass < 3; ++pass) {
-    const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-    const uint32_t dmask = pass == 2 ? 0x3ffu : 0x7ffu;
-    uint32_t* hist = s.hist + (hist_phase & 1) * NHIST;
-    for (int j = threadIdx.x; j < NHIST; j += blockDim.x) hist[j] = 0;
-    __syncthreads();
-    for (int i = t0; i < job.F; i += nt) {
+  int hi = 32;
+  bool first = true;
+  while (hi > 0) {
+    const int width = hi >= bits ? bits : hi;
+    const int shift = hi - width;
+    const uint32_t dmask = (1u << width) - 1u;
+    uint32_t* hist = s.hist;
+    if (!(first && prefilled)) {
+      for (int j = threadIdx.x; j < nbins; j += blockDim.x) hist[j] = 0;
+      __syncthreads();
+      for (int i = t0; i < job.F; i += nt) {
+        // all N loads of the patch are issued back to back (one L2 round trip per patch, not one per value)
+        float vals[N];
 #pragma unroll
-      for (int n = 0; n < N; ++n) {
-        float v = job.absres[n * Fp + i];
-        if (v < 0.f) continue;
-        if (mad) v = fabsf(v - center);
-        const uint32_t key = __float_as_uint(v);
-        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
+        for (int n = 0; n < N; ++n) vals[n] = __ldcg(job.absres + n * Fp + i);
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          float v = vals[n];
+          const bool valid = v >= 0.f;
+          if (mad) v = fabsf(v - center);
+          const uint32_t key = __float_as_uint(v);
+          if (valid && (key & mask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
+        }
       }
     }
     if (csize == 1) {
       __syncthreads();
-      for (int j = threadIdx.x; j < NHIST; j += blockDim.x) s.ghist[j] = hist[j];
     } else {
       cg::cluster_group cluster = cg::this_cluster();
       cluster.sync();
-      for (int j = threadIdx.x; j < NHIST; j += blockDim.x) {
+      for (int j = threadIdx.x; j < nbins; j += blockDim.x) {
         uint32_t sum = 0;
         for (int r = 0; r < csize; ++r) sum += cluster.map_shared_rank(hist, r)[j];
         s.ghist[j] = sum;
       }
+      cluster.sync();  // peers are done reading this CTA's histogram before it is zeroed again
     }
-    __syncthreads();
     if (threadIdx.x < 32) {
       const int lane = threadIdx.x;
+      const int per = nbins >> 5;
       uint32_t local = 0;
-      for (int j = 0; j < NHIST / 32; ++j) local += s.ghist[lane * (NHIST / 32) + j];
+      for (int j = 0; j < per; ++j) local += s.ghist[lane * per + j];
       uint32_t incl = local;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -360,7 +427,7 @@ HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, int t0, int nt,
       }
       const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
       uint32_t k;
-      if (pass == 0) {
+      if (first) {
         k = total / 2;
         if (lane == 0) { s.ctrl->sel_n = total; }
       } else {
@@ -370,10 +437,10 @@ HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, int t0, int nt,
       const bool mine = total > 0 && k >= excl && k < incl;
       if (mine) {
         uint32_t cum = excl;
-        int d = lane * (NHIST / 32);
-        for (int j = 0; j < NHIST / 32; ++j) {
-          const uint32_t c = s.ghist[lane * (NHIST / 32) + j];
-          if (k < cum + c) { d = lane * (NHIST / 32) + j; break; }
+        int d = lane * per;
+        for (int j = 0; j < per; ++j) {
+          const uint32_t c = s.ghist[lane * per + j];
+          if (k < cum + c) { d = lane * per + j; break; }
           cum += c;
         }
         s.ctrl->sel_k = k - cum;
@@ -384,7 +451,8 @@ HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, int t0, int nt,
     __syncthreads();
     prefix = s.ctrl->sel_prefix;
     mask |= dmask << shift;
-    ++hist_phase;
+    hi = shift;
+    first = false;
   }
 }
 
@@ -441,7 +509,11 @@ __device__ __noinline__ void lm_control(TrackCtrl* c, const double* tot, const T
       for (int q = r; q < 7; ++q) { Hl[r * 7 + q] = Hl[q * 7 + r] = c->H[idx]; ++idx; }
     const float lambda = c->lambda;
     for (int k = 0; k < 7; ++k) Hl[k * 7 + k] *= (double)(1.f + lambda);
-    ldlt_solve<7>(Hl, c->b, step);
+    double bl[7];
+    for (int k = 0; k < 7; ++k) bl[k] = c->b[k];
+    // register-resident unpivoted factorisation when the damped system is safely positive definite (the normal case);
+    // the pivoted robust-Cholesky path (Eigen::LDLT semantics) otherwise
+    if (!ldlt_solve_spd_fast<7>(Hl, bl, step)) ldlt_solve<7>(Hl, bl, step);
     float extrap = 1.f;
     if (lambda < 0.001f) extrap = (float)sqrt(sqrt(0.001 / (double)lambda));
     double sum = 0;
@@ -458,7 +530,7 @@ __device__ __noinline__ void lm_control(TrackCtrl* c, const double* tot, const T
   c->done = done ? 1 : 0;
 }
 
-template <int PIDX, bool IC, bool STAGE>
+template <int PIDX, bool IC, bool FAST>
 __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams prm, const TrackJobDev* __restrict__ jobs) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
   constexpr int PAD = (PIDX == 5) ? 3 : (PIDX == 7) ? 4 : (PIDX <= 2) ? 1 : 2;
@@ -469,14 +541,18 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   const int problem = blockIdx.x / csize;
   const TrackJobDev job = jobs[problem];
   const int nwarps = blockDim.x >> 5;
+  const long long clk_start = clock64();
 
   Smem s;
   {
-    size_t ow, oc, ot, oh, og, ox, om;
-    smem_layout(STAGE ? prm.img_bytes : 0, nwarps, &ow, &oc, &ot, &oh, &og, &ox, &om);
+    size_t oc, ov, ow, op, ot, oh, og, ox, om;
+    const size_t cache_bytes = FAST ? (size_t)N * (IC ? 3 : 1) * prm.pc * sizeof(float) : 0;
+    smem_layout(FAST ? prm.img_bytes : 0, cache_bytes, FAST ? (size_t)prm.pc : 0, nwarps, prm.hist_bits, csize, &oc, &ov, &ow, &op, &ot, &oh, &og, &ox, &om);
     s.img = smem_raw;
+    s.cache = reinterpret_cast<float*>(smem_raw + oc);
+    s.vis = smem_raw + ov;
     s.warp_part = reinterpret_cast<double*>(smem_raw + ow);
-    s.cta_part = reinterpret_cast<double*>(smem_raw + oc);
+    s.cta_part = reinterpret_cast<double*>(smem_raw + op);
     s.tot = reinterpret_cast<double*>(smem_raw + ot);
     s.hist = reinterpret_cast<uint32_t*>(smem_raw + oh);
     s.ghist = reinterpret_cast<uint32_t*>(smem_raw + og);
@@ -488,11 +564,19 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   const int nt = csize * blockDim.x;
   const int Fp = job.Fpad;
 
+  PatchStore ps;
+  if (FAST) {
+    ps.cache = s.cache; ps.gx = s.cache + (size_t)N * prm.pc; ps.gy = s.cache + (size_t)2 * N * prm.pc; ps.vis = s.vis; ps.stride = prm.pc;
+  } else {
+    ps.cache = job.ref_cache; ps.gx = job.ref_gx; ps.gy = job.ref_gy; ps.vis = job.vis; ps.stride = Fp;
+  }
+
   // ---- phase 0: stage the current level image (TMA bulk copy), read the accepted state ---------------------------------
   const uint8_t* cur_g = job.cur_pyr + prm.level_off;
   const uint8_t* ref_g = job.ref_pyr + prm.level_off;
   if (threadIdx.x == 0) {
-    if (STAGE) {
+    if (FAST) {
+      // the staging buffer first holds the REFERENCE level (phase 1 gathers the reference patches from it), then the CURRENT level
       mbar_init(s.mbar, 1);
       mbar_fence_init();
       fence_proxy_async();
@@ -501,7 +585,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
       while (done < prm.img_bytes) {
         uint32_t chunk = prm.img_bytes - done;
         if (chunk > 32768u) chunk = 32768u;
-        tma_bulk_g2s(s.img + done, cur_g + done, chunk, s.mbar);
+        tma_bulk_g2s(s.img + done, ref_g + done, chunk, s.mbar);
         done += chunk;
       }
     }
@@ -512,86 +596,113 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   }
 
   LevelCtx L;
-  L.cur = STAGE ? s.img : cur_g;
-  L.w = prm.w; L.h = prm.h; L.N = N; L.border = PAD + 1;
+  L.cur = FAST ? s.img : cur_g;
+  L.w = prm.w; L.h = prm.h; L.border = PAD + 1;
   L.scale = 1.0f / (float)(1 << prm.level);
   L.fxl = (float)(prm.cam.fx * (double)L.scale);
   L.fyl = (float)(prm.cam.fy * (double)L.scale);
   L.top = prm.level == prm.max_level;
 
-  // ---- phase 1: precomputeReferencePatches (src/CoarseTracker.cpp:416-497); overlaps the bulk copy ------------------------
-  for (int i = t0; i < job.F; i += nt) {
-    const float u = (float)(job.px[i] * (double)L.scale), v = (float)(job.px[Fp + i] * (double)L.scale);
-    const float uf = floorf(u), vf = floorf(v);
-    const int ui = __float2int_rd(u), vi = __float2int_rd(v);
-    const bool in = ui >= L.border && vi >= L.border && ui < L.w - L.border && vi < L.h - L.border;  // :441
-    job.vis[i] = in ? 1 : 0;
-    if (!in) continue;
-    const float su = u - uf, sv = v - vf;
-    const float wtl = (float)((1.0 - su) * (1.0 - sv));
-    const float wtr = (float)(su * (1.0 - sv));
-    const float wbl = (float)((1.0 - su) * sv);
-    const float wbr = (float)(1.0 - (double)(wtl + wtr + wbl));  // quirk: differs from the current-image weights (:467 vs :323)
-    const int base = vi * L.w + ui;
+  // ---- phase 1: precomputeReferencePatches (src/CoarseTracker.cpp:416-497) ------------------------------------------------
+  __syncthreads();
+  if (FAST) mbar_wait(s.mbar, 0);
+  const uint8_t* ref_src = FAST ? s.img : ref_g;
+  {
+    int k = 0;
+    for (int i = t0; i < job.F; i += nt, ++k) {
+      const int sl = slot_of<FAST>(i, k);
+      const float u = (float)(job.px[i] * (double)L.scale), v = (float)(job.px[Fp + i] * (double)L.scale);
+      const float uf = floorf(u), vf = floorf(v);
+      const int ui = __float2int_rd(u), vi = __float2int_rd(v);
+      const bool in = ui >= L.border && vi >= L.border && ui < L.w - L.border && vi < L.h - L.border;  // :441
+      ps.vis[sl] = in ? 1 : 0;
+      if (!in) continue;
+      const float su = u - uf, sv = v - vf;
+      const float wtl = (float)((1.0 - su) * (1.0 - sv));
+      const float wtr = (float)(su * (1.0 - sv));
+      const float wbl = (float)((1.0 - su) * sv);
+      const float wbr = (float)(1.0 - (double)(wtl + wtr + wbl));  // quirk: differs from the current-image weights (:467 vs :323)
+      const int base = vi * L.w + ui;
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-      const int addr = base + (int)c_pat[PIDX][n][1] * L.w + (int)c_pat[PIDX][n][0];
-      if (!IC) {
-        const uint32_t r0 = ld4<false>(ref_g, addr);
-        const uint32_t r1 = ld4<false>(ref_g, addr + L.w);
-        job.ref_cache[n * Fp + i] = wtl * b0(r0) + wtr * b1(r0) + wbl * b0(r1) + wbr * b1(r1);
-      } else {
-        const uint32_t rm = ld4<false>(ref_g, addr - L.w - 1);
-        const uint32_t r0 = ld4<false>(ref_g, addr - 1);
-        const uint32_t r1 = ld4<false>(ref_g, addr + L.w - 1);
-        const uint32_t r2 = ld4<false>(ref_g, addr + 2 * L.w - 1);
-        job.ref_cache[n * Fp + i] = wtl * b1(r0) + wtr * b2(r0) + wbl * b1(r1) + wbr * b2(r1);
-        job.ref_gx[n * Fp + i] = 0.5f * ((wtl * b2(r0) + wtr * b3(r0) + wbl * b2(r1) + wbr * b3(r1)) -
-                                         (wtl * b0(r0) + wtr * b1(r0) + wbl * b0(r1) + wbr * b1(r1)));
-        job.ref_gy[n * Fp + i] = 0.5f * ((wtl * b1(r1) + wtr * b2(r1) + wbl * b1(r2) + wbr * b2(r2)) -
-                                         (wtl * b1(rm) + wtr * b2(rm) + wbl * b1(r0) + wbr * b2(r0)));
+      for (int n = 0; n < N; ++n) {
+        const int addr = base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
+        if (!IC) {
+          const uint32_t r0 = ld4<FAST>(ref_src, addr);
+          const uint32_t r1 = ld4<FAST>(ref_src, addr + L.w);
+          ps.cache[n * ps.stride + sl] = wtl * b0(r0) + wtr * b1(r0) + wbl * b0(r1) + wbr * b1(r1);
+        } else {
+          const uint32_t rm = ld4<FAST>(ref_src, addr - L.w - 1);
+          const uint32_t r0 = ld4<FAST>(ref_src, addr - 1);
+          const uint32_t r1 = ld4<FAST>(ref_src, addr + L.w - 1);
+          const uint32_t r2 = ld4<FAST>(ref_src, addr + 2 * L.w - 1);
+          ps.cache[n * ps.stride + sl] = wtl * b1(r0) + wtr * b2(r0) + wbl * b1(r1) + wbr * b2(r1);
+          ps.gx[n * ps.stride + sl] = 0.5f * ((wtl * b2(r0) + wtr * b3(r0) + wbl * b2(r1) + wbr * b3(r1)) -
+                                              (wtl * b0(r0) + wtr * b1(r0) + wbl * b0(r1) + wbr * b1(r1)));
+          ps.gy[n * ps.stride + sl] = 0.5f * ((wtl * b1(r1) + wtr * b2(r1) + wbl * b1(r2) + wbr * b2(r2)) -
+                                              (wtl * b1(rm) + wtr * b2(rm) + wbl * b1(r0) + wbr * b2(r0)));
+        }
       }
     }
   }
   __syncthreads();
-  if (STAGE) mbar_wait(s.mbar, 0);
+  const long long clk_pre = clock64();
+  if (FAST) {
+    // every generic-proxy read of the reference image is done: hand the buffer back to the async proxy for the current level
+    if (threadIdx.x == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(s.mbar, prm.img_bytes);
+      uint32_t done = 0;
+      while (done < prm.img_bytes) {
+        uint32_t chunk = prm.img_bytes - done;
+        if (chunk > 32768u) chunk = 32768u;
+        tma_bulk_g2s(s.img + done, cur_g + done, chunk, s.mbar);
+        done += chunk;
+      }
+    }
+    mbar_wait(s.mbar, 1);
+  }
   if (threadIdx.x == 0) se3_to_rt(c->T_acc, c->Rt);
   __syncthreads();
 
   // ---- phase 2: selectRobustFunctionLevel (src/CoarseTracker.cpp:530-644) ------------------------------------------------
+  long long clk_res = 0, clk_med = 0;
   {
     const float a = c->a_acc;
-    double R[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) R[k] = c->Rt[k];
-    for (int i = t0; i < job.F; i += nt) {
-      bool ok = job.vis[i] != 0;
+    const int hbits = prm.hist_bits;
+    for (int j = threadIdx.x; j < (1 << hbits); j += blockDim.x) s.hist[j] = 0;
+    __syncthreads();
+    int k = 0;
+    for (int i = t0; i < job.F; i += nt, ++k) {
+      const int sl = slot_of<FAST>(i, k);
+      bool ok = ps.vis[sl] != 0;
       Proj p;
       if (ok) {
-        p = project_patch(R, prm.cam, job.xyz[i], job.xyz[Fp + i], job.xyz[2 * Fp + i], L.scale, L.border, L.w, L.h);
+        p = project_patch(c->Rt, prm.cam, job.xyz[i], job.xyz[Fp + i], job.xyz[2 * Fp + i], L.scale, L.border, L.w, L.h);
         ok = p.ok;
       }
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         float out = -1.f;
         if (ok) {
-          const int addr = p.base + (int)c_pat[PIDX][n][1] * L.w + (int)c_pat[PIDX][n][0];
-          const uint32_t r0 = ld4<STAGE>(L.cur, addr);
-          const uint32_t r1 = ld4<STAGE>(L.cur, addr + L.w);
+          const int addr = p.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
+          const uint32_t r0 = ld4<FAST>(L.cur, addr);
+          const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
           const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-          out = fabsf(color - (a * job.ref_cache[n * Fp + i] + 0.f));
+          out = fabsf(color - (a * ps.cache[n * ps.stride + sl] + 0.f));
+          atomicAdd(&s.hist[__float_as_uint(out) >> (32 - hbits)], 1u);  // first digit of the median select, fused
         }
         job.absres[n * Fp + i] = out;
       }
     }
-    int hist_phase = 0;
-    radix_select<N>(job, s, t0, nt, false, 0.f, csize, hist_phase);
+    clk_res = clock64();
+    radix_select<N>(job, s, t0, nt, false, 0.f, csize, hbits, true);
+    clk_med = clock64();
     const uint32_t n_err = c->sel_n;
     float huber = 5.2f, outlier = 100.f;
     if (n_err >= 30) {
       const float median = __uint_as_float(c->sel_prefix);
       __syncthreads();
-      radix_select<N>(job, s, t0, nt, true, median, csize, hist_phase);
+      radix_select<N>(job, s, t0, nt, true, median, csize, hbits, false);
       const float mad = __uint_as_float(c->sel_prefix);
       const float sd = (float)(1.4826 * (double)mad);
       huber = median + sd;
@@ -602,24 +713,29 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     if (threadIdx.x == 0) { c->huber = huber; c->outlier = outlier; c->n_err = (int)n_err; }
     __syncthreads();
   }
+  const long long clk_lm = clock64();
 
   // ---- phase 3: the LM loop of the level (src/CoarseTracker.cpp:100-194) -------------------------------------------------
   const float huber = c->huber, cutoff = c->outlier;
   int slot = 0;
   int level_iters = 0, level_evals = 0;
   unsigned long long patch_evals = 0;
+  long long clk_ctrl = 0;
   for (int iter = -1; iter < prm.n_iter; ++iter) {
     const float a_eval = iter < 0 ? c->a_acc : c->a_try;
     Acc acc;
     acc_zero(acc);
-    eval_patches<PIDX, IC, STAGE>(L, job, prm.cam, c->Rt, a_eval, huber, cutoff, t0, nt, acc);
+    eval_patches<PIDX, IC, FAST>(L, job, ps, prm.cam, c->Rt, a_eval, huber, cutoff, t0, nt, acc);
     reduce_acc(acc, s, slot, csize, nwarps);
     slot ^= 1;
     ++level_evals;
     if (iter >= 0) ++level_iters;
     patch_evals += (unsigned long long)s.tot[38];
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
+      const long long t_in = clock64();
       lm_control(c, s.tot, job, iter, prm.n_iter, prm.level, prm.trace_cap, IC, crank == 0, a_eval, huber, cutoff, N);
+      clk_ctrl += clock64() - t_in;
+    }
     __syncthreads();
     if (c->done) break;
   }
@@ -633,6 +749,14 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     st->n_evals += level_evals;
     st->iters_per_level[prm.level & 7] = level_iters;
     st->patch_evals[prm.level & 7] = patch_evals;
+    const long long clk_end = clock64();
+    st->cycles[0] += (unsigned long long)(clk_end - clk_start);  // whole launch (CTA rank 0)
+    st->cycles[1] += (unsigned long long)(clk_lm - clk_start);   // staging + reference patches + robust thresholds
+    st->cycles[2] += (unsigned long long)clk_ctrl;               // thread-0 control (solve, SE3 update, trace)
+    st->cycles[3] += (unsigned long long)(clk_pre - clk_start);  // staging of the reference level + reference patches
+    st->cycles[4] += (unsigned long long)(clk_res - clk_pre);    // staging of the current level + residuals of the threshold selection
+    st->cycles[5] += (unsigned long long)(clk_med - clk_res);    // median select
+    st->cycles[6] += (unsigned long long)(clk_lm - clk_med);     // MAD select
   }
   if (csize > 1) cluster.sync();  // peers may still be reading this CTA's shared memory
 }
@@ -646,6 +770,7 @@ __global__ void k_track_init(const TrackJobDev* __restrict__ jobs, const double*
   st->n_iters = 0; st->n_evals = 0;
   for (int k = 0; k < 8; ++k) { st->iters_per_level[k] = 0; st->patch_evals[k] = 0; }
   st->last_total_terms = 0; st->last_N = 1; st->trace_len = 0;
+  for (int k = 0; k < 8; ++k) st->cycles[k] = 0;
 }
 
 __global__ void k_track_finish(const TrackJobDev* __restrict__ jobs, hso_track_result* __restrict__ out, int B) {
@@ -661,6 +786,7 @@ __global__ void k_track_finish(const TrackJobDev* __restrict__ jobs, hso_track_r
   // return float(m_total_terms) / PATCH_AREA  (src/CoarseTracker.cpp:207)
   o->n_tracked = (uint64_t)((float)st->last_total_terms / (float)st->last_N);
   o->trace_len = st->trace_len;
+  for (int k = 0; k < 8; ++k) o->cycles[k] = st->cycles[k];
 }
 
 cudaError_t launch_track_init(const TrackJobDev* jobs_dev, const double* T0, const float* a0, int B, cudaStream_t stream, uint64_t* launches) {
@@ -674,10 +800,10 @@ cudaError_t launch_track_finish(const TrackJobDev* jobs_dev, hso_track_result* o
   return cudaGetLastError();
 }
 
-template <int PIDX, bool IC, bool STAGE>
+template <int PIDX, bool IC, bool FAST>
 static cudaError_t launch_one(const TrackLevelParams& p, const TrackJobDev* jobs_dev, int B, int cluster, int threads, size_t smem,
                               cudaStream_t stream) {
-  auto kern = k_track_level<PIDX, IC, STAGE>;
+  auto kern = k_track_level<PIDX, IC, FAST>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -699,10 +825,10 @@ template <int PIDX>
 static cudaError_t launch_pidx(const TrackLevelParams& p, const TrackJobDev* jobs_dev, int B, int cluster, int threads, size_t smem,
                                cudaStream_t stream) {
   if (p.ic) {
-    return p.stage_smem ? launch_one<PIDX, true, true>(p, jobs_dev, B, cluster, threads, smem, stream)
+    return p.fast ? launch_one<PIDX, true, true>(p, jobs_dev, B, cluster, threads, smem, stream)
                         : launch_one<PIDX, true, false>(p, jobs_dev, B, cluster, threads, smem, stream);
   }
-  return p.stage_smem ? launch_one<PIDX, false, true>(p, jobs_dev, B, cluster, threads, smem, stream)
+  return p.fast ? launch_one<PIDX, false, true>(p, jobs_dev, B, cluster, threads, smem, stream)
                       : launch_one<PIDX, false, false>(p, jobs_dev, B, cluster, threads, smem, stream);
 }
 

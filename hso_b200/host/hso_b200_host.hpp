@@ -1,0 +1,264 @@
+// C++ host layer above the C-ABI (include/hso_b200.h): the reference's class / function surface for the tracking hot path,
+// re-stated on dependency-free types so it builds without Eigen / Sophus / OpenCV / Boost (none are present in this image).
+// Inside the reference tree the same calls are made from the real classes; INTEGRATION.md shows that glue line by line.
+//
+//   reference                                                        here
+//   hso::Frame::Frame(cam, img, ts)            frame.h:131          hso::b200::Frame(ctx, img, W, H, stride, ts)   (throws on bad size)
+//   hso::CoarseTracker(ic,max,min,n_iter,v)    CoarseTracker.h:134  hso::b200::CoarseTracker(ctx, ic, max, min, n_iter, v)
+//   size_t CoarseTracker::run(ref, cur)        CoarseTracker.h:141  size_t run(FramePtr ref, FramePtr cur)
+//   CoarseTracker::makeDepthRef()              CoarseTracker.cpp:210  makeDepthRef(ref)  (host: pointer chasing over Feature/Point)
+//   pose_optimizer::optimizeLevenbergMarquardt3rd(...)  pose_optimizer.h:61  hso::b200::pose_optimizer::optimizeLevenbergMarquardt3rd(...)
+//   Matcher::findMatchDirect(pt, cur, px)      matcher.h:153        Matcher::findMatchDirectBatch(candidates, cur)  (after getWarpMatrixAffine)
+//
+// Poses are 3x4 row-major [R|t] (SE3::matrix3x4()). All arithmetic of the path runs on the GPU; this layer only flattens.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/hso_b200.h"
+
+namespace hso {
+namespace b200 {
+
+struct SE3 {  // 3x4 row-major [R | t]
+  double m[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  SE3 inverse() const {
+    SE3 r;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) r.m[4 * i + j] = m[4 * j + i];
+    for (int i = 0; i < 3; ++i) r.m[4 * i + 3] = -(r.m[4 * i] * m[3] + r.m[4 * i + 1] * m[7] + r.m[4 * i + 2] * m[11]);
+    return r;
+  }
+  SE3 operator*(const SE3& o) const {
+    SE3 r;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) r.m[4 * i + j] = m[4 * i] * o.m[j] + m[4 * i + 1] * o.m[4 + j] + m[4 * i + 2] * o.m[8 + j];
+      r.m[4 * i + 3] = m[4 * i] * o.m[3] + m[4 * i + 1] * o.m[7] + m[4 * i + 2] * o.m[11] + m[4 * i + 3];
+    }
+    return r;
+  }
+  void apply(const double p[3], double out[3]) const {
+    for (int i = 0; i < 3; ++i) out[i] = m[4 * i] * p[0] + m[4 * i + 1] * p[1] + m[4 * i + 2] * p[2] + m[4 * i + 3];
+  }
+};
+
+class Context {
+ public:
+  Context(const hso_cam& cam, int device = 0, const hso_cfg* cfg = nullptr) : cam_(cam) {
+    int rc = hso_create(device, &cam, cfg, &h_);
+    if (rc != HSO_OK) throw std::runtime_error("hso_create failed (" + std::to_string(rc) + "): no sm_100 device? there is no CPU fallback");
+  }
+  ~Context() { hso_destroy(h_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  hso_ctx* get() const { return h_; }
+  const hso_cam& cam() const { return cam_; }
+  void check(int rc) const {
+    if (rc != HSO_OK) throw std::runtime_error(std::string("hso_b200: ") + hso_last_error(h_) + " (" + std::to_string(rc) + ")");
+  }
+
+ private:
+  hso_ctx* h_ = nullptr;
+  hso_cam cam_;
+};
+
+struct Frame;
+struct Feature;
+
+struct Point {  // include/hso/point.h:53 (subset the path reads)
+  enum PointType { TYPE_DELETED = 0, TYPE_TEMPORARY = 1, TYPE_CANDIDATE = 2, TYPE_UNKNOWN = 3, TYPE_GOOD = 4 };
+  double idist_ = 1.0;
+  const Feature* hostFeature_ = nullptr;
+  int type_ = TYPE_GOOD;
+};
+
+struct Feature {  // include/hso/feature.h:36-64 (subset)
+  enum FeatureType { CORNER = 0, EDGELET = 1, GRADIENT = 2 };
+  int type = CORNER;
+  Frame* frame = nullptr;
+  double px[2] = {0, 0};
+  double f[3] = {0, 0, 1};
+  int level = 0;
+  Point* point = nullptr;
+  double grad[2] = {1, 0};
+};
+
+struct Frame {  // include/hso/frame.h (subset): the pyramid lives on the device behind `id`
+  Frame(Context& ctx, const uint8_t* img, int W, int H, int stride, double timestamp) : ctx_(ctx), timestamp_(timestamp) {
+    // Frame::initFrame throws std::runtime_error when the image does not match the camera (src/frame.cpp:85-86)
+    int rc = hso_frame_upload(ctx.get(), img, W, H, stride, &id, &integralImage_, &gradMean_);
+    if (rc == HSO_ERR_INVALID) throw std::runtime_error("Frame: provided image has not the same size as the camera model or image is not grayscale");
+    ctx.check(rc);
+  }
+  ~Frame() { hso_frame_release(ctx_.get(), id); }
+  Frame(const Frame&) = delete;
+  Frame& operator=(const Frame&) = delete;
+  Context& ctx_;
+  hso_frame_id id = -1;
+  double timestamp_;
+  SE3 T_f_w_;
+  float integralImage_ = 0, gradMean_ = 0, m_exposure_time = 1.f;
+  std::vector<Feature> fts_;
+  double Cov_[36] = {0};
+  float m_error_in_px = 0;
+};
+typedef std::shared_ptr<Frame> FramePtr;
+
+class CoarseTracker {  // include/hso/CoarseTracker.h:134-143
+ public:
+  CoarseTracker(Context& ctx, bool inverse_composition, int max_level, int min_level, int n_iter, bool verbose = false)
+      : ctx_(ctx), verbose_(verbose) {
+    prm_.inverse_comp = inverse_composition ? 1 : 0; prm_.max_level = max_level; prm_.min_level = min_level; prm_.n_iter = n_iter;
+  }
+
+  // src/CoarseTracker.cpp:210-240 — stays on the host: it chases Feature -> Point -> host Feature -> host Frame pointers.
+  static void makeDepthRef(const Frame& ref, std::vector<double>& dist) {
+    dist.assign(ref.fts_.size(), -1.0);
+    for (size_t i = 0; i < ref.fts_.size(); ++i) {
+      const Feature& ft = ref.fts_[i];
+      if (ft.point == nullptr) continue;
+      const Feature* host = ft.point->hostFeature_;
+      const double inv = 1.0 / ft.point->idist_;
+      const double p_host[3] = {host->f[0] * inv, host->f[1] * inv, host->f[2] * inv};
+      const SE3 T_r_h = ref.T_f_w_ * host->frame->T_f_w_.inverse();
+      double p_ref[3];
+      T_r_h.apply(p_host, p_ref);
+      if (p_ref[2] < 0.00001) continue;
+      dist[i] = std::sqrt(p_ref[0] * p_ref[0] + p_ref[1] * p_ref[1] + p_ref[2] * p_ref[2]);
+    }
+  }
+
+  size_t run(FramePtr ref_frame, FramePtr cur_frame) {
+    if (ref_frame->fts_.empty()) return 0;  // :53
+    const size_t F = ref_frame->fts_.size();
+    std::vector<double> px(2 * F), f(3 * F), dist;
+    makeDepthRef(*ref_frame, dist);
+    for (size_t i = 0; i < F; ++i) {
+      const Feature& ft = ref_frame->fts_[i];
+      px[2 * i] = ft.px[0]; px[2 * i + 1] = ft.px[1];
+      f[3 * i] = ft.f[0]; f[3 * i + 1] = ft.f[1]; f[3 * i + 2] = ft.f[2];
+    }
+    hso_track_job job;
+    std::memset(&job, 0, sizeof job);
+    job.ref = ref_frame->id; job.cur = cur_frame->id; job.n_features = (int32_t)F;
+    job.px = px.data(); job.f = f.data(); job.dist = dist.data();
+    const SE3 T_cur_ref = cur_frame->T_f_w_ * ref_frame->T_f_w_.inverse();  // :63
+    std::memcpy(job.T_cur_ref, T_cur_ref.m, sizeof job.T_cur_ref);
+    job.exposure_rat = cur_frame->integralImage_ / ref_frame->integralImage_;  // :60
+    hso_track_result res;
+    ctx_.check(hso_coarse_track(ctx_.get(), &prm_, &job, &res, nullptr, 0, nullptr));
+    SE3 T;
+    std::memcpy(T.m, res.T_cur_ref, sizeof T.m);
+    cur_frame->T_f_w_ = T * ref_frame->T_f_w_;  // :198
+    cur_frame->m_exposure_time = res.exposure_rat * ref_frame->m_exposure_time;
+    if (res.exposure_rat > 0.99f && res.exposure_rat < 1.01f) cur_frame->m_exposure_time = ref_frame->m_exposure_time;  // :202
+    last_ = res;
+    return (size_t)res.n_tracked;
+  }
+  const hso_track_result& last_result() const { return last_; }
+
+ private:
+  Context& ctx_;
+  hso_track_params prm_;
+  bool verbose_;
+  hso_track_result last_;
+};
+
+namespace pose_optimizer {
+// include/hso/pose_optimizer.h:61-64. Outliers get Feature::point = NULL like src/pose_optimizer.cpp:721,735.
+inline void optimizeLevenbergMarquardt3rd(Context& ctx, const double reproj_thresh, const size_t n_iter, const bool /*verbose*/, FramePtr& frame,
+                                          double& estimated_scale, double& error_init, double& error_final, size_t& num_obs) {
+  std::vector<double> f, p_host, grad, T_host;
+  std::vector<int32_t> host_idx;
+  std::vector<int8_t> level, ftype, ptype;
+  std::vector<const Frame*> hosts;
+  std::vector<size_t> idx;
+  for (size_t i = 0; i < frame->fts_.size(); ++i) {
+    const Feature& ft = frame->fts_[i];
+    if (ft.point == nullptr) continue;
+    const Feature* hf = ft.point->hostFeature_;
+    const double inv = 1.0 / ft.point->idist_;
+    for (int k = 0; k < 3; ++k) { f.push_back(ft.f[k]); p_host.push_back(hf->f[k] * inv); }
+    grad.push_back(ft.grad[0]); grad.push_back(ft.grad[1]);
+    size_t h = 0;
+    for (; h < hosts.size(); ++h) if (hosts[h] == hf->frame) break;
+    if (h == hosts.size()) { hosts.push_back(hf->frame); T_host.insert(T_host.end(), hf->frame->T_f_w_.m, hf->frame->T_f_w_.m + 12); }
+    host_idx.push_back((int32_t)h);
+    level.push_back((int8_t)ft.level); ftype.push_back((int8_t)ft.type); ptype.push_back((int8_t)ft.point->type_);
+    idx.push_back(i);
+  }
+  std::vector<uint8_t> outlier(idx.size() + 1, 0);
+  hso_pose_result res;
+  ctx.check(hso_pose_optimize(ctx.get(), reproj_thresh, (int)n_iter, (int)frame->fts_.size(), (int)idx.size(), f.data(), p_host.data(), host_idx.data(),
+                              (int)hosts.size(), T_host.data(), grad.data(), level.data(), ftype.data(), ptype.data(), frame->T_f_w_.m, outlier.data(),
+                              &res));
+  if (res.early_return) return;  // :456 leaves every output untouched
+  std::memcpy(frame->T_f_w_.m, res.T_f_w, sizeof res.T_f_w);
+  std::memcpy(frame->Cov_, res.cov, sizeof res.cov);
+  for (size_t k = 0; k < idx.size(); ++k) if (outlier[k]) frame->fts_[idx[k]].point = nullptr;
+  estimated_scale = res.estimated_scale; error_init = res.error_init; error_final = res.error_final; num_obs = (size_t)res.num_obs;
+  frame->m_error_in_px = res.error_in_px;
+}
+}  // namespace pose_optimizer
+
+class Matcher {  // include/hso/matcher.h:113-153 (direct part)
+ public:
+  struct Options { int align_max_iter = 10; } options_;
+  struct Candidate {  // what findMatchDirect knows after getCloseViewObs + getWarpMatrixAffine + getBestSearchLevel (matcher.cpp:276-309)
+    const Feature* ref_ftr;
+    double A_cur_ref[4];
+    int search_level;
+    double px_cur[2];  // in: initial estimate, out: refined
+    bool found = false;
+    double h_inv = 0;
+  };
+  explicit Matcher(Context& ctx) : ctx_(ctx) {}
+  // src/matcher.cpp:74-85
+  static int getBestSearchLevel(const double A[4], int max_level) {
+    int search_level = 0;
+    double D = A[0] * A[3] - A[1] * A[2];
+    while (D > 3.0 && search_level < max_level) { search_level += 1; D *= 0.25; }
+    return search_level;
+  }
+  // All candidates of one reprojectMap pass in one launch (the reference calls findMatchDirect once per candidate).
+  void findMatchDirectBatch(std::vector<Candidate>& cands, Frame& cur_frame, int cur_keyFrameId = 0, const std::vector<int>* ref_keyFrameId = nullptr) {
+    const size_t M = cands.size();
+    if (M == 0) return;
+    std::vector<hso_align_job> jobs(M);
+    std::vector<hso_frame_id> refs(M);
+    std::vector<hso_align_result> out(M);
+    for (size_t m = 0; m < M; ++m) {
+      const Feature* r = cands[m].ref_ftr;
+      hso_align_job& j = jobs[m];
+      std::memset(&j, 0, sizeof j);
+      j.ref_level = r->level; j.search_level = cands[m].search_level; j.type = r->type;
+      j.px_ref[0] = r->px[0]; j.px_ref[1] = r->px[1];
+      std::memcpy(j.A_cur_ref, cands[m].A_cur_ref, sizeof j.A_cur_ref);
+      j.grad[0] = r->grad[0]; j.grad[1] = r->grad[1];
+      j.px_cur[0] = cands[m].px_cur[0]; j.px_cur[1] = cands[m].px_cur[1];
+      // exposure scaling of the warped patch (src/matcher.cpp:317-330), LIGHT_THRESHOLD = 30
+      const float a = cur_frame.m_exposure_time / r->frame->m_exposure_time;
+      const bool near_kf = ref_keyFrameId ? (cur_keyFrameId - (*ref_keyFrameId)[m] < 4) : true;
+      j.exposure_rat = a;
+      j.scale_patch = (near_kf && std::fabs(a * 128 - 128) > 30.f) ? 1 : 0;
+      refs[m] = r->frame->id;
+    }
+    ctx_.check(hso_align_batch(ctx_.get(), cur_frame.id, (int)M, jobs.data(), refs.data(), options_.align_max_iter, out.data()));
+    for (size_t m = 0; m < M; ++m) {
+      cands[m].found = out[m].ok != 0;
+      cands[m].px_cur[0] = out[m].px_cur[0]; cands[m].px_cur[1] = out[m].px_cur[1];  // written even on failure (:372)
+      cands[m].h_inv = out[m].h_inv;
+    }
+  }
+
+ private:
+  Context& ctx_;
+};
+
+}  // namespace b200
+}  // namespace hso

@@ -112,6 +112,9 @@ typedef struct {
   uint64_t visible_patch_evals[8]; /* per level: sum over evaluations of patches that produced terms (roofline accounting) */
   int32_t trace_len;           /* trace entries written for this problem */
   int32_t reserved;
+  uint64_t cycles[8];          /* diagnostics, SM clock cycles summed over levels: [0] kernel, [1] setup (staging, reference patches,
+                                  robust thresholds), [2] serial control (solve + SE3 update), [3] reference staging + reference patches,
+                                  [4] current staging + threshold residuals, [5] median select, [6] MAD select */
 } hso_track_result;
 
 /* Per-evaluation trace for parity checking (one entry per computeResiduals call, CoarseTracker.cpp:102,141).

@@ -1,0 +1,48 @@
+"""GPU test of the C++ host layer (hso_b200/host/hso_b200_host.hpp): compiled with g++ against libhso_b200.so, run on one synthetic
+problem, compared with the ctypes path (same C-ABI underneath, so poses must agree to rounding of the 3x4 pose products)."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from hso_b200 import Context, make_cam, synth, _capi
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_host_layer_matches_ctypes_path(tmp_path):
+    exe = tmp_path / "host_smoke"
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(ROOT, "tests", "cpp", "host_smoke.cpp"), "-o", str(exe),
+                           f"-L{libdir}", "-lhso_b200", f"-Wl,-rpath,{libdir}"])
+    p = synth.make_pair(91, "icl", F=600)
+    c = p["cam"]
+    F = len(p["dist"])
+    has = (p["dist"] >= 0).astype(np.int32)
+    idist = np.where(has == 1, 1.0 / np.abs(p["dist"]), 1.0)
+    blob = tmp_path / "problem.bin"
+    with open(blob, "wb") as f:
+        f.write(struct.pack("<iii4d", c["width"], c["height"], F, c["fx"], c["fy"], c["cx"], c["cy"]))
+        f.write(p["ref_img"].tobytes()); f.write(p["cur_img"].tobytes())
+        f.write(np.ascontiguousarray(p["px"], np.float64).tobytes()); f.write(np.ascontiguousarray(p["f"], np.float64).tobytes())
+        f.write(idist.astype(np.float64).tobytes()); f.write(has.tobytes())
+    out = subprocess.run([str(exe), str(blob)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["threw"] == 1  # wrong image size throws like Frame::initFrame
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]))
+    ids, integral, _ = ctx.upload_frames([p["ref_img"], p["cur_img"]])
+    a0 = float(np.float32(integral[1]) / np.float32(integral[0]))
+    # makeDepthRef for self-hosted points: |f / idist| = dist (z > 1e-5 holds)
+    dist = np.where(has == 1, np.linalg.norm(p["f"] * (1.0 / idist)[:, None], axis=1), -1.0)
+    res, _ = ctx.coarse_track_batch([dict(ref=ids[0], cur=ids[1], px=p["px"], f=p["f"], dist=dist, T_cur_ref=np.eye(4)[:3], exposure_rat=a0)])
+    assert abs(r["integral"][0] - integral[0]) < 1e-4 and abs(r["integral"][1] - integral[1]) < 1e-4
+    assert r["n_tracked"] == res[0]["n_tracked"]
+    assert np.abs(np.array(r["T_track"]).reshape(3, 4) - res[0]["T_cur_ref"]).max() < 1e-9
+    assert r["num_obs"] > 0.5 * has.sum() and r["launches"] >= 8
+    assert np.abs(np.array(r["T"]).reshape(3, 4) - p["T_true"][:3]).max() < 5e-3
+    ctx.close()
