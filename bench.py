@@ -183,13 +183,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=296, help="independent frame pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=592, help="independent frame pairs per GPU per step")
     ap.add_argument("--patches", type=int, default=3000)
     ap.add_argument("--cam", default="icl", choices=list(synth.CAMS))
     ap.add_argument("--ic", action="store_true", help="inverse-compositional mode")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--shape", default="", help="per-level launch shape overrides 'level:ctas:threads,...' (tuning)")
     ap.add_argument("--seed", type=int, default=0x450)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -221,6 +222,9 @@ def main():
     lib = ctx.lib
     if args.cluster or args.threads:
         ctx.set_cluster(args.cluster, args.threads)
+    for item in [x for x in args.shape.split(",") if x]:
+        lv, cc, th = (int(v) for v in item.split(":"))
+        ctx._chk(lib.hso_track_set_level_shape(ctx.h, lv, cc, th))
 
     # pinned host copies of every image (e2e uploads from these), device-resident raw current images (for `value`)
     host_cur = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
@@ -261,9 +265,10 @@ def main():
     out = ctx.track_collect()
     iters_per_step = sum(out[b].n_iters for b in range(B))
     patch_evals = {l: sum(out[b].visible_patch_evals[l] for b in range(B)) for l in levels}
-    cyc = [sum(out[b].cycles[k] for b in range(B)) for k in range(7)]
+    cyc = [sum(out[b].cycles[k] for b in range(B)) for k in range(8)]
     diag = {"setup_frac_of_kernel_cycles": cyc[1] / max(cyc[0], 1), "refpatch_frac_of_kernel_cycles": cyc[3] / max(cyc[0], 1), "threshold_residuals_frac": cyc[4] / max(cyc[0], 1),
-            "median_select_frac": cyc[5] / max(cyc[0], 1), "mad_select_frac": cyc[6] / max(cyc[0], 1), "serial_control_frac_of_kernel_cycles": cyc[2] / max(cyc[0], 1),
+            "median_select_frac": cyc[5] / max(cyc[0], 1), "pivoted_solves": cyc[7], "control_cycles_per_iteration": cyc[2] / max(iters_per_step + 4 * B, 1),
+            "kernel_cycles_per_problem_level": cyc[0] / (4 * B), "mad_select_frac": cyc[6] / max(cyc[0], 1), "serial_control_frac_of_kernel_cycles": cyc[2] / max(cyc[0], 1),
             "iters_per_problem": {"mean": iters_per_step / B, "max": max(out[b].n_iters for b in range(B)), "min": min(out[b].n_iters for b in range(B))}}
     ctx._chk(lib.hso_track_set_profile(ctx.h, 1))
     launches0 = ctx.kernel_launches()

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "hso_internal.h"
@@ -64,6 +65,8 @@ struct hso_ctx {
   uint64_t launches = 0;
   std::vector<FrameSlot> frames;
   // pyramid
+  DevBuf pyr_arena, sums_arena;  // [max_frames] pyramids (slot stride = pyr_slot_bytes) and per-tile partial sums
+  size_t pyr_slot_bytes = 0;
   DevBuf pyr_jobs_dev, pyr_counters, resize_tab_dev, stats_table;  // stats_table: [max_frames][2] floats, one D2H per read
   PinBuf pyr_jobs_host, stats_host;
   std::vector<ResizeTabDev> resize_tabs;
@@ -71,6 +74,7 @@ struct hso_ctx {
   hso_track_params tprm;
   int tB = 0, t_trace_cap = 0;
   int t_cluster = 0, t_threads = 0;  // 0 = auto
+  int t_shape[kMaxLevels][2] = {{0}};  // per-level override {cluster, threads}
   DevBuf t_arena, t_jobs_dev, t_T0, t_a0, t_out_dev;
   PinBuf t_stage_host, t_jobs_host, t_out_host;
   std::vector<size_t> t_trace_off;  // byte offset of each job's trace in the arena
@@ -180,9 +184,10 @@ int alloc_frame(hso_ctx* ctx, hso_frame_id* out) {
     FrameSlot& s = ctx->frames[i];
     if (s.used) continue;
     if (!s.pyr) {
-      CU(cudaMalloc((void**)&s.pyr, ctx->geom.bytes));
-      CU(cudaMemsetAsync(s.pyr, 0, ctx->geom.bytes, ctx->stream));
-      CU(cudaMalloc((void**)&s.sums, sizeof(double) * 2 * ctx->n_tiles));
+      // slots live in one arena (zeroed at creation: the pad rows behind every level stay zero), so a batch of equally spaced
+      // host images lands in consecutive slots with ONE 2-D copy
+      s.pyr = (uint8_t*)ctx->pyr_arena.p + i * ctx->pyr_slot_bytes;
+      s.sums = (double*)ctx->sums_arena.p + (size_t)2 * ctx->n_tiles * i;
       s.stats = (float*)ctx->stats_table.p + 2 * i;
       if (ctx->cfg.materialize_sobel) CU(cudaMalloc((void**)&s.sobel, sizeof(int16_t) * ctx->sobel_elems));
     }
@@ -294,6 +299,10 @@ int hso_create(int device, const hso_cam* cam, const hso_cfg* cfg_in, hso_ctx** 
   ctx->stream = ctx->own_stream;
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) return bail("cudaEventCreate");
   if (ctx->stats_table.reserve(sizeof(float) * 2 * ctx->cfg.max_frames) != cudaSuccess) return bail("cudaMalloc stats table");
+  ctx->pyr_slot_bytes = (ctx->geom.bytes + 255) / 256 * 256;
+  if (ctx->pyr_arena.reserve(ctx->pyr_slot_bytes * ctx->cfg.max_frames) != cudaSuccess) return bail("cudaMalloc pyramid arena (hso_cfg.max_frames too large?)");
+  if (cudaMemset(ctx->pyr_arena.p, 0, ctx->pyr_arena.cap) != cudaSuccess) return bail("cudaMemset pyramid arena");
+  if (ctx->sums_arena.reserve(sizeof(double) * 2 * ctx->n_tiles * ctx->cfg.max_frames) != cudaSuccess) return bail("cudaMalloc sums arena");
   if (!ctx->geom.half_path) {
     std::vector<char> blob;
     ctx->resize_tabs.assign(ctx->geom.n_levels, ResizeTabDev{});
@@ -322,11 +331,9 @@ void hso_destroy(hso_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   for (FrameSlot& s : ctx->frames) {
-    if (s.pyr) cudaFree(s.pyr);
     if (s.sobel) cudaFree(s.sobel);
-    if (s.sums) cudaFree(s.sums);
   }
-  DevBuf* db[] = {&ctx->stats_table, &ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
+  DevBuf* db[] = {&ctx->pyr_arena, &ctx->sums_arena, &ctx->stats_table, &ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
                   &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
@@ -368,10 +375,19 @@ int hso_frame_upload_batch(hso_ctx* ctx, int B, const uint8_t* const* imgs, int 
     if (rc != HSO_OK) { for (int j = 0; j < i; ++j) ctx->frames[out[j]].used = false; return rc; }
   }
   StageTimer tm(ctx, 0);
+  // straight into the level-0 slot of each pyramid (row stride == W); the kernel then builds in place. Tightly packed,
+  // equally spaced host images going to consecutive slots take ONE 2-D copy (row = one image, dpitch = slot stride).
+  bool one_copy = B > 1 && stride == W;
+  const ptrdiff_t spacing = B > 1 ? imgs[1] - imgs[0] : 0;
+  for (int i = 1; i < B && one_copy; ++i) one_copy = (imgs[i] - imgs[i - 1] == spacing) && (out[i] == out[i - 1] + 1);
+  one_copy = one_copy && spacing >= (ptrdiff_t)W * H;
+  if (one_copy) {
+    CU(cudaMemcpy2DAsync(get_frame(ctx, out[0])->pyr + ctx->geom.off[0], ctx->pyr_slot_bytes, imgs[0], (size_t)spacing, (size_t)W * H, B,
+                         cudaMemcpyHostToDevice, ctx->stream));
+  }
   for (int i = 0; i < B; ++i) {
     FrameSlot* s = get_frame(ctx, out[i]);
-    // straight into the level-0 slot of the pyramid (row stride == W); the kernel then builds in place
-    CU(cudaMemcpy2DAsync(s->pyr + ctx->geom.off[0], W, imgs[i], stride, W, H, cudaMemcpyHostToDevice, ctx->stream));
+    if (!one_copy) CU(cudaMemcpy2DAsync(s->pyr + ctx->geom.off[0], W, imgs[i], stride, W, H, cudaMemcpyHostToDevice, ctx->stream));
     srcs[i] = s->pyr + ctx->geom.off[0];
   }
   int rc = run_pyramid(ctx, B, out, srcs.data(), W, 1);
@@ -466,6 +482,15 @@ int hso_track_set_cluster(hso_ctx* ctx, int ctas, int threads) {
   return HSO_OK;
 }
 
+int hso_track_set_level_shape(hso_ctx* ctx, int level, int ctas, int threads) {
+  if (!ctx || level < 0 || level >= kMaxLevels) return HSO_ERR_INVALID;
+  if (!(ctas == 0 || ctas == 1 || ctas == 2 || ctas == 4 || ctas == 8)) return fail(ctx, HSO_ERR_INVALID, "cluster size must be 0,1,2,4,8");
+  if (threads != 0 && (threads < 64 || threads > 512 || threads % 32)) return fail(ctx, HSO_ERR_INVALID, "threads must be a multiple of 32 in [64,512]");
+  ctx->t_shape[level][0] = ctas;
+  ctx->t_shape[level][1] = threads;
+  return HSO_OK;
+}
+
 int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_track_job* jobs, int trace_cap) {
   if (!ctx || !prm || B <= 0 || !jobs) return HSO_ERR_INVALID;
   if (prm->max_level >= ctx->geom.n_levels || prm->min_level < 0 || prm->min_level > prm->max_level || prm->max_level - prm->min_level > 5 ||
@@ -521,9 +546,14 @@ int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_
   char* hbase = (char*)ctx->t_stage_host.p;
   char* dbase = (char*)ctx->t_arena.p;
   TrackJobDev* hj = (TrackJobDev*)ctx->t_jobs_host.p;
-  size_t go = 0;
-  for (int b = 0; b < B; ++b) {
+  std::vector<size_t> goff(B);
+  {
+    size_t go = 0;
+    for (int b = 0; b < B; ++b) { goff[b] = go; go += sizeof(double) * 5 * std::max(32, (nvalid[b] + 31) / 32 * 32); }
+  }
+  auto stage_job = [&](int b) {
     const hso_track_job& j = jobs[b];
+    const size_t go = goff[b];
     const int Fpad = std::max(32, (nvalid[b] + 31) / 32 * 32);
     double* px = (double*)(hbase + go);
     double* xyz = px + 2 * Fpad;
@@ -551,7 +581,15 @@ int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_
     d.vis = (uint8_t*)(dbase + off_vis[b]);
     d.state = (TrackState*)(dbase + off_state[b]);
     d.trace = ctx->t_trace_cap ? (hso_trace*)(dbase + off_trace[b]) : nullptr;
-    go += sizeof(double) * 5 * Fpad;
+  };
+  // flattening Feature lists to SoA is host work of the boundary: spread a large batch over a few threads
+  const int n_thr = (B >= 16) ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  if (n_thr <= 1) {
+    for (int b = 0; b < B; ++b) stage_job(b);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_thr; ++t) pool.emplace_back([&, t]() { for (int b = t; b < B; b += n_thr) stage_job(b); });
+    for (auto& th : pool) th.join();
   }
   double* T0 = (double*)(hbase + host_bytes);
   float* a0 = (float*)(T0 + 12 * B);
@@ -641,22 +679,24 @@ int hso_track_run(hso_ctx* ctx) {
     // smallest cluster size whose per-CTA share fits 227 KB, but never fewer CTAs than it takes to cover the 148 SMs when the
     // batch is small (single-problem latency mode). Otherwise fall back to the global-memory path.
     const int maxF = std::max(ctx->t_maxF, 1);
-    int c_min = ctx->t_cluster;
+    const int f_cluster = ctx->t_shape[level][0] ? ctx->t_shape[level][0] : ctx->t_cluster;
+    const int f_threads = ctx->t_shape[level][1] ? ctx->t_shape[level][1] : ctx->t_threads;
+    int c_min = f_cluster;
     if (c_min == 0) c_min = B >= 148 ? 1 : (B >= 74 ? 2 : (B >= 37 ? 4 : 8));
     int cluster = 0, threads = 0;
     for (int cc = c_min; cc <= 8; cc *= 2) {
-      int th = ctx->t_threads ? ctx->t_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
+      int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
       const int kpt = (maxF + cc * th - 1) / (cc * th);
       p.fast = 1; p.pc = kpt * th; p.cluster = cc;
       p.hist_bits = 11;
       if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
       p.hist_bits = 8;
       if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
-      if (ctx->t_cluster) break;  // the caller fixed the cluster size
+      if (f_cluster) break;  // the caller fixed the cluster size
     }
     if (!cluster) {
       cluster = c_min;
-      threads = ctx->t_threads ? ctx->t_threads : std::min(512, std::max(64, ((maxF + cluster - 1) / cluster + 31) / 32 * 32));
+      threads = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cluster - 1) / cluster + 31) / 32 * 32));
       p.fast = 0; p.pc = 0; p.hist_bits = 11; p.cluster = cluster;
     }
     CU(launch_track_level(p, jd, B, cluster, threads, ctx->stream, &ctx->launches));

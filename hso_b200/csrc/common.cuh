@@ -22,8 +22,8 @@ HSO_DEV Quatd quat_mul(const Quatd& a, const Quatd& b) {
   return r;
 }
 HSO_DEV void quat_normalize(Quatd& q) {
-  double n = sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
-  q.w /= n; q.x /= n; q.y /= n; q.z /= n;
+  const double inv = 1.0 / sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);  // one division (serial control path)
+  q.w *= inv; q.x *= inv; q.y *= inv; q.z *= inv;
 }
 HSO_DEV void quat_rotate(const Quatd& q, double vx, double vy, double vz, double& ox, double& oy, double& oz) {
   double ux = q.y * vz - q.z * vy, uy = q.z * vx - q.x * vz, uz = q.x * vy - q.y * vx;
@@ -115,8 +115,11 @@ HSO_DEV Se3d se3_exp(const double* u) {
     quat_to_R(r.q, V);
   } else {
     const double t2 = theta * theta;
-    const double A = (1 - cos(theta)) / t2;
-    const double B = (theta - sin(theta)) / (t2 * theta);
+    double sn, cs;
+    sincos(theta, &sn, &cs);
+    const double inv_t2 = 1.0 / t2;
+    const double A = (1 - cs) * inv_t2;
+    const double B = (theta - sn) * inv_t2 / theta;
     // Omega^2 = omega omega^T - |omega|^2 I
     V[0] = 1 + B * (ox * ox - t2);      V[1] = -A * oz + B * ox * oy;   V[2] = A * oy + B * ox * oz;
     V[3] = A * oz + B * ox * oy;        V[4] = 1 + B * (oy * oy - t2);  V[5] = -A * ox + B * oy * oz;
@@ -188,7 +191,7 @@ HSO_DEV void ldlt_solve(const double* A /*NxN row-major symmetric*/, const doubl
 // On SPD input both give the same solution up to rounding (order cond(A) * 1e-16).
 template <int N>
 HSO_DEV bool ldlt_solve_spd_fast(const double* A /*NxN row-major symmetric*/, const double* b, double* x) {
-  double L[N][N], d[N];
+  double L[N][N], d[N], dinv[N];
   double maxdiag = 0;
 #pragma unroll
   for (int i = 0; i < N; ++i) maxdiag = fmax(maxdiag, fabs(A[i * N + i]));
@@ -202,6 +205,7 @@ HSO_DEV bool ldlt_solve_spd_fast(const double* A /*NxN row-major symmetric*/, co
     d[k] = dk;
     ok = ok && (dk > tiny);
     const double inv = 1.0 / dk;
+    dinv[k] = inv;
 #pragma unroll
     for (int i = k + 1; i < N; ++i) {
       double v = A[i * N + k];
@@ -220,7 +224,7 @@ HSO_DEV bool ldlt_solve_spd_fast(const double* A /*NxN row-major symmetric*/, co
     y[i] = v;
   }
 #pragma unroll
-  for (int i = 0; i < N; ++i) y[i] /= d[i];
+  for (int i = 0; i < N; ++i) y[i] *= dinv[i];
 #pragma unroll
   for (int i = N - 1; i >= 0; --i) {
     double v = y[i];

@@ -513,7 +513,10 @@ __device__ __noinline__ void lm_control(TrackCtrl* c, const double* tot, const T
     for (int k = 0; k < 7; ++k) bl[k] = c->b[k];
     // register-resident unpivoted factorisation when the damped system is safely positive definite (the normal case);
     // the pivoted robust-Cholesky path (Eigen::LDLT semantics) otherwise
-    if (!ldlt_solve_spd_fast<7>(Hl, bl, step)) ldlt_solve<7>(Hl, bl, step);
+    if (!ldlt_solve_spd_fast<7>(Hl, bl, step)) {
+      ldlt_solve<7>(Hl, bl, step);
+      if (rank0) job.state->cycles[7] += 1;  // diagnostics: number of pivoted (slow path) solves
+    }
     float extrap = 1.f;
     if (lambda < 0.001f) extrap = (float)sqrt(sqrt(0.001 / (double)lambda));
     double sum = 0;

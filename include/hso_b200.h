@@ -148,6 +148,8 @@ int hso_track_set_profile(hso_ctx* ctx, int on);
 int hso_track_level_profile(hso_ctx* ctx, int level, double* ms_total, uint64_t* launches);
 /* Tuning knob: CTAs cooperating on one problem through a thread-block cluster (1,2,4,8; 0 = auto). */
 int hso_track_set_cluster(hso_ctx* ctx, int ctas_per_problem, int threads_per_cta);
+/* Same, for one pyramid level only (overrides hso_track_set_cluster for that level; 0,0 restores auto). */
+int hso_track_set_level_shape(hso_ctx* ctx, int level, int ctas_per_problem, int threads_per_cta);
 
 /* ---- F3-inner: direct patch matching — replaces the body of bool hso::Matcher::findMatchDirect(const Point&, Frame&,
  * Vector2d&) after the host-side getCloseViewObs/getWarpMatrixAffine (include/hso/matcher.h:153 ; src/matcher.cpp:310-375),
