@@ -177,6 +177,88 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+def other_rows(ctx, lib, args, dev, torch, K):
+    """Throughput of the other rows of the hot path through the C-ABI with host buffers, beside the CPU oracle:
+    Frame construction, direct patch matching (BASELINE config 4: 5000 candidates) and the pose optimiser (5000 features)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    out = {}
+    pair = synth.make_pair(args.seed + 5, args.cam, F=8)
+    c = pair["cam"]
+    W, H = c["width"], c["height"]
+
+    def timed(fn, reps):
+        fn()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        ctx.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    # ---- F1: pyramid + stats, 64 frames per call -------------------------------------------------------------------------------
+    nb = 64
+    imgs = [pair["cur_img"]] * nb
+    ptrs = (C.c_void_p * nb)(*[im.ctypes.data for im in imgs])
+    ids = (C.c_int32 * nb)()
+    integ = np.zeros(nb, np.float32)
+
+    def up():
+        ctx._chk(lib.hso_frame_upload_batch(ctx.h, nb, ptrs, W, H, W, ids, integ.ctypes.data_as(C.POINTER(C.c_float)), None))
+        for i in range(nb):
+            lib.hso_frame_release(ctx.h, ids[i])
+    dt = timed(up, 5)
+    t0 = time.perf_counter()
+    for _ in range(4):
+        lv, _ = O.create_pyramid(pair["cur_img"], 5)
+        for l in range(3):
+            O.sobel5(lv[l])
+        O.frame_stats(pair["cur_img"])
+    cpu = (time.perf_counter() - t0) / 4
+    out["frame_construction"] = {"gpu_frames_per_s_e2e": nb / dt, "cpu_frames_per_s_1core": 1.0 / cpu, "bytes_per_frame": W * H + (W * H) // 3,
+                                 "note": "hso_frame_upload_batch of 64 host images (H2D + k_pyr_tile + stats read-back) vs oracle pyramid+Sobel L0-L2+stats"}
+    # ---- F3: 5000 candidates ------------------------------------------------------------------------------------------------------
+    fid, _, _ = ctx.upload_frames([pair["ref_img"], pair["cur_img"]])
+    M = 5000
+    jobs = synth.make_align_jobs(args.seed + 6, pair, M=M, frac_edgelet=0.0)
+    arr = (K.hso_align_job * M)()
+    for m, j in enumerate(jobs):
+        a = arr[m]
+        a.ref_level, a.search_level, a.type, a.scale_patch = j["ref_level"], j["search_level"], j["type"], j["scale_patch"]
+        for k in range(2):
+            a.px_ref[k], a.grad[k], a.px_cur[k] = j["px_ref"][k], j["grad"][k], j["px_cur"][k]
+        A = np.asarray(j["A_cur_ref"]).reshape(4)
+        for k in range(4):
+            a.A_cur_ref[k] = A[k]
+        a.exposure_rat = j["exposure_rat"]
+    refs = (C.c_int32 * M)(*([fid[0]] * M))
+    res = (K.hso_align_result * M)()
+    dt = timed(lambda: ctx._chk(lib.hso_align_batch(ctx.h, fid[1], M, arr, refs, 10, res)), 10)
+    rl, _ = O.create_pyramid(pair["ref_img"], 5)
+    cl, _ = O.create_pyramid(pair["cur_img"], 5)
+    sob = [O.sobel5(cl[l]) for l in range(3)]
+    t0 = time.perf_counter()
+    O.match_direct_batch(jobs[:2000], rl, cl, sob)
+    cpu = (time.perf_counter() - t0) / 2000
+    out["align_batch"] = {"gpu_patches_per_s_e2e": M / dt, "cpu_patches_per_s_1core": 1.0 / cpu, "M": M, "ms_per_call": dt * 1e3,
+                          "algorithmic_bytes_per_patch": 580, "achieved_GBps": M * 580 / dt / 1e9,
+                          "note": "hso_align_batch (H2D jobs, k_align, D2H results) vs oracle match_direct_batch (python marshalling excluded from neither)"}
+    # ---- F4: pose optimiser, 5000 features, 8 host frames; batch of 64 frames ----------------------------------------------------------
+    probs = [synth.make_pose_problem(args.seed + 10 + i, args.cam, F=5000, K=8) for i in range(4)]
+    batch = [probs[i % 4] for i in range(64)]
+    dt = timed(lambda: ctx.pose_optimize_batch(batch), 3)
+    t0 = time.perf_counter()
+    trials = sum(O.pose_optimize(p)["n_trials_total"] for p in probs)
+    cpu = (time.perf_counter() - t0) / 4
+    g = ctx.pose_optimize_batch(probs)
+    out["pose_optimizer"] = {"gpu_frames_per_s_e2e": 64 / dt, "cpu_frames_per_s_1core": 1.0 / cpu, "features": 5000, "batch": 64,
+                             "lm_trials_per_frame": trials / 4, "gpu_trials_per_frame": sum(r["n_trials_total"] for r in g) / 4,
+                             "note": "hso_pose_optimize_batch incl. python marshalling vs oracle pose_optimize"}
+    for f_ in fid:
+        ctx.release(f_)
+    return out
+
 # ---------------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -194,6 +276,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0x450)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-rows", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -217,7 +300,7 @@ def main():
     probs = build_workload(B, F, args.cam, args.seed, rank)
     c = probs[0]["cam"]
     W, H = c["width"], c["height"]
-    ctx = Context(make_cam(W, H, c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), device=local_rank, max_frames=2 * B + 2,
+    ctx = Context(make_cam(W, H, c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), device=local_rank, max_frames=2 * B + 72,
                   max_features=max(8192, F))
     lib = ctx.lib
     if args.cluster or args.threads:
@@ -394,6 +477,8 @@ def main():
             line["cpu_baseline"] = {"value": it / dt, "unit": "iterations/s", "cores": cores, "kind": "port",
                                     "sample": f"16 frames of the same workload ({it} LM iterations, {dt:.1f} s) single-threaded like the reference's "
                                               f"tracking thread; host has {os.cpu_count()} cores", "frames_per_s": 16 / dt}
+        if world == 1 and not args.no_other_rows:
+            line["other_rows"] = other_rows(ctx, lib, args, dev, torch, K)
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
