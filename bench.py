@@ -277,6 +277,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-rows", action="store_true")
+    ap.add_argument("--no-ic-dual", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -305,6 +306,8 @@ def main():
     lib = ctx.lib
     if args.cluster or args.threads:
         ctx.set_cluster(args.cluster, args.threads)
+    if args.no_ic_dual:
+        ctx._chk(lib.hso_track_set_ic_dual(ctx.h, 0))
     for item in [x for x in args.shape.split(",") if x]:
         lv, cc, th = (int(v) for v in item.split(":"))
         ctx._chk(lib.hso_track_set_level_shape(ctx.h, lv, cc, th))
@@ -471,12 +474,12 @@ def main():
                            "ms_per_step": ms_e2e_all / e2e["steps"], "steps": e2e["steps"]}
         if world == 1 and not args.no_cpu_baseline:
             cores = 1
-            sample = build_workload(16, F, args.cam, args.seed, 0)
+            sample = build_workload(256, F, args.cam, args.seed, 0)
             run_cpu(sample[:1], args.ic, 1)
             it, dt = run_cpu(sample, args.ic, 1)
             line["cpu_baseline"] = {"value": it / dt, "unit": "iterations/s", "cores": cores, "kind": "port",
-                                    "sample": f"16 frames of the same workload ({it} LM iterations, {dt:.1f} s) single-threaded like the reference's "
-                                              f"tracking thread; host has {os.cpu_count()} cores", "frames_per_s": 16 / dt}
+                                    "sample": f"256 frames of the same workload ({it} LM iterations, {dt:.1f} s) single-threaded like the reference's "
+                                              f"tracking thread; host has {os.cpu_count()} cores", "frames_per_s": 256 / dt}
         if world == 1 and not args.no_other_rows:
             line["other_rows"] = other_rows(ctx, lib, args, dev, torch, K)
         print(json.dumps(line), flush=True)

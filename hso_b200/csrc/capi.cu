@@ -80,7 +80,7 @@ struct hso_ctx {
   std::vector<size_t> t_trace_off;  // byte offset of each job's trace in the arena
   size_t t_arena_bytes = 0;
   int t_maxF = 0;
-  int t_profile = 0, t_prof_pending = 0;
+  int t_profile = 0, t_prof_pending = 0, t_no_dual = 0;
   cudaEvent_t t_ev[kMaxLevels + 1] = {nullptr};
   double t_level_ms[kMaxLevels] = {0};
   uint64_t t_level_launches[kMaxLevels] = {0};
@@ -482,6 +482,12 @@ int hso_track_set_cluster(hso_ctx* ctx, int ctas, int threads) {
   return HSO_OK;
 }
 
+int hso_track_set_ic_dual(hso_ctx* ctx, int enable) {
+  if (!ctx) return HSO_ERR_INVALID;
+  ctx->t_no_dual = enable ? 0 : 1;
+  return HSO_OK;
+}
+
 int hso_track_set_level_shape(hso_ctx* ctx, int level, int ctas, int threads) {
   if (!ctx || level < 0 || level >= kMaxLevels) return HSO_ERR_INVALID;
   if (!(ctas == 0 || ctas == 1 || ctas == 2 || ctas == 4 || ctas == 8)) return fail(ctx, HSO_ERR_INVALID, "cluster size must be 0,1,2,4,8");
@@ -684,7 +690,16 @@ int hso_track_run(hso_ctx* ctx) {
     int c_min = f_cluster;
     if (c_min == 0) c_min = B >= 148 ? 1 : (B >= 74 ? 2 : (B >= 37 ? 4 : 8));
     int cluster = 0, threads = 0;
-    for (int cc = c_min; cc <= 8; cc *= 2) {
+    if (prm.inverse_comp && !ctx->t_no_dual) {
+      // inverse-compositional: keep BOTH levels resident and recompute the reference samples per evaluation — no F-dependent
+      // cache, so one CTA per problem fits whenever two copies of the level do
+      const int cc = c_min;
+      const int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
+      const int kpt = (maxF + cc * th - 1) / (cc * th);
+      p.fast = 2; p.pc = kpt * th; p.cluster = cc; p.hist_bits = 11;
+      if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; }
+    }
+    for (int cc = c_min; cc <= 8 && !cluster; cc *= 2) {
       int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
       const int kpt = (maxF + cc * th - 1) / (cc * th);
       p.fast = 1; p.pc = kpt * th; p.cluster = cc;

@@ -84,7 +84,8 @@ struct TrackLevelParams {
   int trace_cap;
   int w, h;                 // geometry of this level
   size_t level_off;         // byte offset of this level in a pyramid buffer
-  int fast;                 // 1: level image + reference-patch caches of the CTA live in shared memory
+  int fast;                 // 0: everything in global memory; 1: level image + reference-patch caches of the CTA in shared memory;
+                            // 2: (inverse-compositional) current AND reference level in shared memory, no cache
   int pc;                   // FAST: patch slots per CTA = patches-per-thread * threads
   int hist_bits;            // radix-select digit width: 11 when the histogram fits next to the caches, else 8
   int cluster;              // CTAs per problem (shared-memory layout depends on it)

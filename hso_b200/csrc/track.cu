@@ -120,8 +120,9 @@ static __host__ __device__ inline int pattern_n(int pidx) { return pidx <= 0 ? 1
 size_t track_level_smem_bytes(const TrackLevelParams& p, int threads) {
   size_t a, b, c, d, e, f, g, h, i;
   const int N = pattern_n(p.max_level - p.level + 2);
-  const size_t cache = p.fast ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : 0;
-  return smem_layout(p.fast ? p.img_bytes : 0, cache, p.fast ? (size_t)p.pc : 0, threads / 32, p.hist_bits, p.cluster, &a, &b, &c, &d, &e, &f, &g, &h, &i);
+  const size_t cache = p.fast == 1 ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : 0;
+  const uint32_t img = p.fast == 2 ? 2 * (uint32_t)align_up(p.img_bytes, 128) : (p.fast ? p.img_bytes : 0);
+  return smem_layout(img, cache, p.fast ? (size_t)p.pc : 0, threads / 32, p.hist_bits, p.cluster, &a, &b, &c, &d, &e, &f, &g, &h, &i);
 }
 
 // ---- unaligned 4-byte window from a byte image: two aligned words + funnel shift -----------------------------------------
@@ -231,6 +232,7 @@ struct LevelCtx {
 // Where the per-patch caches of the calling thread live. FAST: shared memory, slot = k * blockDim + tid (conflict free);
 // SLOW: global scratch, slot = patch index (coalesced). Layout [pattern px][stride].
 struct PatchStore {
+  const uint8_t* ref;  // MODE 2 (dual image): the reference level in shared memory; intensities/gradients are recomputed per evaluation
   float* cache;    // reference intensities
   float* gx;       // inverse-compositional reference gradients
   float* gy;
@@ -241,25 +243,68 @@ struct PatchStore {
 template <bool FAST>
 HSO_DEV int slot_of(int i, int k) { return FAST ? (k * (int)blockDim.x + (int)threadIdx.x) : i; }
 
+// Reference-side geometry of one patch (src/CoarseTracker.cpp:437-467): integer base pixel and bilinear weights, where
+// w_br = 1 - (tl + tr + bl) (quirk: differs from the current-image weights, :467 vs :323).
+struct RefPatch { bool in; int base; float wtl, wtr, wbl, wbr; };
+HSO_DEV RefPatch ref_patch(double pxu, double pxv, float scale, int border, int w, int h) {
+  RefPatch r;
+  const float u = (float)(pxu * (double)scale), v = (float)(pxv * (double)scale);
+  const float uf = floorf(u), vf = floorf(v);
+  const int ui = __float2int_rd(u), vi = __float2int_rd(v);
+  r.in = ui >= border && vi >= border && ui < w - border && vi < h - border;  // :441
+  const float su = u - uf, sv = v - vf;
+  r.wtl = (float)((1.0 - su) * (1.0 - sv));
+  r.wtr = (float)(su * (1.0 - sv));
+  r.wbl = (float)((1.0 - su) * sv);
+  r.wbr = (float)(1.0 - (double)(r.wtl + r.wtr + r.wbl));
+  r.base = vi * w + ui;
+  return r;
+}
+// reference intensity of one pattern pixel (:482-485)
+template <bool SM>
+HSO_DEV float ref_intensity(const uint8_t* img, const RefPatch& r, int addr, int w) {
+  const uint32_t r0 = ld4<SM>(img, addr);
+  const uint32_t r1 = ld4<SM>(img, addr + w);
+  return r.wtl * b0(r0) + r.wtr * b1(r0) + r.wbl * b0(r1) + r.wbr * b1(r1);
+}
+// reference intensity + central-difference gradients of one pattern pixel, inverse-compositional mode (:482-492)
+template <bool SM>
+HSO_DEV void ref_intensity_grad(const uint8_t* img, const RefPatch& r, int addr, int w, float& c, float& gx, float& gy) {
+  const uint32_t rm = ld4<SM>(img, addr - w - 1);
+  const uint32_t r0 = ld4<SM>(img, addr - 1);
+  const uint32_t r1 = ld4<SM>(img, addr + w - 1);
+  const uint32_t r2 = ld4<SM>(img, addr + 2 * w - 1);
+  c = r.wtl * b1(r0) + r.wtr * b2(r0) + r.wbl * b1(r1) + r.wbr * b2(r1);
+  gx = 0.5f * ((r.wtl * b2(r0) + r.wtr * b3(r0) + r.wbl * b2(r1) + r.wbr * b3(r1)) - (r.wtl * b0(r0) + r.wtr * b1(r0) + r.wbl * b0(r1) + r.wbr * b1(r1)));
+  gy = 0.5f * ((r.wtl * b1(r1) + r.wtr * b2(r1) + r.wbl * b1(r2) + r.wbr * b2(r2)) - (r.wtl * b1(rm) + r.wtr * b2(rm) + r.wbl * b1(r0) + r.wbr * b2(r0)));
+}
+
 // One residual evaluation over the calling thread's patches: computeResiduals + computeGS fused
 // (src/CoarseTracker.cpp:242-414, :499-525).
-template <int PIDX, bool IC, bool FAST>
+template <int PIDX, bool IC, int MODE>
 HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const PatchStore& ps, const CamDev& cam, const double* Rt, float a, float huber,
                           float cutoff, int t0, int nt, Acc& acc) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
+  constexpr bool FAST = MODE != 0, DUAL = MODE == 2;
   const int Fp = job.Fpad, S = ps.stride;
   // max_energy = 2*huber*cutoff - huber^2, evaluated in double like the reference (cutoff_error is a double there)
   const float max_energy = (float)(2.0 * (double)huber * (double)cutoff - (double)(huber * huber));
   // geometry of the next patch is fetched while the current one is processed (the only global loads of the FAST path)
   int i = t0, k = 0;
   bool have = i < job.F && ps.vis[slot_of<FAST>(i, k)] != 0;
-  double X = 0, Y = 0, Z = 1;
-  if (have) { X = job.xyz[i]; Y = job.xyz[Fp + i]; Z = job.xyz[2 * Fp + i]; }
+  double X = 0, Y = 0, Z = 1, PU = 0, PV = 0;
+  if (have) {
+    X = job.xyz[i]; Y = job.xyz[Fp + i]; Z = job.xyz[2 * Fp + i];
+    if (DUAL) { PU = job.px[i]; PV = job.px[Fp + i]; }
+  }
   while (i < job.F) {
     const int in = i + nt, kn = k + 1;
     const bool have_n = in < job.F && ps.vis[slot_of<FAST>(in, kn)] != 0;
-    double Xn = 0, Yn = 0, Zn = 1;
-    if (have_n) { Xn = job.xyz[in]; Yn = job.xyz[Fp + in]; Zn = job.xyz[2 * Fp + in]; }
+    double Xn = 0, Yn = 0, Zn = 1, PUn = 0, PVn = 0;
+    if (have_n) {
+      Xn = job.xyz[in]; Yn = job.xyz[Fp + in]; Zn = job.xyz[2 * Fp + in];
+      if (DUAL) { PUn = job.px[in]; PVn = job.px[Fp + in]; }
+    }
     if (have) {
       const Proj p = project_patch(Rt, cam, X, Y, Z, L.scale, L.border, L.w, L.h);
       if (p.ok) {
@@ -275,11 +320,15 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
         Moments m = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         float Ep = 0.f;
         int sat = 0;
+        RefPatch rp;
+        if (DUAL) rp = ref_patch(PU, PV, L.scale, L.border, L.w, L.h);
 #pragma unroll
         for (int n = 0; n < N; ++n) {
-          const int addr = p.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
-          const float c = ps.cache[n * S + sl];
-          float color, gx, gy;
+          const int poff = pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
+          const int addr = p.base + poff;
+          float c, color, gx, gy;
+          if (DUAL) ref_intensity_grad<true>(ps.ref, rp, rp.base + poff, L.w, c, gx, gy);
+          else c = ps.cache[n * S + sl];
           if (!IC) {
             const uint32_t rm = ld4<FAST>(L.cur, addr - L.w - 1);
             const uint32_t r0 = ld4<FAST>(L.cur, addr - 1);
@@ -294,8 +343,7 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
             const uint32_t r0 = ld4<FAST>(L.cur, addr);
             const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
             color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-            gx = ps.gx[n * S + sl];
-            gy = ps.gy[n * S + sl];
+            if (!DUAL) { gx = ps.gx[n * S + sl]; gy = ps.gy[n * S + sl]; }
           }
           const float r = color - (a * c + 0.f);
           const float ar = fabsf(r);
@@ -319,7 +367,7 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
         acc.patches += 1;
       }
     }
-    i = in; k = kn; have = have_n; X = Xn; Y = Yn; Z = Zn;
+    i = in; k = kn; have = have_n; X = Xn; Y = Yn; Z = Zn; PU = PUn; PV = PVn;
   }
 }
 
@@ -533,10 +581,12 @@ __device__ __noinline__ void lm_control(TrackCtrl* c, const double* tot, const T
   c->done = done ? 1 : 0;
 }
 
-template <int PIDX, bool IC, bool FAST>
+template <int PIDX, bool IC, int MODE>
 __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams prm, const TrackJobDev* __restrict__ jobs) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
   constexpr int PAD = (PIDX == 5) ? 3 : (PIDX == 7) ? 4 : (PIDX <= 2) ? 1 : 2;
+  constexpr bool FAST = MODE != 0, DUAL = MODE == 2;
+  static_assert(!DUAL || IC, "the dual-image mode exists for the inverse-compositional path only");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int csize = (int)cluster.num_blocks();
@@ -549,8 +599,9 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   Smem s;
   {
     size_t oc, ov, ow, op, ot, oh, og, ox, om;
-    const size_t cache_bytes = FAST ? (size_t)N * (IC ? 3 : 1) * prm.pc * sizeof(float) : 0;
-    smem_layout(FAST ? prm.img_bytes : 0, cache_bytes, FAST ? (size_t)prm.pc : 0, nwarps, prm.hist_bits, csize, &oc, &ov, &ow, &op, &ot, &oh, &og, &ox, &om);
+    const size_t cache_bytes = MODE == 1 ? (size_t)N * (IC ? 3 : 1) * prm.pc * sizeof(float) : 0;
+    const uint32_t img_total = DUAL ? 2 * (uint32_t)align_up(prm.img_bytes, 128) : (FAST ? prm.img_bytes : 0);
+    smem_layout(img_total, cache_bytes, FAST ? (size_t)prm.pc : 0, nwarps, prm.hist_bits, csize, &oc, &ov, &ow, &op, &ot, &oh, &og, &ox, &om);
     s.img = smem_raw;
     s.cache = reinterpret_cast<float*>(smem_raw + oc);
     s.vis = smem_raw + ov;
@@ -568,6 +619,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   const int Fp = job.Fpad;
 
   PatchStore ps;
+  ps.ref = s.img + align_up(prm.img_bytes, 128);
   if (FAST) {
     ps.cache = s.cache; ps.gx = s.cache + (size_t)N * prm.pc; ps.gy = s.cache + (size_t)2 * N * prm.pc; ps.vis = s.vis; ps.stride = prm.pc;
   } else {
@@ -583,12 +635,17 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
       mbar_init(s.mbar, 1);
       mbar_fence_init();
       fence_proxy_async();
-      mbar_expect_tx(s.mbar, prm.img_bytes);
+      mbar_expect_tx(s.mbar, DUAL ? 2 * prm.img_bytes : prm.img_bytes);
       uint32_t done = 0;
       while (done < prm.img_bytes) {
         uint32_t chunk = prm.img_bytes - done;
         if (chunk > 32768u) chunk = 32768u;
-        tma_bulk_g2s(s.img + done, ref_g + done, chunk, s.mbar);
+        if (DUAL) {  // both levels stay resident: current at s.img, reference behind it
+          tma_bulk_g2s(s.img + done, cur_g + done, chunk, s.mbar);
+          tma_bulk_g2s(s.img + align_up(prm.img_bytes, 128) + done, ref_g + done, chunk, s.mbar);
+        } else {
+          tma_bulk_g2s(s.img + done, ref_g + done, chunk, s.mbar);
+        }
         done += chunk;
       }
     }
@@ -609,47 +666,32 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   // ---- phase 1: precomputeReferencePatches (src/CoarseTracker.cpp:416-497) ------------------------------------------------
   __syncthreads();
   if (FAST) mbar_wait(s.mbar, 0);
-  const uint8_t* ref_src = FAST ? s.img : ref_g;
+  const uint8_t* ref_src = DUAL ? ps.ref : (FAST ? s.img : ref_g);
   {
     int k = 0;
     for (int i = t0; i < job.F; i += nt, ++k) {
       const int sl = slot_of<FAST>(i, k);
-      const float u = (float)(job.px[i] * (double)L.scale), v = (float)(job.px[Fp + i] * (double)L.scale);
-      const float uf = floorf(u), vf = floorf(v);
-      const int ui = __float2int_rd(u), vi = __float2int_rd(v);
-      const bool in = ui >= L.border && vi >= L.border && ui < L.w - L.border && vi < L.h - L.border;  // :441
-      ps.vis[sl] = in ? 1 : 0;
-      if (!in) continue;
-      const float su = u - uf, sv = v - vf;
-      const float wtl = (float)((1.0 - su) * (1.0 - sv));
-      const float wtr = (float)(su * (1.0 - sv));
-      const float wbl = (float)((1.0 - su) * sv);
-      const float wbr = (float)(1.0 - (double)(wtl + wtr + wbl));  // quirk: differs from the current-image weights (:467 vs :323)
-      const int base = vi * L.w + ui;
+      const RefPatch rp = ref_patch(job.px[i], job.px[Fp + i], L.scale, L.border, L.w, L.h);
+      ps.vis[sl] = rp.in ? 1 : 0;
+      if (!rp.in || DUAL) continue;  // dual-image mode recomputes the reference samples in every evaluation
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        const int addr = base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
+        const int addr = rp.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
         if (!IC) {
-          const uint32_t r0 = ld4<FAST>(ref_src, addr);
-          const uint32_t r1 = ld4<FAST>(ref_src, addr + L.w);
-          ps.cache[n * ps.stride + sl] = wtl * b0(r0) + wtr * b1(r0) + wbl * b0(r1) + wbr * b1(r1);
+          ps.cache[n * ps.stride + sl] = ref_intensity<FAST>(ref_src, rp, addr, L.w);
         } else {
-          const uint32_t rm = ld4<FAST>(ref_src, addr - L.w - 1);
-          const uint32_t r0 = ld4<FAST>(ref_src, addr - 1);
-          const uint32_t r1 = ld4<FAST>(ref_src, addr + L.w - 1);
-          const uint32_t r2 = ld4<FAST>(ref_src, addr + 2 * L.w - 1);
-          ps.cache[n * ps.stride + sl] = wtl * b1(r0) + wtr * b2(r0) + wbl * b1(r1) + wbr * b2(r1);
-          ps.gx[n * ps.stride + sl] = 0.5f * ((wtl * b2(r0) + wtr * b3(r0) + wbl * b2(r1) + wbr * b3(r1)) -
-                                              (wtl * b0(r0) + wtr * b1(r0) + wbl * b0(r1) + wbr * b1(r1)));
-          ps.gy[n * ps.stride + sl] = 0.5f * ((wtl * b1(r1) + wtr * b2(r1) + wbl * b1(r2) + wbr * b2(r2)) -
-                                              (wtl * b1(rm) + wtr * b2(rm) + wbl * b1(r0) + wbr * b2(r0)));
+          float cc, gx, gy;
+          ref_intensity_grad<FAST>(ref_src, rp, addr, L.w, cc, gx, gy);
+          ps.cache[n * ps.stride + sl] = cc;
+          ps.gx[n * ps.stride + sl] = gx;
+          ps.gy[n * ps.stride + sl] = gy;
         }
       }
     }
   }
   __syncthreads();
   const long long clk_pre = clock64();
-  if (FAST) {
+  if (FAST && !DUAL) {
     // every generic-proxy read of the reference image is done: hand the buffer back to the async proxy for the current level
     if (threadIdx.x == 0) {
       fence_proxy_async();
@@ -679,19 +721,23 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
       const int sl = slot_of<FAST>(i, k);
       bool ok = ps.vis[sl] != 0;
       Proj p;
+      RefPatch rp;
       if (ok) {
         p = project_patch(c->Rt, prm.cam, job.xyz[i], job.xyz[Fp + i], job.xyz[2 * Fp + i], L.scale, L.border, L.w, L.h);
         ok = p.ok;
+        if (DUAL) rp = ref_patch(job.px[i], job.px[Fp + i], L.scale, L.border, L.w, L.h);
       }
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         float out = -1.f;
         if (ok) {
-          const int addr = p.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
+          const int poff = pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
+          const int addr = p.base + poff;
           const uint32_t r0 = ld4<FAST>(L.cur, addr);
           const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
           const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-          out = fabsf(color - (a * ps.cache[n * ps.stride + sl] + 0.f));
+          const float cref = DUAL ? ref_intensity<true>(ps.ref, rp, rp.base + poff, L.w) : ps.cache[n * ps.stride + sl];
+          out = fabsf(color - (a * cref + 0.f));
           atomicAdd(&s.hist[__float_as_uint(out) >> (32 - hbits)], 1u);  // first digit of the median select, fused
         }
         job.absres[n * Fp + i] = out;
@@ -728,7 +774,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     const float a_eval = iter < 0 ? c->a_acc : c->a_try;
     Acc acc;
     acc_zero(acc);
-    eval_patches<PIDX, IC, FAST>(L, job, ps, prm.cam, c->Rt, a_eval, huber, cutoff, t0, nt, acc);
+    eval_patches<PIDX, IC, MODE>(L, job, ps, prm.cam, c->Rt, a_eval, huber, cutoff, t0, nt, acc);
     reduce_acc(acc, s, slot, csize, nwarps);
     slot ^= 1;
     ++level_evals;
@@ -803,10 +849,10 @@ cudaError_t launch_track_finish(const TrackJobDev* jobs_dev, hso_track_result* o
   return cudaGetLastError();
 }
 
-template <int PIDX, bool IC, bool FAST>
+template <int PIDX, bool IC, int MODE>
 static cudaError_t launch_one(const TrackLevelParams& p, const TrackJobDev* jobs_dev, int B, int cluster, int threads, size_t smem,
                               cudaStream_t stream) {
-  auto kern = k_track_level<PIDX, IC, FAST>;
+  auto kern = k_track_level<PIDX, IC, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -828,11 +874,12 @@ template <int PIDX>
 static cudaError_t launch_pidx(const TrackLevelParams& p, const TrackJobDev* jobs_dev, int B, int cluster, int threads, size_t smem,
                                cudaStream_t stream) {
   if (p.ic) {
-    return p.fast ? launch_one<PIDX, true, true>(p, jobs_dev, B, cluster, threads, smem, stream)
-                        : launch_one<PIDX, true, false>(p, jobs_dev, B, cluster, threads, smem, stream);
+    if (p.fast == 2) return launch_one<PIDX, true, 2>(p, jobs_dev, B, cluster, threads, smem, stream);
+    return p.fast ? launch_one<PIDX, true, 1>(p, jobs_dev, B, cluster, threads, smem, stream)
+                  : launch_one<PIDX, true, 0>(p, jobs_dev, B, cluster, threads, smem, stream);
   }
-  return p.fast ? launch_one<PIDX, false, true>(p, jobs_dev, B, cluster, threads, smem, stream)
-                      : launch_one<PIDX, false, false>(p, jobs_dev, B, cluster, threads, smem, stream);
+  return p.fast ? launch_one<PIDX, false, 1>(p, jobs_dev, B, cluster, threads, smem, stream)
+                : launch_one<PIDX, false, 0>(p, jobs_dev, B, cluster, threads, smem, stream);
 }
 
 cudaError_t launch_track_level(const TrackLevelParams& p, const TrackJobDev* jobs_dev, int B, int cluster, int threads, cudaStream_t stream,

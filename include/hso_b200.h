@@ -150,6 +150,9 @@ int hso_track_level_profile(hso_ctx* ctx, int level, double* ms_total, uint64_t*
 int hso_track_set_cluster(hso_ctx* ctx, int ctas_per_problem, int threads_per_cta);
 /* Same, for one pyramid level only (overrides hso_track_set_cluster for that level; 0,0 restores auto). */
 int hso_track_set_level_shape(hso_ctx* ctx, int level, int ctas_per_problem, int threads_per_cta);
+/* Inverse-compositional mode: 1 (default) keeps both pyramid levels in shared memory and recomputes the reference samples per evaluation
+ * whenever two copies of the level fit; 0 forces the cached-reference-patch path. Results are identical. */
+int hso_track_set_ic_dual(hso_ctx* ctx, int enable);
 
 /* ---- F3-inner: direct patch matching — replaces the body of bool hso::Matcher::findMatchDirect(const Point&, Frame&,
  * Vector2d&) after the host-side getCloseViewObs/getWarpMatrixAffine (include/hso/matcher.h:153 ; src/matcher.cpp:310-375),

@@ -115,6 +115,20 @@ def test_cluster_shapes_agree(oracle, cluster, threads):
     ctx.close()
 
 
+def test_ic_dual_image_and_cached_paths_agree(oracle):
+    p, ctx, tp, job, a0 = _setup(oracle, 35, "icl", 900)
+    r_dual, t_dual = ctx.coarse_track_batch([job], inverse_comp=True, trace_cap=256)
+    _check_trace(oracle, tp, t_dual[0], True, 4)
+    ctx._chk(ctx.lib.hso_track_set_ic_dual(ctx.h, 0))
+    r_cache, t_cache = ctx.coarse_track_batch([job], inverse_comp=True, trace_cap=256)
+    _check_trace(oracle, tp, t_cache[0], True, 4)
+    e0, e1 = t_dual[0][0], t_cache[0][0]
+    assert e0.total_terms == e1.total_terms and e0.huber == e1.huber
+    assert np.allclose(np.array(e0.H[:]), np.array(e1.H[:]), rtol=1e-5, atol=1e-5 * np.abs(np.array(e0.H[:])).max())
+    assert np.abs(r_dual[0]["T_cur_ref"] - r_cache[0]["T_cur_ref"]).max() < 2e-4
+    ctx.close()
+
+
 def test_batch_of_independent_problems(oracle):
     cam = synth.CAMS["icl"]
     ctx = Context(make_cam(cam["width"], cam["height"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["d"]), max_frames=16)
