@@ -259,6 +259,45 @@ def other_rows(ctx, lib, args, dev, torch, K):
         ctx.release(f_)
     return out
 
+
+def single_stream(args, device, torch):
+    """The reference's real operating point: ONE stream, ~200 features per frame (Config::maxFts), one frame at a time through the
+    synchronous C-ABI calls (upload + track), beside the single-threaded CPU oracle on the same frames."""
+    from hso_b200 import Context, make_cam
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    probs = build_workload(8, 200, args.cam, args.seed + 99, 0)
+    c = probs[0]["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), device=device, max_frames=8)
+    out = {}
+    for mode, ic in (("forward", False), ("inverse-compositional", True)):
+        def frame(p):
+            ids, integ, _ = ctx.upload_frames([p["cur_img"]])
+            job = dict(ref=p["_rid"], cur=ids[0], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=p["T0"],
+                       exposure_rat=float(np.float32(integ[0]) / np.float32(p["_rint"])))
+            res, _ = ctx.coarse_track_batch([job], inverse_comp=ic)
+            ctx.release(ids[0])
+            return res[0]["n_iters"]
+        use = probs[:6]  # 6 resident reference frames + 1 current frame <= 8 slots
+        for p in use:
+            if "_rid" not in p:
+                ids, integ, _ = ctx.upload_frames([p["ref_img"]])
+                p["_rid"], p["_rint"] = ids[0], integ[0]
+        for p in use:
+            frame(p)
+        t0 = time.perf_counter()
+        its = 0
+        reps = 20
+        for _ in range(reps):
+            for p in use:
+                its += frame(p)
+        dt = time.perf_counter() - t0
+        it_c, dt_c = run_cpu(use, ic, 1)
+        out[mode] = {"gpu_frames_per_s": reps * len(use) / dt, "gpu_ms_per_frame": 1e3 * dt / (reps * len(use)), "gpu_iterations_per_s": its / dt,
+                     "cpu_frames_per_s_1core": len(use) / dt_c, "cpu_ms_per_frame": 1e3 * dt_c / len(use), "features": 200}
+    ctx.close()
+    return out
+
 # ---------------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -481,7 +520,24 @@ def main():
                                     "sample": f"256 frames of the same workload ({it} LM iterations, {dt:.1f} s) single-threaded like the reference's "
                                               f"tracking thread; host has {os.cpu_count()} cores", "frames_per_s": 256 / dt}
         if world == 1 and not args.no_other_rows:
+            # the same batch in the other Jacobian mode (the reference picks inverse-compositional unless the new frame's gradients
+            # got stronger, src/frame_handler_mono.cpp:184-203), device-resident like `value`
+            ctx.track_stage(jobs, inverse_comp=not args.ic, max_level=4, min_level=1, n_iter=50)
+            for _ in range(2):
+                device_step()
+            ctx.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(args.steps):
+                device_step()
+            g1.record(stream)
+            ctx.synchronize()
+            o2 = ctx.track_collect()
+            it2 = sum(o2[b].n_iters for b in range(B))
+            line["other_mode"] = {"mode": "forward" if args.ic else "inverse-compositional", "value": it2 * args.steps / (g0.elapsed_time(g1) * 1e-3),
+                                  "unit": "iterations/s", "ms_per_step": g0.elapsed_time(g1) / args.steps}
             line["other_rows"] = other_rows(ctx, lib, args, dev, torch, K)
+            line["single_stream"] = single_stream(args, local_rank, torch)
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -688,7 +688,13 @@ int hso_track_run(hso_ctx* ctx) {
     const int f_cluster = ctx->t_shape[level][0] ? ctx->t_shape[level][0] : ctx->t_cluster;
     const int f_threads = ctx->t_shape[level][1] ? ctx->t_shape[level][1] : ctx->t_threads;
     int c_min = f_cluster;
-    if (c_min == 0) c_min = B >= 148 ? 1 : (B >= 74 ? 2 : (B >= 37 ? 4 : 8));
+    if (c_min == 0) {
+      c_min = B >= 148 ? 1 : (B >= 74 ? 2 : (B >= 37 ? 4 : 8));
+      // ... but never more CTAs than it takes to give every thread one patch (a cluster only adds barriers beyond that)
+      int c_work = 1;
+      while (c_work < 8 && c_work * 512 < maxF) c_work *= 2;
+      c_min = std::min(c_min, c_work);
+    }
     int cluster = 0, threads = 0;
     if (prm.inverse_comp && !ctx->t_no_dual) {
       // inverse-compositional: keep BOTH levels resident and recompute the reference samples per evaluation — no F-dependent
@@ -713,6 +719,10 @@ int hso_track_run(hso_ctx* ctx) {
       cluster = c_min;
       threads = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cluster - 1) / cluster + 31) / 32 * 32));
       p.fast = 0; p.pc = 0; p.hist_bits = 11; p.cluster = cluster;
+    }
+    if (p.fast) {  // keep the |r| scratch of the threshold selection in shared memory too when it still fits
+      p.absres_smem = 1;
+      if (track_level_smem_bytes(p, threads) > 227 * 1024) p.absres_smem = 0;
     }
     CU(launch_track_level(p, jd, B, cluster, threads, ctx->stream, &ctx->launches));
   }

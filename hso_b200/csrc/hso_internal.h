@@ -87,6 +87,7 @@ struct TrackLevelParams {
   int fast;                 // 0: everything in global memory; 1: level image + reference-patch caches of the CTA in shared memory;
                             // 2: (inverse-compositional) current AND reference level in shared memory, no cache
   int pc;                   // FAST: patch slots per CTA = patches-per-thread * threads
+  int absres_smem;          // FAST: the |r| scratch of the threshold selection lives in shared memory ([N][pc] floats)
   int hist_bits;            // radix-select digit width: 11 when the histogram fits next to the caches, else 8
   int cluster;              // CTAs per problem (shared-memory layout depends on it)
   uint32_t img_bytes;       // bytes staged (multiple of 16)

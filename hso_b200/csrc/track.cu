@@ -85,6 +85,7 @@ struct TrackCtrl {
 struct Smem {
   uint8_t* img;
   float* cache;        // FAST: [N (x3 in IC mode)][pc] reference intensities (+ gradients) of this CTA's patches
+  float* absres;       // FAST + absres_smem: [N][pc] |r| of the threshold selection
   uint8_t* vis;        // FAST: [pc]
   double* warp_part;   // [nwarps][NRED]
   double* cta_part;    // [2][NRED]
@@ -97,11 +98,12 @@ struct Smem {
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline size_t smem_layout(uint32_t img_bytes, size_t cache_bytes, size_t vis_bytes, int nwarps, int hist_bits, int csize,
-                                              size_t* o_cache, size_t* o_vis, size_t* o_warp, size_t* o_cta, size_t* o_tot, size_t* o_hist,
+__host__ __device__ inline size_t smem_layout(uint32_t img_bytes, size_t cache_bytes, size_t abs_bytes, size_t vis_bytes, int nwarps, int hist_bits,
+                                              int csize, size_t* o_cache, size_t* o_abs, size_t* o_vis, size_t* o_warp, size_t* o_cta, size_t* o_tot, size_t* o_hist,
                                               size_t* o_ghist, size_t* o_ctrl, size_t* o_mbar) {
   size_t o = align_up(img_bytes, 128);
   *o_cache = o; o += align_up(cache_bytes, 16);
+  *o_abs = o; o += align_up(abs_bytes, 16);
   *o_vis = o; o += align_up(vis_bytes, 16);
   *o_warp = o; o += sizeof(double) * nwarps * NRED;
   *o_cta = o; o += sizeof(double) * 2 * NRED;
@@ -118,11 +120,12 @@ static __host__ __device__ inline int pattern_n(int pidx) { return pidx <= 0 ? 1
 
 // Shared memory of one CTA. fast: image + patch caches resident; pc = patch slots per CTA (patches-per-thread * threads).
 size_t track_level_smem_bytes(const TrackLevelParams& p, int threads) {
-  size_t a, b, c, d, e, f, g, h, i;
+  size_t a, b, c, d, e, f, g, h, i, j;
   const int N = pattern_n(p.max_level - p.level + 2);
+  const size_t absb = (p.fast && p.absres_smem) ? (size_t)N * p.pc * sizeof(float) : 0;
   const size_t cache = p.fast == 1 ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : 0;
   const uint32_t img = p.fast == 2 ? 2 * (uint32_t)align_up(p.img_bytes, 128) : (p.fast ? p.img_bytes : 0);
-  return smem_layout(img, cache, p.fast ? (size_t)p.pc : 0, threads / 32, p.hist_bits, p.cluster, &a, &b, &c, &d, &e, &f, &g, &h, &i);
+  return smem_layout(img, cache, absb, p.fast ? (size_t)p.pc : 0, threads / 32, p.hist_bits, p.cluster, &a, &j, &b, &c, &d, &e, &f, &g, &h, &i);
 }
 
 // ---- unaligned 4-byte window from a byte image: two aligned words + funnel shift -----------------------------------------
@@ -421,8 +424,8 @@ HSO_DEV void hist_add_aggregated(uint32_t* hist, uint32_t bin) {
 // CTAs of a cluster are merged through DSMEM. prefilled: the histogram of the first digit was already accumulated by the caller
 // (fused with the residual computation), so that pass does not re-read the residuals.
 template <int N>
-HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, int t0, int nt, bool mad, float center, int csize, int bits, bool prefilled) {
-  const int Fp = job.Fpad;
+HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, const float* absres, int astride, bool a_smem, int t0, int nt, bool mad, float center,
+                          int csize, int bits, bool prefilled) {
   const int nbins = 1 << bits;
   uint32_t prefix = 0, mask = 0;
   int hi = 32;
@@ -435,11 +438,13 @@ HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, int t0, int nt,
     if (!(first && prefilled)) {
       for (int j = threadIdx.x; j < nbins; j += blockDim.x) hist[j] = 0;
       __syncthreads();
-      for (int i = t0; i < job.F; i += nt) {
+      int kk = 0;
+      for (int i = t0; i < job.F; i += nt, ++kk) {
         // all N loads of the patch are issued back to back (one L2 round trip per patch, not one per value)
+        const int slot = a_smem ? (kk * (int)blockDim.x + (int)threadIdx.x) : i;
         float vals[N];
 #pragma unroll
-        for (int n = 0; n < N; ++n) vals[n] = __ldcg(job.absres + n * Fp + i);
+        for (int n = 0; n < N; ++n) vals[n] = a_smem ? absres[n * astride + slot] : __ldcg(absres + n * astride + slot);
 #pragma unroll
         for (int n = 0; n < N; ++n) {
           float v = vals[n];
@@ -598,10 +603,12 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
 
   Smem s;
   {
-    size_t oc, ov, ow, op, ot, oh, og, ox, om;
+    size_t oc, oa, ov, ow, op, ot, oh, og, ox, om;
+    const size_t abs_bytes = (FAST && prm.absres_smem) ? (size_t)N * prm.pc * sizeof(float) : 0;
     const size_t cache_bytes = MODE == 1 ? (size_t)N * (IC ? 3 : 1) * prm.pc * sizeof(float) : 0;
     const uint32_t img_total = DUAL ? 2 * (uint32_t)align_up(prm.img_bytes, 128) : (FAST ? prm.img_bytes : 0);
-    smem_layout(img_total, cache_bytes, FAST ? (size_t)prm.pc : 0, nwarps, prm.hist_bits, csize, &oc, &ov, &ow, &op, &ot, &oh, &og, &ox, &om);
+    smem_layout(img_total, cache_bytes, abs_bytes, FAST ? (size_t)prm.pc : 0, nwarps, prm.hist_bits, csize, &oc, &oa, &ov, &ow, &op, &ot, &oh, &og, &ox, &om);
+    s.absres = reinterpret_cast<float*>(smem_raw + oa);
     s.img = smem_raw;
     s.cache = reinterpret_cast<float*>(smem_raw + oc);
     s.vis = smem_raw + ov;
@@ -714,6 +721,9 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   {
     const float a = c->a_acc;
     const int hbits = prm.hist_bits;
+    const bool a_smem = FAST && prm.absres_smem;
+    float* absres = a_smem ? s.absres : job.absres;
+    const int astride = a_smem ? prm.pc : Fp;
     for (int j = threadIdx.x; j < (1 << hbits); j += blockDim.x) s.hist[j] = 0;
     __syncthreads();
     int k = 0;
@@ -740,18 +750,18 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
           out = fabsf(color - (a * cref + 0.f));
           atomicAdd(&s.hist[__float_as_uint(out) >> (32 - hbits)], 1u);  // first digit of the median select, fused
         }
-        job.absres[n * Fp + i] = out;
+        absres[n * astride + (a_smem ? sl : i)] = out;
       }
     }
     clk_res = clock64();
-    radix_select<N>(job, s, t0, nt, false, 0.f, csize, hbits, true);
+    radix_select<N>(job, s, absres, astride, a_smem, t0, nt, false, 0.f, csize, hbits, true);
     clk_med = clock64();
     const uint32_t n_err = c->sel_n;
     float huber = 5.2f, outlier = 100.f;
     if (n_err >= 30) {
       const float median = __uint_as_float(c->sel_prefix);
       __syncthreads();
-      radix_select<N>(job, s, t0, nt, true, median, csize, hbits, false);
+      radix_select<N>(job, s, absres, astride, a_smem, t0, nt, true, median, csize, hbits, false);
       const float mad = __uint_as_float(c->sel_prefix);
       const float sd = (float)(1.4826 * (double)mad);
       huber = median + sd;
