@@ -60,6 +60,10 @@ class hso_align_result(C.Structure):
     _fields_ = [("ok", C.c_int32), ("align_converged", C.c_int32), ("px_cur", C.c_double * 2), ("h_inv", C.c_double)]
 
 
+class hso_corner(C.Structure):
+    _fields_ = [("x", C.c_int16), ("y", C.c_int16), ("score", C.c_int32), ("shi_tomasi", C.c_float)]
+
+
 class hso_pose_result(C.Structure):
     _fields_ = [("T_f_w", C.c_double * 12), ("cov", C.c_double * 36), ("estimated_scale", C.c_double), ("error_init", C.c_double),
                 ("error_final", C.c_double), ("num_obs", C.c_uint64), ("error_in_px", C.c_float), ("n_trials_total", C.c_int32),
@@ -106,6 +110,7 @@ SYMBOLS = {
     "hso_pose_optimize_batch": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, _P(C.c_int32), _P(C.c_int32), _P(C.c_double), _P(C.c_double),
                                           _P(C.c_int32), _P(C.c_int32), _P(C.c_double), _P(C.c_double), _P(C.c_int8), _P(C.c_int8),
                                           _P(C.c_int8), _P(C.c_double), _P(C.c_uint8), _P(hso_pose_result)]),
+    "hso_fast_detect": (C.c_int, [_vp, C.c_int32, C.c_int, C.c_int, C.c_int, _P(hso_corner), C.c_int, _P(C.c_int)]),
     "hso_stage_time_ms": (C.c_int, [_vp, C.c_int, _P(C.c_double), _P(C.c_uint64)]),
 }
 

@@ -210,6 +210,16 @@ class Context:
                             n_trials_total=o.n_trials_total, early_return=o.early_return, outlier=outl[offs[b]:offs[b + 1]].copy()))
         return res
 
+    # ---- N2: FeatureExtractor::fastDetectST detector part -----------------------------------------------------------------------
+    def fast_detect(self, fid, level, threshold, border=8, cap=65536):
+        """Returns [(x, y, score, shi_tomasi)] in raster order (level pixels), like fastDetectST before the cell bookkeeping."""
+        out = (K.hso_corner * cap)()
+        n = C.c_int()
+        self._chk(self.lib.hso_fast_detect(self.h, int(fid), level, int(threshold), border, out, cap, C.byref(n)))
+        if n.value > cap:
+            return self.fast_detect(fid, level, threshold, border, n.value)
+        return [(out[i].x, out[i].y, out[i].score, out[i].shi_tomasi) for i in range(n.value)]
+
     def stage_time_ms(self, stage):
         ms, calls = C.c_double(), C.c_uint64()
         self._chk(self.lib.hso_stage_time_ms(self.h, stage, C.byref(ms), C.byref(calls)))

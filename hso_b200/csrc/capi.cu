@@ -84,6 +84,9 @@ struct hso_ctx {
   cudaEvent_t t_ev[kMaxLevels + 1] = {nullptr};
   double t_level_ms[kMaxLevels] = {0};
   uint64_t t_level_launches[kMaxLevels] = {0};
+  // FAST scratch
+  DevBuf f_score, f_rowbuf, f_rowcount, f_out, f_total;
+  PinBuf f_out_host;
   // align / pose scratch
   DevBuf a_jobs_dev, a_out_dev, p_arena, p_jobs_dev, p_out_dev;
   PinBuf a_jobs_host, a_out_host, p_stage_host, p_out_host;
@@ -333,10 +336,10 @@ void hso_destroy(hso_ctx* ctx) {
   for (FrameSlot& s : ctx->frames) {
     if (s.sobel) cudaFree(s.sobel);
   }
-  DevBuf* db[] = {&ctx->pyr_arena, &ctx->sums_arena, &ctx->stats_table, &ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
+  DevBuf* db[] = {&ctx->f_score, &ctx->f_rowbuf, &ctx->f_rowcount, &ctx->f_out, &ctx->f_total, &ctx->pyr_arena, &ctx->sums_arena, &ctx->stats_table, &ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
                   &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
   for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
+  PinBuf* pb[] = {&ctx->f_out_host, &ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
                   &ctx->a_jobs_host, &ctx->a_out_host, &ctx->p_stage_host, &ctx->p_out_host};
   for (PinBuf* b : pb) b->release();
   for (cudaEvent_t e : ctx->t_ev) if (e) cudaEventDestroy(e);
@@ -889,6 +892,40 @@ int hso_pose_optimize(hso_ctx* ctx, double reproj_thresh, int n_iter, int n_fts_
   const int32_t offs[2] = {0, F}, hoffs[2] = {0, K}, nf[1] = {n_fts_total};
   return hso_pose_optimize_batch(ctx, reproj_thresh, n_iter, 1, nf, offs, f, p_host, host_idx, hoffs, T_host_w, grad, level, ftype, ptype,
                                  T_f_w_in, outlier_out, out);
+}
+
+// ---- N2 -------------------------------------------------------------------------------------------------------------------------
+int hso_fast_detect(hso_ctx* ctx, hso_frame_id frame, int level, int threshold, int border, hso_corner* out, int cap, int* count) {
+  if (!ctx || level < 0 || level >= ctx->geom.n_levels || cap < 0 || (cap > 0 && !out) || !count || threshold < 0 || threshold > 254)
+    return HSO_ERR_INVALID;
+  FrameSlot* f = get_frame(ctx, frame);
+  if (!f) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
+  const int w = ctx->geom.w[level], h = ctx->geom.h[level];
+  *count = 0;
+  if (w < 7 || h < 7) return HSO_OK;  // fast_corner_detect_9_sse2 returns nothing (faster_corner_9_sse.cpp:246-250)
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const size_t npx = (size_t)ctx->geom.w[0] * ctx->geom.h[0];
+  CU(ctx->f_score.reserve(npx * sizeof(int16_t)));
+  CU(ctx->f_rowbuf.reserve(npx * sizeof(uint32_t)));
+  CU(ctx->f_rowcount.reserve(sizeof(int) * ctx->geom.h[0]));
+  CU(ctx->f_total.reserve(sizeof(int)));
+  CU(ctx->f_out.reserve(sizeof(hso_corner) * (size_t)std::max(cap, 1)));
+  CU(ctx->f_out_host.reserve(sizeof(hso_corner) * (size_t)std::max(cap, 1) + 4 * sizeof(int)));
+  CU(launch_fast(f->pyr + ctx->geom.off[level], w, h, threshold, border, (int16_t*)ctx->f_score.p, (uint32_t*)ctx->f_rowbuf.p, (int*)ctx->f_rowcount.p,
+                 (hso_corner*)ctx->f_out.p, cap, (int*)ctx->f_total.p, ctx->stream, &ctx->launches));
+  int* total_h = (int*)ctx->f_out_host.p;
+  hso_corner* out_h = (hso_corner*)(total_h + 4);
+  CU(cudaMemcpyAsync(total_h, ctx->f_total.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const int n = std::min(*total_h, cap);
+  if (n > 0) {
+    CU(cudaMemcpyAsync(out_h, ctx->f_out.p, sizeof(hso_corner) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, out_h, sizeof(hso_corner) * n);
+  }
+  *count = *total_h;
+  return HSO_OK;
 }
 
 int hso_stage_time_ms(hso_ctx* ctx, int stage, double* ms, uint64_t* calls) {

@@ -134,4 +134,8 @@ struct PoseScratch {  // per problem, device memory
 cudaError_t launch_pose(const PoseJobDev* jobs_dev, const PoseScratch* scratch_dev, int B, double reproj_thresh, int n_iter, double err_mult2,
                         cudaStream_t stream, uint64_t* launches);
 
+// ---- FAST-9 detector (row N2) ---------------------------------------------------------------------------------------------
+cudaError_t launch_fast(const uint8_t* level_img, int w, int h, int threshold, int border, int16_t* score_map, uint32_t* rowbuf, int* row_count,
+                        hso_corner* out_dev, int cap, int* total_dev, cudaStream_t stream, uint64_t* launches);
+
 }  // namespace hso

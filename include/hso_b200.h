@@ -192,6 +192,18 @@ int hso_pose_optimize_batch(hso_ctx* ctx, double reproj_thresh, int n_iter, int 
                             const double* grad, const int8_t* level, const int8_t* ftype, const int8_t* ptype, const double* T_f_w_in,
                             uint8_t* outlier_out, hso_pose_result* out);
 
+/* ---- N2 (next row): corner detection — replaces the detector part of FeatureExtractor::fastDetectST(const cv::Mat& imageLevel, int Level)
+ * (src/feature_detection.cpp:498-523): fast::fast_corner_detect_9_sse2 + fast_corner_score_9 + fast_nonmax_3x3 (thirdparty/fast), the border
+ * filter (:515) and hso::shiTomasiScore (src/vikit/vision.cpp:111-151), on a level of a device-resident frame. Bit-exact corner list in
+ * raster order. The host caller keeps the cell bookkeeping and the octree distribution. ------------------------------------------------ */
+typedef struct {
+  int16_t x, y;        /* level pixel (multiply by 1 << level for KeyPoint coordinates, feature_detection.cpp:521) */
+  int32_t score;       /* fast_corner_score_9 */
+  float shi_tomasi;    /* hso::shiTomasiScore(imageLevel, x, y) */
+} hso_corner;
+/* threshold = floor(minThresh_); border = 8 in the reference. count receives the number of corners found (may exceed cap: only cap are written). */
+int hso_fast_detect(hso_ctx* ctx, hso_frame_id frame, int level, int threshold, int border, hso_corner* out, int cap, int* count);
+
 /* ---- stage timers, named like the reference's HSO_START_TIMER sites (src/frame_handler_base.cpp:57-66) ------------------- */
 /* Accumulated device time in ms of: 0 "pyramid_creation", 1 "sparse_img_align", 2 "feature_align", 3 "pose_optimizer". */
 int hso_stage_time_ms(hso_ctx* ctx, int stage, double* ms, uint64_t* calls);

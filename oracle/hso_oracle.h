@@ -156,6 +156,15 @@ void orc_pose_optimize(double reproj_thresh, int n_iter, double err_mult2 /* cam
                        const double* grad, const int8_t* level, const int8_t* ftype, const int8_t* ptype,
                        const double T_f_w_in[12], uint8_t* outlier_out /*F*/, orc_pose_result* out);
 
+/* ---- N2: FeatureExtractor::fastDetectST (src/feature_detection.cpp:498-523; thirdparty/fast) ---- */
+typedef struct {
+  int16_t x, y;       /* level pixel */
+  int32_t score;      /* fast_corner_score_9 */
+  float shi_tomasi;   /* hso::shiTomasiScore (src/vikit/vision.cpp:111-151) */
+} orc_corner;
+int orc_fast9_corners(const uint8_t* img, int w, int h, int stride, int threshold, int16_t* xy, int32_t* scores, int cap);
+int orc_fast_detect(const uint8_t* img, int w, int h, int stride, int threshold, int border, orc_corner* out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

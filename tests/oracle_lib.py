@@ -227,3 +227,57 @@ def pose_optimize(p, reproj_thresh=2.0, n_iter=12):
     return dict(T_f_w=np.array(out.T_f_w[:]).reshape(3, 4), cov=np.array(out.cov[:]).reshape(6, 6), estimated_scale=out.estimated_scale,
                 error_init=out.error_init, error_final=out.error_final, num_obs=int(out.num_obs), error_in_px=float(out.error_in_px),
                 n_trials_total=out.n_trials_total, early_return=out.early_return, outlier=outl[:F].copy())
+
+
+# ---- N2: FAST-9 (real reference library when oracle/_ref/libfast_ref.so exists, restatement always) -----------------------------------
+class orc_corner(C.Structure):
+    _fields_ = [("x", C.c_int16), ("y", C.c_int16), ("score", C.c_int32), ("shi_tomasi", C.c_float)]
+
+
+REF_FAST_LIB = os.path.join(ORACLE_DIR, "_ref", "libfast_ref.so")
+_ref_fast = None
+
+
+def ref_fast_available():
+    return os.path.exists(REF_FAST_LIB)
+
+
+def ref_fast9(img, threshold):
+    """The REAL reference: fast_corner_detect_9_sse2 + fast_corner_score_9 + fast_nonmax_3x3. Returns (xy (n,2), scores (n,), nonmax idx)."""
+    global _ref_fast
+    if _ref_fast is None:
+        _ref_fast = C.CDLL(REF_FAST_LIB)
+        _ref_fast.ref_fast9_detect.restype = C.c_int
+    img = np.ascontiguousarray(img)
+    h, w = img.shape
+    cap = w * h
+    xy = np.zeros((cap, 2), np.int16)
+    sc = np.zeros(cap, np.int32)
+    nm = np.zeros(cap, np.int32)
+    nnm = C.c_int()
+    n = _ref_fast.ref_fast9_detect(img.ctypes.data_as(C.c_void_p), w, h, w, int(threshold), xy.ctypes.data_as(C.c_void_p),
+                                   sc.ctypes.data_as(C.c_void_p), nm.ctypes.data_as(C.c_void_p), cap, C.byref(nnm))
+    return xy[:n].copy(), sc[:n].copy(), nm[:nnm.value].copy()
+
+
+def fast9_corners(img, threshold):
+    lib = load()
+    lib.orc_fast9_corners.restype = C.c_int
+    img = np.ascontiguousarray(img)
+    h, w = img.shape
+    cap = w * h
+    xy = np.zeros((cap, 2), np.int16)
+    sc = np.zeros(cap, np.int32)
+    n = lib.orc_fast9_corners(img.ctypes.data_as(C.c_void_p), w, h, w, int(threshold), xy.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), cap)
+    return xy[:n].copy(), sc[:n].copy()
+
+
+def fast_detect(img, threshold, border=8):
+    lib = load()
+    lib.orc_fast_detect.restype = C.c_int
+    img = np.ascontiguousarray(img)
+    h, w = img.shape
+    cap = w * h // 4 + 16
+    out = (orc_corner * cap)()
+    n = lib.orc_fast_detect(img.ctypes.data_as(C.c_void_p), w, h, w, int(threshold), int(border), out, cap)
+    return [(out[i].x, out[i].y, out[i].score, out[i].shi_tomasi) for i in range(n)]
