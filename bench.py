@@ -255,6 +255,24 @@ def other_rows(ctx, lib, args, dev, torch, K):
     out["pose_optimizer"] = {"gpu_frames_per_s_e2e": 64 / dt, "cpu_frames_per_s_1core": 1.0 / cpu, "features": 5000, "batch": 64,
                              "lm_trials_per_frame": trials / 4, "gpu_trials_per_frame": sum(r["n_trials_total"] for r in g) / 4,
                              "note": "hso_pose_optimize_batch incl. python marshalling vs oracle pose_optimize"}
+    # ---- N2: FAST-9 detector on levels 0..2 of one frame (what fastDetectMT does per keyframe, feature_detection.cpp:498-514) ---------
+    thr = 20
+    def fast3():
+        return sum(len(ctx.fast_detect(fid[1], l, thr)) for l in range(3))
+    n_c = fast3()
+    dt = timed(fast3, 10)
+    row = {"gpu_frames_per_s_e2e": 1.0 / dt, "gpu_ms_per_frame": dt * 1e3, "corners_after_nonmax": n_c, "levels": "0..2", "threshold": thr,
+           "algorithmic_bytes_per_frame": int(W * H * (1 + 1 / 4 + 1 / 16)), "note": "hso_fast_detect x3 incl. D2H of the corner lists (python marshalling included)"}
+    if O.ref_fast_available():
+        lv, _ = O.create_pyramid(pair["cur_img"], 5)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            for l in range(3):
+                O.ref_fast9(lv[l], thr)
+        cpu = (time.perf_counter() - t0) / 5
+        row.update({"cpu_frames_per_s_1core": 1.0 / cpu, "cpu_kind": "reference (oracle/_ref/libfast_ref.so = thirdparty/fast compiled from the reference sources; "
+                    "the reference itself runs the three levels on three threads)"})
+    out["fast_detect"] = row
     for f_ in fid:
         ctx.release(f_)
     return out

@@ -141,6 +141,7 @@ HSO_DEV uint32_t ld4(const uint8_t* img, int byte_addr) {
 // (I2F.U8 is quarter rate; the first profile showed it as the top stall reason of the term loop.)
 template <int K>
 HSO_DEV float byte_to_float(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | K)) - 8388608.0f; }
+HSO_DEV float byte_to_float_k(uint32_t w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)k)) - 8388608.0f; }
 HSO_DEV float b0(uint32_t w) { return byte_to_float<0>(w); }
 HSO_DEV float b1(uint32_t w) { return byte_to_float<1>(w); }
 HSO_DEV float b2(uint32_t w) { return byte_to_float<2>(w); }
@@ -223,6 +224,91 @@ HSO_DEV void expand_patch(Acc& a, const Moments& m, const float* A, const float*
   for (int j = 0; j < 6; ++j)
 #pragma unroll
     for (int k = j; k < 6; ++k) a.h[idx++] += A[j] * P[k] + B[j] * Q[k];
+}
+
+// ---- window evaluation -------------------------------------------------------------------------------------------------------
+// All N pattern pixels of a patch and the +-1 taps of their central-difference gradients live in one (2P+4)^2 pixel window. Instead of
+// fetching 12 taps per pattern pixel (8 LDS + 12 conversions + 20 FMA each), the window is streamed row by row ONCE per patch:
+// rows are loaded as aligned words + funnel shift, converted to float once, and the bilinearly interpolated image
+//   Ib(x,y) = wtl p(x,y) + wtr p(x+1,y) + wbl p(x,y+1) + wbr p(x+1,y+1)
+// is formed once per window position (same expression, same operand order as the reference, src/CoarseTracker.cpp:339-342); then
+//   colour = Ib(x,y),  dx = 0.5 (Ib(x+1,y) - Ib(x-1,y)),  dy = 0.5 (Ib(x,y+1) - Ib(x,y-1))      (:368-371, identical expression trees).
+// The loops are fully unrolled with a compile-time pattern, so positions no pattern pixel needs are dead code and disappear.
+template <int PIDX>
+struct PG {
+  static constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
+  static constexpr int P = (PIDX == 5) ? 3 : (PIDX == 7) ? 4 : (PIDX <= 2) ? 1 : 2;
+  static constexpr int WIN = 2 * P + 4;        // window edge in pixels, origin at (u_i - P - 1, v_i - P - 1)
+  static constexpr int NW = (WIN + 6) / 4;     // words loaded per row (any byte alignment)
+  static constexpr int NA = (WIN + 3) / 4;     // aligned words kept per row
+};
+
+template <int PIDX, bool SM>
+HSO_DEV void win_row(const uint8_t* img, int byte_addr, uint32_t* out) {
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(img) + (byte_addr >> 2);
+  const int sh = (byte_addr & 3) << 3;
+  uint32_t wv[PG<PIDX>::NW];
+#pragma unroll
+  for (int j = 0; j < PG<PIDX>::NW; ++j) wv[j] = SM ? wp[j] : __ldg(wp + j);
+#pragma unroll
+  for (int j = 0; j < PG<PIDX>::NA; ++j) out[j] = __funnelshift_r(wv[j], wv[j + 1], sh);
+}
+
+struct TermCtx { float a, huber, cutoff, max_energy; bool top; };
+
+// one residual term: Huber weight, energy, the nine moments (src/CoarseTracker.cpp:345-404 fused with computeGS :499-525)
+HSO_DEV void accumulate_term(const TermCtx& t, float c, float color, float gx, float gy, Moments& m, float& Ep, int& sat) {
+  const float r = color - (t.a * c + 0.f);
+  const float ar = fabsf(r);
+  // Huber weight hw = huber / |r| (:348) with the fast reciprocal (<= 2 ulp): hw only scales terms
+  const float hw = ar < t.huber ? 1.f : __fdividef(t.huber, ar);
+  // branch-free form of :350-361: a saturated term adds max_energy and contributes nothing to H, b
+  const bool saturated = ar > t.cutoff && !t.top;
+  const float e_in = t.top ? hw * r * r : hw * r * r * (2.f - hw);
+  Ep += saturated ? t.max_energy : e_in;
+  sat += saturated ? 1 : 0;
+  const float w = saturated ? 0.f : hw;
+  const float wgx = w * gx, wgy = w * gy, wc = w * c;
+  m.xx += wgx * gx; m.xy += wgx * gy; m.yy += wgy * gy;
+  m.cx += wc * gx;  m.cy += wc * gy;  m.cc += wc * c;
+  m.rx += wgx * r;  m.ry += wgy * r;  m.rc += wc * r;
+}
+
+// Streams the window of one patch of image `img` (bilinear weights w*, integer base pixel `base`) and calls
+// f(n, Ib, dx, dy) for every pattern pixel n. Used for the current image in forward mode and for the reference image in the
+// inverse-compositional dual-image mode.
+template <int PIDX, bool SM, class F>
+HSO_DEV void window_samples(const uint8_t* img, int base, int w, float wtl, float wtr, float wbl, float wbr, F&& f) {
+  constexpr int P = PG<PIDX>::P, WIN = PG<PIDX>::WIN, N = PG<PIDX>::N;
+  const int a0 = base - (P + 1) * w - (P + 1);
+  float pxPrev[WIN], pxCur[WIN];
+  float IbA[WIN - 1], IbB[WIN - 1], IbC[WIN - 1];  // interpolated rows cy-1, cy, cy+1
+#pragma unroll
+  for (int r = 0; r < WIN; ++r) {
+    uint32_t row[PG<PIDX>::NA];
+    win_row<PIDX, SM>(img, a0 + r * w, row);
+#pragma unroll
+    for (int c = 0; c < WIN; ++c) pxCur[c] = byte_to_float_k(row[c >> 2], c & 3);
+    if (r >= 1) {
+#pragma unroll
+      for (int c = 0; c < WIN - 1; ++c) {
+        IbA[c] = IbB[c];
+        IbB[c] = IbC[c];
+        IbC[c] = wtl * pxPrev[c] + wtr * pxPrev[c + 1] + wbl * pxCur[c] + wbr * pxCur[c + 1];
+      }
+    }
+    if (r >= 3) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        if (pat_dy<PIDX>(n) + P + 1 == r - 2) {
+          const int cx = pat_dx<PIDX>(n) + P + 1;
+          f(n, IbB[cx], 0.5f * (IbB[cx + 1] - IbB[cx - 1]), 0.5f * (IbC[cx] - IbA[cx]));
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < WIN; ++c) pxPrev[c] = pxCur[c];
+  }
 }
 
 struct LevelCtx {
@@ -312,6 +398,38 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
       const Proj p = project_patch(Rt, cam, X, Y, Z, L.scale, L.border, L.w, L.h);
       if (p.ok) {
         const int sl = slot_of<FAST>(i, k);
+        Moments m = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float Ep = 0.f;
+        int sat = 0;
+        TermCtx tc;
+        tc.a = a; tc.huber = huber; tc.cutoff = cutoff; tc.max_energy = max_energy; tc.top = L.top;
+        if (!IC) {
+          // forward mode: colour and gradients of the CURRENT image from one streamed window
+          window_samples<PIDX, FAST>(L.cur, p.base, L.w, p.wtl, p.wtr, p.wbl, p.wbr, [&](int n, float color, float gx, float gy) {
+            accumulate_term(tc, ps.cache[n * S + sl], color, gx, gy, m, Ep, sat);
+          });
+        } else if (DUAL) {
+          // inverse-compositional, dual image: intensity and gradients of the REFERENCE image from one streamed window,
+          // the current colour from its four taps
+          const RefPatch rp = ref_patch(PU, PV, L.scale, L.border, L.w, L.h);
+          window_samples<PIDX, true>(ps.ref, rp.base, L.w, rp.wtl, rp.wtr, rp.wbl, rp.wbr, [&](int n, float c, float gx, float gy) {
+            const int addr = p.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
+            const uint32_t r0 = ld4<true>(L.cur, addr);
+            const uint32_t r1 = ld4<true>(L.cur, addr + L.w);
+            const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
+            accumulate_term(tc, c, color, gx, gy, m, Ep, sat);
+          });
+        } else {
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            const int addr = p.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
+            const uint32_t r0 = ld4<FAST>(L.cur, addr);
+            const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
+            const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
+            accumulate_term(tc, ps.cache[n * S + sl], color, ps.gx[n * S + sl], ps.gy[n * S + sl], m, Ep, sat);
+          }
+        }
+        // Jacobian rows of the patch after the term loop (keeps 12 registers free while the window is live)
         float A[6], B[6];
         if (!IC) {
           patch_jacobian(p.x, p.y, p.z, L.fxl, L.fyl, A, B);
@@ -319,49 +437,6 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
           patch_jacobian(X, Y, Z, L.fxl, L.fyl, A, B);
 #pragma unroll
           for (int q = 0; q < 6; ++q) { A[q] *= a; B[q] *= a; }  // m_jacobian_cache_true = exposure_rat * raw (:244-245)
-        }
-        Moments m = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        float Ep = 0.f;
-        int sat = 0;
-        RefPatch rp;
-        if (DUAL) rp = ref_patch(PU, PV, L.scale, L.border, L.w, L.h);
-#pragma unroll
-        for (int n = 0; n < N; ++n) {
-          const int poff = pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
-          const int addr = p.base + poff;
-          float c, color, gx, gy;
-          if (DUAL) ref_intensity_grad<true>(ps.ref, rp, rp.base + poff, L.w, c, gx, gy);
-          else c = ps.cache[n * S + sl];
-          if (!IC) {
-            const uint32_t rm = ld4<FAST>(L.cur, addr - L.w - 1);
-            const uint32_t r0 = ld4<FAST>(L.cur, addr - 1);
-            const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w - 1);
-            const uint32_t r2 = ld4<FAST>(L.cur, addr + 2 * L.w - 1);
-            color = p.wtl * b1(r0) + p.wtr * b2(r0) + p.wbl * b1(r1) + p.wbr * b2(r1);
-            gx = 0.5f * ((p.wtl * b2(r0) + p.wtr * b3(r0) + p.wbl * b2(r1) + p.wbr * b3(r1)) -
-                         (p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1)));
-            gy = 0.5f * ((p.wtl * b1(r1) + p.wtr * b2(r1) + p.wbl * b1(r2) + p.wbr * b2(r2)) -
-                         (p.wtl * b1(rm) + p.wtr * b2(rm) + p.wbl * b1(r0) + p.wbr * b2(r0)));
-          } else {
-            const uint32_t r0 = ld4<FAST>(L.cur, addr);
-            const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
-            color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-            if (!DUAL) { gx = ps.gx[n * S + sl]; gy = ps.gy[n * S + sl]; }
-          }
-          const float r = color - (a * c + 0.f);
-          const float ar = fabsf(r);
-          // Huber weight hw = huber / |r| (src/CoarseTracker.cpp:348) with the fast reciprocal (<= 2 ulp): hw only scales terms
-          const float hw = ar < huber ? 1.f : __fdividef(huber, ar);
-          // branch-free form of :350-361: a saturated term adds max_energy and contributes nothing to H, b
-          const bool saturated = ar > cutoff && !L.top;
-          const float e_in = L.top ? hw * r * r : hw * r * r * (2.f - hw);
-          Ep += saturated ? max_energy : e_in;
-          sat += saturated ? 1 : 0;
-          const float w = saturated ? 0.f : hw;
-          const float wgx = w * gx, wgy = w * gy, wc = w * c;
-          m.xx += wgx * gx; m.xy += wgx * gy; m.yy += wgy * gy;
-          m.cx += wc * gx;  m.cy += wc * gy;  m.cc += wc * c;
-          m.rx += wgx * r;  m.ry += wgy * r;  m.rc += wc * r;
         }
         expand_patch(acc, m, A, B);
         acc.E += Ep;

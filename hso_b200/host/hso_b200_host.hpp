@@ -206,6 +206,19 @@ inline void optimizeLevenbergMarquardt3rd(Context& ctx, const double reproj_thre
 }
 }  // namespace pose_optimizer
 
+// Detector part of FeatureExtractor::fastDetectST (src/feature_detection.cpp:498-523) on a device-resident level. The caller keeps
+// haveFeatures_/getCellIndex bookkeeping and the octree distribution (host), exactly as after the reference's nonmax loop (:511-523).
+struct KeyPointCandidate { int x, y; float shi_tomasi; int level; int fast_score; };
+inline void fastDetectST(Context& ctx, const Frame& frame, int Level, float minThresh, std::vector<KeyPointCandidate>& out) {
+  const int border = 8, scale = 1 << Level;
+  const short fastThresh = (short)std::floor(minThresh);  // :502
+  std::vector<hso_corner> buf(8192);
+  int n = 0;
+  ctx.check(hso_fast_detect(ctx.get(), frame.id, Level, fastThresh, border, buf.data(), (int)buf.size(), &n));
+  if (n > (int)buf.size()) { buf.resize(n); ctx.check(hso_fast_detect(ctx.get(), frame.id, Level, fastThresh, border, buf.data(), n, &n)); }
+  for (int i = 0; i < n; ++i) out.push_back(KeyPointCandidate{buf[i].x * scale, buf[i].y * scale, buf[i].shi_tomasi, Level, buf[i].score});  // :520-521
+}
+
 class Matcher {  // include/hso/matcher.h:113-153 (direct part)
  public:
   struct Options { int align_max_iter = 10; } options_;
