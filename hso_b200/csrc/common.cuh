@@ -99,12 +99,15 @@ HSO_DEV Se3d se3_exp(const double* u) {
   const double theta = sqrt(ox * ox + oy * oy + oz * oz);
   const double half = 0.5 * theta;
   double imag;
-  const double real = cos(half);
+  double sh, ch;
+  sincos(half, &sh, &ch);  // one sincos: sin/cos(theta) below follow from the half angle (serial control path)
+  const double real = ch;
+  const double inv_theta = theta < 1e-10 ? 0.0 : 1.0 / theta;
   if (theta < 1e-10) {
     const double t2 = theta * theta, t4 = t2 * t2;
     imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
   } else {
-    imag = sin(half) / theta;
+    imag = sh * inv_theta;
   }
   Se3d r;
   r.q.w = real; r.q.x = imag * ox; r.q.y = imag * oy; r.q.z = imag * oz;
@@ -115,11 +118,11 @@ HSO_DEV Se3d se3_exp(const double* u) {
     quat_to_R(r.q, V);
   } else {
     const double t2 = theta * theta;
-    double sn, cs;
-    sincos(theta, &sn, &cs);
-    const double inv_t2 = 1.0 / t2;
-    const double A = (1 - cs) * inv_t2;
-    const double B = (theta - sn) * inv_t2 / theta;
+    const double sn = 2.0 * sh * ch;          // sin(theta)
+    const double one_m_cs = 2.0 * sh * sh;    // 1 - cos(theta), without cancellation
+    const double inv_t2 = inv_theta * inv_theta;
+    const double A = one_m_cs * inv_t2;
+    const double B = (theta - sn) * inv_t2 * inv_theta;
     // Omega^2 = omega omega^T - |omega|^2 I
     V[0] = 1 + B * (ox * ox - t2);      V[1] = -A * oz + B * ox * oy;   V[2] = A * oy + B * ox * oz;
     V[3] = A * oz + B * ox * oy;        V[4] = 1 + B * (oy * oy - t2);  V[5] = -A * ox + B * oy * oz;
@@ -247,7 +250,8 @@ struct CamDev {
 };
 
 HSO_DEV void world2cam(const CamDev& c, double X, double Y, double Z, double& pu, double& pv) {
-  const double u = X / Z, v = Y / Z;
+  const double zi = 1.0 / Z;  // one division; X/Z and Y/Z of src/camera.cpp:96 agree to 1 ulp (the pixel is rounded to float next)
+  const double u = X * zi, v = Y * zi;
   if (c.model == 0 && c.distortion) {
     const double r2 = u * u + v * v, r4 = r2 * r2, r6 = r4 * r2;
     const double a1 = 2 * u * v, a2 = r2 + 2 * u * u, a3 = r2 + 2 * v * v;

@@ -80,6 +80,7 @@ struct TrackCtrl {
   double E_old;
   int done, iter, n_err;
   uint32_t sel_prefix, sel_k, sel_n;
+  uint32_t wsum[32];   // per-warp histogram partial sums of the bucket search
 };
 
 struct Smem {
@@ -260,8 +261,10 @@ struct TermCtx { float a, huber, cutoff, max_energy; bool top; };
 HSO_DEV void accumulate_term(const TermCtx& t, float c, float color, float gx, float gy, Moments& m, float& Ep, int& sat) {
   const float r = color - (t.a * c + 0.f);
   const float ar = fabsf(r);
-  // Huber weight hw = huber / |r| (:348) with the fast reciprocal (<= 2 ulp): hw only scales terms
-  const float hw = ar < t.huber ? 1.f : __fdividef(t.huber, ar);
+  // Huber weight hw = huber / |r| (:348) through the approximate reciprocal (1 ulp): hw only scales terms
+  float rcp;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(ar));
+  const float hw = ar < t.huber ? 1.f : t.huber * rcp;
   // branch-free form of :350-361: a saturated term adds max_energy and contributes nothing to H, b
   const bool saturated = ar > t.cutoff && !t.top;
   const float e_in = t.top ? hw * r * r : hw * r * r * (2.f - hw);
@@ -453,14 +456,41 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
 HSO_DEV void reduce_acc(const Acc& acc, const Smem& s, int slot, int csize, int nwarps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* wp = s.warp_part + warp * NRED;
+  // Transposed butterfly: 32 fp32 quantities over 32 lanes in 16+8+4+2+1 = 31 shuffles (instead of 32 x 5): at every step a lane
+  // keeps the half of the values whose index bit matches its lane bit and sends the other half; lane l ends with the total of value l.
+  float v[32];
 #pragma unroll
-  for (int k = 0; k < 28; ++k) { float v = warp_sum(acc.h[k]); if (lane == 0) wp[k] = (double)v; }
+  for (int k = 0; k < 28; ++k) v[k] = acc.h[k];
+  v[28] = acc.E; v[29] = (float)acc.terms; v[30] = (float)acc.sat; v[31] = (float)acc.patches;  // counts < 2^24: exact in fp32
 #pragma unroll
-  for (int k = 0; k < 7; ++k) { double v = warp_sum(acc.b[k]); if (lane == 0) wp[28 + k] = v; }
-  { float v = warp_sum(acc.E); if (lane == 0) wp[35] = (double)v; }
-  { int v = warp_sum(acc.terms); if (lane == 0) wp[36] = (double)v; }
-  { int v = warp_sum(acc.sat); if (lane == 0) wp[37] = (double)v; }
-  { int v = warp_sum(acc.patches); if (lane == 0) wp[38] = (double)v; }
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const float keep = up ? v[j + o] : v[j];
+      const float send = up ? v[j] : v[j + o];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  wp[lane < 28 ? lane : lane + 7] = (double)v[0];  // 0..27 -> H, 28 -> E (35), 29..31 -> terms, saturated, patches (36..38)
+  // the 7 fp64 gradient entries: three transposed steps (4+2+1 shuffles) then two plain butterfly steps
+  double d[8];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) d[k] = acc.b[k];
+  d[7] = 0.0;
+#pragma unroll
+  for (int o = 16, n = 4; o >= 4; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      const double keep = up ? d[j + n] : d[j];
+      const double send = up ? d[j] : d[j + n];
+      d[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  d[0] += __shfl_xor_sync(0xffffffffu, d[0], 2);
+  d[0] += __shfl_xor_sync(0xffffffffu, d[0], 1);
+  if ((lane & 3) == 0 && (lane >> 2) < 7) wp[28 + (lane >> 2)] = d[0];
   __syncthreads();
   if (threadIdx.x < NRED - 1) {
     double sum = 0;
@@ -513,21 +543,29 @@ HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, const float* ab
     if (!(first && prefilled)) {
       for (int j = threadIdx.x; j < nbins; j += blockDim.x) hist[j] = 0;
       __syncthreads();
+      // the loads of up to CH patches (CH * N values) are issued back to back: one L2 round trip per chunk, not one per value
+      constexpr int CH = (N <= 13) ? 4 : 3;
       int kk = 0;
-      for (int i = t0; i < job.F; i += nt, ++kk) {
-        // all N loads of the patch are issued back to back (one L2 round trip per patch, not one per value)
-        const int slot = a_smem ? (kk * (int)blockDim.x + (int)threadIdx.x) : i;
-        float vals[N];
+      for (int i = t0; i < job.F; i += CH * nt, kk += CH) {
+        float vals[CH][N];
 #pragma unroll
-        for (int n = 0; n < N; ++n) vals[n] = a_smem ? absres[n * astride + slot] : __ldcg(absres + n * astride + slot);
+        for (int q = 0; q < CH; ++q) {
+          const int iq = i + q * nt;
+          const int slot = a_smem ? ((kk + q) * (int)blockDim.x + (int)threadIdx.x) : iq;
 #pragma unroll
-        for (int n = 0; n < N; ++n) {
-          float v = vals[n];
-          const bool valid = v >= 0.f;
-          if (mad) v = fabsf(v - center);
-          const uint32_t key = __float_as_uint(v);
-          if (valid && (key & mask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
+          for (int n = 0; n < N; ++n)
+            vals[q][n] = (iq < job.F) ? (a_smem ? absres[n * astride + slot] : __ldcg(absres + n * astride + slot)) : -1.f;
         }
+#pragma unroll
+        for (int q = 0; q < CH; ++q)
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            float v = vals[q][n];
+            const bool valid = v >= 0.f;
+            if (mad) v = fabsf(v - center);
+            const uint32_t key = __float_as_uint(v);
+            if (valid && (key & mask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
+          }
       }
     }
     if (csize == 1) {
@@ -542,39 +580,43 @@ HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, const float* ab
       }
       cluster.sync();  // peers are done reading this CTA's histogram before it is zeroed again
     }
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      const int per = nbins >> 5;
+    {
+      // bucket search by the whole CTA: each thread sums `per` consecutive bins, warp scan, warp totals through shared memory
+      const int T = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = T >> 5;
+      const int per = (nbins + T - 1) / T;
+      const int b0 = threadIdx.x * per;
       uint32_t local = 0;
-      for (int j = 0; j < per; ++j) local += s.ghist[lane * per + j];
+      for (int j = 0; j < per; ++j) local += (b0 + j < nbins) ? s.ghist[b0 + j] : 0u;
       uint32_t incl = local;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
       }
-      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      uint32_t k;
-      if (first) {
-        k = total / 2;
-        if (lane == 0) { s.ctrl->sel_n = total; }
-      } else {
-        k = s.ctrl->sel_k;
+      if (lane == 31) s.ctrl->wsum[warp] = incl;
+      __syncthreads();
+      uint32_t before = 0, total = 0;
+      for (int q = 0; q < nw; ++q) {
+        const uint32_t v = s.ctrl->wsum[q];
+        if (q < warp) before += v;
+        total += v;
       }
-      const uint32_t excl = incl - local;
-      const bool mine = total > 0 && k >= excl && k < incl;
-      if (mine) {
+      const uint32_t k = first ? total / 2 : s.ctrl->sel_k;
+      const uint32_t excl = before + incl - local;
+      __syncthreads();  // everyone has read sel_k / wsum before they are overwritten
+      if (first && threadIdx.x == 0) s.ctrl->sel_n = total;
+      if (total > 0 && k >= excl && k < excl + local) {
         uint32_t cum = excl;
-        int d = lane * per;
+        int d = b0;
         for (int j = 0; j < per; ++j) {
-          const uint32_t c = s.ghist[lane * per + j];
-          if (k < cum + c) { d = lane * per + j; break; }
+          const uint32_t c = s.ghist[b0 + j];
+          if (k < cum + c) { d = b0 + j; break; }
           cum += c;
         }
         s.ctrl->sel_k = k - cum;
         s.ctrl->sel_prefix = prefix | ((uint32_t)d << shift);
       }
-      if (total == 0 && lane == 0) { s.ctrl->sel_k = 0; s.ctrl->sel_prefix = 0; }
+      if (total == 0 && threadIdx.x == 0) { s.ctrl->sel_k = 0; s.ctrl->sel_prefix = 0; }
     }
     __syncthreads();
     prefix = s.ctrl->sel_prefix;
