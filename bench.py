@@ -4,8 +4,8 @@
 A step = one pass of the hot path over one batch of B synthetic frame pairs on one GPU: Frame construction (pyramid + gradient
 statistics) of the B current images, then CoarseTracker::run L4->L1 (n_iter = 50, natural convergence) of every current frame
 against its reference frame. `value` = LM iterations (trials) executed by the whole job per second, inputs resident in HBM.
-`e2e` = the same metric through the C-ABI with HOST buffers (hso_frame_upload_batch + hso_coarse_track_batch: H2D of the images
-and feature arrays, D2H of the results inside the timed region).
+`e2e` = the same metric through the C-ABI with HOST buffers (hso_add_frames_track_batch: H2D of the images and feature arrays,
+D2H of the results inside the timed region; the call pipelines copies against kernels chunk by chunk).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
@@ -448,18 +448,19 @@ def main():
         ref_int32 = np.asarray(ref_int, np.float32)
         fptr = C.POINTER(C.c_float)
 
+        gmean = np.zeros(B, np.float32)
+        for b in range(B):
+            jarr[b].exposure_rat = -1.0  # the device forms cur.integralImage_/ref.integralImage_ (CoarseTracker.cpp:60)
+
         def e2e_step():
             for b in range(B):
                 lib.hso_frame_release(ctx.h, cur_ids_c[b])
-            # H2D of B images + pyramid + stats read-back
-            ctx._chk(lib.hso_frame_upload_batch(ctx.h, B, img_ptrs, W, H, W, new_ids, integ.ctypes.data_as(fptr), None))
-            a = integ / ref_int32
+            # ONE public call on host buffers: H2D of B images and of the flattened feature arrays, pyramids + statistics, CoarseTracker
+            # L4->L1, D2H of the results and statistics (chunk-pipelined inside: copies of chunk c+1 overlap the kernels of chunk c)
+            ctx._chk(lib.hso_add_frames_track_batch(ctx.h, C.byref(prm), B, img_ptrs, W, H, W, jarr, new_ids, integ.ctypes.data_as(fptr),
+                                                    gmean.ctypes.data_as(fptr), res))
             for b in range(B):
                 cur_ids_c[b] = new_ids[b]
-                jarr[b].cur = new_ids[b]
-                jarr[b].exposure_rat = a[b]
-            # H2D of the feature arrays, kernels, D2H of the results
-            ctx._chk(lib.hso_coarse_track_batch(ctx.h, C.byref(prm), B, jarr, res, None, 0, None))
             return sum(res[b].n_iters for b in range(B))
         for _ in range(2):
             e2e_step()
@@ -475,7 +476,7 @@ def main():
         ms_e2e = f0.elapsed_time(f1)
         nvalid = sum(int((p["dist"] >= 0).sum()) for p in probs)
         h2d = B * W * H + sum(40 * max(32, (int((p["dist"] >= 0).sum()) + 31) // 32 * 32) for p in probs) + B * (96 + 4 + 96)
-        d2h = B * (C.sizeof(K.hso_track_result) + 8)
+        d2h = B * (C.sizeof(K.hso_track_result) + 8)  # results + {integralImage_, gradMean_}
         e2e = dict(ms=ms_e2e, steps=n_e2e_steps, iters=it_e2e, h2d=h2d, d2h=d2h)
 
     # ---- reduce over ranks: max time, summed work -----------------------------------------------------------------------------------

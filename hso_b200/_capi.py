@@ -94,6 +94,9 @@ SYMBOLS = {
     "hso_coarse_track": (C.c_int, [_vp, _P(hso_track_params), _P(hso_track_job), _P(hso_track_result), _P(hso_trace), C.c_int, _P(C.c_int)]),
     "hso_coarse_track_batch": (C.c_int, [_vp, _P(hso_track_params), C.c_int, _P(hso_track_job), _P(hso_track_result), _P(hso_trace), C.c_int,
                                          _P(C.c_int)]),
+    "hso_add_frames_track_batch": (C.c_int, [_vp, _P(hso_track_params), C.c_int, _P(_vp), C.c_int, C.c_int, C.c_int, _P(hso_track_job), _P(C.c_int32),
+                                             _P(C.c_float), _P(C.c_float), _P(hso_track_result)]),
+    "hso_set_pipeline": (C.c_int, [_vp, C.c_int, C.c_int]),
     "hso_track_stage": (C.c_int, [_vp, _P(hso_track_params), C.c_int, _P(hso_track_job), C.c_int]),
     "hso_track_restage_frames": (C.c_int, [_vp, C.c_int, _P(C.c_int32), _P(C.c_int32)]),
     "hso_track_run": (C.c_int, [_vp]),

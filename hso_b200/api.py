@@ -141,6 +141,27 @@ class Context:
             traces.append([trace[b * trace_cap + i] for i in range(tlen[b])] if trace_cap else [])
         return res, traces
 
+    def add_frames_track_batch(self, images, jobs, inverse_comp=False, max_level=4, min_level=1, n_iter=50):
+        """Frame construction + CoarseTracker::run for B independent (image, reference frame) pairs in one chunk-pipelined call
+        (FrameHandlerMono::addImage's front end). jobs as in coarse_track_batch without 'cur'; 'exposure_rat' < 0 (default) lets the
+        device form cur.integralImage_/ref.integralImage_. Returns (new frame ids, integral, grad_mean, results)."""
+        B = len(jobs)
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        H, W = imgs[0].shape
+        ptrs = (C.c_void_p * B)(*[im.ctypes.data for im in imgs])
+        prm = K.hso_track_params(int(bool(inverse_comp)), max_level, min_level, n_iter)
+        arr, keep = self._track_jobs([dict(j, cur=j.get("cur", 0), exposure_rat=j.get("exposure_rat", -1.0)) for j in jobs])
+        ids = (C.c_int32 * B)()
+        integ = np.zeros(B, np.float32)
+        gm = np.zeros(B, np.float32)
+        out = (K.hso_track_result * B)()
+        fp = C.POINTER(C.c_float)
+        self._chk(self.lib.hso_add_frames_track_batch(self.h, C.byref(prm), B, ptrs, W, H, W, arr, ids, integ.ctypes.data_as(fp),
+                                                      gm.ctypes.data_as(fp), out))
+        res = [dict(T_cur_ref=np.array(o.T_cur_ref[:]).reshape(3, 4), exposure_rat=float(o.exposure_rat), n_iters=o.n_iters, n_evals=o.n_evals,
+                    iters_per_level=list(o.iters_per_level), n_tracked=int(o.n_tracked)) for o in out]
+        return list(ids), integ, gm, res
+
     def track_stage(self, jobs, inverse_comp=False, max_level=4, min_level=1, n_iter=50):
         prm = K.hso_track_params(int(bool(inverse_comp)), max_level, min_level, n_iter)
         arr, keep = self._track_jobs(jobs)

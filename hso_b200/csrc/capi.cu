@@ -1,5 +1,6 @@
 // C-ABI of hso_b200 (include/hso_b200.h): context, device-resident frame table, staging of flattened feature arrays,
 // kernel sequencing. Host-side only; all arithmetic of the path lives in the kernels. There is no CPU fallback.
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -78,6 +79,14 @@ struct hso_ctx {
   DevBuf t_arena, t_jobs_dev, t_T0, t_a0, t_out_dev;
   PinBuf t_stage_host, t_jobs_host, t_out_host;
   std::vector<size_t> t_trace_off;  // byte offset of each job's trace in the arena
+  std::vector<size_t> t_goff;       // staging plan of the batch in flight (track_plan): byte offset of each job's geometry block
+  size_t t_geo_bytes = 0;
+  // chunk pipeline of hso_add_frames_track_batch: H2D on its own stream, one event per chunk
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
+  std::vector<cudaStream_t> pipe_streams;  // extra compute streams: chunk c runs on stream c % S so that its tail overlaps the next chunk
+  std::vector<cudaEvent_t> pipe_ev;
+  int pipe_chunk = 0, pipe_n_streams = 0;  // 0 = default
   size_t t_arena_bytes = 0;
   int t_maxF = 0;
   int t_profile = 0, t_prof_pending = 0, t_no_dual = 0;
@@ -206,15 +215,19 @@ FrameSlot* get_frame(hso_ctx* ctx, hso_frame_id id) {
   return &ctx->frames[id];
 }
 
-int run_pyramid(hso_ctx* ctx, int B, const hso_frame_id* ids, const uint8_t* const* srcs, int src_stride, int aligned) {
-  if (ctx->pyr_jobs_host.cap < sizeof(PyrJobDev) * (size_t)B) CU(cudaStreamSynchronize(ctx->stream));  // before re-allocating staging
-  CU(ctx->pyr_jobs_host.reserve(sizeof(PyrJobDev) * B));
-  CU(ctx->pyr_jobs_dev.reserve(sizeof(PyrJobDev) * B));
-  if (ctx->pyr_counters.cap < sizeof(unsigned) * (size_t)B) {
-    CU(ctx->pyr_counters.reserve(sizeof(unsigned) * B));
+// slot0: first record of the (pre-reserved) job / counter arrays this call may use — chunks of a pipelined batch keep their records
+// apart because the previous chunk's may still be in flight. The job records travel on `copy`, the kernels run on ctx->stream.
+int run_pyramid(hso_ctx* ctx, int B, const hso_frame_id* ids, const uint8_t* const* srcs, int src_stride, int aligned, int slot0 = 0,
+                cudaStream_t copy = nullptr) {
+  const size_t need = (size_t)slot0 + B;
+  if (ctx->pyr_jobs_host.cap < sizeof(PyrJobDev) * need) CU(cudaStreamSynchronize(ctx->stream));  // before re-allocating staging
+  CU(ctx->pyr_jobs_host.reserve(sizeof(PyrJobDev) * need));
+  CU(ctx->pyr_jobs_dev.reserve(sizeof(PyrJobDev) * need));
+  if (ctx->pyr_counters.cap < sizeof(unsigned) * need) {
+    CU(ctx->pyr_counters.reserve(sizeof(unsigned) * need));
     CU(cudaMemsetAsync(ctx->pyr_counters.p, 0, ctx->pyr_counters.cap, ctx->stream));
   }
-  PyrJobDev* jobs = (PyrJobDev*)ctx->pyr_jobs_host.p;
+  PyrJobDev* jobs = (PyrJobDev*)ctx->pyr_jobs_host.p + slot0;
   for (int i = 0; i < B; ++i) {
     FrameSlot* s = get_frame(ctx, ids[i]);
     jobs[i].src = srcs[i];
@@ -223,9 +236,11 @@ int run_pyramid(hso_ctx* ctx, int B, const hso_frame_id* ids, const uint8_t* con
     jobs[i].sums = s->sums;
     jobs[i].stats = s->stats;
   }
-  CU(cudaMemcpyAsync(ctx->pyr_jobs_dev.p, jobs, sizeof(PyrJobDev) * B, cudaMemcpyHostToDevice, ctx->stream));
-  CU(launch_pyramid(ctx->geom, (const PyrJobDev*)ctx->pyr_jobs_dev.p, B, src_stride, ctx->resize_tabs.data() /* host array; passed by value */,
-                    ctx->cfg.materialize_sobel, (unsigned*)ctx->pyr_counters.p, aligned, ctx->stream, &ctx->launches));
+  PyrJobDev* jobs_dev = (PyrJobDev*)ctx->pyr_jobs_dev.p + slot0;
+  CU(cudaMemcpyAsync(jobs_dev, jobs, sizeof(PyrJobDev) * B, cudaMemcpyHostToDevice, copy ? copy : ctx->stream));
+  if (copy) return HSO_OK;  // the caller launches after its event wait (launch_pyramid_slots)
+  CU(launch_pyramid(ctx->geom, jobs_dev, B, src_stride, ctx->resize_tabs.data() /* host array; passed by value */,
+                    ctx->cfg.materialize_sobel, (unsigned*)ctx->pyr_counters.p + slot0, aligned, ctx->stream, &ctx->launches));
   return HSO_OK;
 }
 
@@ -345,6 +360,10 @@ void hso_destroy(hso_ctx* ctx) {
   for (cudaEvent_t e : ctx->t_ev) if (e) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
+  for (cudaStream_t st : ctx->pipe_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -485,6 +504,11 @@ int hso_track_set_cluster(hso_ctx* ctx, int ctas, int threads) {
   return HSO_OK;
 }
 
+int hso_set_pipeline(hso_ctx* ctx, int chunk, int streams) {
+  if (!ctx || chunk < 0 || streams < 0 || streams > 8) return HSO_ERR_INVALID;
+  ctx->pipe_chunk = chunk; ctx->pipe_n_streams = streams;
+  return HSO_OK;
+}
 int hso_track_set_ic_dual(hso_ctx* ctx, int enable) {
   if (!ctx) return HSO_ERR_INVALID;
   ctx->t_no_dual = enable ? 0 : 1;
@@ -500,7 +524,10 @@ int hso_track_set_level_shape(hso_ctx* ctx, int level, int ctas, int threads) {
   return HSO_OK;
 }
 
-int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_track_job* jobs, int trace_cap) {
+// Staging plan of a batch: validation, compaction counts, arena layout, device job records (host copy). No copies are issued.
+// Staging plan of a batch: validation, arena layout (by the upper bound n_features — the count of features with depth is only known
+// after flattening), device job records (host copy). No copies are issued.
+static int track_plan(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_track_job* jobs, int trace_cap) {
   if (!ctx || !prm || B <= 0 || !jobs) return HSO_ERR_INVALID;
   if (prm->max_level >= ctx->geom.n_levels || prm->min_level < 0 || prm->min_level > prm->max_level || prm->max_level - prm->min_level > 5 ||
       prm->n_iter < 0)
@@ -510,30 +537,26 @@ int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_
   ctx->tprm = *prm;
   ctx->tB = B;
   ctx->t_trace_cap = trace_cap > 0 ? trace_cap : 0;
-  // compact features with a valid depth (dist >= 0): the reference skips the others in every stage
-  // (src/CoarseTracker.cpp:290,433,455,557), so dropping them only changes the summation order.
-  std::vector<int> nvalid(B);
   size_t host_bytes = 0, arena = 0;
   int maxF = 0;
+  ctx->t_goff.assign(B, 0);
   for (int b = 0; b < B; ++b) {
     const hso_track_job& j = jobs[b];
     if (j.n_features < 0 || j.n_features > ctx->cfg.max_features) return fail(ctx, HSO_ERR_CAPACITY, "n_features exceeds hso_cfg.max_features");
     if (!get_frame(ctx, j.ref) || !get_frame(ctx, j.cur)) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id in track job");
     if (j.n_features > 0 && (!j.px || !j.f || !j.dist)) return fail(ctx, HSO_ERR_INVALID, "null feature arrays");
-    int n = 0;
-    for (int i = 0; i < j.n_features; ++i) n += (j.dist[i] >= 0) ? 1 : 0;
-    nvalid[b] = n;
-    maxF = std::max(maxF, n);
-    const int Fpad = std::max(32, (n + 31) / 32 * 32);
+    maxF = std::max(maxF, j.n_features);
+    const int Fpad = std::max(32, (j.n_features + 31) / 32 * 32);
+    ctx->t_goff[b] = host_bytes;
     host_bytes += sizeof(double) * 5 * Fpad;
     arena += sizeof(double) * 5 * Fpad;
   }
   ctx->t_maxF = maxF;
-  const size_t geo_bytes = arena;
+  ctx->t_geo_bytes = arena;
   // per-job scratch behind the geometry block
   std::vector<size_t> off_cache(B), off_gx(B), off_gy(B), off_abs(B), off_vis(B), off_state(B), off_trace(B);
   for (int b = 0; b < B; ++b) {
-    const int Fpad = std::max(32, (nvalid[b] + 31) / 32 * 32);
+    const int Fpad = std::max(32, (jobs[b].n_features + 31) / 32 * 32);
     auto take = [&](size_t bytes) { size_t o = (arena + 127) / 128 * 128; arena = o + bytes; return o; };
     off_cache[b] = take(sizeof(float) * kMaxPatternN * Fpad);
     if (prm->inverse_comp) { off_gx[b] = take(sizeof(float) * kMaxPatternN * Fpad); off_gy[b] = take(sizeof(float) * kMaxPatternN * Fpad); }
@@ -552,36 +575,21 @@ int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_
   CU(ctx->t_a0.reserve(sizeof(float) * B));
   CU(ctx->t_out_dev.reserve(sizeof(hso_track_result) * B));
   CU(ctx->t_out_host.reserve(sizeof(hso_track_result) * B));
-  char* hbase = (char*)ctx->t_stage_host.p;
   char* dbase = (char*)ctx->t_arena.p;
   TrackJobDev* hj = (TrackJobDev*)ctx->t_jobs_host.p;
-  std::vector<size_t> goff(B);
-  {
-    size_t go = 0;
-    for (int b = 0; b < B; ++b) { goff[b] = go; go += sizeof(double) * 5 * std::max(32, (nvalid[b] + 31) / 32 * 32); }
-  }
-  auto stage_job = [&](int b) {
+  for (int b = 0; b < B; ++b) {
     const hso_track_job& j = jobs[b];
-    const size_t go = goff[b];
-    const int Fpad = std::max(32, (nvalid[b] + 31) / 32 * 32);
-    double* px = (double*)(hbase + go);
-    double* xyz = px + 2 * Fpad;
-    int k = 0;
-    for (int i = 0; i < j.n_features; ++i) {
-      const double d = j.dist[i];
-      if (!(d >= 0)) continue;
-      px[k] = j.px[2 * i]; px[Fpad + k] = j.px[2 * i + 1];
-      // Vector3d xyz_ref((*it_ft)->f*dist)  (src/CoarseTracker.cpp:292)
-      xyz[k] = j.f[3 * i] * d; xyz[Fpad + k] = j.f[3 * i + 1] * d; xyz[2 * Fpad + k] = j.f[3 * i + 2] * d;
-      ++k;
-    }
-    for (; k < Fpad; ++k) { px[k] = px[Fpad + k] = 0; xyz[k] = xyz[Fpad + k] = 0; xyz[2 * Fpad + k] = 1; }
+    const int Fpad = std::max(32, (j.n_features + 31) / 32 * 32);
     TrackJobDev& d = hj[b];
-    d.ref_pyr = get_frame(ctx, j.ref)->pyr;
-    d.cur_pyr = get_frame(ctx, j.cur)->pyr;
-    d.F = nvalid[b];
+    FrameSlot* fr = get_frame(ctx, j.ref);
+    FrameSlot* fc = get_frame(ctx, j.cur);
+    d.ref_pyr = fr->pyr;
+    d.cur_pyr = fc->pyr;
+    d.ref_stats = fr->stats;
+    d.cur_stats = fc->stats;
+    d.F = 0;  // set by track_stage_one
     d.Fpad = Fpad;
-    d.px = (const double*)(dbase + go);
+    d.px = (const double*)(dbase + ctx->t_goff[b]);
     d.xyz = d.px + 2 * Fpad;
     d.ref_cache = (float*)(dbase + off_cache[b]);
     d.ref_gx = prm->inverse_comp ? (float*)(dbase + off_gx[b]) : nullptr;
@@ -590,27 +598,90 @@ int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_
     d.vis = (uint8_t*)(dbase + off_vis[b]);
     d.state = (TrackState*)(dbase + off_state[b]);
     d.trace = ctx->t_trace_cap ? (hso_trace*)(dbase + off_trace[b]) : nullptr;
-  };
-  // flattening Feature lists to SoA is host work of the boundary: spread a large batch over a few threads
-  const int n_thr = (B >= 16) ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
-  if (n_thr <= 1) {
-    for (int b = 0; b < B; ++b) stage_job(b);
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < n_thr; ++t) pool.emplace_back([&, t]() { for (int b = t; b < B; b += n_thr) stage_job(b); });
-    for (auto& th : pool) th.join();
   }
-  double* T0 = (double*)(hbase + host_bytes);
-  float* a0 = (float*)(T0 + 12 * B);
-  for (int b = 0; b < B; ++b) {
-    memcpy(T0 + 12 * b, jobs[b].T_cur_ref, sizeof(double) * 12);
-    a0[b] = jobs[b].exposure_rat;
-  }
-  CU(cudaMemcpyAsync(dbase, hbase, geo_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->t_T0.p, T0, sizeof(double) * 12 * B, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->t_a0.p, a0, sizeof(float) * B, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->t_jobs_dev.p, hj, sizeof(TrackJobDev) * B, cudaMemcpyHostToDevice, ctx->stream));
   return HSO_OK;
+}
+
+// Flatten the Feature list of job b to SoA in the pinned staging blob, keeping only features with a valid depth (dist >= 0): the
+// reference skips the others in every stage (src/CoarseTracker.cpp:290,433,455,557), so dropping them only changes the summation
+// order. Thread-safe across different b.
+static void track_stage_one(hso_ctx* ctx, const hso_track_job* jobs, int b) {
+  const int B = ctx->tB;
+  char* hbase = (char*)ctx->t_stage_host.p;
+  TrackJobDev* hj = (TrackJobDev*)ctx->t_jobs_host.p;
+  const hso_track_job& j = jobs[b];
+  const int Fpad = hj[b].Fpad;
+  double* px = (double*)(hbase + ctx->t_goff[b]);
+  double* xyz = px + 2 * Fpad;
+  int k = 0;
+  for (int i = 0; i < j.n_features; ++i) {
+    const double d = j.dist[i];
+    if (!(d >= 0)) continue;
+    px[k] = j.px[2 * i]; px[Fpad + k] = j.px[2 * i + 1];
+    // Vector3d xyz_ref((*it_ft)->f*dist)  (src/CoarseTracker.cpp:292)
+    xyz[k] = j.f[3 * i] * d; xyz[Fpad + k] = j.f[3 * i + 1] * d; xyz[2 * Fpad + k] = j.f[3 * i + 2] * d;
+    ++k;
+  }
+  hj[b].F = k;
+  for (; k < Fpad; ++k) { px[k] = px[Fpad + k] = 0; xyz[k] = xyz[Fpad + k] = 0; xyz[2 * Fpad + k] = 1; }
+  double* T0 = (double*)(hbase + ctx->t_geo_bytes);
+  float* a0 = (float*)(T0 + 12 * B);
+  memcpy(T0 + 12 * b, j.T_cur_ref, sizeof(double) * 12);
+  a0[b] = j.exposure_rat;
+}
+
+// H2D of the staged records of jobs [b0, b1) on `stream`.
+static int track_copy_range(hso_ctx* ctx, int b0, int b1, cudaStream_t stream) {
+  const int B = ctx->tB, n = b1 - b0;
+  char* hbase = (char*)ctx->t_stage_host.p;
+  char* dbase = (char*)ctx->t_arena.p;
+  double* T0 = (double*)(hbase + ctx->t_geo_bytes);
+  float* a0 = (float*)(T0 + 12 * B);
+  const size_t g0 = ctx->t_goff[b0], g1 = (b1 < B) ? ctx->t_goff[b1] : ctx->t_geo_bytes;
+  const TrackJobDev* hj = (const TrackJobDev*)ctx->t_jobs_host.p;
+  CU(cudaMemcpyAsync(dbase + g0, hbase + g0, g1 - g0, cudaMemcpyHostToDevice, stream));
+  CU(cudaMemcpyAsync((double*)ctx->t_T0.p + 12 * b0, T0 + 12 * b0, sizeof(double) * 12 * n, cudaMemcpyHostToDevice, stream));
+  CU(cudaMemcpyAsync((float*)ctx->t_a0.p + b0, a0 + b0, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+  CU(cudaMemcpyAsync((TrackJobDev*)ctx->t_jobs_dev.p + b0, hj + b0, sizeof(TrackJobDev) * n, cudaMemcpyHostToDevice, stream));
+  return HSO_OK;
+}
+
+// Host workers that flatten the jobs of a batch in order; wait_chunk(c) returns once every job of chunk c is staged. Flattening the
+// reference's Feature lists to SoA is host work of the boundary; it runs ahead of the copies and launches the caller enqueues.
+struct StageWorkers {
+  hso_ctx* ctx; const hso_track_job* jobs; int B, chunk;
+  std::atomic<int> next{0};
+  std::vector<std::atomic<int>> done;
+  std::vector<std::thread> pool;
+  StageWorkers(hso_ctx* c, const hso_track_job* j, int B_, int chunk_) : ctx(c), jobs(j), B(B_), chunk(chunk_), done((B_ + chunk_ - 1) / chunk_) {
+    for (auto& d : done) d.store(0);
+    const int n_thr = (B >= 16) ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 0;
+    for (int t = 0; t < n_thr; ++t) pool.emplace_back([this]() { work(); });
+  }
+  void work() {
+    for (;;) {
+      const int b = next.fetch_add(1, std::memory_order_relaxed);
+      if (b >= B) return;
+      track_stage_one(ctx, jobs, b);
+      done[b / chunk].fetch_add(1, std::memory_order_release);
+    }
+  }
+  void wait_chunk(int c) {
+    const int want = std::min(B, (c + 1) * chunk) - c * chunk;
+    if (pool.empty()) work();  // small batch: stage inline
+    while (done[c].load(std::memory_order_acquire) < want) std::this_thread::yield();
+  }
+  ~StageWorkers() { for (auto& th : pool) th.join(); }
+};
+
+int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_track_job* jobs, int trace_cap) {
+  int rc = track_plan(ctx, prm, B, jobs, trace_cap);
+  if (rc != HSO_OK) return rc;
+  {
+    StageWorkers w(ctx, jobs, B, B);
+    w.wait_chunk(0);
+  }
+  return track_copy_range(ctx, 0, B, ctx->stream);
 }
 
 int hso_track_restage_frames(hso_ctx* ctx, int B, const hso_frame_id* ref, const hso_frame_id* cur) {
@@ -663,19 +734,21 @@ int hso_track_level_profile(hso_ctx* ctx, int level, double* ms_total, uint64_t*
   return HSO_OK;
 }
 
-int hso_track_run(hso_ctx* ctx) {
-  if (!ctx || ctx->tB <= 0) return HSO_ERR_INVALID;
-  const int B = ctx->tB;
+// init + one launch per level + finish for jobs [b0, b0 + B) of the staged batch (B = problems in these launches: decides the launch shape)
+// shape_B: problems that share the GPU at the same time (the whole batch of a pipelined call), stream: where to launch
+static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_B = 0, cudaStream_t stream = nullptr) {
   const hso_track_params& prm = ctx->tprm;
-  const TrackJobDev* jd = (const TrackJobDev*)ctx->t_jobs_dev.p;
-  if (ctx->t_profile) {
+  if (!stream) stream = ctx->stream;
+  if (shape_B <= 0) shape_B = B;
+  const TrackJobDev* jd = (const TrackJobDev*)ctx->t_jobs_dev.p + b0;
+  if (profile) {
     int rc = track_profile_flush(ctx);
     if (rc != HSO_OK) return rc;
   }
-  CU(launch_track_init(jd, (const double*)ctx->t_T0.p, (const float*)ctx->t_a0.p, B, ctx->stream, &ctx->launches));
+  CU(launch_track_init(jd, (const double*)ctx->t_T0.p + 12 * b0, (const float*)ctx->t_a0.p + b0, B, stream, &ctx->launches));
   int slot = 0;
   for (int level = prm.max_level; level >= prm.min_level; --level) {
-    if (ctx->t_profile) CU(cudaEventRecord(ctx->t_ev[slot++], ctx->stream));
+    if (profile) CU(cudaEventRecord(ctx->t_ev[slot++], stream));
     TrackLevelParams p;
     memset(&p, 0, sizeof p);
     p.ic = prm.inverse_comp; p.max_level = prm.max_level; p.level = level; p.n_iter = prm.n_iter;
@@ -692,7 +765,7 @@ int hso_track_run(hso_ctx* ctx) {
     const int f_threads = ctx->t_shape[level][1] ? ctx->t_shape[level][1] : ctx->t_threads;
     int c_min = f_cluster;
     if (c_min == 0) {
-      c_min = B >= 148 ? 1 : (B >= 74 ? 2 : (B >= 37 ? 4 : 8));
+      c_min = shape_B >= 148 ? 1 : (shape_B >= 74 ? 2 : (shape_B >= 37 ? 4 : 8));
       // ... but never more CTAs than it takes to give every thread one patch (a cluster only adds barriers beyond that)
       int c_work = 1;
       while (c_work < 8 && c_work * 512 < maxF) c_work *= 2;
@@ -727,14 +800,19 @@ int hso_track_run(hso_ctx* ctx) {
       p.absres_smem = 1;
       if (track_level_smem_bytes(p, threads) > 227 * 1024) p.absres_smem = 0;
     }
-    CU(launch_track_level(p, jd, B, cluster, threads, ctx->stream, &ctx->launches));
+    CU(launch_track_level(p, jd, B, cluster, threads, stream, &ctx->launches));
   }
-  if (ctx->t_profile) {
-    CU(cudaEventRecord(ctx->t_ev[slot], ctx->stream));
+  if (profile) {
+    CU(cudaEventRecord(ctx->t_ev[slot], stream));
     ctx->t_prof_pending = 1;
   }
-  CU(launch_track_finish(jd, (hso_track_result*)ctx->t_out_dev.p, B, ctx->stream, &ctx->launches));
+  CU(launch_track_finish(jd, (hso_track_result*)ctx->t_out_dev.p + b0, B, stream, &ctx->launches));
   return HSO_OK;
+}
+
+int hso_track_run(hso_ctx* ctx) {
+  if (!ctx || ctx->tB <= 0) return HSO_ERR_INVALID;
+  return track_run_range(ctx, 0, ctx->tB, ctx->t_profile != 0);
 }
 
 int hso_track_collect(hso_ctx* ctx, hso_track_result* out, hso_trace* trace, int* trace_len) {
@@ -776,6 +854,103 @@ int hso_coarse_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B, con
 int hso_coarse_track(hso_ctx* ctx, const hso_track_params* prm, const hso_track_job* job, hso_track_result* out, hso_trace* trace, int trace_cap,
                      int* trace_len) {
   return hso_coarse_track_batch(ctx, prm, 1, job, out, trace, trace_cap, trace_len);
+}
+
+// ---- F1 + F2, chunk-pipelined ------------------------------------------------------------------------------------------------
+// The front end of FrameHandlerMono::addImage for B independent streams: new Frame(cam, img) (src/frame_handler_mono.cpp:92) then
+// CoarseTracker::run(ref, new_frame) (:190-204). The batch is cut into chunks; while chunk c's pyramid and tracker kernels run on
+// the context stream, chunk c+1's images and feature arrays are flattened on the host and copied on a second stream.
+int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B, const uint8_t* const* imgs, int W, int H, int stride,
+                               const hso_track_job* jobs_in, hso_frame_id* new_ids, float* integral, float* grad_mean, hso_track_result* out) {
+  if (!ctx || !prm || B <= 0 || !imgs || !jobs_in || !new_ids || !out) return HSO_ERR_INVALID;
+  if (W != ctx->cam.width || H != ctx->cam.height || stride < W) return fail(ctx, HSO_ERR_INVALID, "image size does not match the camera model");
+  CU(cudaSetDevice(ctx->device));
+  for (int i = 0; i < B; ++i)
+    if (!imgs[i]) return fail(ctx, HSO_ERR_INVALID, "null image");
+  for (int i = 0; i < B; ++i) {
+    int rc = alloc_frame(ctx, &new_ids[i]);
+    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) ctx->frames[new_ids[j]].used = false; return rc; }
+  }
+  auto release_all = [&]() { for (int i = 0; i < B; ++i) ctx->frames[new_ids[i]].used = false; };
+  std::vector<hso_track_job> jobs(jobs_in, jobs_in + B);
+  for (int b = 0; b < B; ++b) jobs[b].cur = new_ids[b];
+  int rc = track_plan(ctx, prm, B, jobs.data(), 0);  // synchronises ctx->stream: nothing of a previous call is in flight below
+  if (rc != HSO_OK) { release_all(); return rc; }
+  if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  // chunk = one wave of single-CTA problems (148 SMs); few enough chunks that the per-chunk launch overhead stays small
+  const int unit = ctx->pipe_chunk > 0 ? ctx->pipe_chunk : 111;  // 3/4 of a wave of single-CTA problems: measured best with 3 streams
+  int chunk = B <= unit ? B : unit;
+  while ((B + chunk - 1) / chunk > 32) chunk += unit;
+  const int n_chunks = (B + chunk - 1) / chunk;
+  const int S = std::max(1, std::min(n_chunks, ctx->pipe_n_streams > 0 ? ctx->pipe_n_streams : 3));
+  while ((int)ctx->pipe_streams.size() < S - 1) {
+    cudaStream_t st; cudaEvent_t e;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_streams.push_back(st);
+    ctx->pipe_ev.push_back(e);
+  }
+  while ((int)ctx->chunk_ev.size() < n_chunks) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunk_ev.push_back(e);
+  }
+  // every record array is reserved for the whole batch up front: chunks must not re-allocate what an earlier chunk still uses
+  CU(ctx->pyr_jobs_host.reserve(sizeof(PyrJobDev) * B));
+  CU(ctx->pyr_jobs_dev.reserve(sizeof(PyrJobDev) * B));
+  if (ctx->pyr_counters.cap < sizeof(unsigned) * (size_t)B) {
+    CU(ctx->pyr_counters.reserve(sizeof(unsigned) * B));
+    CU(cudaMemsetAsync(ctx->pyr_counters.p, 0, ctx->pyr_counters.cap, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  StageTimer tm(ctx, 1);
+  std::vector<const uint8_t*> srcs(B);
+  StageWorkers workers(ctx, jobs.data(), B, chunk);
+  for (int c = 0; c < n_chunks; ++c) {
+    const int b0 = c * chunk, b1 = std::min(B, b0 + chunk), n = b1 - b0;
+    // images straight into the level-0 slots (one 2-D copy for equally spaced images going to consecutive slots)
+    bool one_copy = n > 1 && stride == W;
+    const ptrdiff_t spacing = n > 1 ? imgs[b0 + 1] - imgs[b0] : 0;
+    for (int i = b0 + 1; i < b1 && one_copy; ++i) one_copy = (imgs[i] - imgs[i - 1] == spacing) && (new_ids[i] == new_ids[i - 1] + 1);
+    one_copy = one_copy && spacing >= (ptrdiff_t)W * H;
+    if (one_copy)
+      CU(cudaMemcpy2DAsync(get_frame(ctx, new_ids[b0])->pyr + ctx->geom.off[0], ctx->pyr_slot_bytes, imgs[b0], (size_t)spacing, (size_t)W * H, n,
+                           cudaMemcpyHostToDevice, ctx->copy_stream));
+    for (int i = b0; i < b1; ++i) {
+      FrameSlot* s = get_frame(ctx, new_ids[i]);
+      if (!one_copy) CU(cudaMemcpy2DAsync(s->pyr + ctx->geom.off[0], W, imgs[i], stride, W, H, cudaMemcpyHostToDevice, ctx->copy_stream));
+      srcs[i] = s->pyr + ctx->geom.off[0];
+    }
+    rc = run_pyramid(ctx, n, new_ids + b0, srcs.data() + b0, W, 1, b0, ctx->copy_stream);
+    if (rc != HSO_OK) break;
+    workers.wait_chunk(c);
+    rc = track_copy_range(ctx, b0, b1, ctx->copy_stream);
+    if (rc != HSO_OK) break;
+    CU(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+    cudaStream_t cs = (c % S == 0) ? ctx->stream : ctx->pipe_streams[c % S - 1];
+    CU(cudaStreamWaitEvent(cs, ctx->chunk_ev[c], 0));
+    CU(launch_pyramid(ctx->geom, (const PyrJobDev*)ctx->pyr_jobs_dev.p + b0, n, W, ctx->resize_tabs.data(), ctx->cfg.materialize_sobel,
+                      (unsigned*)ctx->pyr_counters.p + b0, 1, cs, &ctx->launches));
+    rc = track_run_range(ctx, b0, n, false, B, cs);
+    if (rc != HSO_OK) break;
+  }
+  for (int k = 0; k < S - 1; ++k) {  // join the extra compute streams into the context stream
+    cudaEventRecord(ctx->pipe_ev[k], ctx->pipe_streams[k]);
+    cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[k], 0);
+  }
+  if (rc != HSO_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); release_all(); return rc; }
+  rc = hso_track_collect(ctx, out, nullptr, nullptr);
+  if (rc != HSO_OK) return rc;
+  rc = read_stats(ctx, B, new_ids, integral, grad_mean);
+  if (rc != HSO_OK) return rc;
+  tm.stop_after_sync();
+  for (int b = 0; b < B; ++b)
+    if (jobs[b].n_features == 0) {  // CoarseTracker::run returns 0 and leaves the pose untouched when the reference has no features (:53)
+      memcpy(out[b].T_cur_ref, jobs[b].T_cur_ref, sizeof(double) * 12);
+      if (jobs[b].exposure_rat >= 0) out[b].exposure_rat = jobs[b].exposure_rat;
+      out[b].n_tracked = 0;
+    }
+  return HSO_OK;
 }
 
 // ---- F3-inner ---------------------------------------------------------------------------------------------------------------

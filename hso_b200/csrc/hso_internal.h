@@ -77,6 +77,8 @@ struct TrackJobDev {
   uint8_t* vis;          // [Fpad]
   TrackState* state;
   hso_trace* trace;      // [trace_cap] or nullptr
+  const float* ref_stats;  // device {integralImage_, gradMean_} of the two frames: the initial exposure ratio is formed on the device
+  const float* cur_stats;  // when the caller passes exposure_rat < 0 (a = cur.integralImage_/ref.integralImage_, src/CoarseTracker.cpp:60)
 };
 
 struct TrackLevelParams {

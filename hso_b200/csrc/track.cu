@@ -942,7 +942,8 @@ __global__ void k_track_init(const TrackJobDev* __restrict__ jobs, const double*
   if (p >= B) return;
   TrackState* st = jobs[p].state;
   st->T = se3_from_rt(T0 + 12 * p);
-  st->a = a0[p];
+  // float a = cur.integralImage_/ref.integralImage_ (src/CoarseTracker.cpp:60) when the caller left it to the device
+  st->a = a0[p] < 0.f ? jobs[p].cur_stats[0] / jobs[p].ref_stats[0] : a0[p];
   st->n_iters = 0; st->n_evals = 0;
   for (int k = 0; k < 8; ++k) { st->iters_per_level[k] = 0; st->patch_evals[k] = 0; }
   st->last_total_terms = 0; st->last_N = 1; st->trace_len = 0;

@@ -98,7 +98,7 @@ typedef struct {
   const double* f;       /* 3F: Feature::f (unit bearing) */
   const double* dist;    /* F : makeDepthRef output, <0 = no point / behind camera (CoarseTracker.cpp:210-240) */
   double T_cur_ref[12];  /* in: cur.T_f_w * ref.T_f_w^-1 (CoarseTracker.cpp:63) */
-  float exposure_rat;    /* in: cur.integralImage_/ref.integralImage_ (CoarseTracker.cpp:60) */
+  float exposure_rat;    /* in: cur.integralImage_/ref.integralImage_ (CoarseTracker.cpp:60); < 0: formed on the device from the two frames' statistics */
   float reserved2;
 } hso_track_job;
 
@@ -153,6 +153,17 @@ int hso_track_set_level_shape(hso_ctx* ctx, int level, int ctas_per_problem, int
 /* Inverse-compositional mode: 1 (default) keeps both pyramid levels in shared memory and recomputes the reference samples per evaluation
  * whenever two copies of the level fit; 0 forces the cached-reference-patch path. Results are identical. */
 int hso_track_set_ic_dual(hso_ctx* ctx, int enable);
+
+/* F1 + F2 in one call for B independent streams — the front end of FrameHandlerMono::addImage (src/frame_handler_mono.cpp:92 new Frame(cam, img),
+ * :190-204 CoarseTracker::run(last_frame, new_frame)). imgs[b] becomes a new device frame (id in new_ids[b], statistics in integral / grad_mean,
+ * either may be NULL); jobs[b].cur is ignored and replaced by that frame; jobs[b].exposure_rat < 0 lets the device form
+ * cur.integralImage_/ref.integralImage_ like CoarseTracker.cpp:60. Internally the batch is chunk-pipelined: the H2D copies and the host-side
+ * flattening of chunk c+1 overlap the pyramid and tracker kernels of chunk c. Results are identical to hso_frame_upload_batch followed by
+ * hso_coarse_track_batch on the same chunking. */
+int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B, const uint8_t* const* imgs, int W, int H, int stride,
+                               const hso_track_job* jobs, hso_frame_id* new_ids, float* integral, float* grad_mean, hso_track_result* out);
+/* Tuning knob of the call above: problems per chunk and number of compute streams the chunks rotate over (0 = default: 111, 3). */
+int hso_set_pipeline(hso_ctx* ctx, int chunk, int streams);
 
 /* ---- F3-inner: direct patch matching — replaces the body of bool hso::Matcher::findMatchDirect(const Point&, Frame&,
  * Vector2d&) after the host-side getCloseViewObs/getWarpMatrixAffine (include/hso/matcher.h:153 ; src/matcher.cpp:310-375),

@@ -167,3 +167,45 @@ def test_edge_cases(oracle):
     res, tr = ctx.coarse_track_batch([job], min_level=0, n_iter=15, trace_cap=256)
     _check_trace(oracle, tp, tr[0], False, 4)
     ctx.close()
+
+
+@pytest.mark.parametrize("B,ic", [(5, False), (5, True), (300, False)])
+def test_pipelined_add_frames_equals_two_calls(oracle, B, ic):
+    """hso_add_frames_track_batch (chunk-pipelined Frame construction + CoarseTracker::run, device-side exposure ratio) against
+    hso_frame_upload_batch + hso_coarse_track_batch: same kernels on the same data. B = 300 spans three chunks (148 + 148 + 4),
+    so chunk boundaries, the per-chunk launch shapes and the cross-stream ordering are exercised."""
+    pairs = [synth.make_pair(100 + s, "icl", F=300 + 40 * (s % 3)) for s in range(min(B, 6))]
+    c = pairs[0]["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]), max_frames=2 * B + 8 + 6)
+    ref_ids, ref_int, _ = ctx.upload_frames([p["ref_img"] for p in pairs])
+    rng = np.random.default_rng(7)
+    T0s = [synth.se3_exp(np.concatenate([rng.normal(0, 0.003, 3), rng.normal(0, 0.001, 3)]))[:3] for _ in range(B)]
+    sel = [b % len(pairs) for b in range(B)]
+    # two-call path
+    cur_ids, cur_int, cur_gm = ctx.upload_frames([pairs[s]["cur_img"] for s in sel])
+    jobs = []
+    for b, s in enumerate(sel):
+        p = pairs[s]
+        a0 = float(np.float32(cur_int[b]) / np.float32(ref_int[s]))
+        jobs.append(dict(ref=ref_ids[s], cur=cur_ids[b], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=T0s[b], exposure_rat=a0))
+    res_a, _ = ctx.coarse_track_batch(jobs, inverse_comp=ic)
+    for fid in cur_ids:
+        ctx.release(fid)
+    # pipelined path
+    ids, integ, gm, res_b = ctx.add_frames_track_batch([pairs[s]["cur_img"] for s in sel],
+                                                       [dict(ref=j["ref"], px=j["px"], f=j["f"], dist=j["dist"], T_cur_ref=j["T_cur_ref"]) for j in jobs],
+                                                       inverse_comp=ic)
+    assert len(set(ids)) == B
+    assert np.array_equal(integ, np.asarray(cur_int, np.float32)) and np.array_equal(gm, np.asarray(cur_gm, np.float32))
+    rl, _ = oracle.create_pyramid(pairs[sel[B - 1]]["cur_img"], 5)
+    for l in range(5):
+        assert np.array_equal(ctx.download_level(ids[B - 1], l), rl[l])
+    same_shape = B <= 148  # identical launch shapes => identical summation order => identical bits
+    for b in range(B):
+        ra, rb = res_a[b], res_b[b]
+        if same_shape:
+            assert np.array_equal(ra["T_cur_ref"], rb["T_cur_ref"]) and ra["exposure_rat"] == rb["exposure_rat"] and ra["n_iters"] == rb["n_iters"]
+        else:
+            assert np.abs(ra["T_cur_ref"] - rb["T_cur_ref"]).max() < 2e-4 and abs(ra["exposure_rat"] - rb["exposure_rat"]) < 1e-4
+        assert ra["n_tracked"] == rb["n_tracked"] or not same_shape
+    ctx.close()
