@@ -60,6 +60,27 @@ class hso_align_result(C.Structure):
     _fields_ = [("ok", C.c_int32), ("align_converged", C.c_int32), ("px_cur", C.c_double * 2), ("h_inv", C.c_double)]
 
 
+class hso_reproj_cand(C.Structure):
+    _fields_ = [("p_host", C.c_double * 3), ("px_ref", C.c_double * 2), ("f_ref", C.c_double * 3), ("grad", C.c_double * 2),
+                ("depth_ref", C.c_double), ("host_pose", C.c_int32), ("ref_pose", C.c_int32), ("ref_frame", C.c_int32),
+                ("ref_level", C.c_int32), ("ftr_type", C.c_int32), ("pt_type", C.c_int32), ("pt_ftr_type", C.c_int32),
+                ("scale_patch", C.c_int32), ("exposure_rat", C.c_float), ("pad_", C.c_float)]
+
+
+class hso_reproj_grid(C.Structure):
+    _fields_ = [("cell_size", C.c_int32), ("n_cols", C.c_int32), ("n_rows", C.c_int32), ("max_fts", C.c_int32),
+                ("align_max_iter", C.c_int32), ("pad_", C.c_int32)]
+
+
+class hso_reproj_result(C.Structure):
+    _fields_ = [("in_frame", C.c_int32), ("cell", C.c_int32), ("tried", C.c_int32), ("matched", C.c_int32), ("search_level", C.c_int32),
+                ("order", C.c_int32), ("align_ok", C.c_int32), ("pad_", C.c_int32), ("px", C.c_double * 2), ("A_cur_ref", C.c_double * 4)]
+
+
+class hso_reproj_summary(C.Structure):
+    _fields_ = [("n_in_frame", C.c_int32), ("n_matches", C.c_int32), ("n_trials", C.c_int32), ("used_cell_all", C.c_int32)]
+
+
 class hso_corner(C.Structure):
     _fields_ = [("x", C.c_int16), ("y", C.c_int16), ("score", C.c_int32), ("shi_tomasi", C.c_float)]
 
@@ -107,6 +128,8 @@ SYMBOLS = {
     "hso_track_set_level_shape": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "hso_track_set_ic_dual": (C.c_int, [_vp, C.c_int]),
     "hso_align_batch": (C.c_int, [_vp, C.c_int32, C.c_int, _P(hso_align_job), _P(C.c_int32), C.c_int, _P(hso_align_result)]),
+    "hso_reproject_match": (C.c_int, [_vp, C.c_int32, _P(C.c_double), C.c_int, _P(C.c_double), C.c_int, _P(hso_reproj_cand), _P(hso_reproj_grid),
+                                      _P(C.c_int32), _P(hso_reproj_result), _P(hso_reproj_summary)]),
     "hso_pose_optimize": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_int32), C.c_int,
                                     _P(C.c_double), _P(C.c_double), _P(C.c_int8), _P(C.c_int8), _P(C.c_int8), _P(C.c_double),
                                     _P(C.c_uint8), _P(hso_pose_result)]),

@@ -200,6 +200,39 @@ class Context:
         self._chk(self.lib.hso_align_batch(self.h, int(cur), M, jobs, refs, align_max_iter, out))
         return out
 
+    # ---- N1: Reprojector::reprojectMap data path ---------------------------------------------------------------------------
+    @staticmethod
+    def reproj_cands(cands, frame_ids=None):
+        """list of dicts (hso_reproj_cand field names; 'ref_frame' indexes frame_ids when given) -> ctypes array."""
+        arr = (K.hso_reproj_cand * max(len(cands), 1))()
+        for i, c in enumerate(cands):
+            a = arr[i]
+            for k in range(3):
+                a.p_host[k], a.f_ref[k] = float(c["p_host"][k]), float(c["f_ref"][k])
+            for k in range(2):
+                a.px_ref[k], a.grad[k] = float(c["px_ref"][k]), float(c["grad"][k])
+            a.depth_ref = float(c["depth_ref"])
+            a.host_pose, a.ref_pose = int(c["host_pose"]), int(c["ref_pose"])
+            a.ref_frame = int(frame_ids[c["ref_frame"]]) if frame_ids is not None else int(c["ref_frame"])
+            a.ref_level, a.ftr_type, a.pt_type, a.pt_ftr_type = int(c["ref_level"]), int(c["ftr_type"]), int(c["pt_type"]), int(c["pt_ftr_type"])
+            a.scale_patch, a.exposure_rat = int(c.get("scale_patch", 0)), float(c.get("exposure_rat", 1.0))
+        return arr
+
+    def reproject_match(self, cur, T_cur_w, T_f_w, cands, grid, cell_order, M=None):
+        """cands: ctypes array from reproj_cands(); grid: dict(cell_size, n_cols, n_rows, max_fts, align_max_iter).
+        Returns (ctypes array of hso_reproj_result, hso_reproj_summary)."""
+        M = len(cands) if M is None else M
+        T = np.ascontiguousarray(T_cur_w, np.float64).reshape(12)
+        Tk = np.ascontiguousarray(T_f_w, np.float64).reshape(-1)
+        g = K.hso_reproj_grid(int(grid["cell_size"]), int(grid["n_cols"]), int(grid["n_rows"]), int(grid["max_fts"]),
+                              int(grid.get("align_max_iter", 10)), 0)
+        order = np.ascontiguousarray(cell_order, np.int32)
+        out = (K.hso_reproj_result * max(M, 1))()
+        summ = K.hso_reproj_summary()
+        self._chk(self.lib.hso_reproject_match(self.h, int(cur), _dp(T), Tk.size // 12, _dp(Tk), M, cands, C.byref(g),
+                                               order.ctypes.data_as(C.POINTER(C.c_int32)), out, C.byref(summ)))
+        return out, summ
+
     # ---- F4: pose_optimizer::optimizeLevenbergMarquardt3rd -----------------------------------------------------------------
     def pose_optimize_batch(self, problems, reproj_thresh=2.0, n_iter=12):
         """problems: list of dicts {f (F,3), p_host (F,3), host_idx (F,), T_host_w (K,3,4), grad (F,2), level, ftype, ptype (F,),

@@ -55,6 +55,10 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32) k_align(const AlignKParams P
   if (m >= P.M) return;
   const AlignJobDev& jd = jobs[m];
   const hso_align_job& jb = jd.job;
+  if (jb.ref_level < 0) {  // produced on the device by k_reproject: findMatchDirect returns false before the alignment (src/matcher.cpp:276-291)
+    if (lane == 0) { out[m].ok = 0; out[m].align_converged = 0; out[m].px_cur[0] = jb.px_cur[0]; out[m].px_cur[1] = jb.px_cur[1]; out[m].h_inv = 0; }
+    return;
+  }
   float* patch = s_patch[warp];
   const int rl = jb.ref_level, sl = jb.search_level;
 

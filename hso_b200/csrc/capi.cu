@@ -96,6 +96,9 @@ struct hso_ctx {
   // FAST scratch
   DevBuf f_score, f_rowbuf, f_rowcount, f_out, f_total;
   PinBuf f_out_host;
+  // reprojection (row N1) scratch
+  DevBuf r_arena;
+  PinBuf r_stage_host, r_out_host;
   // align / pose scratch
   DevBuf a_jobs_dev, a_out_dev, p_arena, p_jobs_dev, p_out_dev;
   PinBuf a_jobs_host, a_out_host, p_stage_host, p_out_host;
@@ -352,10 +355,10 @@ void hso_destroy(hso_ctx* ctx) {
     if (s.sobel) cudaFree(s.sobel);
   }
   DevBuf* db[] = {&ctx->f_score, &ctx->f_rowbuf, &ctx->f_rowcount, &ctx->f_out, &ctx->f_total, &ctx->pyr_arena, &ctx->sums_arena, &ctx->stats_table, &ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
-                  &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
+                  &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->r_arena, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ctx->f_out_host, &ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
-                  &ctx->a_jobs_host, &ctx->a_out_host, &ctx->p_stage_host, &ctx->p_out_host};
+                  &ctx->a_jobs_host, &ctx->a_out_host, &ctx->r_stage_host, &ctx->r_out_host, &ctx->p_stage_host, &ctx->p_out_host};
   for (PinBuf* b : pb) b->release();
   for (cudaEvent_t e : ctx->t_ev) if (e) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -985,6 +988,91 @@ int hso_align_batch(hso_ctx* ctx, hso_frame_id cur, int M, const hso_align_job* 
   CU(cudaMemcpyAsync(ctx->a_out_host.p, ctx->a_out_dev.p, sizeof(hso_align_result) * M, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   memcpy(out, ctx->a_out_host.p, sizeof(hso_align_result) * M);
+  tm.stop_after_sync();
+  return HSO_OK;
+}
+
+// ---- N1 ---------------------------------------------------------------------------------------------------------------------
+int hso_reproject_match(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], int n_poses, const double* T_f_w, int M,
+                        const hso_reproj_cand* cands, const hso_reproj_grid* grid, const int32_t* cell_order, hso_reproj_result* out,
+                        hso_reproj_summary* summary) {
+  if (!ctx || !T_cur_w || !grid || !summary || M < 0 || n_poses < 0) return HSO_ERR_INVALID;
+  memset(summary, 0, sizeof *summary);
+  const int n_cells = grid->n_cols * grid->n_rows;
+  if (grid->cell_size <= 0 || grid->n_cols <= 0 || grid->n_rows <= 0 || n_cells > 4096 || grid->max_fts < 0 || !cell_order)
+    return fail(ctx, HSO_ERR_INVALID, "bad reprojection grid (cells must be <= 4096)");
+  if ((long long)grid->n_cols * grid->cell_size < ctx->cam.width || (long long)grid->n_rows * grid->cell_size < ctx->cam.height)
+    return fail(ctx, HSO_ERR_INVALID, "reprojection grid does not cover the image");
+  if (M == 0) { summary->used_cell_all = 1; return HSO_OK; }
+  if (!cands || !out || !T_f_w || n_poses == 0) return HSO_ERR_INVALID;
+  if (M > 16384) return fail(ctx, HSO_ERR_CAPACITY, "more than 16384 reprojection candidates");
+  FrameSlot* fc = get_frame(ctx, cur);
+  if (!fc) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown current frame id");
+  {
+    std::vector<uint8_t> seen(n_cells, 0);
+    for (int i = 0; i < n_cells; ++i) {
+      if (cell_order[i] < 0 || cell_order[i] >= n_cells || seen[cell_order[i]]) return fail(ctx, HSO_ERR_INVALID, "cell_order is not a permutation");
+      seen[cell_order[i]] = 1;
+    }
+  }
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  // staging blob: [cands | ref_pyr pointers | poses | cell_order], then device-only [align jobs | align results | results | summary]
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = (o + 127) / 128 * 128; o = r + bytes; return r; };
+  const size_t o_c = take(sizeof(hso_reproj_cand) * M), o_rp = take(sizeof(void*) * M), o_T = take(sizeof(double) * 12 * n_poses),
+               o_co = take(sizeof(int32_t) * n_cells);
+  const size_t staged = o;
+  const size_t o_j = take(sizeof(AlignJobDev) * M), o_ar = take(sizeof(hso_align_result) * M), o_res = take(sizeof(hso_reproj_result) * M),
+               o_sum = take(sizeof(hso_reproj_summary));
+  CU(ctx->r_arena.reserve(o));
+  CU(ctx->r_stage_host.reserve(staged));
+  CU(ctx->r_out_host.reserve(sizeof(hso_reproj_result) * M + sizeof(hso_reproj_summary)));
+  char* h = (char*)ctx->r_stage_host.p;
+  char* d = (char*)ctx->r_arena.p;
+  memcpy(h + o_c, cands, sizeof(hso_reproj_cand) * M);
+  const uint8_t** rp = (const uint8_t**)(h + o_rp);
+  const int max_search = std::min(ctx->cfg.n_pyr_levels, ctx->geom.n_levels) - 1;  // getBestSearchLevel(A, nPyrLevels-1)
+  for (int i = 0; i < M; ++i) {
+    const hso_reproj_cand& c = cands[i];
+    rp[i] = nullptr;
+    if (c.host_pose < 0 || c.host_pose >= n_poses || c.ref_pose >= n_poses) return fail(ctx, HSO_ERR_INVALID, "pose index out of range in reprojection candidate");
+    if (c.pt_type < 0 || c.pt_type > 4 || c.pt_ftr_type < 0 || c.pt_ftr_type > 2) return fail(ctx, HSO_ERR_INVALID, "bad point type in reprojection candidate");
+    if (c.ref_pose >= 0) {
+      FrameSlot* fr = get_frame(ctx, c.ref_frame);
+      if (!fr) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown reference frame id in reprojection candidate");
+      if (c.ref_level < 0 || c.ref_level >= ctx->geom.n_levels) return fail(ctx, HSO_ERR_INVALID, "reference level out of range");
+      if (c.ftr_type == 1 && !fc->sobel) return fail(ctx, HSO_ERR_INVALID, "edgelet candidates need hso_cfg.materialize_sobel (checkNormal reads sobelX_/Y_)");
+      rp[i] = fr->pyr;
+    }
+  }
+  memcpy(h + o_T, T_f_w, sizeof(double) * 12 * n_poses);
+  memcpy(h + o_co, cell_order, sizeof(int32_t) * n_cells);
+  StageTimer tm(ctx, 2);
+  CU(cudaMemcpyAsync(d, h, staged, cudaMemcpyHostToDevice, ctx->stream));
+  ReprojKParams kp;
+  memset(&kp, 0, sizeof kp);
+  kp.cam = ctx->camdev;
+  memcpy(kp.T_cur_w, T_cur_w, sizeof kp.T_cur_w);
+  kp.T_f_w = (const double*)(d + o_T);
+  kp.n_poses = n_poses; kp.M = M; kp.cell_size = grid->cell_size; kp.n_cols = grid->n_cols; kp.max_search_level = max_search;
+  CU(launch_reproject(kp, (const hso_reproj_cand*)(d + o_c), (const uint8_t* const*)(d + o_rp), (AlignJobDev*)(d + o_j),
+                      (hso_reproj_result*)(d + o_res), ctx->stream, &ctx->launches));
+  CU(launch_align(ctx->geom, fc->pyr, fc->sobel, (const AlignJobDev*)(d + o_j), M, grid->align_max_iter, (hso_align_result*)(d + o_ar), ctx->stream,
+                  &ctx->launches));
+  ReprojSelParams sp;
+  sp.M = M; sp.n_cells = n_cells; sp.max_fts = grid->max_fts;
+  sp.n_sort = 2;
+  while (sp.n_sort < M) sp.n_sort *= 2;
+  CU(launch_reproj_select(sp, (const hso_reproj_cand*)(d + o_c), (const hso_align_result*)(d + o_ar), (const int32_t*)(d + o_co),
+                          (hso_reproj_result*)(d + o_res), (hso_reproj_summary*)(d + o_sum), ctx->stream, &ctx->launches));
+  // results and summary are adjacent in the arena only up to alignment: two copies
+  char* oh = (char*)ctx->r_out_host.p;
+  CU(cudaMemcpyAsync(oh, d + o_res, sizeof(hso_reproj_result) * M, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(oh + sizeof(hso_reproj_result) * M, d + o_sum, sizeof(hso_reproj_summary), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, oh, sizeof(hso_reproj_result) * M);
+  memcpy(summary, oh + sizeof(hso_reproj_result) * M, sizeof(hso_reproj_summary));
   tm.stop_after_sync();
   return HSO_OK;
 }

@@ -111,6 +111,25 @@ struct AlignJobDev {
 cudaError_t launch_align(const PyrGeom& g, const uint8_t* cur_pyr, const int16_t* cur_sobel, const AlignJobDev* jobs_dev, int M, int max_iter,
                          hso_align_result* out_dev, cudaStream_t stream, uint64_t* launches);
 
+// ---- reprojection + grid selection (row N1) -------------------------------------------------------------------------------
+struct ReprojKParams {
+  CamDev cam;
+  double T_cur_w[12];      // frame->T_f_w_
+  const double* T_f_w;     // device [n_poses][12]
+  int n_poses, M;
+  int cell_size, n_cols;
+  int max_search_level;    // Config::nPyrLevels() - 1
+};
+struct ReprojSelParams {
+  int M, n_sort /* power of two >= M */, n_cells, max_fts;
+};
+cudaError_t launch_reproject(const ReprojKParams& p, const hso_reproj_cand* cands_dev, const uint8_t* const* ref_pyr_dev, AlignJobDev* jobs_dev,
+                             hso_reproj_result* res_dev, cudaStream_t stream, uint64_t* launches);
+size_t reproj_select_smem(int n_sort, int n_cells);
+cudaError_t launch_reproj_select(const ReprojSelParams& p, const hso_reproj_cand* cands_dev, const hso_align_result* align_dev,
+                                 const int32_t* cell_order_dev, hso_reproj_result* res_dev, hso_reproj_summary* summ_dev, cudaStream_t stream,
+                                 uint64_t* launches);
+
 // ---- pose optimiser -----------------------------------------------------------------------------------------------------
 struct PoseJobDev {
   int F, K, n_fts_total, pad_;

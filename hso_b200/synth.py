@@ -145,3 +145,60 @@ def make_pose_problem(seed, cam="icl", F=400, K=8, noise_px=0.5, frac_outlier=0.
                 ftype=(rng.uniform(size=F) < frac_edgelet).astype(np.int8),
                 ptype=np.where(rng.uniform(size=F) < 0.1, 1, 4).astype(np.int8), T_f_w=T0[:3], T_true=T_fw[:3], n_fts_total=F + 7,
                 err_mult2=fbar)
+
+
+def world2cam(c, P):
+    """AbstractCamera::world2cam of the three models (src/camera.cpp:94-125,199-221,307-315) for an (N,3) array."""
+    P = np.asarray(P, float).reshape(-1, 3)
+    u, v = P[:, 0] / P[:, 2], P[:, 1] / P[:, 2]
+    d = c["d"]
+    if c.get("model", 0) == 0 and abs(d[0]) > 1e-7:
+        r2 = u * u + v * v
+        cd = 1 + d[0] * r2 + d[1] * r2 * r2 + d[4] * r2 ** 3
+        a1, a2, a3 = 2 * u * v, r2 + 2 * u * u, r2 + 2 * v * v
+        u, v = u * cd + d[2] * a1 + d[3] * a2, v * cd + d[2] * a3 + d[3] * a1
+    elif c.get("model", 0) == 1 and not c.get("undistort", 0):
+        dist = np.sqrt(u * u + v * v)
+        ratio = np.where(dist > 0, np.arctan(2 * dist * np.tan(d[0] / 2)) / np.maximum(dist * d[0], 1e-300), 1.0)
+        u, v = ratio * u, ratio * v
+    return np.stack([c["fx"] * u + c["cx"], c["fy"] * v + c["cy"]], axis=1)
+
+
+def make_reproject_scene(seed, cam="icl", M=3000, n_kf=4, max_fts=200, depth=4.0, gain=1.05, frac_edgelet=0.25):
+    """Inputs of Reprojector::reprojectMap's data path (row N1): n_kf keyframes and a current frame looking at a textured plane
+    z = depth of keyframe 0 (= world), M map points on the plane, each hosted in one keyframe and observed (ref_ftr_) in another.
+    Returns dict(cam, kf_imgs, cur_img, T_f_w (n_kf,3,4), T_cur_w (3,4), cands [dict], grid dict, cell_order)."""
+    rng = np.random.default_rng(seed)
+    c = CAMS[cam] if isinstance(cam, str) else cam
+    W, H = c["width"], c["height"]
+    K = np.array([[c["fx"], 0, c["cx"]], [0, c["fy"], c["cy"]], [0, 0, 1.0]])
+    base = texture(rng, W, H)
+    T_kf = [np.eye(4)] + [se3_exp(np.concatenate([rng.normal(0, 0.05, 3), rng.normal(0, 0.01, 3)])) for _ in range(n_kf - 1)]
+    kf_imgs = [base] + [warp_plane(base, K, T, depth) for T in T_kf[1:]]
+    T_cur = se3_exp(np.concatenate([rng.normal(0, 0.04, 3), rng.normal(0, 0.008, 3)]))
+    cur_img = warp_plane(base, K, T_cur, depth, gain)
+    # points on the plane, spread a little beyond the field of view so that some fall outside the current image
+    x = rng.uniform(-1.12, 1.12, M) * depth * (W / 2) / c["fx"]
+    y = rng.uniform(-1.12, 1.12, M) * depth * (H / 2) / c["fy"]
+    Pw = np.stack([x, y, np.full(M, depth)], axis=1)
+    cands = []
+    for i in range(M):
+        h, r = int(rng.integers(0, n_kf)), int(rng.integers(0, n_kf))
+        if i % 3 == 0:
+            r = h
+        Ph = T_kf[h][:3, :3] @ Pw[i] + T_kf[h][:3, 3]
+        Pr = T_kf[r][:3, :3] @ Pw[i] + T_kf[r][:3, 3]
+        px_ref = world2cam(c, Pr)[0]
+        ang = rng.uniform(0, 2 * np.pi)
+        ref_pose = r if rng.uniform() > 0.03 else -1  # getCloseViewObs fails for a few
+        cands.append(dict(p_host=Ph, px_ref=px_ref, f_ref=Pr / np.linalg.norm(Pr), grad=np.array([np.cos(ang), np.sin(ang)]),
+                          depth_ref=float(np.linalg.norm(Pr)), host_pose=h, ref_pose=ref_pose, ref_frame=r, ref_level=int(rng.integers(0, 3)),
+                          ftr_type=(1 if rng.uniform() < frac_edgelet else (2 if rng.uniform() < 0.2 else 0)),
+                          pt_type=int(rng.choice([0, 1, 2, 3, 4], p=[0.02, 0.13, 0.25, 0.3, 0.3])), pt_ftr_type=int(rng.integers(0, 3)),
+                          scale_patch=int(i % 5 == 0), exposure_rat=float(gain)))
+    cell_size = int(np.floor(np.float32(np.sqrt(np.float32(W * H) / max_fts)) * np.float32(0.6)))  # Reprojector::caculateGridSize
+    n_cols, n_rows = int(np.ceil(W / cell_size)), int(np.ceil(H / cell_size))
+    grid = dict(cell_size=cell_size, n_cols=n_cols, n_rows=n_rows, max_fts=max_fts, align_max_iter=10)
+    cell_order = rng.permutation(n_cols * n_rows).astype(np.int32)  # std::random_shuffle(grid_.cell_order)
+    return dict(cam=c, kf_imgs=kf_imgs, cur_img=cur_img, T_f_w=np.stack([T[:3] for T in T_kf]), T_cur_w=T_cur[:3], cands=cands, grid=grid,
+                cell_order=cell_order)

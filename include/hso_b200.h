@@ -184,6 +184,60 @@ typedef struct {
 int hso_align_batch(hso_ctx* ctx, hso_frame_id cur, int M, const hso_align_job* jobs, const hso_frame_id* ref_frames,
                     int align_max_iter, hso_align_result* out);
 
+/* ---- N1 (next row): map reprojection + grid selection + direct matching in one call — replaces the data path of
+ * Reprojector::reprojectMap after the host has enumerated the points to project (src/reprojector.cpp:88-331): reprojectPoint (:504-529),
+ * the per-cell candidate ordering (pointQualityComparator :333-344, list::sort is stable), the three selection passes over grid_.cell_order
+ * (:262-303) or reprojectCellAll (:545-615) when fewer than maxFts+50 points project into the image, and for every candidate the whole
+ * Matcher::findMatchDirect (src/matcher.cpp:270-375) including warp::getWarpMatrixAffine (:46-72), getBestSearchLevel (:74-85) and
+ * cam2world (src/camera.cpp:66-87,169-190,297-300). The host keeps the pointer chasing: Point::getCloseViewObs (src/point.cpp:116-136)
+ * picks ref_ftr_, and the side effects on Point counters / Feature creation are applied from the per-candidate flags returned here.
+ * Candidates are given in the order the reference calls reprojectPoint. std::random_shuffle's cell order is the caller's (cell_order). ---- */
+typedef struct {
+  double p_host[3];      /* point->hostFeature_->f * (1.0 / point->idist_)  (reprojector.cpp:508) */
+  double px_ref[2];      /* ref_ftr_->px (level 0) */
+  double f_ref[3];       /* ref_ftr_->f */
+  double grad[2];        /* ref_ftr_->grad (edgelets) */
+  double depth_ref;      /* matcher.cpp:298-309: 1/idist_ when ref_ftr_'s frame is the host frame, else |ref frame pos - pt.pos_| */
+  int32_t host_pose;     /* index into T_f_w of point->hostFeature_->frame */
+  int32_t ref_pose;      /* index into T_f_w of ref_ftr_->frame; < 0: getCloseViewObs returned false (matcher.cpp:276-287) */
+  hso_frame_id ref_frame; /* device frame of ref_ftr_->frame */
+  int32_t ref_level;     /* ref_ftr_->level */
+  int32_t ftr_type;      /* ref_ftr_->type: 0 corner, 1 edgelet, 2 gradient */
+  int32_t pt_type;       /* Point::type_: 0 deleted, 1 temporary, 2 candidate, 3 unknown, 4 good (point.h:53) */
+  int32_t pt_ftr_type;   /* Point::ftr_type_: 0 gradient, 1 edgelet, 2 corner (point.h:54) */
+  int32_t scale_patch;   /* matcher.cpp:317-321: keyframe gap < 4 and |128 a - 128| > 30 */
+  float exposure_rat;    /* cur.m_exposure_time / ref.m_exposure_time */
+  float pad_;
+} hso_reproj_cand;
+typedef struct {
+  int32_t cell_size, n_cols, n_rows;  /* Reprojector::initializeGrid (reprojector.cpp:58-77) */
+  int32_t max_fts;                    /* Config::maxFts() */
+  int32_t align_max_iter;             /* Matcher::Options::align_max_iter (10) */
+  int32_t pad_;
+} hso_reproj_grid;
+typedef struct {
+  int32_t in_frame;      /* reprojectPoint returned true: the candidate entered cell `cell` */
+  int32_t cell;
+  int32_t tried;         /* findMatchDirect was called for it; tried && !matched => n_failed_reproj_++ on the host */
+  int32_t matched;       /* a Feature(frame, px, search_level) is created */
+  int32_t search_level;  /* matcher_.search_level_ */
+  int32_t order;         /* position of that Feature in the order of creation (frame->fts_), -1 otherwise */
+  int32_t align_ok;      /* diagnostics: what findMatchDirect returns for this candidate, evaluated speculatively for every candidate in a cell */
+  int32_t pad_;
+  double px[2];          /* reprojected pixel; for tried candidates the pixel findMatchDirect left in Candidate::px */
+  double A_cur_ref[4];   /* matcher_.A_cur_ref_ (edgelet gradient update, reprojector.cpp:404-409) */
+} hso_reproj_result;
+typedef struct {
+  int32_t n_in_frame;    /* nFeatures_ */
+  int32_t n_matches;     /* n_matches_ */
+  int32_t n_trials;      /* n_trials_ (deleted points are skipped before counting) */
+  int32_t used_cell_all; /* 1: the reprojectCellAll branch ran (n_in_frame < max_fts + 50) */
+} hso_reproj_summary;
+/* T_cur_w: frame->T_f_w_ (3x4 row-major); T_f_w: n_poses keyframe poses (3x4 each). cell_order: n_cols*n_rows cell indices. */
+int hso_reproject_match(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], int n_poses, const double* T_f_w, int M,
+                        const hso_reproj_cand* cands, const hso_reproj_grid* grid, const int32_t* cell_order, hso_reproj_result* out,
+                        hso_reproj_summary* summary);
+
 /* ---- F4: pose refinement — replaces void pose_optimizer::optimizeLevenbergMarquardt3rd(double reproj_thresh, size_t n_iter,
  * bool verbose, FramePtr&, double& scale, double& err_init, double& err_final, size_t& num_obs)
  * (include/hso/pose_optimizer.h:61-64 ; src/pose_optimizer.cpp:399-771). ------------------------------------------------- */

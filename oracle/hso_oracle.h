@@ -138,6 +138,38 @@ void orc_match_direct_batch(int M, const orc_align_job* jobs, const uint8_t* con
                             const int* lw, const int* lh, const int16_t* const* cur_sobx, const int16_t* const* cur_soby,
                             int align_max_iter, orc_align_result* out);
 
+/* ---- N1: Reprojector::reprojectMap data path (src/reprojector.cpp:88-331,504-615) + whole Matcher::findMatchDirect ----
+ * Record layouts shared with include/hso_b200.h (hso_reproj_*); see there for the field meaning. */
+typedef struct {
+  double p_host[3], px_ref[2], f_ref[3], grad[2], depth_ref;
+  int32_t host_pose, ref_pose, ref_frame, ref_level, ftr_type, pt_type, pt_ftr_type, scale_patch;
+  float exposure_rat, pad_;
+} orc_reproj_cand;
+typedef struct { int32_t cell_size, n_cols, n_rows, max_fts, align_max_iter, pad_; } orc_reproj_grid;
+typedef struct {
+  int32_t in_frame, cell, tried, matched, search_level, order, align_ok, pad_;
+  double px[2], A_cur_ref[4];
+} orc_reproj_result;
+typedef struct { int32_t n_in_frame, n_matches, n_trials, used_cell_all; } orc_reproj_summary;
+/* cam2world of the three camera models (src/camera.cpp:66-87,169-190,297-300); unit-norm bearing. */
+void orc_cam2world(const orc_cam* cam, double u, double v, double xyz_out[3]);
+/* warp::getWarpMatrixAffine (src/matcher.cpp:46-72); A row-major. */
+void orc_get_warp_matrix_affine(const orc_cam* cam, const double px_ref[2], const double f_ref[3], double depth_ref, const double T_cur_ref[12],
+                                int level_ref, double A_cur_ref[4]);
+/* ref_levels[frame][level]: pyramids of the frames hso_reproj_cand::ref_frame indexes. max_search_level = Config::nPyrLevels()-1. */
+void orc_reproject_match(const orc_cam* cam, const double T_cur_w[12], int n_poses, const double* T_f_w, int M, const orc_reproj_cand* cands,
+                         const orc_reproj_grid* grid, const int32_t* cell_order, int max_search_level,
+                         const uint8_t* const* const* ref_levels, const uint8_t* const* cur_levels, const int* lw, const int* lh,
+                         const int16_t* const* cur_sobx, const int16_t* const* cur_soby, orc_reproj_result* out, orc_reproj_summary* summary);
+void orc_reproject_speculative(const orc_cam* cam, const double T_cur_w[12], int n_poses, const double* T_f_w, int M, const orc_reproj_cand* cands,
+                               const orc_reproj_grid* grid, int max_search_level, const uint8_t* const* const* ref_levels,
+                               const uint8_t* const* cur_levels, const int* lw, const int* lh, const int16_t* const* cur_sobx,
+                               const int16_t* const* cur_soby, orc_reproj_result* out, double* px_after);
+/* The selection walk alone (cells, ordering, three passes / reprojectCellAll) with findMatchDirect's outcome supplied per candidate:
+ * io[i].in_frame / cell are inputs, tried / matched / order are written. */
+void orc_reproject_select(int M, const orc_reproj_cand* cands, const uint8_t* match_ok, const orc_reproj_grid* grid, const int32_t* cell_order,
+                          orc_reproj_result* io, orc_reproj_summary* summary);
+
 /* ---- a16,a17: pose_optimizer::optimizeLevenbergMarquardt3rd (src/pose_optimizer.cpp:399-771) ---- */
 typedef struct {
   double T_f_w[12];       /* optimised pose */

@@ -281,3 +281,103 @@ def fast_detect(img, threshold, border=8):
     out = (orc_corner * cap)()
     n = lib.orc_fast_detect(img.ctypes.data_as(C.c_void_p), w, h, w, int(threshold), int(border), out, cap)
     return [(out[i].x, out[i].y, out[i].score, out[i].shi_tomasi) for i in range(n)]
+
+
+# ---- N1: Reprojector::reprojectMap data path + Matcher::findMatchDirect ------------------------------------------------------------
+class orc_reproj_cand(C.Structure):
+    _fields_ = [("p_host", C.c_double * 3), ("px_ref", C.c_double * 2), ("f_ref", C.c_double * 3), ("grad", C.c_double * 2),
+                ("depth_ref", C.c_double), ("host_pose", C.c_int32), ("ref_pose", C.c_int32), ("ref_frame", C.c_int32),
+                ("ref_level", C.c_int32), ("ftr_type", C.c_int32), ("pt_type", C.c_int32), ("pt_ftr_type", C.c_int32),
+                ("scale_patch", C.c_int32), ("exposure_rat", C.c_float), ("pad_", C.c_float)]
+
+
+class orc_reproj_grid(C.Structure):
+    _fields_ = [("cell_size", C.c_int32), ("n_cols", C.c_int32), ("n_rows", C.c_int32), ("max_fts", C.c_int32),
+                ("align_max_iter", C.c_int32), ("pad_", C.c_int32)]
+
+
+class orc_reproj_result(C.Structure):
+    _fields_ = [("in_frame", C.c_int32), ("cell", C.c_int32), ("tried", C.c_int32), ("matched", C.c_int32), ("search_level", C.c_int32),
+                ("order", C.c_int32), ("align_ok", C.c_int32), ("pad_", C.c_int32), ("px", C.c_double * 2), ("A_cur_ref", C.c_double * 4)]
+
+
+class orc_reproj_summary(C.Structure):
+    _fields_ = [("n_in_frame", C.c_int32), ("n_matches", C.c_int32), ("n_trials", C.c_int32), ("used_cell_all", C.c_int32)]
+
+
+def cam2world(cam, u, v):
+    lib = load()
+    out = np.zeros(3)
+    lib.orc_cam2world(C.byref(cam_of(cam)), C.c_double(u), C.c_double(v), dp(out))
+    return out
+
+
+def get_warp_matrix_affine(cam, px_ref, f_ref, depth_ref, T_cur_ref, level_ref):
+    lib = load()
+    A = np.zeros(4)
+    px = np.ascontiguousarray(px_ref, np.float64)
+    f = np.ascontiguousarray(f_ref, np.float64)
+    T = np.ascontiguousarray(T_cur_ref, np.float64).reshape(12)
+    lib.orc_get_warp_matrix_affine(C.byref(cam_of(cam)), dp(px), dp(f), C.c_double(depth_ref), dp(T), int(level_ref), dp(A))
+    return A.reshape(2, 2)
+
+
+def _reproj_args(T_cur_w, T_f_w, ref_pyramids, cur_levels, cur_sobel):
+    T = np.ascontiguousarray(T_cur_w, np.float64).reshape(12)
+    Tk = np.ascontiguousarray(T_f_w, np.float64).reshape(-1)
+    nl = len(cur_levels)
+    keep = [T, Tk]
+    frames = (C.POINTER(C.c_void_p) * len(ref_pyramids))()
+    for i, pyr in enumerate(ref_pyramids):
+        lv = [np.ascontiguousarray(l) for l in pyr]
+        arr = (C.c_void_p * nl)(*[a.ctypes.data for a in lv])
+        keep += [lv, arr]
+        frames[i] = C.cast(arr, C.POINTER(C.c_void_p))
+    cl = [np.ascontiguousarray(l) for l in cur_levels]
+    curp = (C.c_void_p * nl)(*[a.ctypes.data for a in cl])
+    lw = (C.c_int * nl)(*[l.shape[1] for l in cl])
+    lh = (C.c_int * nl)(*[l.shape[0] for l in cl])
+    sx = [np.ascontiguousarray(g[0]) for g in cur_sobel]
+    sy = [np.ascontiguousarray(g[1]) for g in cur_sobel]
+    sxp = (C.c_void_p * 3)(*[a.ctypes.data for a in sx])
+    syp = (C.c_void_p * 3)(*[a.ctypes.data for a in sy])
+    keep += [cl, sx, sy]
+    return T, Tk, frames, curp, lw, lh, sxp, syp, keep
+
+
+def reproject_match(cam, T_cur_w, T_f_w, cands, grid, cell_order, max_search_level, ref_pyramids, cur_levels, cur_sobel):
+    """cands: ctypes array of orc_reproj_cand (same layout as hso_reproj_cand); ref_pyramids: list (by ref_frame index) of lists of level
+    images; cur_sobel: [(gx, gy)] for levels 0..2. Returns (results array, summary)."""
+    lib = load()
+    M = len(cands)
+    T, Tk, frames, curp, lw, lh, sxp, syp, keep = _reproj_args(T_cur_w, T_f_w, ref_pyramids, cur_levels, cur_sobel)
+    order = np.ascontiguousarray(cell_order, np.int32)
+    out = (orc_reproj_result * max(M, 1))()
+    summ = orc_reproj_summary()
+    lib.orc_reproject_match(C.byref(cam_of(cam)), dp(T), Tk.size // 12, dp(Tk), M, cands, C.byref(grid), order.ctypes.data_as(C.POINTER(C.c_int32)),
+                            int(max_search_level), frames, curp, lw, lh, sxp, syp, out, C.byref(summ))
+    return out, summ
+
+
+def reproject_speculative(cam, T_cur_w, T_f_w, cands, grid, max_search_level, ref_pyramids, cur_levels, cur_sobel):
+    """findMatchDirect for every candidate that entered a cell. Returns (results array with align_ok / A / search_level, px_after (M,2))."""
+    lib = load()
+    M = len(cands)
+    T, Tk, frames, curp, lw, lh, sxp, syp, keep = _reproj_args(T_cur_w, T_f_w, ref_pyramids, cur_levels, cur_sobel)
+    out = (orc_reproj_result * max(M, 1))()
+    px_after = np.zeros((max(M, 1), 2))
+    lib.orc_reproject_speculative(C.byref(cam_of(cam)), dp(T), Tk.size // 12, dp(Tk), M, cands, C.byref(grid), int(max_search_level), frames, curp,
+                                  lw, lh, sxp, syp, out, dp(px_after))
+    return out, px_after
+
+
+def reproject_select(cands, match_ok, grid, cell_order, io):
+    """The selection walk with findMatchDirect's outcome supplied (match_ok uint8 per candidate); io: results array whose in_frame / cell
+    are inputs. Returns the summary; tried / matched / order are written into io."""
+    lib = load()
+    ok = np.ascontiguousarray(match_ok, np.uint8)
+    order = np.ascontiguousarray(cell_order, np.int32)
+    summ = orc_reproj_summary()
+    lib.orc_reproject_select(len(cands), cands, ok.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(grid), order.ctypes.data_as(C.POINTER(C.c_int32)),
+                             io, C.byref(summ))
+    return summ

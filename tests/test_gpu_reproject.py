@@ -1,0 +1,139 @@
+"""GPU parity, row N1: hso_reproject_match (reprojectPoint + grid cells + per-cell ordering + the three selection passes + the whole
+Matcher::findMatchDirect incl. getWarpMatrixAffine) vs the CPU oracle.
+
+Three layers, because the alignment itself is a float pipeline whose convergence can flip for a handful of candidates (see
+test_gpu_align.py): (1) the fp64 geometry of every candidate (pixel, cell, warp matrix, search level) against the oracle, exact for the
+integers; (2) the speculative findMatchDirect outcome of every candidate against the oracle's (<= 0.5 % flips); (3) the selection replayed
+by the oracle's literal std::list walk on the device's own outcomes — tried / matched / creation order must agree EXACTLY."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from hso_b200 import Context, HsoError, make_cam, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(oracle, cam, seed, M, max_fts, **kw):
+    s = synth.make_reproject_scene(seed, cam, M=M, max_fts=max_fts, **kw)
+    c = s["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), materialize_sobel=True)
+    kf_ids, _, _ = ctx.upload_frames(s["kf_imgs"])
+    cur_id = ctx.upload_frames([s["cur_img"]])[0][0]
+    arr = Context.reproj_cands(s["cands"], frame_ids=kf_ids)
+    got, gsum = ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], arr, s["grid"], s["cell_order"], M=M)
+    # oracle inputs: ref_frame indexes the list of keyframe pyramids
+    oarr = Context.reproj_cands(s["cands"])
+    oc = (oracle.orc_reproj_cand * max(M, 1)).from_buffer_copy(bytes(oarr))
+    pyrs = [oracle.create_pyramid(im, 5)[0] for im in s["kf_imgs"]]
+    cl, _ = oracle.create_pyramid(s["cur_img"], 5)
+    sob = [oracle.sobel5(cl[l]) for l in range(3)]
+    g = oracle.orc_reproj_grid(*[s["grid"][k] for k in ("cell_size", "n_cols", "n_rows", "max_fts", "align_max_iter")], 0)
+    ctx.close()
+    return s, got, gsum, oc, g, pyrs, cl, sob
+
+
+@pytest.mark.parametrize("cam,M,max_fts", [("icl", 3000, 200), ("icl", 330, 200), ("icl", 500, 300), ("icl", 150, 200), ("euroc", 2500, 800),
+                                           ("tum_fov", 1500, 200)])
+def test_reproject_match_parity(oracle, cam, M, max_fts):
+    s, got, gsum, oc, g, pyrs, cl, sob = _run(oracle, cam, 21, M, max_fts)
+    spec, px_after = oracle.reproject_speculative(s["cam"], s["T_cur_w"], s["T_f_w"], oc, g, 2, pyrs, cl, sob)
+    # (1) geometry
+    inf_g = np.array([got[i].in_frame for i in range(M)])
+    inf_o = np.array([spec[i].in_frame for i in range(M)])
+    assert np.array_equal(inf_g, inf_o)
+    assert 0.5 < inf_o.mean() <= 1.0
+    assert [got[i].cell for i in range(M)] == [spec[i].cell for i in range(M)]
+    elig = [i for i in range(M) if spec[i].in_frame and oc[i].pt_type != 0]
+    n_job = 0
+    for i in elig:
+        Ao = np.array(spec[i].A_cur_ref[:])
+        Ag = np.array(got[i].A_cur_ref[:])
+        if np.any(Ao != 0):
+            n_job += 1
+            assert np.allclose(Ag, Ao, rtol=1e-9, atol=1e-9), (i, Ag, Ao)  # float in/out of undistortPoints is replicated, the rest is fp64
+            assert got[i].search_level == spec[i].search_level
+        else:
+            assert not np.any(Ag != 0)  # getCloseViewObs failed or the reference pixel is too close to the border: no warp, no alignment
+    assert n_job > 0.8 * len(elig)
+    # (2) speculative outcome of findMatchDirect
+    ok_g = np.array([got[i].align_ok for i in elig])
+    ok_o = np.array([spec[i].align_ok for i in elig])
+    assert 0.3 < ok_o.mean() < 0.99
+    assert (ok_g != ok_o).mean() <= 0.005, (ok_g != ok_o).sum()
+    # (3) the selection, replayed by the oracle on the device's outcomes
+    io = (oracle.orc_reproj_result * M)()
+    for i in range(M):
+        io[i].in_frame, io[i].cell = got[i].in_frame, got[i].cell
+    okd = np.array([got[i].align_ok for i in range(M)], np.uint8)
+    osum = oracle.reproject_select(oc, okd, g, s["cell_order"], io)
+    assert (gsum.used_cell_all, gsum.n_matches, gsum.n_trials, gsum.n_in_frame) == (osum.used_cell_all, osum.n_matches, osum.n_trials, osum.n_in_frame)
+    assert [got[i].tried for i in range(M)] == [io[i].tried for i in range(M)]
+    assert [got[i].matched for i in range(M)] == [io[i].matched for i in range(M)]
+    assert [got[i].order for i in range(M)] == [io[i].order for i in range(M)]
+    assert gsum.n_matches <= max_fts
+    # pixels: untouched reprojection for untried candidates, the aligned pixel for tried ones
+    for i in range(M):
+        if not spec[i].in_frame:
+            continue
+        if got[i].tried:
+            if ok_o[elig.index(i)] == got[i].align_ok and got[i].align_ok:
+                assert np.hypot(got[i].px[0] - px_after[i, 0], got[i].px[1] - px_after[i, 1]) < 0.05, i
+        else:
+            assert abs(got[i].px[0] - spec[i].px[0]) < 1e-9 and abs(got[i].px[1] - spec[i].px[1]) < 1e-9
+
+
+def test_reproject_match_end_to_end_equals_oracle_when_no_flip(oracle):
+    """Whole call vs whole oracle (its own sequential walk with its own alignments). Seeds are scanned for a scene in which no
+    speculative outcome differs; there every flag and the creation order must be identical."""
+    for seed in range(30, 40):
+        M, max_fts = 700, 200
+        s, got, gsum, oc, g, pyrs, cl, sob = _run(oracle, "icl", seed, M, max_fts)
+        spec, _ = oracle.reproject_speculative(s["cam"], s["T_cur_w"], s["T_f_w"], oc, g, 2, pyrs, cl, sob)
+        if any(got[i].align_ok != spec[i].align_ok for i in range(M)):
+            continue
+        exp, esum = oracle.reproject_match(s["cam"], s["T_cur_w"], s["T_f_w"], oc, g, s["cell_order"], 2, pyrs, cl, sob)
+        assert (gsum.n_matches, gsum.n_trials, gsum.n_in_frame, gsum.used_cell_all) == (esum.n_matches, esum.n_trials, esum.n_in_frame, esum.used_cell_all)
+        for i in range(M):
+            assert (got[i].tried, got[i].matched, got[i].order, got[i].cell) == (exp[i].tried, exp[i].matched, exp[i].order, exp[i].cell), i
+            if got[i].matched:
+                assert np.hypot(got[i].px[0] - exp[i].px[0], got[i].px[1] - exp[i].px[1]) < 0.05
+                assert got[i].search_level == exp[i].search_level
+        return
+    pytest.fail("no flip-free scene in 10 seeds")
+
+
+def test_reproject_edge_cases(oracle):
+    s = synth.make_reproject_scene(5, "icl", M=40)
+    c = s["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]), materialize_sobel=True)
+    kf_ids, _, _ = ctx.upload_frames(s["kf_imgs"])
+    cur_id = ctx.upload_frames([s["cur_img"]])[0][0]
+    arr = Context.reproj_cands(s["cands"], frame_ids=kf_ids)
+    # empty candidate list: nothing to do, reprojectCellAll branch
+    out, summ = ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], arr, s["grid"], s["cell_order"], M=0)
+    assert summ.n_matches == 0 and summ.n_in_frame == 0
+    # a point behind the camera and a point with a bad pose index
+    cands = [dict(s["cands"][0], p_host=np.array([0.0, 0.0, -3.0]))]
+    out, summ = ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], Context.reproj_cands(cands, frame_ids=kf_ids), s["grid"], s["cell_order"], M=1)
+    assert out[0].in_frame == 0 and out[0].tried == 0 and summ.n_in_frame == 0
+    with pytest.raises(HsoError):
+        ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], Context.reproj_cands([dict(s["cands"][0], host_pose=99)], frame_ids=kf_ids), s["grid"],
+                            s["cell_order"], M=1)
+    # cell_order must be a permutation
+    bad = s["cell_order"].copy()
+    bad[0] = bad[1]
+    with pytest.raises(HsoError):
+        ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], arr, s["grid"], bad)
+    # max_fts = 0: the reference's loops break at once after the first cell / candidate
+    g0 = dict(s["grid"], max_fts=0)
+    out, summ = ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], arr, g0, s["cell_order"])
+    oc = (oracle.orc_reproj_cand * 40).from_buffer_copy(bytes(Context.reproj_cands(s["cands"])))
+    io = (oracle.orc_reproj_result * 40)()
+    for i in range(40):
+        io[i].in_frame, io[i].cell = out[i].in_frame, out[i].cell
+    og = oracle.orc_reproj_grid(*[g0[k] for k in ("cell_size", "n_cols", "n_rows", "max_fts", "align_max_iter")], 0)
+    osum = oracle.reproject_select(oc, np.array([out[i].align_ok for i in range(40)], np.uint8), og, s["cell_order"], io)
+    assert [out[i].tried for i in range(40)] == [io[i].tried for i in range(40)] and summ.n_matches == osum.n_matches
+    ctx.close()
