@@ -273,6 +273,75 @@ def other_rows(ctx, lib, args, dev, torch, K):
         row.update({"cpu_frames_per_s_1core": 1.0 / cpu, "cpu_kind": "reference (oracle/_ref/libfast_ref.so = thirdparty/fast compiled from the reference sources; "
                     "the reference itself runs the three levels on three threads)"})
     out["fast_detect"] = row
+    # ---- N1: map reprojection + grid selection + findMatchDirect, 3000 map points against 4 keyframes --------------------------------------
+    try:
+        from hso_b200 import Context, make_cam
+        sc = synth.make_reproject_scene(args.seed + 20, args.cam, M=3000, n_kf=4, max_fts=200)
+        ctxs = Context(make_cam(W, H, c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), device=dev.index, max_frames=8, materialize_sobel=True)
+        kf_ids, _, _ = ctxs.upload_frames(sc["kf_imgs"])
+        cur_id = ctxs.upload_frames([sc["cur_img"]])[0][0]
+        carr = Context.reproj_cands(sc["cands"], frame_ids=kf_ids)
+        ctxs.reproject_match(cur_id, sc["T_cur_w"], sc["T_f_w"], carr, sc["grid"], sc["cell_order"])
+        t0 = time.perf_counter()
+        for _ in range(20):
+            _, summ = ctxs.reproject_match(cur_id, sc["T_cur_w"], sc["T_f_w"], carr, sc["grid"], sc["cell_order"])
+        dt = (time.perf_counter() - t0) / 20
+        oc = (O.orc_reproj_cand * 3000).from_buffer_copy(bytes(Context.reproj_cands(sc["cands"])))
+        pyrs = [O.create_pyramid(im, 5)[0] for im in sc["kf_imgs"]]
+        cl2, _ = O.create_pyramid(sc["cur_img"], 5)
+        sob2 = [O.sobel5(cl2[l]) for l in range(3)]
+        og = O.orc_reproj_grid(*[sc["grid"][k] for k in ("cell_size", "n_cols", "n_rows", "max_fts", "align_max_iter")], 0)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            _, osum = O.reproject_match(sc["cam"], sc["T_cur_w"], sc["T_f_w"], oc, og, sc["cell_order"], 2, pyrs, cl2, sob2)
+        cpu = (time.perf_counter() - t0) / 20
+        t0 = time.perf_counter()
+        O.reproject_speculative(sc["cam"], sc["T_cur_w"], sc["T_f_w"], oc, og, 2, pyrs, cl2, sob2)
+        cpu_all = time.perf_counter() - t0
+        out["reproject_match"] = {"gpu_frames_per_s_e2e": 1.0 / dt, "gpu_ms_per_frame": dt * 1e3, "cpu_frames_per_s_1core": 1.0 / cpu,
+                                  "cpu_ms_per_frame": cpu * 1e3, "cpu_ms_all_candidates": cpu_all * 1e3, "candidates": 3000, "max_fts": 200,
+                                  "gpu_matches": int(summ.n_matches), "gpu_trials": int(summ.n_trials), "cpu_trials": int(osum.n_trials),
+                                  "note": "hso_reproject_match (H2D candidates, k_reproject + k_align on ALL candidates + k_reproj_select, D2H) vs the "
+                                          "oracle's sequential walk, which stops at the first match per cell and so aligns only ~n_trials candidates; "
+                                          "cpu_ms_all_candidates = the oracle aligning every candidate like the device does"}
+        ctxs.close()
+    except Exception as e:  # a next-row diagnostic must not take the headline line down
+        out["reproject_match"] = {"error": repr(e)}
+    # ---- N4: raw 1280x1024 image -> ImageReader resize -> undistortion remap -> Frame (TUM monoVO wide, FOV model), 32 frames per call --------
+    try:
+        from hso_b200 import Context, make_cam
+        cf = synth.CAMS["tum_fov"]
+        ctxi = Context(make_cam(cf["width"], cf["height"], cf["fx"], cf["fy"], cf["cx"], cf["cy"], cf["d"], cf["model"]), device=dev.index, max_frames=40)
+        rng = np.random.default_rng(args.seed + 30)
+        raw = torch.from_numpy(np.stack([synth.texture(rng, 1280, 1024)] * 32)).pin_memory().numpy()
+        raws = [raw[i] for i in range(32)]
+
+        def up_raw():
+            ids_, _, _ = ctxi.upload_raw_frames(raws, undistort=True)
+            for i_ in ids_:
+                ctxi.release(i_)
+        up_raw()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            up_raw()
+        dt = (time.perf_counter() - t0) / 5
+        t0 = time.perf_counter()
+        m1, m2 = O.init_undistort_maps(cf)
+        t_maps = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(3):
+            im = O.remap_linear(O.resize_linear(raws[0], cf["width"], cf["height"]), m1, m2)
+            lv, _ = O.create_pyramid(im, 5)
+            O.frame_stats(im)
+        cpu = (time.perf_counter() - t0) / 3
+        out["raw_input"] = {"gpu_frames_per_s_e2e": 32 / dt, "gpu_ms_per_frame": dt * 1e3 / 32, "cpu_frames_per_s_1core": 1.0 / cpu, "raw": "1280x1024",
+                            "frame": f"{cf['width']}x{cf['height']}", "bytes_per_frame": 1280 * 1024 + 2 * cf["width"] * cf["height"] * 4,
+                            "cpu_map_build_ms": t_maps * 1e3,
+                            "note": "hso_frame_upload_raw_batch (H2D raw + k_resize_u8 + k_remap_u8 + pyramid + stats read-back) vs the oracle's "
+                                    "cv::resize + cv::remap restatement + pyramid + stats (scalar C, not OpenCV's SIMD)"}
+        ctxi.close()
+    except Exception as e:
+        out["raw_input"] = {"error": repr(e)}
     for f_ in fid:
         ctx.release(f_)
     return out

@@ -105,6 +105,8 @@ SYMBOLS = {
     "hso_kernel_launches": (C.c_uint64, [_vp]),
     "hso_frame_upload": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _P(C.c_int32), _P(C.c_float), _P(C.c_float)]),
     "hso_frame_upload_batch": (C.c_int, [_vp, C.c_int, _P(_vp), C.c_int, C.c_int, C.c_int, _P(C.c_int32), _P(C.c_float), _P(C.c_float)]),
+    "hso_frame_upload_raw_batch": (C.c_int, [_vp, C.c_int, _P(_vp), C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_int32), _P(C.c_float), _P(C.c_float)]),
+    "hso_undistort_maps": (C.c_int, [_vp, _vp, _vp]),
     "hso_frame_build_batch_device": (C.c_int, [_vp, C.c_int, _P(_vp), C.c_int, C.c_int, C.c_int, _P(C.c_int32)]),
     "hso_frame_rebuild_batch_device": (C.c_int, [_vp, C.c_int, _P(_vp), C.c_int, C.c_int, C.c_int, _P(C.c_int32)]),
     "hso_frame_stats": (C.c_int, [_vp, C.c_int32, _P(C.c_float), _P(C.c_float)]),

@@ -81,6 +81,28 @@ class Context:
                                                   integral.ctypes.data_as(C.POINTER(C.c_float)), gm.ctypes.data_as(C.POINTER(C.c_float))))
         return list(ids), integral, gm
 
+    def upload_raw_frames(self, imgs, undistort=False):
+        """Raw images (any size; resized to the camera size like ImageReader::readImage when it differs) -> optional undistortion remap
+        (AbstractCamera::undistortImage) -> Frame. Returns (ids, integral, grad_mean)."""
+        B = len(imgs)
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in imgs]
+        H, W = imgs[0].shape
+        ptrs = (C.c_void_p * B)(*[im.ctypes.data for im in imgs])
+        ids = (C.c_int32 * B)()
+        integral = np.zeros(B, np.float32)
+        gm = np.zeros(B, np.float32)
+        fp = C.POINTER(C.c_float)
+        self._chk(self.lib.hso_frame_upload_raw_batch(self.h, B, ptrs, W, H, imgs[0].strides[0], int(bool(undistort)), ids,
+                                                      integral.ctypes.data_as(fp), gm.ctypes.data_as(fp)))
+        return list(ids), integral, gm
+
+    def undistort_maps(self):
+        w, h = self.level_size(0)
+        m1 = np.zeros((h, w, 2), np.int16)
+        m2 = np.zeros((h, w), np.uint16)
+        self._chk(self.lib.hso_undistort_maps(self.h, m1.ctypes.data, m2.ctypes.data))
+        return m1, m2
+
     def level_size(self, level):
         w, h = C.c_int(), C.c_int()
         self._chk(self.lib.hso_frame_level_size(self.h, 0, level, C.byref(w), C.byref(h)))

@@ -96,6 +96,14 @@ struct hso_ctx {
   // FAST scratch
   DevBuf f_score, f_rowbuf, f_rowcount, f_out, f_total;
   PinBuf f_out_host;
+  // input side (row N4): raw staging, undistortion maps (built on first use), resize tables of the last raw size
+  DevBuf in_raw, in_mid, in_ptrs, u_map1, u_map2, in_tab_blob;
+  PinBuf in_ptrs_host;
+  bool u_maps_ready = false;
+  std::vector<short> u_map1_host;
+  std::vector<uint16_t> u_map2_host;
+  ResizeTabDev in_tab{};
+  int in_tab_w = 0, in_tab_h = 0;
   // reprojection (row N1) scratch
   DevBuf r_arena;
   PinBuf r_stage_host, r_out_host;
@@ -355,10 +363,10 @@ void hso_destroy(hso_ctx* ctx) {
     if (s.sobel) cudaFree(s.sobel);
   }
   DevBuf* db[] = {&ctx->f_score, &ctx->f_rowbuf, &ctx->f_rowcount, &ctx->f_out, &ctx->f_total, &ctx->pyr_arena, &ctx->sums_arena, &ctx->stats_table, &ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
-                  &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->r_arena, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
+                  &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->in_raw, &ctx->in_mid, &ctx->in_ptrs, &ctx->u_map1, &ctx->u_map2, &ctx->in_tab_blob, &ctx->r_arena, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ctx->f_out_host, &ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
-                  &ctx->a_jobs_host, &ctx->a_out_host, &ctx->r_stage_host, &ctx->r_out_host, &ctx->p_stage_host, &ctx->p_out_host};
+                  &ctx->a_jobs_host, &ctx->a_out_host, &ctx->in_ptrs_host, &ctx->r_stage_host, &ctx->r_out_host, &ctx->p_stage_host, &ctx->p_out_host};
   for (PinBuf* b : pb) b->release();
   for (cudaEvent_t e : ctx->t_ev) if (e) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -419,6 +427,88 @@ int hso_frame_upload_batch(hso_ctx* ctx, int B, const uint8_t* const* imgs, int 
   if (rc != HSO_OK) return rc;
   rc = read_stats(ctx, B, out, integral, grad_mean);
   if (rc != HSO_OK) return rc;
+  tm.stop_after_sync();
+  return HSO_OK;
+}
+
+// ---- N4: raw image -> (resize) -> (undistort) -> Frame --------------------------------------------------------------------------
+static int ensure_undistort_maps(hso_ctx* ctx) {
+  if (ctx->u_maps_ready) return HSO_OK;
+  build_undistort_maps(ctx->cam, ctx->u_map1_host, ctx->u_map2_host);
+  CU(ctx->u_map1.reserve(ctx->u_map1_host.size() * sizeof(short)));
+  CU(ctx->u_map2.reserve(ctx->u_map2_host.size() * sizeof(uint16_t)));
+  CU(cudaMemcpy(ctx->u_map1.p, ctx->u_map1_host.data(), ctx->u_map1_host.size() * sizeof(short), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->u_map2.p, ctx->u_map2_host.data(), ctx->u_map2_host.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  ctx->u_maps_ready = true;
+  return HSO_OK;
+}
+
+int hso_undistort_maps(hso_ctx* ctx, int16_t* map1, uint16_t* map2) {
+  if (!ctx) return HSO_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_undistort_maps(ctx);
+  if (rc != HSO_OK) return rc;
+  if (map1) memcpy(map1, ctx->u_map1_host.data(), ctx->u_map1_host.size() * sizeof(short));
+  if (map2) memcpy(map2, ctx->u_map2_host.data(), ctx->u_map2_host.size() * sizeof(uint16_t));
+  return HSO_OK;
+}
+
+int hso_frame_upload_raw_batch(hso_ctx* ctx, int B, const uint8_t* const* imgs, int raw_w, int raw_h, int stride, int undistort, hso_frame_id* out,
+                               float* integral, float* grad_mean) {
+  if (!ctx || B <= 0 || !imgs || !out || raw_w <= 1 || raw_h <= 1 || stride < raw_w) return HSO_ERR_INVALID;
+  const int W = ctx->cam.width, H = ctx->cam.height;
+  const bool need_resize = raw_w != W || raw_h != H;
+  if (!need_resize && !undistort) return hso_frame_upload_batch(ctx, B, imgs, W, H, stride, out, integral, grad_mean);
+  CU(cudaSetDevice(ctx->device));
+  for (int i = 0; i < B; ++i)
+    if (!imgs[i]) return fail(ctx, HSO_ERR_INVALID, "null image");
+  if (undistort) { int rc = ensure_undistort_maps(ctx); if (rc != HSO_OK) return rc; }
+  CU(cudaStreamSynchronize(ctx->stream));  // staging buffers below are reused between calls
+  if (need_resize && (ctx->in_tab_w != raw_w || ctx->in_tab_h != raw_h)) {
+    std::vector<char> blob;
+    ResizeTabDev t{};
+    build_resize_tab(ctx, raw_w, raw_h, W, H, blob, t);
+    CU(ctx->in_tab_blob.reserve(blob.size()));
+    CU(cudaMemcpy(ctx->in_tab_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    char* base = (char*)ctx->in_tab_blob.p;
+    t.xofs = (const int*)(base + (size_t)t.xofs); t.ialpha = (const short*)(base + (size_t)t.ialpha);
+    t.yofs = (const int*)(base + (size_t)t.yofs); t.ibeta = (const short*)(base + (size_t)t.ibeta);
+    ctx->in_tab = t; ctx->in_tab_w = raw_w; ctx->in_tab_h = raw_h;
+  }
+  for (int i = 0; i < B; ++i) {
+    int rc = alloc_frame(ctx, &out[i]);
+    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) ctx->frames[out[j]].used = false; return rc; }
+  }
+  const size_t raw_bytes = ((size_t)raw_w * raw_h + 255) / 256 * 256, mid_bytes = ((size_t)W * H + 255) / 256 * 256;
+  CU(ctx->in_raw.reserve(raw_bytes * B));
+  if (need_resize && undistort) CU(ctx->in_mid.reserve(mid_bytes * B));
+  CU(ctx->in_ptrs.reserve(sizeof(void*) * 3 * B));
+  CU(ctx->in_ptrs_host.reserve(sizeof(void*) * 3 * B));
+  const uint8_t** hp = (const uint8_t**)ctx->in_ptrs_host.p;  // [raw | mid | level-0 slot] x B
+  std::vector<const uint8_t*> srcs(B);
+  for (int i = 0; i < B; ++i) {
+    hp[i] = (const uint8_t*)ctx->in_raw.p + raw_bytes * i;
+    hp[B + i] = (need_resize && undistort) ? (const uint8_t*)ctx->in_mid.p + mid_bytes * i : nullptr;
+    hp[2 * B + i] = get_frame(ctx, out[i])->pyr + ctx->geom.off[0];
+    srcs[i] = hp[2 * B + i];
+  }
+  StageTimer tm(ctx, 0);
+  CU(cudaMemcpyAsync(ctx->in_ptrs.p, hp, sizeof(void*) * 3 * B, cudaMemcpyHostToDevice, ctx->stream));
+  for (int i = 0; i < B; ++i)
+    CU(cudaMemcpy2DAsync((void*)hp[i], raw_w, imgs[i], stride, raw_w, raw_h, cudaMemcpyHostToDevice, ctx->stream));
+  const uint8_t* const* d_raw = (const uint8_t* const*)ctx->in_ptrs.p;
+  uint8_t* const* d_mid = (uint8_t* const*)ctx->in_ptrs.p + B;
+  uint8_t* const* d_dst = (uint8_t* const*)ctx->in_ptrs.p + 2 * B;
+  if (need_resize)  // ImageReader::readImage: cv::resize(image, image, m_img_new_size)
+    CU(launch_resize(d_raw, raw_w, raw_h, raw_w, ctx->in_tab, undistort ? d_mid : d_dst, W, H, B, ctx->stream, &ctx->launches));
+  if (undistort)    // cam_->undistortImage(image, image)
+    CU(launch_remap(need_resize ? (const uint8_t* const*)d_mid : d_raw, W, H, W, (const short2*)ctx->u_map1.p, (const uint16_t*)ctx->u_map2.p, d_dst,
+                    W, H, B, ctx->stream, &ctx->launches));
+  int rc = run_pyramid(ctx, B, out, srcs.data(), W, 1);
+  if (rc != HSO_OK) return rc;
+  rc = read_stats(ctx, B, out, integral, grad_mean);
+  if (rc != HSO_OK) return rc;
+  if (!integral && !grad_mean) CU(cudaStreamSynchronize(ctx->stream));
   tm.stop_after_sync();
   return HSO_OK;
 }

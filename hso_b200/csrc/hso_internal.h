@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/hso_b200.h"
 #include "common.cuh"
 
@@ -110,6 +112,13 @@ struct AlignJobDev {
 };
 cudaError_t launch_align(const PyrGeom& g, const uint8_t* cur_pyr, const int16_t* cur_sobel, const AlignJobDev* jobs_dev, int M, int max_iter,
                          hso_align_result* out_dev, cudaStream_t stream, uint64_t* launches);
+
+// ---- input side (row N4): resize + undistortion remap ---------------------------------------------------------------------------
+void build_undistort_maps(const hso_cam& cam, std::vector<short>& map1, std::vector<uint16_t>& map2);  // host, once per camera
+cudaError_t launch_remap(const uint8_t* const* srcs_dev, int sw, int sh, int sstride, const short2* map1, const uint16_t* map2,
+                         uint8_t* const* dsts_dev, int dw, int dh, int B, cudaStream_t stream, uint64_t* launches);
+cudaError_t launch_resize(const uint8_t* const* srcs_dev, int sw, int sh, int sstride, const ResizeTabDev& tab, uint8_t* const* dsts_dev, int dw,
+                          int dh, int B, cudaStream_t stream, uint64_t* launches);
 
 // ---- reprojection + grid selection (row N1) -------------------------------------------------------------------------------
 struct ReprojKParams {

@@ -80,6 +80,15 @@ int hso_frame_level_size(hso_ctx* ctx, hso_frame_id id, int level, int* w, int* 
 int hso_frame_download_level(hso_ctx* ctx, hso_frame_id id, int level, uint8_t* dst);
 int hso_frame_download_sobel(hso_ctx* ctx, hso_frame_id id, int level, int16_t* gx, int16_t* gy);
 int hso_frame_release(hso_ctx* ctx, hso_frame_id id);
+/* ---- N4 (next row): input side — what test/test_dataset.cpp:262-283 does to a raw image before addImage: ImageReader::readImage's
+ * cv::resize(image, image, m_img_new_size) (src/ImageReader.cpp:80) when (raw_w, raw_h) differs from the camera size, then
+ * cam->undistortImage(image, image) = cv::remap(INTER_LINEAR) through the CV_16SC2 maps the camera constructor builds
+ * (src/camera.cpp:47-54,127-131 pinhole; :223-271 FOV; :317-369 equidistant) when undistort != 0, then new Frame (pyramid + statistics).
+ * Bit-exact against OpenCV (cv2 4.13 golden vectors). hso_undistort_maps returns the maps ([H][W][2] int16, [H][W] uint16) for host consumers. */
+int hso_frame_upload_raw_batch(hso_ctx* ctx, int B, const uint8_t* const* imgs, int raw_w, int raw_h, int stride, int undistort, hso_frame_id* out,
+                               float* integral, float* grad_mean);
+int hso_undistort_maps(hso_ctx* ctx, int16_t* map1, uint16_t* map2);
+
 
 /* ---- F2: sparse direct image alignment — replaces size_t hso::CoarseTracker::run(FramePtr ref, FramePtr cur)
  * (include/hso/CoarseTracker.h:134,141 ; src/CoarseTracker.cpp:51-208). ------------------------------------------------ */

@@ -188,6 +188,11 @@ void orc_pose_optimize(double reproj_thresh, int n_iter, double err_mult2 /* cam
                        const double* grad, const int8_t* level, const int8_t* ftype, const int8_t* ptype,
                        const double T_f_w_in[12], uint8_t* outlier_out /*F*/, orc_pose_result* out);
 
+/* ---- N4: undistortion maps (src/camera.cpp:47-54,223-265,317-363) and cv::remap INTER_LINEAR (:127-131,267-271,365-369) ---- */
+void orc_convert_maps(const float* mapx, const float* mapy, int n, int16_t* map1, uint16_t* map2);
+int orc_init_undistort_maps(const orc_cam* cam, int16_t* map1 /*[h][w][2]*/, uint16_t* map2 /*[h][w]*/);
+void orc_remap_linear_u8(const uint8_t* src, int sw, int sh, int sstride, const int16_t* map1, const uint16_t* map2, int dw, int dh, uint8_t* dst);
+
 /* ---- N2: FeatureExtractor::fastDetectST (src/feature_detection.cpp:498-523; thirdparty/fast) ---- */
 typedef struct {
   int16_t x, y;       /* level pixel */

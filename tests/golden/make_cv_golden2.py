@@ -39,6 +39,13 @@ m1b, m2b = cv2.initUndistortRectifyMap(K4f, d2f, np.eye(3), K4f, (W, H), cv2.CV_
 out["remap2_d"] = d2
 out["remap2_map1"], out["remap2_map2"] = m1b, m2b
 out["remap2_dst"] = cv2.remap(img, m1b, m2b, cv2.INTER_LINEAR)
+# cv::convertMaps(float, float -> CV_16SC2) as FOVCamera/EquidistantCamera::getRemap call it (camera.cpp:244,339), on maps that leave the
+# source on every side, and the remap through them (BORDER_CONSTANT branches)
+mx = (np.arange(W, dtype=np.float32)[None, :] * np.float32(1.13) - np.float32(9.3) + rng.normal(0, 0.7, (H, W)).astype(np.float32)).astype(np.float32)
+my = (np.arange(H, dtype=np.float32)[:, None] * np.float32(1.17) - np.float32(7.1) + rng.normal(0, 0.7, (H, W)).astype(np.float32)).astype(np.float32)
+c1, c2 = cv2.convertMaps(mx, my, cv2.CV_16SC2)
+out["conv_mapx"], out["conv_mapy"], out["conv_map1"], out["conv_map2"] = mx, my, c1, c2
+out["conv_dst"] = cv2.remap(img, c1, c2, cv2.INTER_LINEAR)
 # ImageReader-style resize (src/ImageReader.cpp:80 cv::resize to a target size, INTER_LINEAR default): 1280x1024 -> 920x736 scaled by 1/8
 src = np.clip(rng.normal(110, 60, (128, 160)), 0, 255).astype(np.uint8)
 out["reader_src"] = src

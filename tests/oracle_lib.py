@@ -381,3 +381,47 @@ def reproject_select(cands, match_ok, grid, cell_order, io):
     lib.orc_reproject_select(len(cands), cands, ok.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(grid), order.ctypes.data_as(C.POINTER(C.c_int32)),
                              io, C.byref(summ))
     return summ
+
+
+# ---- N4: undistortion maps + cv::remap -----------------------------------------------------------------------------------------------
+def init_undistort_maps(cam):
+    lib = load()
+    W, H = cam["width"], cam["height"]
+    m1 = np.zeros((H, W, 2), np.int16)
+    m2 = np.zeros((H, W), np.uint16)
+    lib.orc_init_undistort_maps.restype = C.c_int
+    rc = lib.orc_init_undistort_maps(C.byref(cam_of(cam)), m1.ctypes.data_as(C.c_void_p), m2.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return m1, m2
+
+
+def remap_linear(src, m1, m2):
+    lib = load()
+    src = np.ascontiguousarray(src, np.uint8)
+    m1 = np.ascontiguousarray(m1, np.int16)
+    m2 = np.ascontiguousarray(m2, np.uint16)
+    dh, dw = m2.shape
+    dst = np.zeros((dh, dw), np.uint8)
+    lib.orc_remap_linear_u8(src.ctypes.data_as(C.c_void_p), src.shape[1], src.shape[0], src.shape[1], m1.ctypes.data_as(C.c_void_p),
+                            m2.ctypes.data_as(C.c_void_p), dw, dh, dst.ctypes.data_as(C.c_void_p))
+    return dst
+
+
+def resize_linear(src, dw, dh):
+    """cv::resize(INTER_LINEAR) restatement (orc_resize_linear_u8, pinned against cv2 golden vectors in test_oracle_pins.py)."""
+    lib = load()
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib.orc_resize_linear_u8(src.ctypes.data_as(C.c_void_p), src.shape[1], src.shape[0], dst.ctypes.data_as(C.c_void_p), int(dw), int(dh))
+    return dst
+
+
+def convert_maps(mx, my):
+    lib = load()
+    mx = np.ascontiguousarray(mx, np.float32)
+    my = np.ascontiguousarray(my, np.float32)
+    h, w = mx.shape
+    m1 = np.zeros((h, w, 2), np.int16)
+    m2 = np.zeros((h, w), np.uint16)
+    lib.orc_convert_maps(mx.ctypes.data_as(C.c_void_p), my.ctypes.data_as(C.c_void_p), h * w, m1.ctypes.data_as(C.c_void_p), m2.ctypes.data_as(C.c_void_p))
+    return m1, m2
