@@ -9,6 +9,8 @@
 //   CoarseTracker::makeDepthRef()              CoarseTracker.cpp:210  makeDepthRef(ref)  (host: pointer chasing over Feature/Point)
 //   pose_optimizer::optimizeLevenbergMarquardt3rd(...)  pose_optimizer.h:61  hso::b200::pose_optimizer::optimizeLevenbergMarquardt3rd(...)
 //   Matcher::findMatchDirect(pt, cur, px)      matcher.h:153        Matcher::findMatchDirectBatch(candidates, cur)  (after getWarpMatrixAffine)
+//   Reprojector::reprojectMap(frame, ...)      reprojector.h        Reprojector::reprojectMap(frame, points, keyframes)  (row N1: one device call)
+//   FrameHandlerMono::addImage front end       frame_handler_mono.cpp:92,190-204  addImagesAndTrack(...)  (B streams, chunk-pipelined)
 //
 // Poses are 3x4 row-major [R|t] (SE3::matrix3x4()). All arithmetic of the path runs on the GPU; this layer only flattens.
 #pragma once
@@ -70,11 +72,19 @@ class Context {
 struct Frame;
 struct Feature;
 
-struct Point {  // include/hso/point.h:53 (subset the path reads)
+struct Point {  // include/hso/point.h:53-120 (subset the path reads)
   enum PointType { TYPE_DELETED = 0, TYPE_TEMPORARY = 1, TYPE_CANDIDATE = 2, TYPE_UNKNOWN = 3, TYPE_GOOD = 4 };
+  enum FeatureType { FEATURE_GRADIENT = 0, FEATURE_EDGELET = 1, FEATURE_CORNER = 2 };
   double idist_ = 1.0;
   const Feature* hostFeature_ = nullptr;
   int type_ = TYPE_GOOD;
+  int ftr_type_ = FEATURE_CORNER;
+  double pos_[3] = {0, 0, 0};              // world position
+  std::vector<const Feature*> obs_;        // keyframe observations (std::list<Feature*> in the reference)
+  int n_failed_reproj_ = 0, n_succeeded_reproj_ = 0;
+  bool isBad_ = false;
+  // src/point.cpp:116-136 — pointer chasing over the observations stays on the host
+  inline bool getCloseViewObs(const double framepos[3], const Feature*& ftr) const;
 };
 
 struct Feature {  // include/hso/feature.h:36-64 (subset)
@@ -106,8 +116,32 @@ struct Frame {  // include/hso/frame.h (subset): the pyramid lives on the device
   std::vector<Feature> fts_;
   double Cov_[36] = {0};
   float m_error_in_px = 0;
+  int keyFrameId_ = 0;
+  void pos(double out[3]) const {  // Frame::pos() = T_f_w_.inverse().translation()
+    const SE3 Ti = T_f_w_.inverse();
+    out[0] = Ti.m[3]; out[1] = Ti.m[7]; out[2] = Ti.m[11];
+  }
 };
 typedef std::shared_ptr<Frame> FramePtr;
+
+inline bool Point::getCloseViewObs(const double framepos[3], const Feature*& ftr) const {
+  if (obs_.empty()) return false;
+  double od[3] = {framepos[0] - pos_[0], framepos[1] - pos_[1], framepos[2] - pos_[2]};
+  const double on = std::sqrt(od[0] * od[0] + od[1] * od[1] + od[2] * od[2]);
+  for (double& v : od) v /= on;
+  size_t best = 0;
+  double min_cos_angle = 0;
+  for (size_t i = 0; i < obs_.size(); ++i) {
+    double fp[3];
+    obs_[i]->frame->pos(fp);
+    double d[3] = {fp[0] - pos_[0], fp[1] - pos_[1], fp[2] - pos_[2]};
+    const double dn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const double cos_angle = (od[0] * d[0] + od[1] * d[1] + od[2] * d[2]) / dn;
+    if (cos_angle > min_cos_angle) { min_cos_angle = cos_angle; best = i; }
+  }
+  ftr = obs_[best];
+  return !(min_cos_angle < 0.5);  // observations more than 60 degrees apart are useless
+}
 
 class CoarseTracker {  // include/hso/CoarseTracker.h:134-143
  public:
@@ -272,6 +306,153 @@ class Matcher {  // include/hso/matcher.h:113-153 (direct part)
  private:
   Context& ctx_;
 };
+
+// include/hso/reprojector.h — the data path of Reprojector::reprojectMap (src/reprojector.cpp:88-331) in ONE device call. The caller
+// enumerates the points exactly like the reference's loops over the covisible / close keyframes, the candidates and the temporary points
+// (those loops chase Map / Frame lists and stay on the host) and hands them over in that order.
+class Reprojector {
+ public:
+  struct Grid { int cell_size = 0, grid_n_cols = 0, grid_n_rows = 0; std::vector<int32_t> cell_order; } grid_;
+  size_t n_matches_ = 0, n_trials_ = 0;
+  int nFeatures_ = 0;
+  Reprojector(Context& ctx, size_t max_fts) : ctx_(ctx), max_fts_(max_fts) {
+    // Reprojector::initializeGrid (:58-77), caculateGridSize (:53-56)
+    const int W = ctx.cam().width, H = ctx.cam().height;
+    grid_.cell_size = (int)std::floor(std::sqrt((float)(W * H) / (float)max_fts) * 0.6);
+    grid_.grid_n_cols = (int)std::ceil((double)W / grid_.cell_size);
+    grid_.grid_n_rows = (int)std::ceil((double)H / grid_.cell_size);
+    grid_.cell_order.resize((size_t)grid_.grid_n_cols * grid_.grid_n_rows);
+    for (size_t i = 0; i < grid_.cell_order.size(); ++i) grid_.cell_order[i] = (int32_t)i;
+  }
+  // Reprojector::resetGrid (:79-86) re-shuffles grid_.cell_order with std::random_shuffle; the permutation is the caller's to choose
+  // (pass any UniformRandomBitGenerator) so that runs are reproducible.
+  template <class Rng>
+  void resetGrid(Rng& rng) {
+    n_matches_ = 0; n_trials_ = 0; nFeatures_ = 0;
+    for (size_t i = grid_.cell_order.size(); i > 1; --i) std::swap(grid_.cell_order[i - 1], grid_.cell_order[rng() % i]);
+  }
+  // points: in the order the reference calls reprojectPoint. Side effects of reprojectCell / reprojectCellAll (:351-424,545-615) are applied
+  // here: n_failed_reproj_ / n_succeeded_reproj_, TYPE_UNKNOWN -> TYPE_GOOD promotion, isBad_, and the new Features of `frame`.
+  void reprojectMap(FramePtr frame, const std::vector<Point*>& points, std::vector<Frame*>& keyframes) {
+    const size_t M = points.size();
+    std::vector<hso_reproj_cand> cands(M);
+    std::vector<const Feature*> ref_ftrs(M, nullptr);
+    std::vector<double> T_f_w;
+    auto pose_index = [&](const Frame* f) {
+      for (size_t k = 0; k < keyframes.size(); ++k) if (keyframes[k] == f) return (int32_t)k;
+      keyframes.push_back(const_cast<Frame*>(f));
+      return (int32_t)(keyframes.size() - 1);
+    };
+    double cur_pos[3];
+    frame->pos(cur_pos);
+    for (size_t i = 0; i < M; ++i) {
+      const Point* pt = points[i];
+      hso_reproj_cand& c = cands[i];
+      std::memset(&c, 0, sizeof c);
+      const Feature* host = pt->hostFeature_;
+      const double inv = 1.0 / pt->idist_;
+      for (int k = 0; k < 3; ++k) c.p_host[k] = host->f[k] * inv;                       // :508
+      c.host_pose = pose_index(host->frame);
+      c.pt_type = pt->type_; c.pt_ftr_type = pt->ftr_type_;
+      const Feature* ref = nullptr;
+      c.ref_pose = -1;
+      if (pt->getCloseViewObs(cur_pos, ref)) {                                            // matcher.cpp:276
+        ref_ftrs[i] = ref;
+        c.ref_pose = pose_index(ref->frame);
+        c.ref_frame = ref->frame->id;
+        c.ref_level = ref->level; c.ftr_type = ref->type;
+        c.px_ref[0] = ref->px[0]; c.px_ref[1] = ref->px[1];
+        for (int k = 0; k < 3; ++k) c.f_ref[k] = ref->f[k];
+        c.grad[0] = ref->grad[0]; c.grad[1] = ref->grad[1];
+        if (ref->frame == host->frame) {                                                  // matcher.cpp:298-309
+          c.depth_ref = inv;
+        } else {
+          double rp[3];
+          ref->frame->pos(rp);
+          c.depth_ref = std::sqrt((rp[0] - pt->pos_[0]) * (rp[0] - pt->pos_[0]) + (rp[1] - pt->pos_[1]) * (rp[1] - pt->pos_[1]) +
+                                  (rp[2] - pt->pos_[2]) * (rp[2] - pt->pos_[2]));
+        }
+        const float a = frame->m_exposure_time / ref->frame->m_exposure_time;           // matcher.cpp:317-321
+        c.exposure_rat = a;
+        c.scale_patch = (frame->keyFrameId_ - ref->frame->keyFrameId_ < 4 && std::fabs(a * 128 - 128) > 30.f) ? 1 : 0;
+      }
+    }
+    for (Frame* kf : keyframes) T_f_w.insert(T_f_w.end(), kf->T_f_w_.m, kf->T_f_w_.m + 12);
+    hso_reproj_grid g;
+    g.cell_size = grid_.cell_size; g.n_cols = grid_.grid_n_cols; g.n_rows = grid_.grid_n_rows; g.max_fts = (int32_t)max_fts_;
+    g.align_max_iter = 10; g.pad_ = 0;
+    std::vector<hso_reproj_result> res(M + 1);
+    hso_reproj_summary summ;
+    ctx_.check(hso_reproject_match(ctx_.get(), frame->id, frame->T_f_w_.m, (int)keyframes.size(), T_f_w.data(), (int)M, cands.data(), &g,
+                                   grid_.cell_order.data(), res.data(), &summ));
+    n_matches_ = (size_t)summ.n_matches; n_trials_ = (size_t)summ.n_trials; nFeatures_ = summ.n_in_frame;
+    // new Features in the reference's order of creation
+    std::vector<int> by_order(summ.n_matches, -1);
+    for (size_t i = 0; i < M; ++i) {
+      Point* pt = points[i];
+      const hso_reproj_result& r = res[i];
+      if (!r.tried) continue;
+      if (!r.matched) {
+        pt->n_failed_reproj_++;                                                           // :368-378
+        if (pt->type_ == Point::TYPE_TEMPORARY && pt->n_failed_reproj_ > 30) pt->isBad_ = true;
+        continue;
+      }
+      pt->n_succeeded_reproj_++;
+      if (pt->type_ == Point::TYPE_UNKNOWN && pt->n_succeeded_reproj_ > 10) pt->type_ = Point::TYPE_GOOD;  // :385-386
+      by_order[r.order] = (int)i;
+    }
+    for (int i : by_order) {
+      if (i < 0) continue;
+      const hso_reproj_result& r = res[i];
+      Feature nf;                                                                         // new Feature(frame.get(), it->px, matcher_.search_level_)
+      nf.frame = frame.get(); nf.px[0] = r.px[0]; nf.px[1] = r.px[1]; nf.level = r.search_level; nf.point = points[i];
+      const Feature* ref = ref_ftrs[i];
+      if (ref->type == Feature::EDGELET) {                                                // :398-409
+        nf.type = Feature::EDGELET;
+        const double gx = r.A_cur_ref[0] * ref->grad[0] + r.A_cur_ref[1] * ref->grad[1], gy = r.A_cur_ref[2] * ref->grad[0] + r.A_cur_ref[3] * ref->grad[1];
+        const double n = std::sqrt(gx * gx + gy * gy);
+        nf.grad[0] = gx / n; nf.grad[1] = gy / n;
+      } else {
+        nf.type = ref->type == Feature::GRADIENT ? Feature::GRADIENT : Feature::CORNER;
+      }
+      frame->fts_.push_back(nf);
+    }
+  }
+
+ private:
+  Context& ctx_;
+  size_t max_fts_;
+};
+
+// The front end of FrameHandlerMono::addImage for B independent streams in one chunk-pipelined call: new Frame(cam, img) for every image and
+// CoarseTracker::run(ref_frames[b], new frame) (src/frame_handler_mono.cpp:92,190-204).
+inline void addImagesAndTrack(Context& ctx, const std::vector<const uint8_t*>& imgs, int W, int H, int stride, const std::vector<FramePtr>& ref_frames,
+                              const std::vector<SE3>& T_cur_ref_init, bool inverse_composition, int max_level, int min_level, int n_iter,
+                              std::vector<hso_frame_id>& new_ids, std::vector<hso_track_result>& results) {
+  const size_t B = imgs.size();
+  std::vector<hso_track_job> jobs(B);
+  std::vector<std::vector<double>> px(B), f(B), dist(B);
+  for (size_t b = 0; b < B; ++b) {
+    const Frame& ref = *ref_frames[b];
+    const size_t F = ref.fts_.size();
+    px[b].resize(2 * F); f[b].resize(3 * F);
+    CoarseTracker::makeDepthRef(ref, dist[b]);
+    for (size_t i = 0; i < F; ++i) {
+      px[b][2 * i] = ref.fts_[i].px[0]; px[b][2 * i + 1] = ref.fts_[i].px[1];
+      for (int k = 0; k < 3; ++k) f[b][3 * i + k] = ref.fts_[i].f[k];
+    }
+    hso_track_job& j = jobs[b];
+    std::memset(&j, 0, sizeof j);
+    j.ref = ref.id; j.n_features = (int32_t)F;
+    j.px = px[b].data(); j.f = f[b].data(); j.dist = dist[b].data();
+    std::memcpy(j.T_cur_ref, T_cur_ref_init[b].m, sizeof j.T_cur_ref);
+    j.exposure_rat = -1.f;  // formed on the device from the two frames' integralImage_ (CoarseTracker.cpp:60)
+  }
+  hso_track_params prm;
+  prm.inverse_comp = inverse_composition ? 1 : 0; prm.max_level = max_level; prm.min_level = min_level; prm.n_iter = n_iter;
+  new_ids.resize(B); results.resize(B);
+  ctx.check(hso_add_frames_track_batch(ctx.get(), &prm, (int)B, imgs.data(), W, H, stride, jobs.data(), new_ids.data(), nullptr, nullptr, results.data()));
+}
 
 }  // namespace b200
 }  // namespace hso

@@ -65,7 +65,48 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 12; ++k) std::printf("%.17g%s", fc->T_f_w_.m[k], k < 11 ? ", " : "");
     std::printf("], \"T_track\": [");
     for (int k = 0; k < 12; ++k) std::printf("%.17g%s", tracker.last_result().T_cur_ref[k], k < 11 ? ", " : "");
-    std::printf("], \"num_obs\": %zu, \"error_final\": %.9g, \"launches\": %llu}\n", nobs, e1, (unsigned long long)hso_kernel_launches(ctx.get()));
+    std::printf("], \"num_obs\": %zu, \"error_final\": %.9g, \"launches\": %llu", nobs, e1, (unsigned long long)hso_kernel_launches(ctx.get()));
+    // ---- FrameHandlerMono::addImage front end for 3 streams in one call: must reproduce the single-frame tracker result -----------------
+    {
+      std::vector<const uint8_t*> imgs(3, cur.data());
+      std::vector<FramePtr> refs(3, fr);
+      std::vector<SE3> T0(3);
+      std::vector<hso_frame_id> ids;
+      std::vector<hso_track_result> res;
+      addImagesAndTrack(ctx, imgs, W, H, W, refs, T0, false, 4, 1, 50, ids, res);
+      std::printf(", \"T_batch\": [");
+      for (int k = 0; k < 12; ++k) std::printf("%.17g%s", res[2].T_cur_ref[k], k < 11 ? ", " : "");
+      std::printf("], \"batch_iters\": [%d, %d, %d]", res[0].n_iters, res[1].n_iters, res[2].n_iters);
+      for (hso_frame_id id : ids) hso_frame_release(ctx.get(), id);
+    }
+    // ---- Reprojector::reprojectMap: the reference frame is the only keyframe, every point is observed there ----------------------------------
+    {
+      FramePtr fn(new Frame(ctx, cur.data(), W, H, W, 2.0));
+      std::memcpy(fn->T_f_w_.m, tracker.last_result().T_cur_ref, sizeof fn->T_f_w_.m);  // ref pose is the identity
+      std::vector<Point*> plist;
+      for (int i = 0; i < F; ++i) {
+        if (!has[i]) continue;
+        Point& p = pts[i];
+        const double inv = 1.0 / idist[i];
+        for (int k = 0; k < 3; ++k) p.pos_[k] = f[3 * i + k] * inv;
+        p.obs_.assign(1, &fr->fts_[i]);
+        p.type_ = 1 + i % 4; p.ftr_type_ = i % 3;
+        plist.push_back(&p);
+      }
+      Reprojector rep(ctx, 200);
+      unsigned long long state = 12345;
+      auto rng = [&]() { state = state * 6364136223846793005ULL + 1442695040888963407ULL; return (unsigned)(state >> 33); };
+      rep.resetGrid(rng);
+      std::vector<Frame*> kfs;
+      rep.reprojectMap(fn, plist, kfs);
+      int n_unknown_failed = 0;
+      for (Point* p : plist) n_unknown_failed += p->n_failed_reproj_;
+      std::printf(", \"reproj\": {\"n_matches\": %zu, \"n_trials\": %zu, \"n_in_frame\": %d, \"new_features\": %zu, \"failed\": %d, \"cell_size\": %d, "
+                  "\"cell_order\": [", rep.n_matches_, rep.n_trials_, rep.nFeatures_, fn->fts_.size(), n_unknown_failed, rep.grid_.cell_size);
+      for (size_t k = 0; k < rep.grid_.cell_order.size(); ++k) std::printf("%d%s", rep.grid_.cell_order[k], k + 1 < rep.grid_.cell_order.size() ? ", " : "");
+      std::printf("], \"first_px\": [%.12g, %.12g]}", fn->fts_.empty() ? 0.0 : fn->fts_[0].px[0], fn->fts_.empty() ? 0.0 : fn->fts_[0].px[1]);
+    }
+    std::printf("}\n");
   } catch (const std::exception& e) {
     std::fprintf(stderr, "host_smoke: %s\n", e.what());
     return 1;

@@ -45,4 +45,25 @@ def test_cpp_host_layer_matches_ctypes_path(tmp_path):
     assert np.abs(np.array(r["T_track"]).reshape(3, 4) - res[0]["T_cur_ref"]).max() < 1e-9
     assert r["num_obs"] > 0.5 * has.sum() and r["launches"] >= 8
     assert np.abs(np.array(r["T"]).reshape(3, 4) - p["T_true"][:3]).max() < 5e-3
+    # addImagesAndTrack (chunk-pipelined batch entry) reproduces the single-frame tracker exactly
+    assert np.array_equal(np.array(r["T_batch"]).reshape(3, 4), np.array(r["T_track"]).reshape(3, 4))
+    assert r["batch_iters"][0] == r["batch_iters"][1] == r["batch_iters"][2] == res[0]["n_iters"]
+    # Reprojector::reprojectMap through the C++ layer == the same candidates through the ctypes path
+    rp = r["reproj"]
+    T_track = np.array(r["T_track"]).reshape(3, 4)
+    idx = [i for i in range(F) if has[i]]
+    cands = []
+    for i in idx:
+        ph = p["f"][i] / idist[i]
+        cands.append(dict(p_host=ph, px_ref=p["px"][i], f_ref=p["f"][i], grad=np.array([1.0, 0.0]), depth_ref=1.0 / idist[i], host_pose=0, ref_pose=0,
+                          ref_frame=ids[0], ref_level=0, ftr_type=0, pt_type=1 + i % 4, pt_ftr_type=i % 3, scale_patch=0, exposure_rat=1.0))
+    cur2 = ctx.upload_frames([p["cur_img"]])[0][0]
+    W_, H_ = c["width"], c["height"]
+    cs = rp["cell_size"]
+    grid = dict(cell_size=cs, n_cols=int(np.ceil(W_ / cs)), n_rows=int(np.ceil(H_ / cs)), max_fts=200, align_max_iter=10)
+    out, summ = ctx.reproject_match(cur2, T_track, np.eye(4)[:3][None], Context.reproj_cands(cands), grid, np.array(rp["cell_order"], np.int32))
+    assert (summ.n_matches, summ.n_trials, summ.n_in_frame) == (rp["n_matches"], rp["n_trials"], rp["n_in_frame"])
+    assert rp["new_features"] == rp["n_matches"] > 50 and rp["failed"] == rp["n_trials"] - rp["n_matches"]
+    first = [i for i in range(len(idx)) if out[i].order == 0][0]
+    assert abs(out[first].px[0] - rp["first_px"][0]) < 1e-9 and abs(out[first].px[1] - rp["first_px"][1]) < 1e-9
     ctx.close()
