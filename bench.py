@@ -342,6 +342,34 @@ def other_rows(ctx, lib, args, dev, torch, K):
         ctxi.close()
     except Exception as e:
         out["raw_input"] = {"error": repr(e)}
+    # ---- N3: depth-filter observation of 2000 seeds (3 keyframes) against one active frame ------------------------------------------------
+    try:
+        from hso_b200 import Context, make_cam
+        sd = synth.make_depth_scene(args.seed + 40, args.cam, S=2000)
+        ctxd = Context(make_cam(W, H, c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), device=dev.index, max_frames=8, materialize_sobel=True)
+        kf_ids, _, _ = ctxd.upload_frames(sd["kf_imgs"])
+        cur_id = ctxd.upload_frames([sd["cur_img"]])[0][0]
+        sarr = Context.seed_obs(sd["seeds"], frame_ids=kf_ids)
+        ctxd.depth_observe(cur_id, sd["T_cur_w"], sd["T_f_w"], sarr, sd["px_error_angle"])
+        t0 = time.perf_counter()
+        for _ in range(20):
+            gres = ctxd.depth_observe(cur_id, sd["T_cur_w"], sd["T_f_w"], sarr, sd["px_error_angle"])
+        dt = (time.perf_counter() - t0) / 20
+        oc = (O.orc_seed_obs * 2000).from_buffer_copy(bytes(Context.seed_obs(sd["seeds"])))
+        pyrs = [O.create_pyramid(im, 5)[0] for im in sd["kf_imgs"]]
+        cl3, _ = O.create_pyramid(sd["cur_img"], 5)
+        sob3 = [O.sobel5(cl3[l]) for l in range(3)]
+        t0 = time.perf_counter()
+        for _ in range(5):
+            O.depth_observe(sd["cam"], sd["T_cur_w"], sd["T_f_w"], oc, sd["px_error_angle"], pyrs, cl3, sob3)
+        cpu = (time.perf_counter() - t0) / 5
+        out["depth_observe"] = {"gpu_seeds_per_s_e2e": 2000 / dt, "gpu_ms_per_frame": dt * 1e3, "cpu_seeds_per_s_1core": 2000 / cpu,
+                                "cpu_ms_per_frame": cpu * 1e3, "seeds": 2000, "updated": int(sum(gres[i].res == 1 for i in range(2000))),
+                                "note": "hso_depth_observe (H2D seeds, k_depth_observe, D2H results) vs the oracle's observeDepthRow on one core "
+                                        "(the reference splits the seed list over 4 threads)"}
+        ctxd.close()
+    except Exception as e:
+        out["depth_observe"] = {"error": repr(e)}
     for f_ in fid:
         ctx.release(f_)
     return out

@@ -81,6 +81,17 @@ class hso_reproj_summary(C.Structure):
     _fields_ = [("n_in_frame", C.c_int32), ("n_matches", C.c_int32), ("n_trials", C.c_int32), ("used_cell_all", C.c_int32)]
 
 
+class hso_seed_obs(C.Structure):
+    _fields_ = [("px", C.c_double * 2), ("f", C.c_double * 3), ("grad", C.c_double * 2), ("ref_frame", C.c_int32), ("ref_pose", C.c_int32),
+                ("level", C.c_int32), ("ftr_type", C.c_int32), ("mu", C.c_float), ("sigma2", C.c_float), ("exposure_rat", C.c_float),
+                ("pad_", C.c_float)]
+
+
+class hso_seed_result(C.Structure):
+    _fields_ = [("is_update", C.c_int32), ("is_valid", C.c_int32), ("res", C.c_int32), ("search_level", C.c_int32), ("epl_start", C.c_int32 * 2),
+                ("epl_end", C.c_int32 * 2), ("mu", C.c_float), ("sigma2", C.c_float), ("z", C.c_double), ("px_cur", C.c_double * 2)]
+
+
 class hso_corner(C.Structure):
     _fields_ = [("x", C.c_int16), ("y", C.c_int16), ("score", C.c_int32), ("shi_tomasi", C.c_float)]
 
@@ -132,6 +143,8 @@ SYMBOLS = {
     "hso_align_batch": (C.c_int, [_vp, C.c_int32, C.c_int, _P(hso_align_job), _P(C.c_int32), C.c_int, _P(hso_align_result)]),
     "hso_reproject_match": (C.c_int, [_vp, C.c_int32, _P(C.c_double), C.c_int, _P(C.c_double), C.c_int, _P(hso_reproj_cand), _P(hso_reproj_grid),
                                       _P(C.c_int32), _P(hso_reproj_result), _P(hso_reproj_summary)]),
+    "hso_depth_observe": (C.c_int, [_vp, C.c_int32, _P(C.c_double), C.c_int, _P(C.c_double), C.c_double, C.c_int, C.c_int, _P(hso_seed_obs),
+                                    _P(hso_seed_result)]),
     "hso_pose_optimize": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_int32), C.c_int,
                                     _P(C.c_double), _P(C.c_double), _P(C.c_int8), _P(C.c_int8), _P(C.c_int8), _P(C.c_double),
                                     _P(C.c_uint8), _P(hso_pose_result)]),

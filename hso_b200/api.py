@@ -255,6 +255,31 @@ class Context:
                                                order.ctypes.data_as(C.POINTER(C.c_int32)), out, C.byref(summ)))
         return out, summ
 
+    # ---- N3: DepthFilter::observeDepthRow -------------------------------------------------------------------------------------
+    @staticmethod
+    def seed_obs(seeds, frame_ids=None):
+        """list of dicts (hso_seed_obs field names; 'ref_frame' indexes frame_ids when given) -> ctypes array."""
+        arr = (K.hso_seed_obs * max(len(seeds), 1))()
+        for i, s in enumerate(seeds):
+            a = arr[i]
+            for k in range(2):
+                a.px[k], a.grad[k] = float(s["px"][k]), float(s["grad"][k])
+            for k in range(3):
+                a.f[k] = float(s["f"][k])
+            a.ref_frame = int(frame_ids[s["ref_frame"]]) if frame_ids is not None else int(s["ref_frame"])
+            a.ref_pose, a.level, a.ftr_type = int(s["ref_pose"]), int(s["level"]), int(s["ftr_type"])
+            a.mu, a.sigma2, a.exposure_rat = float(s["mu"]), float(s["sigma2"]), float(s.get("exposure_rat", 1.0))
+        return arr
+
+    def depth_observe(self, cur, T_cur_w, T_f_w, seeds, px_error_angle, align_max_iter=10, S=None):
+        """seeds: ctypes array from seed_obs(). Returns a ctypes array of hso_seed_result."""
+        S = len(seeds) if S is None else S
+        T = np.ascontiguousarray(T_cur_w, np.float64).reshape(12)
+        Tk = np.ascontiguousarray(T_f_w, np.float64).reshape(-1)
+        out = (K.hso_seed_result * max(S, 1))()
+        self._chk(self.lib.hso_depth_observe(self.h, int(cur), _dp(T), Tk.size // 12, _dp(Tk), float(px_error_angle), int(align_max_iter), S, seeds, out))
+        return out
+
     # ---- F4: pose_optimizer::optimizeLevenbergMarquardt3rd -----------------------------------------------------------------
     def pose_optimize_batch(self, problems, reproj_thresh=2.0, n_iter=12):
         """problems: list of dicts {f (F,3), p_host (F,3), host_idx (F,), T_host_w (K,3,4), grad (F,2), level, ftype, ptype (F,),

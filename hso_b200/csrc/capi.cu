@@ -104,6 +104,9 @@ struct hso_ctx {
   std::vector<uint16_t> u_map2_host;
   ResizeTabDev in_tab{};
   int in_tab_w = 0, in_tab_h = 0;
+  // depth filter (row N3) scratch
+  DevBuf d_arena;
+  PinBuf d_stage_host, d_out_host;
   // reprojection (row N1) scratch
   DevBuf r_arena;
   PinBuf r_stage_host, r_out_host;
@@ -363,10 +366,10 @@ void hso_destroy(hso_ctx* ctx) {
     if (s.sobel) cudaFree(s.sobel);
   }
   DevBuf* db[] = {&ctx->f_score, &ctx->f_rowbuf, &ctx->f_rowcount, &ctx->f_out, &ctx->f_total, &ctx->pyr_arena, &ctx->sums_arena, &ctx->stats_table, &ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
-                  &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->in_raw, &ctx->in_mid, &ctx->in_ptrs, &ctx->u_map1, &ctx->u_map2, &ctx->in_tab_blob, &ctx->r_arena, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
+                  &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->in_raw, &ctx->in_mid, &ctx->in_ptrs, &ctx->u_map1, &ctx->u_map2, &ctx->in_tab_blob, &ctx->d_arena, &ctx->r_arena, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ctx->f_out_host, &ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
-                  &ctx->a_jobs_host, &ctx->a_out_host, &ctx->in_ptrs_host, &ctx->r_stage_host, &ctx->r_out_host, &ctx->p_stage_host, &ctx->p_out_host};
+                  &ctx->a_jobs_host, &ctx->a_out_host, &ctx->in_ptrs_host, &ctx->d_stage_host, &ctx->d_out_host, &ctx->r_stage_host, &ctx->r_out_host, &ctx->p_stage_host, &ctx->p_out_host};
   for (PinBuf* b : pb) b->release();
   for (cudaEvent_t e : ctx->t_ev) if (e) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1163,6 +1166,63 @@ int hso_reproject_match(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12]
   CU(cudaStreamSynchronize(ctx->stream));
   memcpy(out, oh, sizeof(hso_reproj_result) * M);
   memcpy(summary, oh + sizeof(hso_reproj_result) * M, sizeof(hso_reproj_summary));
+  tm.stop_after_sync();
+  return HSO_OK;
+}
+
+// ---- N3 ---------------------------------------------------------------------------------------------------------------------
+int hso_depth_observe(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], int n_poses, const double* T_f_w, double px_error_angle,
+                      int align_max_iter, int S, const hso_seed_obs* seeds, hso_seed_result* out) {
+  if (!ctx || !T_cur_w || S < 0 || n_poses < 0 || align_max_iter < 0) return HSO_ERR_INVALID;
+  if (S == 0) return HSO_OK;
+  if (!seeds || !out || !T_f_w || n_poses == 0) return HSO_ERR_INVALID;
+  FrameSlot* fc = get_frame(ctx, cur);
+  if (!fc) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown active frame id");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = (o + 127) / 128 * 128; o = r + bytes; return r; };
+  const size_t o_s = take(sizeof(hso_seed_obs) * S), o_rp = take(sizeof(void*) * S), o_T = take(sizeof(double) * 12 * n_poses);
+  const size_t staged = o;
+  const size_t o_out = take(sizeof(hso_seed_result) * S);
+  CU(ctx->d_arena.reserve(o));
+  CU(ctx->d_stage_host.reserve(staged));
+  CU(ctx->d_out_host.reserve(sizeof(hso_seed_result) * S));
+  char* h = (char*)ctx->d_stage_host.p;
+  char* d = (char*)ctx->d_arena.p;
+  memcpy(h + o_s, seeds, sizeof(hso_seed_obs) * S);
+  const uint8_t** rp = (const uint8_t**)(h + o_rp);
+  for (int i = 0; i < S; ++i) {
+    const hso_seed_obs& s = seeds[i];
+    if (s.ref_pose < 0 || s.ref_pose >= n_poses) return fail(ctx, HSO_ERR_INVALID, "pose index out of range in seed");
+    FrameSlot* fr = get_frame(ctx, s.ref_frame);
+    if (!fr) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown reference frame id in seed");
+    if (s.level < 0 || s.level >= ctx->geom.n_levels) return fail(ctx, HSO_ERR_INVALID, "seed level out of range");
+    if (s.ftr_type == 1 && !fc->sobel) return fail(ctx, HSO_ERR_INVALID, "edgelet seeds need hso_cfg.materialize_sobel (checkNormal reads sobelX_/Y_)");
+    rp[i] = fr->pyr;
+  }
+  memcpy(h + o_T, T_f_w, sizeof(double) * 12 * n_poses);
+  StageTimer tm(ctx, 2);
+  CU(cudaMemcpyAsync(d, h, staged, cudaMemcpyHostToDevice, ctx->stream));
+  DepthKParams kp;
+  memset(&kp, 0, sizeof kp);
+  kp.g = ctx->geom; kp.cam = ctx->camdev;
+  memcpy(kp.T_cur_w, T_cur_w, sizeof kp.T_cur_w);
+  kp.T_f_w = (const double*)(d + o_T);
+  kp.S = S; kp.max_iter = align_max_iter;
+  kp.max_search_level = std::min(ctx->cfg.n_pyr_levels, ctx->geom.n_levels) - 1;
+  kp.px_error_angle = px_error_angle;
+  kp.cur_pyr = fc->pyr; kp.cur_sobel = fc->sobel;
+  size_t so = 0;
+  for (int l = 0; l < 3; ++l) {
+    kp.sobel_off[l] = so;
+    if (l < ctx->geom.n_levels) so += (size_t)2 * ctx->geom.w[l] * ctx->geom.h[l];
+  }
+  CU(launch_depth_observe(kp, (const hso_seed_obs*)(d + o_s), (const uint8_t* const*)(d + o_rp), (hso_seed_result*)(d + o_out), ctx->stream,
+                          &ctx->launches));
+  CU(cudaMemcpyAsync(ctx->d_out_host.p, d + o_out, sizeof(hso_seed_result) * S, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->d_out_host.p, sizeof(hso_seed_result) * S);
   tm.stop_after_sync();
   return HSO_OK;
 }

@@ -272,6 +272,75 @@ HSO_DEV void world2cam(const CamDev& c, double X, double Y, double Z, double& pu
   }
 }
 
+// PinholeCamera/FOVCamera/EquidistantCamera::world2cam with the reference's true divisions (src/camera.cpp:94-125,199-221,307-315):
+// the pixel is truncated to an integer for the in-frame test and the cell index, so no reciprocal shortcut here.
+HSO_DEV void world2cam_exact(const CamDev& c, double X, double Y, double Z, double& pu, double& pv) {
+  const double u = X / Z, v = Y / Z;
+  if (c.model == 0 && c.distortion) {
+    const double r2 = u * u + v * v, r4 = r2 * r2, r6 = r4 * r2;
+    const double a1 = 2 * u * v, a2 = r2 + 2 * u * u, a3 = r2 + 2 * v * v;
+    const double cdist = 1 + c.d[0] * r2 + c.d[1] * r4 + c.d[4] * r6;
+    const double xd = u * cdist + c.d[2] * a1 + c.d[3] * a2;
+    const double yd = v * cdist + c.d[2] * a3 + c.d[3] * a1;
+    pu = xd * c.fx + c.cx;
+    pv = yd * c.fy + c.cy;
+  } else if (c.model == 1 && !c.undistort) {
+    const double omega = c.d[0];
+    const double dist = sqrt(u * u + v * v);
+    const double ratio = (omega == 0 || dist == 0) ? 1.0 : atan(2 * dist * tan(omega / 2)) / (dist * omega);
+    pu = ratio * c.fx * u + c.cx;
+    pv = ratio * c.fy * v + c.cy;
+  } else {
+    pu = c.fx * u + c.cx;
+    pv = c.fy * v + c.cy;
+  }
+}
+
+// cam2world of the three models, unit-norm bearing (src/camera.cpp:66-87,169-190,297-300). The radtan branch is cv::undistortPoints on one
+// CV_32FC2 point with the float camera matrix / coefficients the reference builds (camera.cpp:43-45): 5 fixed-point iterations in double,
+// float in, float out.
+HSO_DEV void cam2world(const CamDev& c, double u, double v, double& ox, double& oy, double& oz) {
+  double x, y;
+  if (c.model == 0 && c.distortion) {
+    const float uf = (float)u, vf = (float)v;
+    const double fx = (double)(float)c.fx, fy = (double)(float)c.fy, cx = (double)(float)c.cx, cy = (double)(float)c.cy;
+    const double k0 = (double)(float)c.d[0], k1 = (double)(float)c.d[1], k2 = (double)(float)c.d[2], k3 = (double)(float)c.d[3],
+                 k4 = (double)(float)c.d[4];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    double xx = ((double)uf - cx) * ifx, yy = ((double)vf - cy) * ify;
+    const double x0 = xx, y0 = yy;
+    for (int j = 0; j < 5; ++j) {
+      const double r2 = xx * xx + yy * yy;
+      const double icdist = 1.0 / (1 + ((k4 * r2 + k1) * r2 + k0) * r2);
+      if (icdist < 0) { xx = x0; yy = y0; break; }
+      const double deltaX = 2 * k2 * xx * yy + k3 * (r2 + 2 * xx * xx);
+      const double deltaY = k2 * (r2 + 2 * yy * yy) + 2 * k3 * xx * yy;
+      xx = (x0 - deltaX) * icdist;
+      yy = (y0 - deltaY) * icdist;
+    }
+    x = (double)(float)xx;
+    y = (double)(float)yy;
+  } else if (c.model == 1 && !c.undistort) {
+    const double ud = (u - c.cx) / c.fx, vd = (v - c.cy) / c.fy;
+    const double dist = sqrt(ud * ud + vd * vd);
+    const double omega = c.d[0];
+    const double rd = tan(dist * omega) / (2 * dist * tan(omega / 2));
+    x = rd * ud;
+    y = rd * vd;
+  } else {
+    x = (u - c.cx) / c.fx;
+    y = (v - c.cy) / c.fy;
+  }
+  const double n = sqrt(x * x + y * y + 1.0);
+  ox = x / n; oy = y / n; oz = 1.0 / n;
+}
+
+HSO_DEV void se3_apply(const Se3d& T, double x, double y, double z, double& ox, double& oy, double& oz) {
+  quat_rotate(T.q, x, y, z, ox, oy, oz);
+  ox += T.tx; oy += T.ty; oz += T.tz;
+}
+
+
 // ---- warp / block reductions -------------------------------------------------------------------------------------------
 HSO_DEV double warp_sum(double v) {
 #pragma unroll

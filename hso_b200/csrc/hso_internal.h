@@ -139,6 +139,21 @@ cudaError_t launch_reproj_select(const ReprojSelParams& p, const hso_reproj_cand
                                  const int32_t* cell_order_dev, hso_reproj_result* res_dev, hso_reproj_summary* summ_dev, cudaStream_t stream,
                                  uint64_t* launches);
 
+// ---- depth filter observation (row N3) ---------------------------------------------------------------------------------------
+struct DepthKParams {
+  PyrGeom g;
+  CamDev cam;
+  double T_cur_w[12];      // active_frame_->T_f_w_
+  const double* T_f_w;     // device [n_poses][12] keyframe poses
+  int S, max_iter, max_search_level;
+  double px_error_angle;
+  const uint8_t* cur_pyr;
+  const int16_t* cur_sobel;  // or nullptr
+  size_t sobel_off[3];
+};
+cudaError_t launch_depth_observe(const DepthKParams& p, const hso_seed_obs* seeds_dev, const uint8_t* const* ref_pyr_dev, hso_seed_result* out_dev,
+                                 cudaStream_t stream, uint64_t* launches);
+
 // ---- pose optimiser -----------------------------------------------------------------------------------------------------
 struct PoseJobDev {
   int F, K, n_fts_total, pad_;

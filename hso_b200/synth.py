@@ -202,3 +202,42 @@ def make_reproject_scene(seed, cam="icl", M=3000, n_kf=4, max_fts=200, depth=4.0
     cell_order = rng.permutation(n_cols * n_rows).astype(np.int32)  # std::random_shuffle(grid_.cell_order)
     return dict(cam=c, kf_imgs=kf_imgs, cur_img=cur_img, T_f_w=np.stack([T[:3] for T in T_kf]), T_cur_w=T_cur[:3], cands=cands, grid=grid,
                 cell_order=cell_order)
+
+
+def make_depth_scene(seed, cam="icl", S=2000, n_kf=3, depth=4.0, gain=1.0, frac_edgelet=0.25, baseline=0.12):
+    """Inputs of DepthFilter::observeDepthRow (row N3): n_kf keyframes and an active frame looking at a textured plane z = depth of
+    keyframe 0 (= world); S seeds, each a feature of one keyframe with an inverse-depth estimate (mu, sigma2) around the truth.
+    Returns dict(cam, kf_imgs, cur_img, T_f_w, T_cur_w, seeds [dict], px_error_angle)."""
+    rng = np.random.default_rng(seed)
+    c = CAMS[cam] if isinstance(cam, str) else cam
+    W, H = c["width"], c["height"]
+    K = np.array([[c["fx"], 0, c["cx"]], [0, c["fy"], c["cy"]], [0, 0, 1.0]])
+    base = texture(rng, W, H)
+    T_kf = [np.eye(4)] + [se3_exp(np.concatenate([rng.normal(0, 0.05, 3), rng.normal(0, 0.01, 3)])) for _ in range(n_kf - 1)]
+    kf_imgs = [base] + [warp_plane(base, K, T, depth) for T in T_kf[1:]]
+    T_cur = se3_exp(np.concatenate([rng.normal(0, baseline, 3) * [1, 1, 0.3], rng.normal(0, 0.01, 3)]))
+    cur_img = warp_plane(base, K, T_cur, depth, gain)
+    seeds = []
+    for i in range(S):
+        r = int(rng.integers(0, n_kf))
+        # a pixel of keyframe r, its bearing and the true distance to the plane along it
+        px = np.array([rng.uniform(20, W - 20), rng.uniform(20, H - 20)])
+        ray = np.array([(px[0] - c["cx"]) / c["fx"], (px[1] - c["cy"]) / c["fy"], 1.0])
+        f = ray / np.linalg.norm(ray)
+        Tinv = np.linalg.inv(T_kf[r])
+        o, d = Tinv[:3, 3], Tinv[:3, :3] @ f          # ray in the world frame
+        lam = (depth - o[2]) / d[2]                    # intersection with z = depth
+        mu_true = 1.0 / lam
+        rel = rng.choice([0.03, 0.1, 0.3, 0.8])        # width of the search interval relative to mu
+        sigma = rel * mu_true / 2.0
+        mu = mu_true + rng.normal(0, 0.5 * sigma)
+        if i % 97 == 0:
+            mu = -abs(mu)                               # behind the camera
+        ang = rng.uniform(0, 2 * np.pi)
+        lvl = int(rng.integers(0, 3))
+        seeds.append(dict(px=px, f=f, grad=np.array([np.cos(ang), np.sin(ang)]), ref_frame=r, ref_pose=r, level=lvl,
+                          ftr_type=(1 if rng.uniform() < frac_edgelet else (2 if rng.uniform() < 0.2 else 0)),
+                          mu=float(np.float32(mu)), sigma2=float(np.float32(sigma * sigma)), exposure_rat=float(gain)))
+    focal = abs((c["fx"] + c["fy"]) * 0.5)
+    return dict(cam=c, kf_imgs=kf_imgs, cur_img=cur_img, T_f_w=np.stack([T[:3] for T in T_kf]), T_cur_w=T_cur[:3], seeds=seeds,
+                px_error_angle=float(np.arctan(1.0 / (2.0 * focal)) * 2.0))

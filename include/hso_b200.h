@@ -247,6 +247,35 @@ int hso_reproject_match(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12]
                         const hso_reproj_cand* cands, const hso_reproj_grid* grid, const int32_t* cell_order, hso_reproj_result* out,
                         hso_reproj_summary* summary);
 
+/* ---- N3 (next row): depth-filter observation — replaces the per-seed body of DepthFilter::observeDepthRow (src/depth_filter.cpp:580-675) for all
+ * seeds of the active frame in one launch: visibility test (:591-607), inverse-depth interval (:616-618), Matcher::doLineStereo
+ * (src/matcher.cpp:802-1049 with KLTLimited1D / KLTLimited2D :1296-1606, ZMNCC_F include/hso/vikit/patch_score.h:268-305, warp::createPatch
+ * :159-196, depthFromTriangulation :242-255), DepthFilter::computeTau (:539-555) and DepthFilter::updateSeed (:528-537). The host keeps the seed
+ * list (std::list<Seed>, seeds_mut_), applies b++ / eplStart / vec_distance / last_update_frame from the results, and calls
+ * featureExtractor_->setGridOccpuancy for keyframes. ---- */
+typedef struct {
+  double px[2], f[3], grad[2];  /* seed.ftr->px, ->f, ->grad */
+  hso_frame_id ref_frame;       /* device frame of seed.ftr->frame */
+  int32_t ref_pose;             /* index into T_f_w of seed.ftr->frame */
+  int32_t level, ftr_type;      /* seed.ftr->level, ->type (0 corner, 1 edgelet, 2 gradient) */
+  float mu, sigma2;             /* seed.mu, seed.sigma2 */
+  float exposure_rat;           /* active_frame.m_exposure_time / ref_frame.m_exposure_time (matcher.cpp:820) */
+  float pad_;
+} hso_seed_obs;
+typedef struct {
+  int32_t is_update;            /* Seed::is_update: the seed is in view of the active frame */
+  int32_t is_valid;             /* 0: z_inv_min is NaN => Seed::isValid = false (:619) */
+  int32_t res;                  /* doLineStereo: 1 ok, -1 epipolar segment / edgelet angle, -2 triangulation, -3 alignment, -4 score; 0 when !is_update */
+  int32_t search_level;         /* matcher.search_level_ -> Seed::last_matched_level */
+  int32_t epl_start[2], epl_end[2]; /* Seed::eplStart / eplEnd; (0,0) unless res == 1 (:634-635) */
+  float mu, sigma2;             /* after updateSeed (unchanged unless res == 1) */
+  double z;                     /* result_depth */
+  double px_cur[2];             /* matcher.px_cur_ -> Seed::last_matched_px */
+} hso_seed_result;
+/* px_error_angle: DepthFilter::px_error_angle_ = atan(px_noise / (2 focal_length)) * 2 (:360-365). align_max_iter: Matcher::Options (10). */
+int hso_depth_observe(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], int n_poses, const double* T_f_w, double px_error_angle,
+                      int align_max_iter, int S, const hso_seed_obs* seeds, hso_seed_result* out);
+
 /* ---- F4: pose refinement — replaces void pose_optimizer::optimizeLevenbergMarquardt3rd(double reproj_thresh, size_t n_iter,
  * bool verbose, FramePtr&, double& scale, double& err_init, double& err_final, size_t& num_obs)
  * (include/hso/pose_optimizer.h:61-64 ; src/pose_optimizer.cpp:399-771). ------------------------------------------------- */

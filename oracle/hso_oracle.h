@@ -188,6 +188,25 @@ void orc_pose_optimize(double reproj_thresh, int n_iter, double err_mult2 /* cam
                        const double* grad, const int8_t* level, const int8_t* ftype, const int8_t* ptype,
                        const double T_f_w_in[12], uint8_t* outlier_out /*F*/, orc_pose_result* out);
 
+/* ---- N3: DepthFilter::observeDepthRow (src/depth_filter.cpp:580-675) + Matcher::doLineStereo (src/matcher.cpp:802-1049) ----
+ * Record layouts shared with include/hso_b200.h (hso_seed_obs / hso_seed_result). */
+typedef struct {
+  double px[2], f[3], grad[2];
+  int32_t ref_frame, ref_pose, level, ftr_type;
+  float mu, sigma2, exposure_rat, pad_;
+} orc_seed_obs;
+typedef struct {
+  int32_t is_update, is_valid, res, search_level;
+  int32_t epl_start[2], epl_end[2];
+  float mu, sigma2;
+  double z;
+  double px_cur[2];
+} orc_seed_result;
+void orc_depth_observe(const orc_cam* cam, const double T_cur_w[12], int n_poses, const double* T_f_w, double px_error_angle, int S,
+                       const orc_seed_obs* seeds, int max_search_level, int align_max_iter, const uint8_t* const* const* ref_levels,
+                       const uint8_t* const* cur_levels, const int* lw, const int* lh, const int16_t* const* cur_sobx, const int16_t* const* cur_soby,
+                       orc_seed_result* out);
+
 /* ---- N4: undistortion maps (src/camera.cpp:47-54,223-265,317-363) and cv::remap INTER_LINEAR (:127-131,267-271,365-369) ---- */
 void orc_convert_maps(const float* mapx, const float* mapy, int n, int16_t* map1, uint16_t* map2);
 int orc_init_undistort_maps(const orc_cam* cam, int16_t* map1 /*[h][w][2]*/, uint16_t* map2 /*[h][w]*/);

@@ -425,3 +425,26 @@ def convert_maps(mx, my):
     m2 = np.zeros((h, w), np.uint16)
     lib.orc_convert_maps(mx.ctypes.data_as(C.c_void_p), my.ctypes.data_as(C.c_void_p), h * w, m1.ctypes.data_as(C.c_void_p), m2.ctypes.data_as(C.c_void_p))
     return m1, m2
+
+
+# ---- N3: DepthFilter::observeDepthRow --------------------------------------------------------------------------------------------------
+class orc_seed_obs(C.Structure):
+    _fields_ = [("px", C.c_double * 2), ("f", C.c_double * 3), ("grad", C.c_double * 2), ("ref_frame", C.c_int32), ("ref_pose", C.c_int32),
+                ("level", C.c_int32), ("ftr_type", C.c_int32), ("mu", C.c_float), ("sigma2", C.c_float), ("exposure_rat", C.c_float),
+                ("pad_", C.c_float)]
+
+
+class orc_seed_result(C.Structure):
+    _fields_ = [("is_update", C.c_int32), ("is_valid", C.c_int32), ("res", C.c_int32), ("search_level", C.c_int32), ("epl_start", C.c_int32 * 2),
+                ("epl_end", C.c_int32 * 2), ("mu", C.c_float), ("sigma2", C.c_float), ("z", C.c_double), ("px_cur", C.c_double * 2)]
+
+
+def depth_observe(cam, T_cur_w, T_f_w, seeds, px_error_angle, ref_pyramids, cur_levels, cur_sobel, max_search_level=2, align_max_iter=10):
+    """seeds: ctypes array of orc_seed_obs (same layout as hso_seed_obs; ref_frame indexes ref_pyramids)."""
+    lib = load()
+    S = len(seeds)
+    T, Tk, frames, curp, lw, lh, sxp, syp, keep = _reproj_args(T_cur_w, T_f_w, ref_pyramids, cur_levels, cur_sobel)
+    out = (orc_seed_result * max(S, 1))()
+    lib.orc_depth_observe(C.byref(cam_of(cam)), dp(T), Tk.size // 12, dp(Tk), C.c_double(px_error_angle), S, seeds, int(max_search_level),
+                          int(align_max_iter), frames, curp, lw, lh, sxp, syp, out)
+    return out
