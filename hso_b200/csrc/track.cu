@@ -79,7 +79,7 @@ struct TrackCtrl {
   double step[7];
   double E_old;
   int done, iter, n_err;
-  uint32_t sel_prefix, sel_k, sel_n;
+  uint32_t sel_prefix, sel_k, sel_n, sel_bin, sel_cnt, list_n;
   uint32_t wsum[32];   // per-warp histogram partial sums of the bucket search
 };
 
@@ -523,11 +523,88 @@ HSO_DEV void hist_add_aggregated(uint32_t* hist, uint32_t bin) {
   if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
 }
 
-// Exact k-th smallest (k = n/2, hso::getMedian, include/hso/vikit/math_utils.h:119-126) of the non-negative floats
-// { f(absres) : absres >= 0 } owned by the cluster; MAD = true selects over fabsf(v - center). Result in ctrl->sel_prefix.
-// Radix select over the IEEE bit pattern (monotone for non-negative floats), digits of `bits` bits from the top; histograms of the
-// CTAs of a cluster are merged through DSMEM. prefilled: the histogram of the first digit was already accumulated by the caller
-// (fused with the residual computation), so that pass does not re-read the residuals.
+// Merge the histograms of the cluster's CTAs (DSMEM) and locate the bucket that holds rank k (k = total / 2 when `first`: hso::getMedian,
+// include/hso/vikit/math_utils.h:119-126, else ctrl->sel_k). Block-parallel: each thread sums `per` consecutive bins, warp scan, warp totals
+// through shared memory. Results (identical in every CTA of the cluster): ctrl->sel_bin, ->sel_k (rank inside the bucket), ->sel_cnt (bucket
+// population), ->sel_n (total, when first).
+HSO_DEV void find_bucket(const Smem& s, int nbins, int csize, bool first) {
+  if (csize == 1) {
+    __syncthreads();
+  } else {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    for (int j = threadIdx.x; j < nbins; j += blockDim.x) {
+      uint32_t sum = 0;
+      for (int r = 0; r < csize; ++r) sum += cluster.map_shared_rank(s.hist, r)[j];
+      s.ghist[j] = sum;
+    }
+    cluster.sync();  // peers are done reading this CTA's histogram before it is zeroed again
+  }
+  const int T = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = T >> 5;
+  const int per = (nbins + T - 1) / T;
+  const int b0 = threadIdx.x * per;
+  uint32_t local = 0;
+  for (int j = 0; j < per; ++j) local += (b0 + j < nbins) ? s.ghist[b0 + j] : 0u;
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s.ctrl->wsum[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+  for (int q = 0; q < nw; ++q) {
+    const uint32_t v = s.ctrl->wsum[q];
+    if (q < warp) before += v;
+    total += v;
+  }
+  const uint32_t k = first ? total / 2 : s.ctrl->sel_k;
+  const uint32_t excl = before + incl - local;
+  __syncthreads();  // everyone has read sel_k / wsum before they are overwritten
+  if (first && threadIdx.x == 0) s.ctrl->sel_n = total;
+  if (total > 0 && k >= excl && k < excl + local) {
+    uint32_t cum = excl;
+    int d = b0;
+    uint32_t cnt = 0;
+    for (int j = 0; j < per; ++j) {
+      const uint32_t c = s.ghist[b0 + j];
+      if (k < cum + c) { d = b0 + j; cnt = c; break; }
+      cum += c;
+    }
+    s.ctrl->sel_k = k - cum;
+    s.ctrl->sel_bin = (uint32_t)d;
+    s.ctrl->sel_cnt = cnt;
+  }
+  if (total == 0 && threadIdx.x == 0) { s.ctrl->sel_k = 0; s.ctrl->sel_bin = 0; s.ctrl->sel_cnt = 0; }
+  __syncthreads();
+}
+
+// Visit every value f(absres) the CTA owns (MAD: fabsf(v - center)); invalid slots (absres < 0) are skipped. The N values of a patch are
+// loaded back to back (one round trip per patch) into N registers — a larger chunk spills at the kernel's 128-register budget. `absres` is a
+// generic pointer (shared memory or the L2-resident global scratch): one load instruction serves both layouts.
+template <int N, class Fn>
+HSO_DEV void for_each_abs(const TrackJobDev& job, const float* absres, int astride, bool a_smem, int t0, int nt, bool mad, float center, Fn fn) {
+  int kk = 0;
+  for (int i = t0; i < job.F; i += nt, ++kk) {
+    const float* p = absres + (a_smem ? kk * (int)blockDim.x + (int)threadIdx.x : i);
+    float vals[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) vals[n] = p[n * astride];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      float v = vals[n];
+      if (v >= 0.f) {
+        if (mad) v = fabsf(v - center);
+        fn(v);
+      }
+    }
+  }
+}
+
+// Exact k-th smallest (k = n/2) of the non-negative floats { f(absres) : absres >= 0 } owned by the cluster; result in ctrl->sel_prefix
+// (the float's bit pattern), population in ctrl->sel_n. Radix select over the IEEE bit pattern (monotone for non-negative floats), digits of
+// `bits` bits from the top; prefilled: the histogram of the first digit was already accumulated by the caller (fused with the residuals).
 template <int N>
 HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, const float* absres, int astride, bool a_smem, int t0, int nt, bool mad, float center,
                           int csize, int bits, bool prefilled) {
@@ -543,87 +620,81 @@ HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, const float* ab
     if (!(first && prefilled)) {
       for (int j = threadIdx.x; j < nbins; j += blockDim.x) hist[j] = 0;
       __syncthreads();
-      // the loads of up to CH patches (CH * N values) are issued back to back: one L2 round trip per chunk, not one per value
-      constexpr int CH = (N <= 13) ? 4 : 3;
-      int kk = 0;
-      for (int i = t0; i < job.F; i += CH * nt, kk += CH) {
-        float vals[CH][N];
-#pragma unroll
-        for (int q = 0; q < CH; ++q) {
-          const int iq = i + q * nt;
-          const int slot = a_smem ? ((kk + q) * (int)blockDim.x + (int)threadIdx.x) : iq;
-#pragma unroll
-          for (int n = 0; n < N; ++n)
-            vals[q][n] = (iq < job.F) ? (a_smem ? absres[n * astride + slot] : __ldcg(absres + n * astride + slot)) : -1.f;
-        }
-#pragma unroll
-        for (int q = 0; q < CH; ++q)
-#pragma unroll
-          for (int n = 0; n < N; ++n) {
-            float v = vals[q][n];
-            const bool valid = v >= 0.f;
-            if (mad) v = fabsf(v - center);
-            const uint32_t key = __float_as_uint(v);
-            if (valid && (key & mask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
-          }
-      }
+      for_each_abs<N>(job, absres, astride, a_smem, t0, nt, mad, center, [&](float v) {
+        const uint32_t key = __float_as_uint(v);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
+      });
     }
-    if (csize == 1) {
-      __syncthreads();
-    } else {
-      cg::cluster_group cluster = cg::this_cluster();
-      cluster.sync();
-      for (int j = threadIdx.x; j < nbins; j += blockDim.x) {
-        uint32_t sum = 0;
-        for (int r = 0; r < csize; ++r) sum += cluster.map_shared_rank(hist, r)[j];
-        s.ghist[j] = sum;
-      }
-      cluster.sync();  // peers are done reading this CTA's histogram before it is zeroed again
-    }
-    {
-      // bucket search by the whole CTA: each thread sums `per` consecutive bins, warp scan, warp totals through shared memory
-      const int T = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = T >> 5;
-      const int per = (nbins + T - 1) / T;
-      const int b0 = threadIdx.x * per;
-      uint32_t local = 0;
-      for (int j = 0; j < per; ++j) local += (b0 + j < nbins) ? s.ghist[b0 + j] : 0u;
-      uint32_t incl = local;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      if (lane == 31) s.ctrl->wsum[warp] = incl;
-      __syncthreads();
-      uint32_t before = 0, total = 0;
-      for (int q = 0; q < nw; ++q) {
-        const uint32_t v = s.ctrl->wsum[q];
-        if (q < warp) before += v;
-        total += v;
-      }
-      const uint32_t k = first ? total / 2 : s.ctrl->sel_k;
-      const uint32_t excl = before + incl - local;
-      __syncthreads();  // everyone has read sel_k / wsum before they are overwritten
-      if (first && threadIdx.x == 0) s.ctrl->sel_n = total;
-      if (total > 0 && k >= excl && k < excl + local) {
-        uint32_t cum = excl;
-        int d = b0;
-        for (int j = 0; j < per; ++j) {
-          const uint32_t c = s.ghist[b0 + j];
-          if (k < cum + c) { d = b0 + j; break; }
-          cum += c;
-        }
-        s.ctrl->sel_k = k - cum;
-        s.ctrl->sel_prefix = prefix | ((uint32_t)d << shift);
-      }
-      if (total == 0 && threadIdx.x == 0) { s.ctrl->sel_k = 0; s.ctrl->sel_prefix = 0; }
-    }
-    __syncthreads();
-    prefix = s.ctrl->sel_prefix;
+    find_bucket(s, nbins, csize, first);
+    prefix |= s.ctrl->sel_bin << shift;
     mask |= dmask << shift;
     hi = shift;
     first = false;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) s.ctrl->sel_prefix = s.ctrl->sel_n ? prefix : 0u;
+  __syncthreads();
+}
+
+// Monotone bucket of the first selection pass: 1/16 grey level per bin. The residual magnitudes of a level cluster around a few grey levels,
+// so float-exponent digits would put >10 % of all values into one bin (atomics serialise, and the bin's members must be re-scanned twice);
+// linear bins spread them (~1 % per bin) and the members of the chosen bin fit a small list.
+constexpr float LIN_SCALE = 16.f;
+constexpr int LIST_CAP = 2048 - 256;  // the list shares the 2048-word histogram buffer with a 256-bin histogram
+HSO_DEV uint32_t lin_bin(float v, int nbins) {
+  const int b = (int)(v * LIN_SCALE);
+  return (uint32_t)(b < nbins - 1 ? b : nbins - 1);
+}
+
+// Same result as radix_select, fewer full passes: (1) histogram over linear bins (already accumulated when `prefilled`), (2) ONE pass that
+// compacts the members of the chosen bin into a list in shared memory, (3) radix select (8-bit digits) over that list only. Falls back to the
+// plain radix select when the bin is the unbounded top one or too populated for the list (e.g. identical images: every |r| is 0).
+template <int N>
+HSO_DEV void select_kth(const TrackJobDev& job, const Smem& s, const float* absres, int astride, bool a_smem, int t0, int nt, bool mad, float center,
+                        int csize, bool prefilled) {
+  constexpr int NB = 2048;
+  if (!prefilled) {
+    for (int j = threadIdx.x; j < NB; j += blockDim.x) s.hist[j] = 0;
+    __syncthreads();
+    for_each_abs<N>(job, absres, astride, a_smem, t0, nt, mad, center, [&](float v) { atomicAdd(&s.hist[lin_bin(v, NB)], 1u); });
+  }
+  find_bucket(s, NB, csize, true);
+  const uint32_t total = s.ctrl->sel_n, bin = s.ctrl->sel_bin, cnt = s.ctrl->sel_cnt;
+  if (total == 0) {
+    if (threadIdx.x == 0) s.ctrl->sel_prefix = 0;
+    __syncthreads();
+    return;
+  }
+  if (bin == NB - 1 || cnt > (uint32_t)LIST_CAP) {
+    __syncthreads();
+    radix_select<N>(job, s, absres, astride, a_smem, t0, nt, mad, center, csize, 11, false);
+    return;
+  }
+  // (2) compaction of the bin's members (this CTA's share) behind the 256-bin histogram
+  uint32_t* list = s.hist + 256;
+  if (threadIdx.x == 0) s.ctrl->list_n = 0;
+  __syncthreads();
+  for_each_abs<N>(job, absres, astride, a_smem, t0, nt, mad, center, [&](float v) {
+    if (lin_bin(v, NB) == bin) list[atomicAdd(&s.ctrl->list_n, 1u)] = __float_as_uint(v);
+  });
+  __syncthreads();
+  const int ln = (int)s.ctrl->list_n;
+  // (3) rank sel_k inside the bin: 4 passes of 8 bits over the list
+  uint32_t prefix = 0, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int j = threadIdx.x; j < 256; j += blockDim.x) s.hist[j] = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < ln; j += blockDim.x) {
+      const uint32_t key = list[j];
+      if ((key & mask) == prefix) atomicAdd(&s.hist[(key >> shift) & 255u], 1u);
+    }
+    find_bucket(s, 256, csize, false);
+    prefix |= s.ctrl->sel_bin << shift;
+    mask |= 255u << shift;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s.ctrl->sel_prefix = prefix;
+  __syncthreads();
 }
 
 // Thread-0 control step after a residual evaluation: accept/reject, damping update, convergence test, damped 7x7 solve and
@@ -839,6 +910,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     const float a = c->a_acc;
     const int hbits = prm.hist_bits;
     const bool a_smem = FAST && prm.absres_smem;
+    const bool lin = hbits == 11;  // the 2048-word buffer holds the linear histogram, then a 256-bin histogram + the candidate list
     float* absres = a_smem ? s.absres : job.absres;
     const int astride = a_smem ? prm.pc : Fp;
     for (int j = threadIdx.x; j < (1 << hbits); j += blockDim.x) s.hist[j] = 0;
@@ -865,20 +937,22 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
           const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
           const float cref = DUAL ? ref_intensity<true>(ps.ref, rp, rp.base + poff, L.w) : ps.cache[n * ps.stride + sl];
           out = fabsf(color - (a * cref + 0.f));
-          atomicAdd(&s.hist[__float_as_uint(out) >> (32 - hbits)], 1u);  // first digit of the median select, fused
+          atomicAdd(&s.hist[lin ? lin_bin(out, 2048) : (__float_as_uint(out) >> (32 - hbits))], 1u);  // first pass of the median select, fused
         }
         absres[n * astride + (a_smem ? sl : i)] = out;
       }
     }
     clk_res = clock64();
-    radix_select<N>(job, s, absres, astride, a_smem, t0, nt, false, 0.f, csize, hbits, true);
+    if (lin) select_kth<N>(job, s, absres, astride, a_smem, t0, nt, false, 0.f, csize, true);
+    else radix_select<N>(job, s, absres, astride, a_smem, t0, nt, false, 0.f, csize, hbits, true);
     clk_med = clock64();
     const uint32_t n_err = c->sel_n;
     float huber = 5.2f, outlier = 100.f;
     if (n_err >= 30) {
       const float median = __uint_as_float(c->sel_prefix);
       __syncthreads();
-      radix_select<N>(job, s, absres, astride, a_smem, t0, nt, true, median, csize, hbits, false);
+      if (lin) select_kth<N>(job, s, absres, astride, a_smem, t0, nt, true, median, csize, false);
+      else radix_select<N>(job, s, absres, astride, a_smem, t0, nt, true, median, csize, hbits, false);
       const float mad = __uint_as_float(c->sel_prefix);
       const float sd = (float)(1.4826 * (double)mad);
       huber = median + sd;

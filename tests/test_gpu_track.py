@@ -209,3 +209,24 @@ def test_pipelined_add_frames_equals_two_calls(oracle, B, ic):
             assert np.abs(ra["T_cur_ref"] - rb["T_cur_ref"]).max() < 2e-4 and abs(ra["exposure_rat"] - rb["exposure_rat"]) < 1e-4
         assert ra["n_tracked"] == rb["n_tracked"] or not same_shape
     ctx.close()
+
+
+@pytest.mark.parametrize("ic", [False, True])
+def test_threshold_selection_fallback_on_degenerate_residuals(oracle, ic):
+    """Identical images at the true pose: every |r| is exactly 0, so the linear first-pass histogram puts ALL values into one bin, the
+    candidate list overflows and the selection falls back to the plain radix select. Thresholds must still equal the oracle's
+    (median = MAD = 0 -> huber 0, outlier 10) and the tracker must stay at the identity."""
+    p = synth.make_pair(5, "icl", F=900)
+    c = p["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]))
+    ids, integral, _ = ctx.upload_frames([p["ref_img"], p["ref_img"]])
+    job = dict(ref=ids[0], cur=ids[1], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=np.eye(4)[:3], exposure_rat=1.0)
+    res, traces = ctx.coarse_track_batch([job], inverse_comp=ic, trace_cap=64)
+    rl, _ = oracle.create_pyramid(p["ref_img"], 5)
+    tp = oracle.TrackProblem(c, rl, rl, p["px"], p["f"], p["dist"])
+    for lvl in (4, 3, 2, 1):
+        e = [t for t in traces[0] if t.level == lvl][0]
+        hub, outl, n = tp.select_robust(lvl, 4, np.eye(4)[:3], 1.0)
+        assert e.huber == hub and e.outlier == outl, (lvl, e.huber, hub, e.outlier, outl)
+    assert np.abs(res[0]["T_cur_ref"] - np.eye(4)[:3]).max() < 1e-9
+    ctx.close()
