@@ -540,11 +540,12 @@ HSO_DEV void find_bucket(const Smem& s, int nbins, int csize, bool first) {
     }
     cluster.sync();  // peers are done reading this CTA's histogram before it is zeroed again
   }
+  const uint32_t* gh = csize == 1 ? s.hist : s.ghist;  // csize == 1 is also used by a cluster's CTAs on identical private copies
   const int T = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = T >> 5;
   const int per = (nbins + T - 1) / T;
   const int b0 = threadIdx.x * per;
   uint32_t local = 0;
-  for (int j = 0; j < per; ++j) local += (b0 + j < nbins) ? s.ghist[b0 + j] : 0u;
+  for (int j = 0; j < per; ++j) local += (b0 + j < nbins) ? gh[b0 + j] : 0u;
   uint32_t incl = local;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -568,7 +569,7 @@ HSO_DEV void find_bucket(const Smem& s, int nbins, int csize, bool first) {
     int d = b0;
     uint32_t cnt = 0;
     for (int j = 0; j < per; ++j) {
-      const uint32_t c = s.ghist[b0 + j];
+      const uint32_t c = gh[b0 + j];
       if (k < cum + c) { d = b0 + j; cnt = c; break; }
       cum += c;
     }
@@ -639,16 +640,19 @@ HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, const float* ab
 // Monotone bucket of the first selection pass: 1/16 grey level per bin. The residual magnitudes of a level cluster around a few grey levels,
 // so float-exponent digits would put >10 % of all values into one bin (atomics serialise, and the bin's members must be re-scanned twice);
 // linear bins spread them (~1 % per bin) and the members of the chosen bin fit a small list.
-constexpr float LIN_SCALE = 16.f;
-constexpr int LIST_CAP = 2048 - 256;  // the list shares the 2048-word histogram buffer with a 256-bin histogram
+constexpr float LIN_SCALE = 32.f;
+constexpr int LIST_BINS = 512;              // digit width of the list passes
+constexpr int LIST_CAP = 2048 - LIST_BINS;  // the list shares the 2048-word histogram buffer with a LIST_BINS-bin histogram
 HSO_DEV uint32_t lin_bin(float v, int nbins) {
   const int b = (int)(v * LIN_SCALE);
   return (uint32_t)(b < nbins - 1 ? b : nbins - 1);
 }
 
 // Same result as radix_select, fewer full passes: (1) histogram over linear bins (already accumulated when `prefilled`), (2) ONE pass that
-// compacts the members of the chosen bin into a list in shared memory, (3) radix select (8-bit digits) over that list only. Falls back to the
-// plain radix select when the bin is the unbounded top one or too populated for the list (e.g. identical images: every |r| is 0).
+// compacts the members of the chosen bin into a list in shared memory — the CTAs of a cluster then copy each other's lists through DSMEM so
+// that every CTA holds the whole bin, (3) radix select over that list only, CTA-local (no cluster barriers), on the key's offset from the
+// bin's lower bound: a bin of 1/32 grey level spans <= 2^18 bit patterns for v >= 1, i.e. two 9-bit passes. Falls back to the plain radix
+// select when the bin is the unbounded top one or too populated for the list (e.g. identical images: every |r| is 0).
 template <int N>
 HSO_DEV void select_kth(const TrackJobDev& job, const Smem& s, const float* absres, int astride, bool a_smem, int t0, int nt, bool mad, float center,
                         int csize, bool prefilled) {
@@ -670,30 +674,56 @@ HSO_DEV void select_kth(const TrackJobDev& job, const Smem& s, const float* absr
     radix_select<N>(job, s, absres, astride, a_smem, t0, nt, mad, center, csize, 11, false);
     return;
   }
-  // (2) compaction of the bin's members (this CTA's share) behind the 256-bin histogram
-  uint32_t* list = s.hist + 256;
+  // (2) compaction of the bin's members (this CTA's share) behind the LIST_BINS-bin histogram
+  uint32_t* list = s.hist + LIST_BINS;
   if (threadIdx.x == 0) s.ctrl->list_n = 0;
   __syncthreads();
   for_each_abs<N>(job, absres, astride, a_smem, t0, nt, mad, center, [&](float v) {
     if (lin_bin(v, NB) == bin) list[atomicAdd(&s.ctrl->list_n, 1u)] = __float_as_uint(v);
   });
-  __syncthreads();
-  const int ln = (int)s.ctrl->list_n;
-  // (3) rank sel_k inside the bin: 4 passes of 8 bits over the list
+  int ln;
+  if (csize == 1) {
+    __syncthreads();
+    ln = (int)s.ctrl->list_n;
+  } else {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();  // every CTA's share is complete
+    const int own = (int)s.ctrl->list_n;
+    const unsigned me = cluster.block_rank();
+    int off = own;
+    for (int r = 0; r < csize; ++r) {
+      if ((unsigned)r == me) continue;
+      const int rn = (int)cluster.map_shared_rank(&s.ctrl->list_n, r)[0];
+      const uint32_t* rl = cluster.map_shared_rank(list, r);
+      for (int j = threadIdx.x; j < rn; j += blockDim.x) list[off + j] = rl[j];  // appended behind the own share, which peers are reading
+      off += rn;
+    }
+    ln = off;
+    cluster.sync();  // peers have read this CTA's share and count: the buffer may be reused after the select
+  }
+  // (3) rank sel_k inside the bin, on the key's offset from the bin's lower bound
+  const uint32_t key_lo = __float_as_uint((float)bin / LIN_SCALE);
+  const uint32_t range = __float_as_uint((float)(bin + 1) / LIN_SCALE) - key_lo;  // keys of the bin lie in [key_lo, key_lo + range)
+  int hi = 32 - __clz((int)(range - 1));
+  if (range <= 1) hi = 0;
   uint32_t prefix = 0, mask = 0;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int j = threadIdx.x; j < 256; j += blockDim.x) s.hist[j] = 0;
+  while (hi > 0) {
+    const int width = hi >= 9 ? 9 : hi;
+    const int shift = hi - width;
+    const uint32_t dmask = (1u << width) - 1u;
+    for (int j = threadIdx.x; j < LIST_BINS; j += blockDim.x) s.hist[j] = 0;
     __syncthreads();
     for (int j = threadIdx.x; j < ln; j += blockDim.x) {
-      const uint32_t key = list[j];
-      if ((key & mask) == prefix) atomicAdd(&s.hist[(key >> shift) & 255u], 1u);
+      const uint32_t rel = list[j] - key_lo;
+      if ((rel & mask) == prefix) atomicAdd(&s.hist[(rel >> shift) & dmask], 1u);
     }
-    find_bucket(s, 256, csize, false);
+    find_bucket(s, LIST_BINS, 1, false);
     prefix |= s.ctrl->sel_bin << shift;
-    mask |= 255u << shift;
+    mask |= dmask << shift;
+    hi = shift;
   }
   __syncthreads();
-  if (threadIdx.x == 0) s.ctrl->sel_prefix = prefix;
+  if (threadIdx.x == 0) s.ctrl->sel_prefix = key_lo + prefix;
   __syncthreads();
 }
 
