@@ -507,7 +507,7 @@ def main():
     patch_evals = {l: sum(out[b].visible_patch_evals[l] for b in range(B)) for l in levels}
     cyc = [sum(out[b].cycles[k] for b in range(B)) for k in range(8)]
     diag = {"setup_frac_of_kernel_cycles": cyc[1] / max(cyc[0], 1), "refpatch_frac_of_kernel_cycles": cyc[3] / max(cyc[0], 1), "threshold_residuals_frac": cyc[4] / max(cyc[0], 1),
-            "median_select_frac": cyc[5] / max(cyc[0], 1), "pivoted_solves": cyc[7], "control_cycles_per_iteration": cyc[2] / max(iters_per_step + 4 * B, 1),
+            "median_select_frac": cyc[5] / max(cyc[0], 1), "pivoted_solves": cyc[7] & 0xFFFFFFFF, "select_fallbacks_per_problem_level": (cyc[7] >> 32) / (4 * B), "control_cycles_per_iteration": cyc[2] / max(iters_per_step + 4 * B, 1),
             "kernel_cycles_per_problem_level": cyc[0] / (4 * B), "mad_select_frac": cyc[6] / max(cyc[0], 1), "serial_control_frac_of_kernel_cycles": cyc[2] / max(cyc[0], 1),
             "iters_per_problem": {"mean": iters_per_step / B, "max": max(out[b].n_iters for b in range(B)), "min": min(out[b].n_iters for b in range(B))}}
     ctx._chk(lib.hso_track_set_profile(ctx.h, 1))

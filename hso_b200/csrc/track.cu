@@ -637,10 +637,10 @@ HSO_DEV void radix_select(const TrackJobDev& job, const Smem& s, const float* ab
   __syncthreads();
 }
 
-// Monotone bucket of the first selection pass: 1/16 grey level per bin. The residual magnitudes of a level cluster around a few grey levels,
+// Monotone bucket of the first selection pass: 1/64 grey level per bin (values >= 32 share the top bin). The residual magnitudes of a level cluster around a few grey levels,
 // so float-exponent digits would put >10 % of all values into one bin (atomics serialise, and the bin's members must be re-scanned twice);
-// linear bins spread them (~1 % per bin) and the members of the chosen bin fit a small list.
-constexpr float LIN_SCALE = 32.f;
+// linear bins of 1/64 grey level spread them (<1 % per bin) and the members of the chosen bin fit a small list.
+constexpr float LIN_SCALE = 64.f;
 constexpr int LIST_BINS = 512;              // digit width of the list passes
 constexpr int LIST_CAP = 2048 - LIST_BINS;  // the list shares the 2048-word histogram buffer with a LIST_BINS-bin histogram
 HSO_DEV uint32_t lin_bin(float v, int nbins) {
@@ -651,7 +651,7 @@ HSO_DEV uint32_t lin_bin(float v, int nbins) {
 // Same result as radix_select, fewer full passes: (1) histogram over linear bins (already accumulated when `prefilled`), (2) ONE pass that
 // compacts the members of the chosen bin into a list in shared memory — the CTAs of a cluster then copy each other's lists through DSMEM so
 // that every CTA holds the whole bin, (3) radix select over that list only, CTA-local (no cluster barriers), on the key's offset from the
-// bin's lower bound: a bin of 1/32 grey level spans <= 2^18 bit patterns for v >= 1, i.e. two 9-bit passes. Falls back to the plain radix
+// bin's lower bound: a bin of 1/64 grey level spans <= 2^17 bit patterns for v >= 1, i.e. two 9-bit passes. Falls back to the plain radix
 // select when the bin is the unbounded top one or too populated for the list (e.g. identical images: every |r| is 0).
 template <int N>
 HSO_DEV void select_kth(const TrackJobDev& job, const Smem& s, const float* absres, int astride, bool a_smem, int t0, int nt, bool mad, float center,
@@ -671,6 +671,7 @@ HSO_DEV void select_kth(const TrackJobDev& job, const Smem& s, const float* absr
   }
   if (bin == NB - 1 || cnt > (uint32_t)LIST_CAP) {
     __syncthreads();
+    if (threadIdx.x == 0 && cg::this_cluster().block_rank() == 0) job.state->cycles[7] += 1ull << 32;  // diagnostics: fallbacks (upper word)
     radix_select<N>(job, s, absres, astride, a_smem, t0, nt, mad, center, csize, 11, false);
     return;
   }
