@@ -745,12 +745,17 @@ static int track_copy_range(hso_ctx* ctx, int b0, int b1, cudaStream_t stream) {
 // Host workers that flatten the jobs of a batch in order; wait_chunk(c) returns once every job of chunk c is staged. Flattening the
 // reference's Feature lists to SoA is host work of the boundary; it runs ahead of the copies and launches the caller enqueues.
 struct StageWorkers {
-  hso_ctx* ctx; const hso_track_job* jobs; int B, chunk;
+  hso_ctx* ctx; const hso_track_job* jobs; int B;
+  std::vector<int> bounds;    // chunk c = jobs [bounds[c], bounds[c + 1])
+  std::vector<int> chunk_of;  // job -> chunk
   std::atomic<int> next{0};
   std::vector<std::atomic<int>> done;
   std::vector<std::thread> pool;
-  StageWorkers(hso_ctx* c, const hso_track_job* j, int B_, int chunk_) : ctx(c), jobs(j), B(B_), chunk(chunk_), done((B_ + chunk_ - 1) / chunk_) {
+  StageWorkers(hso_ctx* c, const hso_track_job* j, int B_, const std::vector<int>& bounds_)
+      : ctx(c), jobs(j), B(B_), bounds(bounds_), chunk_of(B_), done(bounds_.size() - 1) {
     for (auto& d : done) d.store(0);
+    for (size_t k = 0; k + 1 < bounds.size(); ++k)
+      for (int b = bounds[k]; b < bounds[k + 1]; ++b) chunk_of[b] = (int)k;
     const int n_thr = (B >= 16) ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 0;
     for (int t = 0; t < n_thr; ++t) pool.emplace_back([this]() { work(); });
   }
@@ -759,11 +764,11 @@ struct StageWorkers {
       const int b = next.fetch_add(1, std::memory_order_relaxed);
       if (b >= B) return;
       track_stage_one(ctx, jobs, b);
-      done[b / chunk].fetch_add(1, std::memory_order_release);
+      done[chunk_of[b]].fetch_add(1, std::memory_order_release);
     }
   }
   void wait_chunk(int c) {
-    const int want = std::min(B, (c + 1) * chunk) - c * chunk;
+    const int want = bounds[c + 1] - bounds[c];
     if (pool.empty()) work();  // small batch: stage inline
     while (done[c].load(std::memory_order_acquire) < want) std::this_thread::yield();
   }
@@ -774,7 +779,7 @@ int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_
   int rc = track_plan(ctx, prm, B, jobs, trace_cap);
   if (rc != HSO_OK) return rc;
   {
-    StageWorkers w(ctx, jobs, B, B);
+    StageWorkers w(ctx, jobs, B, std::vector<int>{0, B});
     w.wait_chunk(0);
   }
   return track_copy_range(ctx, 0, B, ctx->stream);
@@ -977,7 +982,11 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   const int unit = ctx->pipe_chunk > 0 ? ctx->pipe_chunk : 111;  // 3/4 of a wave of single-CTA problems: measured best with 3 streams
   int chunk = B <= unit ? B : unit;
   while ((B + chunk - 1) / chunk > 32) chunk += unit;
-  const int n_chunks = (B + chunk - 1) / chunk;
+  // the first two chunks ramp up (1/3, 2/3 of a chunk): the GPU starts after a third of a chunk's flattening + copy instead of a whole one
+  std::vector<int> bounds{0};
+  if (B > 2 * chunk && chunk >= 12 && ctx->pipe_chunk >= 0) { bounds.push_back(chunk / 3); bounds.push_back(chunk / 3 + 2 * chunk / 3); }
+  while (bounds.back() < B) bounds.push_back(std::min(B, bounds.back() + chunk));
+  const int n_chunks = (int)bounds.size() - 1;
   const int S = std::max(1, std::min(n_chunks, ctx->pipe_n_streams > 0 ? ctx->pipe_n_streams : 3));
   while ((int)ctx->pipe_streams.size() < S - 1) {
     cudaStream_t st; cudaEvent_t e;
@@ -1001,9 +1010,9 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   }
   StageTimer tm(ctx, 1);
   std::vector<const uint8_t*> srcs(B);
-  StageWorkers workers(ctx, jobs.data(), B, chunk);
+  StageWorkers workers(ctx, jobs.data(), B, bounds);
   for (int c = 0; c < n_chunks; ++c) {
-    const int b0 = c * chunk, b1 = std::min(B, b0 + chunk), n = b1 - b0;
+    const int b0 = bounds[c], b1 = bounds[c + 1], n = b1 - b0;
     // images straight into the level-0 slots (one 2-D copy for equally spaced images going to consecutive slots)
     bool one_copy = n > 1 && stride == W;
     const ptrdiff_t spacing = n > 1 ? imgs[b0 + 1] - imgs[b0] : 0;
