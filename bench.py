@@ -103,6 +103,25 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout. Libraries print there too (NCCL's version banner under torchrun), so the real stdout is
+    kept aside for the JSON line and file descriptor 1 is pointed at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -174,7 +193,7 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": cores, "kind": "port",
                              "sample": f"{n} frames/step x {steps} steps, one frame per thread, oracle/liboracle_hso.so (-O3 x86-64-v3)"},
             "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 
@@ -433,6 +452,7 @@ def main():
     ap.add_argument("--no-other-rows", action="store_true")
     ap.add_argument("--no-ic-dual", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -654,7 +674,7 @@ def main():
                                   "unit": "iterations/s", "ms_per_step": g0.elapsed_time(g1) / args.steps}
             line["other_rows"] = other_rows(ctx, lib, args, dev, torch, K)
             line["single_stream"] = single_stream(args, local_rank, torch)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
