@@ -728,17 +728,30 @@ HSO_DEV void select_kth(const TrackJobDev& job, const Smem& s, const float* absr
   __syncthreads();
 }
 
+// Slow path of the damped solve: diagonal-pivoted LDL^T with Eigen::LDLT's semantics on a stack copy (dynamic indexing).
+__device__ __noinline__ void solve_pivoted(const TrackCtrl* c, float lambda, double* step) {
+  double Hl[49], bl[7];
+  int idx = 0;
+  for (int r = 0; r < 7; ++r)
+    for (int q = r; q < 7; ++q) { Hl[r * 7 + q] = Hl[q * 7 + r] = c->H[idx]; ++idx; }
+  for (int k = 0; k < 7; ++k) Hl[k * 7 + k] *= (double)(1.f + lambda);
+  for (int k = 0; k < 7; ++k) bl[k] = c->b[k];
+  ldlt_solve<7>(Hl, bl, step);
+}
+
 // Thread-0 control step after a residual evaluation: accept/reject, damping update, convergence test, damped 7x7 solve and
 // SE3 update for the next trial (src/CoarseTracker.cpp:108-194). Every CTA of a cluster runs it redundantly on identical totals.
-__device__ __noinline__ void lm_control(TrackCtrl* c, const double* tot, const TrackJobDev& job, int iter, int n_iter, int level, int trace_cap,
-                                        bool ic, bool rank0, float a_eval, float huber, float cutoff, int N) {
+// (The job's pointers come by value: a reference to the kernel's local TrackJobDev copy would pin that copy to the local-memory stack, and every
+// control step would start with dependent loads that miss the small L1 left beside 180-230 KB of shared memory.)
+__device__ __noinline__ void lm_control(TrackCtrl* c, const double* tot, hso_trace* job_trace, TrackState* job_state, int iter, int n_iter, int level,
+                                        int trace_cap, bool ic, bool rank0, float a_eval, float huber, float cutoff, int N) {
   const int terms = (int)tot[36];
   const double E = (double)((float)tot[35] / (float)terms);  // return E/m_total_terms (float / int), :413
   const bool accepted = iter < 0 ? true : (E < c->E_old);
-  if (job.trace != nullptr && rank0) {
-    const int tl = job.state->trace_len;
+  if (job_trace != nullptr && rank0) {
+    const int tl = job_state->trace_len;
     if (tl < trace_cap) {
-      hso_trace* e = job.trace + tl;
+      hso_trace* e = job_trace + tl;
       e->level = level; e->iter = iter;
       for (int k = 0; k < 12; ++k) e->T_eval[k] = c->Rt[k];
       e->a_eval = a_eval; e->lambda = iter < 0 ? 0.f : c->lambda;
@@ -748,7 +761,7 @@ __device__ __noinline__ void lm_control(TrackCtrl* c, const double* tot, const T
       for (int k = 0; k < 7; ++k) { e->b[k] = tot[28 + k]; e->step[k] = iter < 0 ? 0.0 : c->step[k]; }
       e->energy = E; e->total_terms = terms; e->saturated_terms = (int)tot[37];
       e->accepted = accepted ? 1 : 0; e->huber = huber; e->outlier = cutoff;
-      job.state->trace_len = tl + 1;
+      job_state->trace_len = tl + 1;
     }
   }
   if (iter < 0) c->lambda = 0.1f;
@@ -772,22 +785,31 @@ __device__ __noinline__ void lm_control(TrackCtrl* c, const double* tot, const T
     if (!(sqrt(nrm) > 1e-4)) done = true;  // :188
   }
   if (iter + 1 >= n_iter) done = true;
-  if (rank0) { job.state->last_total_terms = terms; job.state->last_N = N; }
+  if (rank0) { job_state->last_total_terms = terms; job_state->last_N = N; }
   if (!done) {
     // damped solve, extrapolation, NaN guard (:112-124)
-    double Hl[49], step[7];
-    int idx = 0;
-    for (int r = 0; r < 7; ++r)
-      for (int q = r; q < 7; ++q) { Hl[r * 7 + q] = Hl[q * 7 + r] = c->H[idx]; ++idx; }
+    double step[7];
     const float lambda = c->lambda;
-    for (int k = 0; k < 7; ++k) Hl[k * 7 + k] *= (double)(1.f + lambda);
-    double bl[7];
-    for (int k = 0; k < 7; ++k) bl[k] = c->b[k];
-    // register-resident unpivoted factorisation when the damped system is safely positive definite (the normal case);
-    // the pivoted robust-Cholesky path (Eigen::LDLT semantics) otherwise
-    if (!ldlt_solve_spd_fast<7>(Hl, bl, step)) {
-      ldlt_solve<7>(Hl, bl, step);
-      if (rank0) job.state->cycles[7] += 1;  // diagnostics: number of pivoted (slow path) solves
+    bool solved;
+    {
+      // register-resident unpivoted factorisation when the damped system is safely positive definite (the normal case). Every index below is
+      // a compile-time constant and no address escapes, so Hl / bl live in registers (a stack copy would be read back through an L1 that is
+      // almost entirely carved out as shared memory).
+      double Hl[49], bl[7];
+      int idx = 0;
+#pragma unroll
+      for (int r = 0; r < 7; ++r)
+#pragma unroll
+        for (int q = r; q < 7; ++q) { Hl[r * 7 + q] = Hl[q * 7 + r] = c->H[idx]; ++idx; }
+#pragma unroll
+      for (int k = 0; k < 7; ++k) Hl[k * 7 + k] *= (double)(1.f + lambda);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) bl[k] = c->b[k];
+      solved = ldlt_solve_spd_fast<7>(Hl, bl, step);
+    }
+    if (!solved) {  // the pivoted robust-Cholesky path (Eigen::LDLT semantics)
+      solve_pivoted(c, lambda, step);
+      if (rank0) job_state->cycles[7] += 1;  // diagnostics: number of pivoted (slow path) solves
     }
     float extrap = 1.f;
     if (lambda < 0.001f) extrap = (float)sqrt(sqrt(0.001 / (double)lambda));
@@ -1014,7 +1036,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     patch_evals += (unsigned long long)s.tot[38];
     if (threadIdx.x == 0) {
       const long long t_in = clock64();
-      lm_control(c, s.tot, job, iter, prm.n_iter, prm.level, prm.trace_cap, IC, crank == 0, a_eval, huber, cutoff, N);
+      lm_control(c, s.tot, job.trace, job.state, iter, prm.n_iter, prm.level, prm.trace_cap, IC, crank == 0, a_eval, huber, cutoff, N);
       clk_ctrl += clock64() - t_in;
     }
     __syncthreads();
