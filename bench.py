@@ -427,7 +427,33 @@ def single_stream(args, device, torch):
                 its += frame(p)
         dt = time.perf_counter() - t0
         it_c, dt_c = run_cpu(use, ic, 1)
+        # the same frames through ONE C-ABI call per frame (hso_add_frames_track_batch, B = 1) with argument records built once, as a C++
+        # caller holding long-lived Frame / Feature objects would: no Python marshalling inside the timed loop
+        from hso_b200 import _capi as K
+        prm = K.hso_track_params(int(ic), 4, 1, 50)
+        recs = []
+        for p in use:
+            jarr, keep = ctx._track_jobs([dict(ref=p["_rid"], cur=0, px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=p["T0"], exposure_rat=-1.0)])
+            img = np.ascontiguousarray(p["cur_img"])
+            recs.append((jarr, keep, img, (C.c_void_p * 1)(img.ctypes.data)))
+        nid, res1 = (C.c_int32 * 1)(), (K.hso_track_result * 1)()
+        Wc, Hc = c["width"], c["height"]
+
+        def frame1(r):
+            ctx._chk(ctx.lib.hso_add_frames_track_batch(ctx.h, C.byref(prm), 1, r[3], Wc, Hc, Wc, r[0], nid, None, None, res1))
+            ctx.lib.hso_frame_release(ctx.h, nid[0])
+            return res1[0].n_iters
+        for r in recs:
+            frame1(r)
+        t0 = time.perf_counter()
+        its1 = 0
+        for _ in range(reps):
+            for r in recs:
+                its1 += frame1(r)
+        dt1 = time.perf_counter() - t0
         out[mode] = {"gpu_frames_per_s": reps * len(use) / dt, "gpu_ms_per_frame": 1e3 * dt / (reps * len(use)), "gpu_iterations_per_s": its / dt,
+                     "gpu_ms_per_frame_single_call": 1e3 * dt1 / (reps * len(use)), "gpu_frames_per_s_single_call": reps * len(use) / dt1,
+                     "single_call_iterations": its1, "two_call_iterations": its,
                      "cpu_frames_per_s_1core": len(use) / dt_c, "cpu_ms_per_frame": 1e3 * dt_c / len(use), "features": 200}
     ctx.close()
     return out
