@@ -19,6 +19,7 @@ constexpr int TW = 128, TH = 32, HX = 16, HY = 2;
 constexpr int TPITCH = TW + 2 * HX;  // 160
 constexpr int TROWS = TH + 2 * HY;   // 36
 constexpr int PYR_THREADS = 256;
+static_assert(TW == 128 && TH == 32, "the tile loops index with shifts for a 128x32 tile");
 
 struct PyrKParams {
   PyrGeom g;
@@ -78,9 +79,11 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_tile(const PyrKParams P, co
   if (job.src == pyr + P.g.off[0]) {
     // built in place: the upload went straight into the level-0 slot
   } else if ((W & 15) == 0) {
+    // (index arithmetic on the full 128x32 tile: shifts instead of divisions by the clipped tile size; edge tiles mask the excess)
     const int chunks = tw >> 4;
-    for (int idx = tid; idx < th * chunks; idx += PYR_THREADS) {
-      const int r = idx / chunks, cix = idx - r * chunks;
+    for (int idx = tid; idx < TH * (TW / 16); idx += PYR_THREADS) {
+      const int r = idx >> 3, cix = idx & 7;
+      if (r >= th || cix >= chunks) continue;
       const uint4 v = *reinterpret_cast<const uint4*>(tile + (r + HY) * TPITCH + HX + cix * 16);
       *reinterpret_cast<uint4*>(pyr + P.g.off[0] + (size_t)(ty * TH + r) * W + tx * TW + cix * 16) = v;
     }
@@ -106,8 +109,9 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_tile(const PyrKParams P, co
     {
       const int w1 = P.g.w[1], sse = P.g.sse_rounding[1];
       const int cw = tw >> 3;  // groups of 4 output px per row
-      for (int idx = tid; idx < (th >> 1) * cw; idx += PYR_THREADS) {
-        const int r = idx / cw, cg4 = idx - r * cw;
+      for (int idx = tid; idx < (TH / 2) * (TW / 8); idx += PYR_THREADS) {
+        const int r = idx >> 4, cg4 = idx & 15;
+        if (r >= (th >> 1) || cg4 >= cw) continue;
         const uint8_t* t = tile + (2 * r + HY) * TPITCH + HX + cg4 * 8;
         const uint8_t* b = t + TPITCH;
         uchar4 o;
@@ -123,8 +127,9 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_tile(const PyrKParams P, co
     if (P.g.n_levels > 2) {
       const int w2 = P.g.w[2], sse = P.g.sse_rounding[2];
       const int cw = tw >> 2;
-      for (int idx = tid; idx < (th >> 2) * cw; idx += PYR_THREADS) {
-        const int r = idx / cw, cix = idx - r * cw;
+      for (int idx = tid; idx < (TH / 4) * (TW / 4); idx += PYR_THREADS) {
+        const int r = idx >> 5, cix = idx & 31;
+        if (r >= (th >> 2) || cix >= cw) continue;
         const uint8_t* t = l1 + (2 * r) * (TW / 2) + 2 * cix;
         const uint8_t* b = t + TW / 2;
         const uint8_t o = half_px(t[0], t[1], b[0], b[1], sse);
@@ -136,8 +141,9 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_tile(const PyrKParams P, co
     if (P.g.n_levels > 3) {
       const int w3 = P.g.w[3], sse = P.g.sse_rounding[3];
       const int cw = tw >> 3;
-      for (int idx = tid; idx < (th >> 3) * cw; idx += PYR_THREADS) {
-        const int r = idx / cw, cix = idx - r * cw;
+      for (int idx = tid; idx < (TH / 8) * (TW / 8); idx += PYR_THREADS) {
+        const int r = idx >> 4, cix = idx & 15;
+        if (r >= (th >> 3) || cix >= cw) continue;
         const uint8_t* t = l2 + (2 * r) * (TW / 4) + 2 * cix;
         const uint8_t* b = t + TW / 4;
         const uint8_t o = half_px(t[0], t[1], b[0], b[1], sse);
@@ -149,8 +155,9 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_tile(const PyrKParams P, co
     if (P.g.n_levels > 4) {
       const int w4 = P.g.w[4], sse = P.g.sse_rounding[4];
       const int cw = tw >> 4;
-      for (int idx = tid; idx < (th >> 4) * cw; idx += PYR_THREADS) {
-        const int r = idx / cw, cix = idx - r * cw;
+      for (int idx = tid; idx < (TH / 16) * (TW / 16); idx += PYR_THREADS) {
+        const int r = idx >> 3, cix = idx & 7;
+        if (r >= (th >> 4) || cix >= cw) continue;
         const uint8_t* t = l3 + (2 * r) * (TW / 8) + 2 * cix;
         const uint8_t* b = t + TW / 8;
         pyr[P.g.off[4] + (size_t)(ty * (TH / 16) + r) * w4 + tx * (TW / 16) + cix] = half_px(t[0], t[1], b[0], b[1], sse);
@@ -163,10 +170,10 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_tile(const PyrKParams P, co
   // ---- vertical Sobel pass + interior sums (src/frame.cpp:223-245) ---------------------------------------------------------
   float gsum = 0.f;
   unsigned int isum = 0;
-  for (int idx = tid; idx < th * tw; idx += PYR_THREADS) {
-    const int r = idx / tw, cix = idx - r * tw;
+  for (int idx = tid; idx < TH * TW; idx += PYR_THREADS) {
+    const int r = idx >> 7, cix = idx & (TW - 1);
     const int x = tx * TW + cix, y = ty * TH + r;
-    if (x < 16 || x >= W - 16 || y < 16 || y >= H - 16) continue;
+    if (x < 16 || x >= W - 16 || y < 16 || y >= H - 16) continue;  // also masks the excess of edge tiles (x >= W, y >= H)
     const int16_t* d = hd + r * TW + cix;  // tile row r is image row y-2
     const int16_t* s = hs + r * TW + cix;
     const int gx = d[0] + 4 * d[TW] + 6 * d[2 * TW] + 4 * d[3 * TW] + d[4 * TW];
