@@ -610,7 +610,7 @@ def main():
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
-        n_e2e_steps = max(2, min(args.steps, 5))
+        n_e2e_steps = max(2, args.steps)
         it_e2e = 0
         for _ in range(n_e2e_steps):
             it_e2e += e2e_step()

@@ -19,7 +19,7 @@ constexpr int TW = 128, TH = 32, HX = 16, HY = 2;
 constexpr int TPITCH = TW + 2 * HX;  // 160
 constexpr int TROWS = TH + 2 * HY;   // 36
 constexpr int PYR_THREADS = 256;
-static_assert(TW == 128 && TH == 32, "the tile loops index with shifts for a 128x32 tile");
+static_assert(TW == 128 && TH == 32 && PYR_THREADS == 256, "the tile loops index with shifts for a 128x32 tile");
 
 struct PyrKParams {
   PyrGeom g;
@@ -95,12 +95,15 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_tile(const PyrKParams P, co
   }
 
   // ---- Sobel 5x5 on the tile: horizontal pass (derivative [-1,-2,0,2,1], smoothing [1,4,6,4,1]) ---------------------------
-  for (int idx = tid; idx < TROWS * TW; idx += PYR_THREADS) {
-    const int r = idx / TW, cix = idx - r * TW;
+  // (two adjacent pixels per thread share four of their six taps; the two int16 results go out as one 32-bit store)
+  for (int idx = tid; idx < TROWS * (TW / 2); idx += PYR_THREADS) {
+    const int r = idx >> 6, cix = (idx & 63) * 2;
     const uint8_t* p = tile + r * TPITCH + HX + cix;
-    const int m2 = p[-2], m1 = p[-1], c0 = p[0], p1 = p[1], p2 = p[2];
-    hd[idx] = (int16_t)(-m2 - 2 * m1 + 2 * p1 + p2);
-    hs[idx] = (int16_t)(m2 + 4 * m1 + 6 * c0 + 4 * p1 + p2);
+    const int m2 = p[-2], m1 = p[-1], c0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
+    const int d0 = -m2 - 2 * m1 + 2 * p1 + p2, d1 = -m1 - 2 * c0 + 2 * p2 + p3;
+    const int s0 = m2 + 4 * m1 + 6 * c0 + 4 * p1 + p2, s1 = m1 + 4 * c0 + 6 * p1 + 4 * p2 + p3;
+    *reinterpret_cast<uint32_t*>(hd + r * TW + cix) = (uint32_t)(d0 & 0xFFFF) | ((uint32_t)d1 << 16);
+    *reinterpret_cast<uint32_t*>(hs + r * TW + cix) = (uint32_t)(s0 & 0xFFFF) | ((uint32_t)s1 << 16);
   }
 
   // ---- halfSample chain inside the tile ---------------------------------------------------------------------------------
@@ -168,19 +171,34 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_tile(const PyrKParams P, co
   }
 
   // ---- vertical Sobel pass + interior sums (src/frame.cpp:223-245) ---------------------------------------------------------
+  // Each thread walks one column of one 16-row half of the tile and keeps the last five horizontal results in registers: two shared-memory
+  // loads per pixel instead of nine.
   float gsum = 0.f;
   unsigned int isum = 0;
-  for (int idx = tid; idx < TH * TW; idx += PYR_THREADS) {
-    const int r = idx >> 7, cix = idx & (TW - 1);
-    const int x = tx * TW + cix, y = ty * TH + r;
-    if (x < 16 || x >= W - 16 || y < 16 || y >= H - 16) continue;  // also masks the excess of edge tiles (x >= W, y >= H)
-    const int16_t* d = hd + r * TW + cix;  // tile row r is image row y-2
-    const int16_t* s = hs + r * TW + cix;
-    const int gx = d[0] + 4 * d[TW] + 6 * d[2 * TW] + 4 * d[3 * TW] + d[4 * TW];
-    const int gy = -s[0] - 2 * s[TW] + 2 * s[3 * TW] + s[4 * TW];
-    const float fx = (float)gx, fy = (float)gy;
-    gsum += sqrtf(fx * fx + fy * fy);
-    isum += tile[(r + HY) * TPITCH + HX + cix];
+  {
+    const int col = tid & (TW - 1), r0 = (tid >> 7) * (TH / 2);
+    const int x = tx * TW + col;
+    if (x >= 16 && x < W - 16) {  // also masks the excess of edge tiles (x >= W)
+      const int16_t* dc = hd + r0 * TW + col;  // tile row r is image row y-2
+      const int16_t* sc = hs + r0 * TW + col;
+      const uint8_t* tc = tile + (r0 + HY) * TPITCH + HX + col;
+      int d0 = dc[0], d1 = dc[TW], d2 = dc[2 * TW], d3 = dc[3 * TW];
+      int s0 = sc[0], s1 = sc[TW], s2 = sc[2 * TW], s3 = sc[3 * TW];
+#pragma unroll
+      for (int k = 0; k < TH / 2; ++k) {
+        const int d4 = dc[(k + 4) * TW], s4 = sc[(k + 4) * TW];
+        const int y = ty * TH + r0 + k;
+        if (y >= 16 && y < H - 16) {
+          const int gx = (d0 + d4) + 4 * (d1 + d3) + 6 * d2;
+          const int gy = (s4 - s0) + 2 * (s3 - s1);
+          const float fx = (float)gx, fy = (float)gy;
+          gsum += sqrtf(fx * fx + fy * fy);
+          isum += tc[k * TPITCH];
+        }
+        d0 = d1; d1 = d2; d2 = d3; d3 = d4;
+        s0 = s1; s1 = s2; s2 = s3; s3 = s4;
+      }
+    }
   }
   {
     double g = (double)gsum;
