@@ -57,7 +57,7 @@ print("total", sum(np.median(v[2:]) for v in T.values()))
 gm = np.zeros(B, np.float32)
 for b in range(B):
     jarr[b].exposure_rat = -1.0
-for chunk, streams in [(148, 2), (74, 3), (111, 3), (111, 4), (148, 3), (0, 0), (0, 0)]:
+for chunk, streams in [(74, 3), (74, 4), (56, 4), (111, 3), (111, 4), (148, 4), (0, 0)]:
     ctx._chk(lib.hso_set_pipeline(ctx.h, chunk, streams))
     tt = []
     for it in range(8):
