@@ -281,9 +281,9 @@ class Context:
         return out
 
     # ---- F4: pose_optimizer::optimizeLevenbergMarquardt3rd -----------------------------------------------------------------
-    def pose_optimize_batch(self, problems, reproj_thresh=2.0, n_iter=12):
-        """problems: list of dicts {f (F,3), p_host (F,3), host_idx (F,), T_host_w (K,3,4), grad (F,2), level, ftype, ptype (F,),
-        T_f_w (3,4), n_fts_total}. Returns list of dicts with the reference's outputs + outlier mask."""
+    def pose_args(self, problems, reproj_thresh=2.0, n_iter=12):
+        """Flattens the problems once and returns (call, (offs, outlier, results)): call() runs hso_pose_optimize_batch on those buffers
+        (what a C++ caller holding flattened arrays does per frame)."""
         B = len(problems)
         cat = lambda key, dt, w: np.ascontiguousarray(np.concatenate([np.asarray(p[key], dt).reshape(-1, w) for p in problems]) if B else np.zeros((0, w), dt))
         f, ph, g = cat("f", np.float64, 3), cat("p_host", np.float64, 3), cat("grad", np.float64, 2)
@@ -300,9 +300,20 @@ class Context:
         outl = np.zeros(max(int(offs[B]), 1), np.uint8)
         out = (K.hso_pose_result * B)()
         i32, i8, u8 = C.POINTER(C.c_int32), C.POINTER(C.c_int8), C.POINTER(C.c_uint8)
-        self._chk(self.lib.hso_pose_optimize_batch(self.h, reproj_thresh, n_iter, B, nf.ctypes.data_as(i32), offs.ctypes.data_as(i32), _dp(f), _dp(ph),
-                                                   hi.ctypes.data_as(i32), hoffs.ctypes.data_as(i32), _dp(Th), _dp(g), lv.ctypes.data_as(i8),
-                                                   ft.ctypes.data_as(i8), pt.ctypes.data_as(i8), _dp(T0), outl.ctypes.data_as(u8), out))
+        keep = (f, ph, g, hi, lv, ft, pt, Th, T0, hoffs, nf)
+
+        def call(_keep=keep):
+            self._chk(self.lib.hso_pose_optimize_batch(self.h, reproj_thresh, n_iter, B, nf.ctypes.data_as(i32), offs.ctypes.data_as(i32), _dp(f), _dp(ph),
+                                                       hi.ctypes.data_as(i32), hoffs.ctypes.data_as(i32), _dp(Th), _dp(g), lv.ctypes.data_as(i8),
+                                                       ft.ctypes.data_as(i8), pt.ctypes.data_as(i8), _dp(T0), outl.ctypes.data_as(u8), out))
+        return call, (offs, outl, out)
+
+    def pose_optimize_batch(self, problems, reproj_thresh=2.0, n_iter=12):
+        """problems: list of dicts {f (F,3), p_host (F,3), host_idx (F,), T_host_w (K,3,4), grad (F,2), level, ftype, ptype (F,),
+        T_f_w (3,4), n_fts_total}. Returns list of dicts with the reference's outputs + outlier mask."""
+        B = len(problems)
+        call, (offs, outl, out) = self.pose_args(problems, reproj_thresh, n_iter)
+        call()
         res = []
         for b in range(B):
             o = out[b]
