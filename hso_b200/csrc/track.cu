@@ -64,8 +64,6 @@ template <int PIDX>
 HSO_DEV constexpr int pat_dy(int n) {
   return (int)(((n < 8 ? PatBits<PIDX>::w0 : n < 16 ? PatBits<PIDX>::w1 : n < 24 ? PatBits<PIDX>::w2 : PatBits<PIDX>::w3) >> ((n & 7) * 8 + 4)) & 0xfull) - 8;
 }
-static const int h_pat_num[8] = {1, 5, 9, 13, 13, 21, 25, 25};
-static const int h_pat_pad[8] = {1, 1, 1, 2, 2, 3, 2, 4};
 
 constexpr int NRED = 40;       // 28 H + 7 b + E + terms + saturated + patches (+1 pad)
 // radix-select digit width: 11 bits (2048 bins; passes 11+11+10) when shared memory allows, else 8 bits (256 bins; 4 passes)
@@ -513,14 +511,6 @@ HSO_DEV void reduce_acc(const Acc& acc, const Smem& s, int slot, int csize, int 
     s.tot[threadIdx.x] = sum;
   }
   __syncthreads();
-}
-
-// Warp-aggregated histogram increment: lanes of the warp that hit the same bin elect one leader which adds their count.
-// The top digit of |r| takes only a few dozen distinct values, so plain shared-memory atomics would serialise 32-way.
-HSO_DEV void hist_add_aggregated(uint32_t* hist, uint32_t bin) {
-  const unsigned act = __activemask();
-  const unsigned peers = __match_any_sync(act, bin);
-  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
 }
 
 // Merge the histograms of the cluster's CTAs (DSMEM) and locate the bucket that holds rank k (k = total / 2 when `first`: hso::getMedian,
@@ -1155,7 +1145,6 @@ cudaError_t launch_track_level(const TrackLevelParams& p, const TrackJobDev* job
                                uint64_t* launches) {
   const int pidx = p.max_level - p.level + 2;  // m_offset_all (src/CoarseTracker.cpp:80, CoarseTracker.h:122)
   if (pidx < 2 || pidx > 7) return cudaErrorInvalidValue;
-  (void)h_pat_num; (void)h_pat_pad;
   const size_t smem = track_level_smem_bytes(p, threads);
   ++*launches;
   switch (pidx) {
