@@ -653,7 +653,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "track_l1_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))  # ncu --set full capture of the level-1 kernel (tools/ncu_summary.py); DRAM bytes scale with the batch
+                traffic = tj["dram_bytes_per_problem"] * B if "dram_bytes_per_problem" in tj else tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
