@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -1008,6 +1009,9 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
     CU(cudaMemsetAsync(ctx->pyr_counters.p, 0, ctx->pyr_counters.cap, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  // tuning aid (tools/e2e_breakdown.py): HSO_PIPE_DEBUG bit 0 skips the kernel launches, bit 1 the image / feature copies, to time the stages alone
+  const char* dbg_env = getenv("HSO_PIPE_DEBUG");
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
   StageTimer tm(ctx, 1);
   std::vector<const uint8_t*> srcs(B);
   StageWorkers workers(ctx, jobs.data(), B, bounds);
@@ -1018,22 +1022,23 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
     const ptrdiff_t spacing = n > 1 ? imgs[b0 + 1] - imgs[b0] : 0;
     for (int i = b0 + 1; i < b1 && one_copy; ++i) one_copy = (imgs[i] - imgs[i - 1] == spacing) && (new_ids[i] == new_ids[i - 1] + 1);
     one_copy = one_copy && spacing >= (ptrdiff_t)W * H;
-    if (one_copy)
+    if (one_copy && !(dbg & 2))
       CU(cudaMemcpy2DAsync(get_frame(ctx, new_ids[b0])->pyr + ctx->geom.off[0], ctx->pyr_slot_bytes, imgs[b0], (size_t)spacing, (size_t)W * H, n,
                            cudaMemcpyHostToDevice, ctx->copy_stream));
     for (int i = b0; i < b1; ++i) {
       FrameSlot* s = get_frame(ctx, new_ids[i]);
-      if (!one_copy) CU(cudaMemcpy2DAsync(s->pyr + ctx->geom.off[0], W, imgs[i], stride, W, H, cudaMemcpyHostToDevice, ctx->copy_stream));
+      if (!one_copy && !(dbg & 2)) CU(cudaMemcpy2DAsync(s->pyr + ctx->geom.off[0], W, imgs[i], stride, W, H, cudaMemcpyHostToDevice, ctx->copy_stream));
       srcs[i] = s->pyr + ctx->geom.off[0];
     }
     rc = run_pyramid(ctx, n, new_ids + b0, srcs.data() + b0, W, 1, b0, ctx->copy_stream);
     if (rc != HSO_OK) break;
     workers.wait_chunk(c);
-    rc = track_copy_range(ctx, b0, b1, ctx->copy_stream);
+    rc = (dbg & 2) ? HSO_OK : track_copy_range(ctx, b0, b1, ctx->copy_stream);
     if (rc != HSO_OK) break;
     CU(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
     cudaStream_t cs = (c % S == 0) ? ctx->stream : ctx->pipe_streams[c % S - 1];
     CU(cudaStreamWaitEvent(cs, ctx->chunk_ev[c], 0));
+    if (dbg & 1) continue;
     CU(launch_pyramid(ctx->geom, (const PyrJobDev*)ctx->pyr_jobs_dev.p + b0, n, W, ctx->resize_tabs.data(), ctx->cfg.materialize_sobel,
                       (unsigned*)ctx->pyr_counters.p + b0, 1, cs, &ctx->launches));
     rc = track_run_range(ctx, b0, n, false, B, cs);

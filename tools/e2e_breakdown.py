@@ -7,7 +7,7 @@ import torch
 import bench
 from hso_b200 import Context, make_cam, _capi as K
 
-B, F = 592, 3000
+B, F = int(os.environ.get("HSO_BD_BATCH", "1184")), 3000
 probs = bench.build_workload(B, F, "icl", 0x450, 0)
 c = probs[0]["cam"]; W, H = c["width"], c["height"]
 ctx = Context(make_cam(W, H, c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), device=0, max_frames=2 * B + 72, max_features=8192)
@@ -67,3 +67,16 @@ for chunk, streams in [(74, 3), (74, 4), (56, 4), (111, 3), (111, 4), (148, 4), 
         tt.append(1e3 * (time.perf_counter() - t))
         for b in range(B): cur_ids_c[b] = new_ids[b]
     print(f"hso_add_frames_track_batch chunk={chunk} streams={streams} ms: median {np.median(tt[2:]):.2f} min {min(tt):.2f}  iters", sum(res[b].n_iters for b in range(B)))
+
+# ---- the stages of the pipelined call alone (HSO_PIPE_DEBUG): copies + host flattening only / kernels only (data resident from the run above)
+ctx._chk(lib.hso_set_pipeline(ctx.h, 0, 0))
+for name, flag in (("copies + flattening only", "1"), ("kernels only (no image / feature copies)", "2"), ("everything", "0")):
+    os.environ["HSO_PIPE_DEBUG"] = flag
+    tt = []
+    for it in range(6):
+        for b in range(B): lib.hso_frame_release(ctx.h, cur_ids_c[b])
+        t = time.perf_counter()
+        ctx._chk(lib.hso_add_frames_track_batch(ctx.h, C.byref(prm), B, img_ptrs, W, H, W, jarr, new_ids, integ.ctypes.data_as(fptr), gm.ctypes.data_as(fptr), res))
+        tt.append(1e3 * (time.perf_counter() - t))
+        for b in range(B): cur_ids_c[b] = new_ids[b]
+    print(f"pipelined call, {name}: median {np.median(tt[2:]):.2f} ms")
