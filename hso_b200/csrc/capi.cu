@@ -983,10 +983,14 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   const int unit = ctx->pipe_chunk > 0 ? ctx->pipe_chunk : 111;  // 3/4 of a wave of single-CTA problems: measured best with 3 streams
   int chunk = B <= unit ? B : unit;
   while ((B + chunk - 1) / chunk > 32) chunk += unit;
-  // the first two chunks ramp up (1/3, 2/3 of a chunk): the GPU starts after a third of a chunk's flattening + copy instead of a whole one
+  // the first two chunks ramp up (1/3, 2/3 of a chunk): the GPU starts after a third of a chunk's flattening + copy instead of a whole one;
+  // the last two ramp down the same way: what is left to compute after the final copy is a third of a chunk (the call is copy bound)
   std::vector<int> bounds{0};
-  if (B > 2 * chunk && chunk >= 12 && ctx->pipe_chunk >= 0) { bounds.push_back(chunk / 3); bounds.push_back(chunk / 3 + 2 * chunk / 3); }
-  while (bounds.back() < B) bounds.push_back(std::min(B, bounds.back() + chunk));
+  const bool ramp = B > 4 * chunk && chunk >= 12;
+  if (ramp) { bounds.push_back(chunk / 3); bounds.push_back(chunk / 3 + 2 * chunk / 3); }
+  const int tail_sz = ramp ? (chunk / 3 + 2 * chunk / 3) : 0;
+  while (bounds.back() < B - tail_sz) bounds.push_back(std::min(B - tail_sz, bounds.back() + chunk));
+  if (ramp) { bounds.push_back(B - chunk / 3); bounds.push_back(B); }
   const int n_chunks = (int)bounds.size() - 1;
   const int S = std::max(1, std::min(n_chunks, ctx->pipe_n_streams > 0 ? ctx->pipe_n_streams : 3));
   while ((int)ctx->pipe_streams.size() < S - 1) {
