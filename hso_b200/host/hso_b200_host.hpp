@@ -16,8 +16,10 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <memory>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -452,6 +454,52 @@ inline void addImagesAndTrack(Context& ctx, const std::vector<const uint8_t*>& i
   prm.inverse_comp = inverse_composition ? 1 : 0; prm.max_level = max_level; prm.min_level = min_level; prm.n_iter = n_iter;
   new_ids.resize(B); results.resize(B);
   ctx.check(hso_add_frames_track_batch(ctx.get(), &prm, (int)B, imgs.data(), W, H, stride, jobs.data(), new_ids.data(), nullptr, nullptr, results.data()));
+}
+
+// ---- wire / disk formats of the driver around the path (row N4) — plain host code ------------------------------------------------------
+// ImageReader's timestamp file (src/ImageReader.cpp:30-66): four line formats tried in this order —
+//   "stamp x y z a b c d" (TUM ground-truth style), "id stamp exposure" (TUM monoVO times.txt), "id stamp", "stamp".
+// Returns false for a line none of them matches (the reference skips it). Quirk kept: the cascade is tried in that order, so a bare numeric
+// stamp such as "1403636580.263555" is consumed by "%d %s" (id = 1403636580, stamp = ".263555") before the single-token format is reached.
+inline bool parseTimestampLine(const char* buf, std::string& stamp_out) {
+  int id;
+  char stamp[100];
+  float x, y, z, a, b, c, d, exposure = 0;
+  if (8 == std::sscanf(buf, "%99s %f %f %f %f %f %f %f", stamp, &x, &y, &z, &a, &b, &c, &d)) { stamp_out = stamp; return true; }
+  if (3 == std::sscanf(buf, "%d %99s %f", &id, stamp, &exposure)) { stamp_out = stamp; return true; }
+  if (2 == std::sscanf(buf, "%d %99s", &id, stamp)) { stamp_out = stamp; return true; }
+  if (1 == std::sscanf(buf, "%99s", stamp)) { stamp_out = stamp; return true; }
+  return false;
+}
+
+// One line of BenchmarkNode::saveResult (test/test_dataset.cpp:312-335): "stamp tx ty tz qx qy qz qw" of T_w_f = T_f_w^-1 (TUM trajectory
+// format; the keyframe id replaces the stamp when the sequence has no timestamps), default ostream precision like the reference.
+inline void writeTrajectoryLine(std::ostream& os, bool stamp_valid, int id, const std::string& timestamp_s, const SE3& T_f_w) {
+  const SE3 Tinv = T_f_w.inverse();
+  const double* m = Tinv.m;
+  // unit quaternion of the rotation block (Eigen's Quaternion(Matrix3) branches)
+  double qw, qx, qy, qz;
+  const double tr = m[0] + m[5] + m[10];
+  if (tr > 0) {
+    double r = std::sqrt(tr + 1.0);
+    qw = 0.5 * r; r = 0.5 / r;
+    qx = (m[9] - m[6]) * r; qy = (m[2] - m[8]) * r; qz = (m[4] - m[1]) * r;
+  } else {
+    const double mm[3][3] = {{m[0], m[1], m[2]}, {m[4], m[5], m[6]}, {m[8], m[9], m[10]}};
+    int i = 0;
+    if (mm[1][1] > mm[0][0]) i = 1;
+    if (mm[2][2] > mm[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double r = std::sqrt(mm[i][i] - mm[j][j] - mm[k][k] + 1.0);
+    double v[3];
+    v[i] = 0.5 * r; r = 0.5 / r;
+    qw = (mm[k][j] - mm[j][k]) * r;
+    v[j] = (mm[j][i] + mm[i][j]) * r;
+    v[k] = (mm[k][i] + mm[i][k]) * r;
+    qx = v[0]; qy = v[1]; qz = v[2];
+  }
+  if (!stamp_valid) os << id << " "; else os << timestamp_s << " ";
+  os << m[3] << " " << m[7] << " " << m[11] << " " << qx << " " << qy << " " << qz << " " << qw << std::endl;
 }
 
 }  // namespace b200

@@ -105,3 +105,16 @@ def test_bench_reference_arm_and_gloo_reduce(tmp_path):
     env2 = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True, timeout=60, env=env2)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_host_layer_wire_formats(tmp_path):
+    """ImageReader's four timestamp line formats and the TUM trajectory line of saveResult (row N4), C++ host layer, CPU only."""
+    import subprocess
+    from hso_b200 import _capi
+    exe = tmp_path / "host_formats"
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "cpp", "host_formats.cpp"), "-o", str(exe), f"-L{libdir}", "-lhso_b200",
+                           f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip() == "OK", out.stderr
