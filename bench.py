@@ -76,19 +76,25 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples that arrived inside [t0, t1] (the timed region, host clock); the sampler is started before the warm-up steps because
+        nvidia-smi needs ~0.1 s to deliver its first line and the timed region may be shorter than that."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for (ts, ln) in self.lines if t0 is None or (t0 <= ts <= t1 + 0.03)]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: fall back to the samples under the identical warm-up load
+            inside, window = [ln for (_, ln) in self.lines], "warm-up + timed region"
+        for ln in inside:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -100,7 +106,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 _JSON_OUT = None
@@ -553,6 +559,8 @@ def main():
 
     # ---- value: inputs resident in HBM -------------------------------------------------------------------------------------
     ctx.track_stage(jobs, inverse_comp=args.ic, max_level=4, min_level=1, n_iter=50)
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # before the warm-up: nvidia-smi's first line takes ~0.1 s, the timed region may be shorter
     for _ in range(args.warmup):
         device_step()
     ctx.synchronize()
@@ -566,16 +574,16 @@ def main():
             "iters_per_problem": {"mean": iters_per_step / B, "max": max(out[b].n_iters for b in range(B)), "min": min(out[b].n_iters for b in range(B))}}
     ctx._chk(lib.hso_track_set_profile(ctx.h, 1))
     launches0 = ctx.kernel_launches()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         device_step()
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    t_region1 = time.perf_counter()
+    clocks = sampler.stop(t_region0, t_region1)
     ms_total = e0.elapsed_time(e1)
     launches = ctx.kernel_launches() - launches0
     lvl_ms = {}
