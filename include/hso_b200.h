@@ -242,7 +242,8 @@ typedef struct {
   int32_t n_trials;      /* n_trials_ (deleted points are skipped before counting) */
   int32_t used_cell_all; /* 1: the reprojectCellAll branch ran (n_in_frame < max_fts + 50) */
 } hso_reproj_summary;
-/* T_cur_w: frame->T_f_w_ (3x4 row-major); T_f_w: n_poses keyframe poses (3x4 each). cell_order: n_cols*n_rows cell indices. */
+/* T_cur_w: frame->T_f_w_ (3x4 row-major); T_f_w: n_poses keyframe poses (3x4 each). cell_order: a permutation of the n_cols*n_rows cell indices.
+ * Limits (HSO_ERR_CAPACITY / HSO_ERR_INVALID beyond them): M <= 16384 candidates, n_cols*n_rows <= 4096 cells; the grid must cover the image. */
 int hso_reproject_match(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], int n_poses, const double* T_f_w, int M,
                         const hso_reproj_cand* cands, const hso_reproj_grid* grid, const int32_t* cell_order, hso_reproj_result* out,
                         hso_reproj_summary* summary);
