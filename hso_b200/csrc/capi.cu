@@ -1,5 +1,7 @@
 // C-ABI of hso_b200 (include/hso_b200.h): context, device-resident frame table, staging of flattened feature arrays,
 // kernel sequencing. Host-side only; all arithmetic of the path lives in the kernels. There is no CPU fallback.
+#include <immintrin.h>
+
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -699,6 +701,12 @@ static int track_plan(hso_ctx* ctx, const hso_track_params* prm, int B, const hs
   return HSO_OK;
 }
 
+static inline void nt_store(double* p, double v) {
+  long long bits;
+  memcpy(&bits, &v, sizeof bits);
+  _mm_stream_si64(reinterpret_cast<long long*>(p), bits);
+}
+
 // Flatten the Feature list of job b to SoA in the pinned staging blob, keeping only features with a valid depth (dist >= 0): the
 // reference skips the others in every stage (src/CoarseTracker.cpp:290,433,455,557), so dropping them only changes the summation
 // order. Thread-safe across different b.
@@ -714,12 +722,15 @@ static void track_stage_one(hso_ctx* ctx, const hso_track_job* jobs, int b) {
   for (int i = 0; i < j.n_features; ++i) {
     const double d = j.dist[i];
     if (!(d >= 0)) continue;
-    px[k] = j.px[2 * i]; px[Fpad + k] = j.px[2 * i + 1];
+    // non-temporal stores: the staging blob is written once and read by the DMA engine only; keeping it out of the caches (and skipping the
+    // read-for-ownership) leaves more host memory bandwidth to the H2D copies that run concurrently with this loop
+    nt_store(px + k, j.px[2 * i]); nt_store(px + Fpad + k, j.px[2 * i + 1]);
     // Vector3d xyz_ref((*it_ft)->f*dist)  (src/CoarseTracker.cpp:292)
-    xyz[k] = j.f[3 * i] * d; xyz[Fpad + k] = j.f[3 * i + 1] * d; xyz[2 * Fpad + k] = j.f[3 * i + 2] * d;
+    nt_store(xyz + k, j.f[3 * i] * d); nt_store(xyz + Fpad + k, j.f[3 * i + 1] * d); nt_store(xyz + 2 * Fpad + k, j.f[3 * i + 2] * d);
     ++k;
   }
   hj[b].F = k;
+  _mm_sfence();
   for (; k < Fpad; ++k) { px[k] = px[Fpad + k] = 0; xyz[k] = xyz[Fpad + k] = 0; xyz[2 * Fpad + k] = 1; }
   double* T0 = (double*)(hbase + ctx->t_geo_bytes);
   float* a0 = (float*)(T0 + 12 * B);
@@ -1013,7 +1024,7 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
     CU(cudaMemsetAsync(ctx->pyr_counters.p, 0, ctx->pyr_counters.cap, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
   }
-  // tuning aid (tools/e2e_breakdown.py): HSO_PIPE_DEBUG bit 0 skips the kernel launches, bit 1 the image / feature copies, to time the stages alone
+  // tuning aid (tools/e2e_breakdown.py): HSO_PIPE_DEBUG bit 0 skips the kernel launches, bit 1 the image / feature copies (bit 2: images only, bit 3: features only), to time the stages alone
   const char* dbg_env = getenv("HSO_PIPE_DEBUG");
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   StageTimer tm(ctx, 1);
@@ -1026,18 +1037,18 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
     const ptrdiff_t spacing = n > 1 ? imgs[b0 + 1] - imgs[b0] : 0;
     for (int i = b0 + 1; i < b1 && one_copy; ++i) one_copy = (imgs[i] - imgs[i - 1] == spacing) && (new_ids[i] == new_ids[i - 1] + 1);
     one_copy = one_copy && spacing >= (ptrdiff_t)W * H;
-    if (one_copy && !(dbg & 2))
+    if (one_copy && !(dbg & 2) && !(dbg & 4))
       CU(cudaMemcpy2DAsync(get_frame(ctx, new_ids[b0])->pyr + ctx->geom.off[0], ctx->pyr_slot_bytes, imgs[b0], (size_t)spacing, (size_t)W * H, n,
                            cudaMemcpyHostToDevice, ctx->copy_stream));
     for (int i = b0; i < b1; ++i) {
       FrameSlot* s = get_frame(ctx, new_ids[i]);
-      if (!one_copy && !(dbg & 2)) CU(cudaMemcpy2DAsync(s->pyr + ctx->geom.off[0], W, imgs[i], stride, W, H, cudaMemcpyHostToDevice, ctx->copy_stream));
+      if (!one_copy && !(dbg & 2) && !(dbg & 4)) CU(cudaMemcpy2DAsync(s->pyr + ctx->geom.off[0], W, imgs[i], stride, W, H, cudaMemcpyHostToDevice, ctx->copy_stream));
       srcs[i] = s->pyr + ctx->geom.off[0];
     }
     rc = run_pyramid(ctx, n, new_ids + b0, srcs.data() + b0, W, 1, b0, ctx->copy_stream);
     if (rc != HSO_OK) break;
     workers.wait_chunk(c);
-    rc = (dbg & 2) ? HSO_OK : track_copy_range(ctx, b0, b1, ctx->copy_stream);
+    rc = (dbg & (2 | 8)) ? HSO_OK : track_copy_range(ctx, b0, b1, ctx->copy_stream);
     if (rc != HSO_OK) break;
     CU(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
     cudaStream_t cs = (c % S == 0) ? ctx->stream : ctx->pipe_streams[c % S - 1];

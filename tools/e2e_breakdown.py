@@ -70,7 +70,7 @@ for chunk, streams in [(74, 3), (74, 4), (56, 4), (111, 3), (111, 4), (148, 4), 
 
 # ---- the stages of the pipelined call alone (HSO_PIPE_DEBUG): copies + host flattening only / kernels only (data resident from the run above)
 ctx._chk(lib.hso_set_pipeline(ctx.h, 0, 0))
-for name, flag in (("copies + flattening only", "1"), ("kernels only (no image / feature copies)", "2"), ("everything", "0")):
+for name, flag in (("copies + flattening only", "1"), ("image copies + flattening only", "9"), ("feature copies + flattening only", "5"), ("flattening only", "3"), ("kernels only (no image / feature copies)", "2"), ("everything", "0")):
     os.environ["HSO_PIPE_DEBUG"] = flag
     tt = []
     for it in range(6):
@@ -80,3 +80,18 @@ for name, flag in (("copies + flattening only", "1"), ("kernels only (no image /
         tt.append(1e3 * (time.perf_counter() - t))
         for b in range(B): cur_ids_c[b] = new_ids[b]
     print(f"pipelined call, {name}: median {np.median(tt[2:]):.2f} ms")
+# ---- kernels-only / everything per pipeline shape
+for chunk, streams in [(111, 3), (148, 3), (148, 4), (222, 3), (222, 4), (296, 3), (296, 4), (74, 4)]:
+    ctx._chk(lib.hso_set_pipeline(ctx.h, chunk, streams))
+    line = f"chunk={chunk} streams={streams}:"
+    for name, flag in (("kernels", "2"), ("all", "0")):
+        os.environ["HSO_PIPE_DEBUG"] = flag
+        tt = []
+        for it in range(6):
+            for b in range(B): lib.hso_frame_release(ctx.h, cur_ids_c[b])
+            t = time.perf_counter()
+            ctx._chk(lib.hso_add_frames_track_batch(ctx.h, C.byref(prm), B, img_ptrs, W, H, W, jarr, new_ids, integ.ctypes.data_as(fptr), gm.ctypes.data_as(fptr), res))
+            tt.append(1e3 * (time.perf_counter() - t))
+            for b in range(B): cur_ids_c[b] = new_ids[b]
+        line += f"  {name} {np.median(tt[2:]):.2f} ms"
+    print(line)
