@@ -85,7 +85,7 @@ class Context:
         """Raw images (any size; resized to the camera size like ImageReader::readImage when it differs) -> optional undistortion remap
         (AbstractCamera::undistortImage) -> Frame. Returns (ids, integral, grad_mean)."""
         B = len(imgs)
-        imgs = [np.ascontiguousarray(im, np.uint8) for im in imgs]
+        imgs = [im if (im.dtype == np.uint8 and im.strides[1] == 1) else np.ascontiguousarray(im, np.uint8) for im in imgs]  # row padding is allowed
         H, W = imgs[0].shape
         ptrs = (C.c_void_p * B)(*[im.ctypes.data for im in imgs])
         ids = (C.c_int32 * B)()

@@ -77,3 +77,20 @@ def test_raw_upload_rejects_bad_arguments():
     with pytest.raises(HsoError):
         ctx._chk(ctx.lib.hso_frame_upload_raw_batch(ctx.h, 1, None, 640, 480, 640, 1, None, None, None))
     ctx.close()
+
+
+def test_raw_upload_with_row_padding_equals_tight(oracle):
+    """cv::Mat rows may be padded (step.p[0] > cols): the stride argument is honoured on both the resize and the undistort path."""
+    c = synth.CAMS["euroc"]
+    W, H = c["width"], c["height"]
+    rng = np.random.default_rng(4)
+    img = synth.texture(rng, W, H)
+    padded = np.zeros((H, W + 48), np.uint8)
+    padded[:, :W] = img
+    ctx = _ctx(c, max_frames=8)
+    a, ia, ga = ctx.upload_raw_frames([img], undistort=True)
+    b, ib, gb = ctx.upload_raw_frames([padded[:, :W]], undistort=True)   # a view: strides[0] = W + 48
+    for l in range(5):
+        assert np.array_equal(ctx.download_level(a[0], l), ctx.download_level(b[0], l)), l
+    assert ia[0] == ib[0] and ga[0] == gb[0]
+    ctx.close()

@@ -137,3 +137,19 @@ def test_reproject_edge_cases(oracle):
     osum = oracle.reproject_select(oc, np.array([out[i].align_ok for i in range(40)], np.uint8), og, s["cell_order"], io)
     assert [out[i].tried for i in range(40)] == [io[i].tried for i in range(40)] and summ.n_matches == osum.n_matches
     ctx.close()
+
+
+def test_reproject_capacity_and_grid_errors():
+    s = synth.make_reproject_scene(5, "icl", M=8)
+    c = s["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]), materialize_sobel=True)
+    kf_ids, _, _ = ctx.upload_frames(s["kf_imgs"])
+    cur_id = ctx.upload_frames([s["cur_img"]])[0][0]
+    big = Context.reproj_cands([s["cands"][0]] * 16385, frame_ids=kf_ids)
+    with pytest.raises(HsoError) as e:
+        ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], big, s["grid"], s["cell_order"])
+    assert e.value.code == -4  # HSO_ERR_CAPACITY
+    small_grid = dict(s["grid"], n_cols=2, n_rows=2)    # does not cover the image
+    with pytest.raises(HsoError):
+        ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], Context.reproj_cands(s["cands"], frame_ids=kf_ids), small_grid, np.arange(4, dtype=np.int32))
+    ctx.close()

@@ -230,3 +230,27 @@ def test_threshold_selection_fallback_on_degenerate_residuals(oracle, ic):
         assert e.huber == hub and e.outlier == outl, (lvl, e.huber, hub, e.outlier, outl)
     assert np.abs(res[0]["T_cur_ref"] - np.eye(4)[:3]).max() < 1e-9
     ctx.close()
+
+
+def test_pipelined_entry_edge_cases(oracle):
+    """A reference frame without features inside a pipelined batch (CoarseTracker::run returns 0 and leaves the pose untouched, :53), an
+    explicit exposure ratio next to device-formed ones, and bad arguments."""
+    from hso_b200 import HsoError
+    p = synth.make_pair(12, "icl", F=300)
+    c = p["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]), max_frames=16)
+    rid, rint, _ = ctx.upload_frames([p["ref_img"]])
+    T0 = synth.se3_exp(np.array([0.002, -0.001, 0.001, 0.0005, 0.0, -0.0004]))[:3]
+    empty = dict(ref=rid[0], px=np.zeros((0, 2)), f=np.zeros((0, 3)), dist=np.zeros(0), T_cur_ref=T0)
+    full = dict(ref=rid[0], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=np.eye(4)[:3])
+    ids, integ, gm, res = ctx.add_frames_track_batch([p["cur_img"]] * 3, [full, empty, dict(full, exposure_rat=1.05)])
+    assert res[1]["n_tracked"] == 0 and np.array_equal(res[1]["T_cur_ref"], T0)
+    assert res[0]["n_tracked"] > 100 and res[2]["n_tracked"] > 100
+    # the device-formed ratio equals the host's float division of the two statistics
+    two, _ = ctx.coarse_track_batch([dict(full, cur=ids[0], exposure_rat=float(np.float32(integ[0]) / np.float32(rint[0])))])
+    assert np.array_equal(two[0]["T_cur_ref"], res[0]["T_cur_ref"])
+    with pytest.raises(HsoError):
+        ctx.add_frames_track_batch([p["cur_img"][:100]], [full])  # wrong image size, like Frame::initFrame's exception
+    with pytest.raises(HsoError):
+        ctx.add_frames_track_batch([p["cur_img"]], [dict(full, ref=12345)])
+    ctx.close()
