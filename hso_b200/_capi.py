@@ -125,6 +125,7 @@ SYMBOLS = {
     "hso_frame_download_level": (C.c_int, [_vp, C.c_int32, C.c_int, _vp]),
     "hso_frame_download_sobel": (C.c_int, [_vp, C.c_int32, C.c_int, _vp, _vp]),
     "hso_frame_release": (C.c_int, [_vp, C.c_int32]),
+    "hso_frame_release_batch": (C.c_int, [_vp, C.c_int, _P(C.c_int32)]),
     "hso_coarse_track": (C.c_int, [_vp, _P(hso_track_params), _P(hso_track_job), _P(hso_track_result), _P(hso_trace), C.c_int, _P(C.c_int)]),
     "hso_coarse_track_batch": (C.c_int, [_vp, _P(hso_track_params), C.c_int, _P(hso_track_job), _P(hso_track_result), _P(hso_trace), C.c_int,
                                          _P(C.c_int)]),

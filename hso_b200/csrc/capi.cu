@@ -594,6 +594,16 @@ int hso_frame_release(hso_ctx* ctx, hso_frame_id id) {
 }
 
 // ---- F2 ---------------------------------------------------------------------------------------------------------------------
+int hso_frame_release_batch(hso_ctx* ctx, int n, const hso_frame_id* ids) {
+  if (!ctx || n < 0 || (n > 0 && !ids)) return HSO_ERR_INVALID;
+  int rc = HSO_OK;
+  for (int i = 0; i < n; ++i) {
+    const int r = hso_frame_release(ctx, ids[i]);
+    if (r != HSO_OK) rc = r;
+  }
+  return rc;
+}
+
 int hso_track_set_cluster(hso_ctx* ctx, int ctas, int threads) {
   if (!ctx) return HSO_ERR_INVALID;
   if (!(ctas == 0 || ctas == 1 || ctas == 2 || ctas == 4 || ctas == 8)) return fail(ctx, HSO_ERR_INVALID, "cluster size must be 0,1,2,4,8");

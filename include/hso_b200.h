@@ -80,6 +80,7 @@ int hso_frame_level_size(hso_ctx* ctx, hso_frame_id id, int level, int* w, int* 
 int hso_frame_download_level(hso_ctx* ctx, hso_frame_id id, int level, uint8_t* dst);
 int hso_frame_download_sobel(hso_ctx* ctx, hso_frame_id id, int level, int16_t* gx, int16_t* gy);
 int hso_frame_release(hso_ctx* ctx, hso_frame_id id);
+int hso_frame_release_batch(hso_ctx* ctx, int n, const hso_frame_id* ids);  /* ~Frame for n frames; returns the last error, releases the rest */
 /* ---- N4 (next row): input side — what test/test_dataset.cpp:262-283 does to a raw image before addImage: ImageReader::readImage's
  * cv::resize(image, image, m_img_new_size) (src/ImageReader.cpp:80) when (raw_w, raw_h) differs from the camera size, then
  * cam->undistortImage(image, image) = cv::remap(INTER_LINEAR) through the CV_16SC2 maps the camera constructor builds
