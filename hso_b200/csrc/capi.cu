@@ -68,6 +68,7 @@ struct hso_ctx {
   std::string err;
   uint64_t launches = 0;
   std::vector<FrameSlot> frames;
+  size_t free_lo = 0;  // no free slot below this index: allocation returns the LOWEST free slot without rescanning the used prefix
   // pyramid
   DevBuf pyr_arena, sums_arena;  // [max_frames] pyramids (slot stride = pyr_slot_bytes) and per-tile partial sums
   size_t pyr_slot_bytes = 0;
@@ -208,8 +209,13 @@ int build_resize_tab(hso_ctx* ctx, int sw, int sh, int dw, int dh, std::vector<c
   return 0;
 }
 
+void unuse_frame(hso_ctx* ctx, hso_frame_id id) {
+  ctx->frames[id].used = false;
+  if ((size_t)id < ctx->free_lo) ctx->free_lo = (size_t)id;
+}
+
 int alloc_frame(hso_ctx* ctx, hso_frame_id* out) {
-  for (size_t i = 0; i < ctx->frames.size(); ++i) {
+  for (size_t i = ctx->free_lo; i < ctx->frames.size(); ++i) {
     FrameSlot& s = ctx->frames[i];
     if (s.used) continue;
     if (!s.pyr) {
@@ -221,6 +227,7 @@ int alloc_frame(hso_ctx* ctx, hso_frame_id* out) {
       if (ctx->cfg.materialize_sobel) CU(cudaMalloc((void**)&s.sobel, sizeof(int16_t) * ctx->sobel_elems));
     }
     s.used = true;
+    ctx->free_lo = i + 1;
     *out = (hso_frame_id)i;
     return HSO_OK;
   }
@@ -411,7 +418,7 @@ int hso_frame_upload_batch(hso_ctx* ctx, int B, const uint8_t* const* imgs, int 
   for (int i = 0; i < B; ++i) {
     if (!imgs[i]) return fail(ctx, HSO_ERR_INVALID, "null image");
     int rc = alloc_frame(ctx, &out[i]);
-    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) ctx->frames[out[j]].used = false; return rc; }
+    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) unuse_frame(ctx, out[j]); return rc; }
   }
   StageTimer tm(ctx, 0);
   // straight into the level-0 slot of each pyramid (row stride == W); the kernel then builds in place. Tightly packed,
@@ -483,7 +490,7 @@ int hso_frame_upload_raw_batch(hso_ctx* ctx, int B, const uint8_t* const* imgs, 
   }
   for (int i = 0; i < B; ++i) {
     int rc = alloc_frame(ctx, &out[i]);
-    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) ctx->frames[out[j]].used = false; return rc; }
+    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) unuse_frame(ctx, out[j]); return rc; }
   }
   const size_t raw_bytes = ((size_t)raw_w * raw_h + 255) / 256 * 256, mid_bytes = ((size_t)W * H + 255) / 256 * 256;
   CU(ctx->in_raw.reserve(raw_bytes * B));
@@ -531,7 +538,7 @@ int hso_frame_build_batch_device(hso_ctx* ctx, int B, const void* const* dev_img
   for (int i = 0; i < B; ++i) {
     if (((uintptr_t)dev_imgs[i] & 15) != 0) aligned = 0;
     int rc = alloc_frame(ctx, &out[i]);
-    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) ctx->frames[out[j]].used = false; return rc; }
+    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) unuse_frame(ctx, out[j]); return rc; }
   }
   return run_pyramid(ctx, B, out, (const uint8_t* const*)dev_imgs, stride, aligned);
 }
@@ -589,7 +596,7 @@ int hso_frame_release(hso_ctx* ctx, hso_frame_id id) {
   if (!ctx) return HSO_ERR_INVALID;
   FrameSlot* s = get_frame(ctx, id);
   if (!s) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
-  s->used = false;  // buffers are kept for reuse; stream order protects in-flight work on this context
+  unuse_frame(ctx, id);  // buffers are kept for reuse; stream order protects in-flight work on this context
   return HSO_OK;
 }
 
@@ -992,9 +999,9 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
     if (!imgs[i]) return fail(ctx, HSO_ERR_INVALID, "null image");
   for (int i = 0; i < B; ++i) {
     int rc = alloc_frame(ctx, &new_ids[i]);
-    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) ctx->frames[new_ids[j]].used = false; return rc; }
+    if (rc != HSO_OK) { for (int j = 0; j < i; ++j) unuse_frame(ctx, new_ids[j]); return rc; }
   }
-  auto release_all = [&]() { for (int i = 0; i < B; ++i) ctx->frames[new_ids[i]].used = false; };
+  auto release_all = [&]() { for (int i = 0; i < B; ++i) unuse_frame(ctx, new_ids[i]); };
   std::vector<hso_track_job> jobs(jobs_in, jobs_in + B);
   for (int b = 0; b < B; ++b) jobs[b].cur = new_ids[b];
   int rc = track_plan(ctx, prm, B, jobs.data(), 0);  // synchronises ctx->stream: nothing of a previous call is in flight below
