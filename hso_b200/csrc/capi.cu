@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1046,7 +1047,7 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   StageTimer tm(ctx, 1);
   std::vector<const uint8_t*> srcs(B);
-  StageWorkers workers(ctx, jobs.data(), B, bounds);
+  std::unique_ptr<StageWorkers> workers;  // started right after the first chunk's image copy is on its way (spawning 8 threads takes ~0.3 ms)
   for (int c = 0; c < n_chunks; ++c) {
     const int b0 = bounds[c], b1 = bounds[c + 1], n = b1 - b0;
     // images straight into the level-0 slots (one 2-D copy for equally spaced images going to consecutive slots)
@@ -1062,9 +1063,10 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
       if (!one_copy && !(dbg & 2) && !(dbg & 4)) CU(cudaMemcpy2DAsync(s->pyr + ctx->geom.off[0], W, imgs[i], stride, W, H, cudaMemcpyHostToDevice, ctx->copy_stream));
       srcs[i] = s->pyr + ctx->geom.off[0];
     }
+    if (!workers) workers.reset(new StageWorkers(ctx, jobs.data(), B, bounds));
     rc = run_pyramid(ctx, n, new_ids + b0, srcs.data() + b0, W, 1, b0, ctx->copy_stream);
     if (rc != HSO_OK) break;
-    workers.wait_chunk(c);
+    workers->wait_chunk(c);
     rc = (dbg & (2 | 8)) ? HSO_OK : track_copy_range(ctx, b0, b1, ctx->copy_stream);
     if (rc != HSO_OK) break;
     CU(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
