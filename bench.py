@@ -206,16 +206,16 @@ def reference_arm(args, rank, world):
     cores = os.cpu_count() or 1
     n = 4 * max(cores, 2)
     probs = build_workload(n, args.patches, args.cam, args.seed, 0)
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):  # W untimed warm-up steps on a small slice (page-in, thread start-up)
         run_cpu(probs[: max(2, cores // 4)], args.ic, cores)
     tot_it, tot_t = 0, 0.0
-    steps = min(args.steps, 5)
+    steps = max(1, args.steps)  # exactly K timed steps; a step is a bounded sample (4 frames per host thread, ~0.2 s)
     for _ in range(steps):
         it, dt = run_cpu(probs, args.ic, cores)
         tot_it += it; tot_t += dt
     v = tot_it / tot_t
     line = {"impl": "reference", "metric": "CoarseTracker LM iterations/sec @640x480, 3k patches", "value": v, "unit": "iterations/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "frames_per_s": steps * n / tot_t,
             "config": {"workload": f"{args.cam} {probs[0]['cam']['width']}x{probs[0]['cam']['height']}, {args.patches} patches/frame, "
