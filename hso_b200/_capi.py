@@ -144,6 +144,8 @@ SYMBOLS = {
     "hso_align_batch": (C.c_int, [_vp, C.c_int32, C.c_int, _P(hso_align_job), _P(C.c_int32), C.c_int, _P(hso_align_result)]),
     "hso_reproject_match": (C.c_int, [_vp, C.c_int32, _P(C.c_double), C.c_int, _P(C.c_double), C.c_int, _P(hso_reproj_cand), _P(hso_reproj_grid),
                                       _P(C.c_int32), _P(hso_reproj_result), _P(hso_reproj_summary)]),
+    "hso_reproject_select_only": (C.c_int, [_vp, C.c_int, _P(hso_reproj_cand), _P(C.c_int32), _P(C.c_int32), _P(C.c_uint8), _P(hso_reproj_grid),
+                                            _P(C.c_int32), _P(hso_reproj_result), _P(hso_reproj_summary)]),
     "hso_depth_observe": (C.c_int, [_vp, C.c_int32, _P(C.c_double), C.c_int, _P(C.c_double), C.c_double, C.c_int, C.c_int, _P(hso_seed_obs),
                                     _P(hso_seed_result)]),
     "hso_pose_optimize": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_int32), C.c_int,

@@ -255,6 +255,22 @@ class Context:
                                                order.ctypes.data_as(C.POINTER(C.c_int32)), out, C.byref(summ)))
         return out, summ
 
+    def reproject_select_only(self, cands, in_frame, cell, align_ok, grid, cell_order):
+        """Test hook: the selection kernel alone on given per-candidate facts. Returns (results, summary)."""
+        M = len(in_frame)
+        g = K.hso_reproj_grid(int(grid["cell_size"]), int(grid["n_cols"]), int(grid["n_rows"]), int(grid["max_fts"]),
+                              int(grid.get("align_max_iter", 10)), 0)
+        inf = np.ascontiguousarray(in_frame, np.int32)
+        cl = np.ascontiguousarray(cell, np.int32)
+        ok = np.ascontiguousarray(align_ok, np.uint8)
+        order = np.ascontiguousarray(cell_order, np.int32)
+        out = (K.hso_reproj_result * max(M, 1))()
+        summ = K.hso_reproj_summary()
+        ip = C.POINTER(C.c_int32)
+        self._chk(self.lib.hso_reproject_select_only(self.h, M, cands, inf.ctypes.data_as(ip), cl.ctypes.data_as(ip), ok.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                     C.byref(g), order.ctypes.data_as(ip), out, C.byref(summ)))
+        return out, summ
+
     # ---- N3: DepthFilter::observeDepthRow -------------------------------------------------------------------------------------
     @staticmethod
     def seed_obs(seeds, frame_ids=None):

@@ -1218,6 +1218,53 @@ int hso_reproject_match(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12]
   return HSO_OK;
 }
 
+// Test hook for row N1: only the selection kernel, on caller-given per-candidate facts (what k_reproject / k_align would have produced).
+int hso_reproject_select_only(hso_ctx* ctx, int M, const hso_reproj_cand* cands, const int32_t* in_frame, const int32_t* cell, const uint8_t* align_ok,
+                              const hso_reproj_grid* grid, const int32_t* cell_order, hso_reproj_result* out, hso_reproj_summary* summary) {
+  if (!ctx || M <= 0 || M > 16384 || !cands || !in_frame || !cell || !align_ok || !grid || !cell_order || !out || !summary) return HSO_ERR_INVALID;
+  const int n_cells = grid->n_cols * grid->n_rows;
+  if (n_cells <= 0 || n_cells > 4096) return fail(ctx, HSO_ERR_INVALID, "bad reprojection grid (cells must be <= 4096)");
+  for (int i = 0; i < M; ++i)
+    if (in_frame[i] && (cell[i] < 0 || cell[i] >= n_cells)) return fail(ctx, HSO_ERR_INVALID, "cell index out of range");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = (o + 127) / 128 * 128; o = r + bytes; return r; };
+  const size_t o_c = take(sizeof(hso_reproj_cand) * M), o_ar = take(sizeof(hso_align_result) * M), o_res = take(sizeof(hso_reproj_result) * M),
+               o_co = take(sizeof(int32_t) * n_cells);
+  const size_t staged = o;
+  const size_t o_sum = take(sizeof(hso_reproj_summary));
+  CU(ctx->r_arena.reserve(o));
+  CU(ctx->r_stage_host.reserve(staged));
+  CU(ctx->r_out_host.reserve(sizeof(hso_reproj_result) * M + sizeof(hso_reproj_summary)));
+  char* h = (char*)ctx->r_stage_host.p;
+  char* d = (char*)ctx->r_arena.p;
+  memcpy(h + o_c, cands, sizeof(hso_reproj_cand) * M);
+  hso_align_result* har = (hso_align_result*)(h + o_ar);
+  hso_reproj_result* hres = (hso_reproj_result*)(h + o_res);
+  memset(har, 0, sizeof(hso_align_result) * M);
+  memset(hres, 0, sizeof(hso_reproj_result) * M);
+  for (int i = 0; i < M; ++i) {
+    har[i].ok = align_ok[i] ? 1 : 0;
+    hres[i].in_frame = in_frame[i] ? 1 : 0; hres[i].cell = in_frame[i] ? cell[i] : -1; hres[i].order = -1;
+  }
+  memcpy(h + o_co, cell_order, sizeof(int32_t) * n_cells);
+  CU(cudaMemcpyAsync(d, h, staged, cudaMemcpyHostToDevice, ctx->stream));
+  ReprojSelParams sp;
+  sp.M = M; sp.n_cells = n_cells; sp.max_fts = grid->max_fts;
+  sp.n_sort = 2;
+  while (sp.n_sort < M) sp.n_sort *= 2;
+  CU(launch_reproj_select(sp, (const hso_reproj_cand*)(d + o_c), (const hso_align_result*)(d + o_ar), (const int32_t*)(d + o_co),
+                          (hso_reproj_result*)(d + o_res), (hso_reproj_summary*)(d + o_sum), ctx->stream, &ctx->launches));
+  char* oh = (char*)ctx->r_out_host.p;
+  CU(cudaMemcpyAsync(oh, d + o_res, sizeof(hso_reproj_result) * M, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(oh + sizeof(hso_reproj_result) * M, d + o_sum, sizeof(hso_reproj_summary), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, oh, sizeof(hso_reproj_result) * M);
+  memcpy(summary, oh + sizeof(hso_reproj_result) * M, sizeof(hso_reproj_summary));
+  return HSO_OK;
+}
+
 // ---- N3 ---------------------------------------------------------------------------------------------------------------------
 int hso_depth_observe(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], int n_poses, const double* T_f_w, double px_error_angle,
                       int align_max_iter, int S, const hso_seed_obs* seeds, hso_seed_result* out) {

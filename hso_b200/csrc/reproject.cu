@@ -100,6 +100,28 @@ __global__ void __launch_bounds__(128) k_reproject(const ReprojKParams P, const 
 // ---- selection -------------------------------------------------------------------------------------------------------------------
 constexpr int SEL_THREADS = 1024;
 
+// Exclusive prefix over the block of one value per thread (thread order); *total receives the block sum. s_warp: 32 ints of scratch.
+HSO_DEV int block_excl_scan(int v, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();  // s_warp may still be read from the previous scan
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int before = 0, tot = 0;
+  for (int q = 0; q < SEL_THREADS / 32; ++q) {
+    const int t = s_warp[q];
+    if (q < warp) before += t;
+    tot += t;
+  }
+  *total = tot;
+  return before + incl - v;
+}
+
 __global__ void __launch_bounds__(SEL_THREADS) k_reproj_select(const ReprojSelParams P, const hso_reproj_cand* __restrict__ cands,
                                                                const hso_align_result* __restrict__ ar, const int32_t* __restrict__ cell_order,
                                                                hso_reproj_result* __restrict__ res, hso_reproj_summary* __restrict__ summ) {
@@ -110,55 +132,56 @@ __global__ void __launch_bounds__(SEL_THREADS) k_reproj_select(const ReprojSelPa
   int* base1 = ce + P.n_cells;                                            // creation order of the pass-1 / 2 / 3 matches of a cell
   int* base2 = base1 + P.n_cells;
   int* base3 = base2 + P.n_cells;
-  uint8_t* has1 = reinterpret_cast<uint8_t*>(base3 + P.n_cells);          // per-cell summaries
+  int* ord = base3 + P.n_cells;                                           // grid_.cell_order staged in shared memory
+  uint8_t* has1 = reinterpret_cast<uint8_t*>(ord + P.n_cells);            // per-cell summaries
   uint8_t* has2 = has1 + P.n_cells;
-  uint8_t* n3 = has2 + P.n_cells;
-  uint8_t* proc = n3 + P.n_cells;                                         // bit p: pass p+1 visited the cell
+  uint8_t* n3 = has2 + P.n_cells;                                         // successes (<= 3) behind the pass-2 position
+  uint8_t* n3b = n3 + P.n_cells;                                          // successes (<= 3) behind the pass-1 position (cell_order[0]: the 2nd pass never visits it)
+  uint8_t* proc = n3b + P.n_cells;                                        // bit p: pass p+1 visited the cell
   uint8_t* lim3 = proc + P.n_cells;
+  uint8_t* flag = lim3 + P.n_cells;                                       // [M] bit 0: findMatchDirect succeeded, bit 1: in frame, bit 2: TYPE_DELETED
   __shared__ int s_warp[32];
   __shared__ int s_n_in, s_trials, s_matches;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int M = P.M;
 
   if (tid == 0) { s_n_in = 0; s_trials = 0; s_matches = 0; }
   __syncthreads();
   {
     int cnt = 0;
-    for (int i = tid; i < M; i += SEL_THREADS) res[i].align_ok = ar[i].ok;
-    for (int i = tid; i < M; i += SEL_THREADS) cnt += res[i].in_frame;
+    for (int i = tid; i < M; i += SEL_THREADS) {
+      const int ok = ar[i].ok != 0, inf = res[i].in_frame != 0, del = cands[i].pt_type == 0;
+      res[i].align_ok = ok;
+      flag[i] = (uint8_t)((ok && !del ? 1 : 0) | (inf ? 2 : 0) | (del ? 4 : 0));  // a deleted point is erased before findMatchDirect: never a match
+      cnt += inf;
+    }
     cnt = warp_sum(cnt);
     if (lane == 0 && cnt) atomicAdd(&s_n_in, cnt);
   }
   __syncthreads();
   const int n_in = s_n_in;
-  const bool cell_all = n_in < P.max_fts + 50;  // allPixelToDistribute.size() < Config::maxFts()+50 (src/reprojector.cpp:257)
+  const int maxf = P.max_fts;
+  const bool cell_all = n_in < maxf + 50;  // allPixelToDistribute.size() < Config::maxFts()+50 (src/reprojector.cpp:257)
 
   if (cell_all) {
     // ---- Reprojector::reprojectCellAll (src/reprojector.cpp:545-615): candidates in insertion order until max_fts matches ---------
     const int per = (M + SEL_THREADS - 1) / SEL_THREADS;
-    const int i0 = tid * per, i1 = min(M, i0 + per);
+    const int i0 = min(M, tid * per), i1 = min(M, i0 + per);
     int local = 0;
-    for (int i = i0; i < i1; ++i) local += (res[i].in_frame && cands[i].pt_type != 0 && ar[i].ok) ? 1 : 0;
-    int incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    int before = 0;
-    for (int q = 0; q < warp; ++q) before += s_warp[q];
-    int pre = before + incl - local;  // successes among earlier eligible candidates
+    for (int i = i0; i < i1; ++i) local += ((flag[i] & 3) == 3) ? 1 : 0;
+    int tot;
+    int pre = block_excl_scan(local, s_warp, &tot);  // successes among earlier candidates
     int trials = 0, matches = 0;
     for (int i = i0; i < i1; ++i) {
-      const bool eligible = res[i].in_frame && cands[i].pt_type != 0;
-      if (!eligible) continue;
-      const bool ok = ar[i].ok != 0;
-      if (pre < max(P.max_fts, 1)) {  // the loop only returns after a success (n_matches_ >= maxFts is tested there, :611-612)
+      const uint8_t f = flag[i];
+      if (!(f & 2)) continue;
+      const bool reached = pre < max(maxf, 1);  // the loop only returns after a success (n_matches_ >= maxFts is tested there, :611-612)
+      if (reached) ++trials;                    // ++n_trials_ comes before the TYPE_DELETED test (:553-559)
+      if (f & 4) continue;
+      const bool ok = (f & 1) != 0;
+      if (reached) {
         res[i].tried = 1;
         res[i].px[0] = ar[i].px_cur[0]; res[i].px[1] = ar[i].px_cur[1];
-        ++trials;
         if (ok) { res[i].matched = 1; res[i].order = pre; ++matches; }
       }
       pre += ok ? 1 : 0;
@@ -173,13 +196,18 @@ __global__ void __launch_bounds__(SEL_THREADS) k_reproj_select(const ReprojSelPa
   // ---- per-cell ordering: key = cell | inverted quality | insertion index; one bitonic sort ------------------------------------------
   for (int i = tid; i < P.n_sort; i += SEL_THREADS) {
     uint32_t k = 0xFFFFFFFFu;
-    if (i < M && res[i].in_frame && cands[i].pt_type != 0) {
-      const int q = cands[i].pt_type * 3 + cands[i].pt_ftr_type;  // pointQualityComparator: type desc, then ftr_type desc
+    if (i < M && (flag[i] & 2)) {
+      // pointQualityComparator: type desc, then ftr_type desc. TYPE_DELETED (0) points stay in the cell lists (they sort last): the walk
+      // counts a trial for each one it reaches before erasing it (src/reprojector.cpp:361-367)
+      const int q = cands[i].pt_type * 3 + cands[i].pt_ftr_type;
       k = ((uint32_t)res[i].cell << 20) | ((uint32_t)(15 - q) << 16) | (uint32_t)i;
     }
     keys[i] = k;
   }
-  for (int c = tid; c < P.n_cells; c += SEL_THREADS) { cs[c] = 0; ce[c] = 0; proc[c] = 0; has1[c] = has2[c] = n3[c] = lim3[c] = 0; }
+  for (int c = tid; c < P.n_cells; c += SEL_THREADS) {
+    cs[c] = 0; ce[c] = 0; proc[c] = 0; has1[c] = has2[c] = n3[c] = n3b[c] = lim3[c] = 0;
+    ord[c] = cell_order[c];
+  }
   __syncthreads();
   for (int k = 2; k <= P.n_sort; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -204,46 +232,67 @@ __global__ void __launch_bounds__(SEL_THREADS) k_reproj_select(const ReprojSelPa
   __syncthreads();
   // ---- per-cell summaries: what each pass would find in this cell -------------------------------------------------------------------
   for (int c = tid; c < P.n_cells; c += SEL_THREADS) {
-    const int s = cs[c], e = ce[c];
-    int p = s;
-    uint8_t h1 = 0, h2 = 0, k3 = 0;
-    for (; p < e; ++p) if (ar[keys[p] & 0xFFFFu].ok) { h1 = 1; ++p; break; }
-    for (; p < e; ++p) if (ar[keys[p] & 0xFFFFu].ok) { h2 = 1; ++p; break; }
-    for (; p < e && k3 < 3; ++p) if (ar[keys[p] & 0xFFFFu].ok) ++k3;
-    has1[c] = h1; has2[c] = h2; n3[c] = k3;
+    const int e = ce[c];
+    int p = cs[c];
+    uint8_t h1 = 0, h2 = 0, k3 = 0, k3b = 0;
+    for (; p < e; ++p) if (flag[keys[p] & 0xFFFFu] & 1) { h1 = 1; ++p; break; }
+    for (int q = p; q < e && k3b < 3; ++q) if (flag[keys[q] & 0xFFFFu] & 1) ++k3b;  // pass 3 right behind pass 1
+    for (; p < e; ++p) if (flag[keys[p] & 0xFFFFu] & 1) { h2 = 1; ++p; break; }
+    for (; p < e && k3 < 3; ++p) if (flag[keys[p] & 0xFFFFu] & 1) ++k3;
+    has1[c] = h1; has2[c] = h2; n3[c] = k3; n3b[c] = k3b;
   }
   __syncthreads();
-  // ---- the three passes over grid_.cell_order (src/reprojector.cpp:262-303), O(cells) on the summaries ------------------------------
-  if (tid == 0) {
-    int n = 0;
-    const int maxf = P.max_fts;
-    for (int i = 0; i < P.n_cells; ++i) {  // 1st
-      const int c = cell_order[i];
-      proc[c] |= 1;
-      if (has1[c]) { base1[c] = n; ++n; }
-      if (n >= maxf) break;
+  // ---- the three passes over grid_.cell_order (src/reprojector.cpp:262-303) as three block-wide prefix scans over the order positions. A pass
+  // stops behind the first position at which n_matches_ reaches maxFts, so position i is visited iff i is the pass's first position or the
+  // running count in front of it is still below maxFts; the count a cell's matches start at is that running count. ------------------------------
+  const int nc = P.n_cells;
+  const int per = (nc + SEL_THREADS - 1) / SEL_THREADS;
+  const int p0 = min(nc, tid * per), p1 = min(nc, p0 + per);
+  int n1, n2 = 0, n3tot = 0;
+  {  // 1st: i = 0 .. n_cells-1, one match per cell
+    int local = 0;
+    for (int i = p0; i < p1; ++i) local += has1[ord[i]];
+    int tot;
+    int run = block_excl_scan(local, s_warp, &tot);
+    for (int i = p0; i < p1; ++i) {
+      const int c = ord[i];
+      if (i == 0 || run < maxf) { proc[c] |= 1; base1[c] = run; }
+      run += has1[c];
     }
-    if (n < maxf) {  // 2nd: for(size_t i=cells.size()-1; i>0; --i) — never visits cell_order[0]
-      for (int i = P.n_cells - 1; i > 0; --i) {
-        const int c = cell_order[i];
-        proc[c] |= 2;
-        if (has2[c]) { base2[c] = n; ++n; }
-        if (n >= maxf) break;
-      }
-    }
-    if (n < maxf) {  // 3rd: up to 3 per cell, n_matches_ counted inside reprojectCell
-      for (int i = 0; i < P.n_cells; ++i) {
-        const int c = cell_order[i];
-        proc[c] |= 4;
-        const int lim = min(3, maxf - n);
-        lim3[c] = (uint8_t)lim;
-        base3[c] = n;
-        n += min((int)n3[c], lim);
-        if (n >= maxf) break;
-      }
-    }
-    s_matches = n;
+    n1 = min(tot, max(maxf, (int)has1[ord[0]]));  // matches of the visited prefix (position 0 is visited even when maxFts == 0)
   }
+  const bool run2 = n1 < maxf, run3_possible = run2;
+  if (run2) {  // 2nd: i = n_cells-1 .. 1 — for(size_t i=cells.size()-1; i>0; --i) never visits cell_order[0]
+    // thread t owns the mirrored positions so that the scan still runs in thread order: j = n_cells-1-i, j = 0 .. n_cells-2
+    const int m = nc - 1;
+    const int q0 = min(m, tid * per), q1 = min(m, q0 + per);
+    int local = 0;
+    for (int j = q0; j < q1; ++j) local += has2[ord[nc - 1 - j]];
+    int tot;
+    int run = n1 + block_excl_scan(local, s_warp, &tot);
+    for (int j = q0; j < q1; ++j) {
+      const int c = ord[nc - 1 - j];
+      if (j == 0 || run < maxf) { proc[c] |= 2; base2[c] = run; }
+      run += has2[c];
+    }
+    n2 = min(n1 + tot, maxf);  // n1 < maxFts and one match per cell: the count reaches maxFts exactly
+  }
+  const bool run3 = run3_possible && n2 < maxf;
+  if (run3) {  // 3rd: i = 0 .. n_cells-1, up to 3 per cell; n_matches_ is counted inside reprojectCell and saturates at maxFts
+    __syncthreads();  // proc bits of pass 2 are complete
+    int local = 0;
+    for (int i = p0; i < p1; ++i) { const int c = ord[i]; local += (proc[c] & 2) ? n3[c] : n3b[c]; }
+    int tot;
+    int run = n2 + block_excl_scan(local, s_warp, &tot);
+    for (int i = p0; i < p1; ++i) {
+      const int c = ord[i];
+      const int avail = (proc[c] & 2) ? n3[c] : n3b[c];
+      if (i == 0 || run < maxf) { proc[c] |= 4; base3[c] = min(run, maxf); lim3[c] = (uint8_t)max(0, min(3, maxf - run)); }
+      run += avail;
+    }
+    n3tot = min(n2 + tot, maxf);
+  }
+  const int n_matches = run3 ? n3tot : (run2 ? n2 : n1);
   __syncthreads();
   // ---- mark what the walk tried / matched ------------------------------------------------------------------------------------------------
   int trials = 0;
@@ -253,10 +302,13 @@ __global__ void __launch_bounds__(SEL_THREADS) k_reproj_select(const ReprojSelPa
     const uint8_t pr = proc[c];
     auto visit = [&](int pos, bool& ok) {
       const int idx = (int)(keys[pos] & 0xFFFFu);
-      ok = ar[idx].ok != 0;
+      const uint8_t f = flag[idx];
+      ++trials;  // ++n_trials_ comes before the TYPE_DELETED test (:361-367)
+      ok = false;
+      if (f & 4) return idx;  // erased without a findMatchDirect call
+      ok = (f & 1) != 0;
       res[idx].tried = 1;
       res[idx].px[0] = ar[idx].px_cur[0]; res[idx].px[1] = ar[idx].px_cur[1];
-      ++trials;
       return idx;
     };
     if (pr & 1) {
@@ -277,10 +329,10 @@ __global__ void __launch_bounds__(SEL_THREADS) k_reproj_select(const ReprojSelPa
   trials = warp_sum(trials);
   if (lane == 0 && trials) atomicAdd(&s_trials, trials);
   __syncthreads();
-  if (tid == 0) { summ->n_in_frame = n_in; summ->n_matches = s_matches; summ->n_trials = s_trials; summ->used_cell_all = 0; }
+  if (tid == 0) { summ->n_in_frame = n_in; summ->n_matches = n_matches; summ->n_trials = s_trials; summ->used_cell_all = 0; }
 }
 
-size_t reproj_select_smem(int n_sort, int n_cells) { return sizeof(uint32_t) * n_sort + sizeof(int) * 5 * n_cells + 5 * (size_t)n_cells + 16; }
+size_t reproj_select_smem(int n_sort, int n_cells) { return sizeof(uint32_t) * n_sort + sizeof(int) * 6 * n_cells + 6 * (size_t)n_cells + (size_t)n_sort + 16; }
 
 cudaError_t launch_reproject(const ReprojKParams& p, const hso_reproj_cand* cands_dev, const uint8_t* const* ref_pyr_dev, AlignJobDev* jobs_dev,
                              hso_reproj_result* res_dev, cudaStream_t stream, uint64_t* launches) {

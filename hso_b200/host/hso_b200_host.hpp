@@ -317,6 +317,9 @@ class Reprojector {
   struct Grid { int cell_size = 0, grid_n_cols = 0, grid_n_rows = 0; std::vector<int32_t> cell_order; } grid_;
   size_t n_matches_ = 0, n_trials_ = 0;
   int nFeatures_ = 0;
+  // Points the reference hands to map_.safeDeletePoint / point_candidates_.deleteCandidatePoint after a failed match (:369-372,565-568). The Map
+  // is the caller's, so the deletions are surfaced here in the order the reference would issue them within a call.
+  std::vector<Point*> points_to_delete_, candidates_to_delete_;
   Reprojector(Context& ctx, size_t max_fts) : ctx_(ctx), max_fts_(max_fts) {
     // Reprojector::initializeGrid (:58-77), caculateGridSize (:53-56)
     const int W = ctx.cam().width, H = ctx.cam().height;
@@ -388,6 +391,7 @@ class Reprojector {
     ctx_.check(hso_reproject_match(ctx_.get(), frame->id, frame->T_f_w_.m, (int)keyframes.size(), T_f_w.data(), (int)M, cands.data(), &g,
                                    grid_.cell_order.data(), res.data(), &summ));
     n_matches_ = (size_t)summ.n_matches; n_trials_ = (size_t)summ.n_trials; nFeatures_ = summ.n_in_frame;
+    points_to_delete_.clear(); candidates_to_delete_.clear();
     // new Features in the reference's order of creation
     std::vector<int> by_order(summ.n_matches, -1);
     for (size_t i = 0; i < M; ++i) {
@@ -396,11 +400,15 @@ class Reprojector {
       if (!r.tried) continue;
       if (!r.matched) {
         pt->n_failed_reproj_++;                                                           // :368-378
+        if (pt->type_ == Point::TYPE_UNKNOWN && pt->n_failed_reproj_ > 15) points_to_delete_.push_back(pt);        // map_.safeDeletePoint
+        if (pt->type_ == Point::TYPE_CANDIDATE && pt->n_failed_reproj_ > 30) candidates_to_delete_.push_back(pt);  // deleteCandidatePoint
         if (pt->type_ == Point::TYPE_TEMPORARY && pt->n_failed_reproj_ > 30) pt->isBad_ = true;
         continue;
       }
       pt->n_succeeded_reproj_++;
       if (pt->type_ == Point::TYPE_UNKNOWN && pt->n_succeeded_reproj_ > 10) pt->type_ = Point::TYPE_GOOD;  // :385-386
+      if (r.order < 0 || r.order >= summ.n_matches || by_order[r.order] >= 0)
+        throw std::runtime_error("hso_reproject_match: inconsistent creation order");  // would drop or overwrite a Feature
       by_order[r.order] = (int)i;
     }
     for (int i : by_order) {

@@ -240,7 +240,7 @@ typedef struct {
 typedef struct {
   int32_t n_in_frame;    /* nFeatures_ */
   int32_t n_matches;     /* n_matches_ */
-  int32_t n_trials;      /* n_trials_ (deleted points are skipped before counting) */
+  int32_t n_trials;      /* n_trials_: every list entry the walk reaches, TYPE_DELETED points included (++n_trials_ precedes the test, reprojector.cpp:361-367,553-559) */
   int32_t used_cell_all; /* 1: the reprojectCellAll branch ran (n_in_frame < max_fts + 50) */
 } hso_reproj_summary;
 /* T_cur_w: frame->T_f_w_ (3x4 row-major); T_f_w: n_poses keyframe poses (3x4 each). cell_order: a permutation of the n_cols*n_rows cell indices.
@@ -248,6 +248,11 @@ typedef struct {
 int hso_reproject_match(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], int n_poses, const double* T_f_w, int M,
                         const hso_reproj_cand* cands, const hso_reproj_grid* grid, const int32_t* cell_order, hso_reproj_result* out,
                         hso_reproj_summary* summary);
+/* Test hook: the selection kernel of the call above alone, on caller-given per-candidate facts — in_frame / cell (what reprojectPoint decided) and
+ * align_ok (what findMatchDirect returned). Only cands[i].pt_type / pt_ftr_type are read. Lets the parity tests drive the three passes through
+ * every corner (src/reprojector.cpp:262-303) without having to construct images that produce a given match pattern. */
+int hso_reproject_select_only(hso_ctx* ctx, int M, const hso_reproj_cand* cands, const int32_t* in_frame, const int32_t* cell, const uint8_t* align_ok,
+                              const hso_reproj_grid* grid, const int32_t* cell_order, hso_reproj_result* out, hso_reproj_summary* summary);
 
 /* ---- N3 (next row): depth-filter observation — replaces the per-seed body of DepthFilter::observeDepthRow (src/depth_filter.cpp:580-675) for all
  * seeds of the active frame in one launch: visibility test (:591-607), inverse-depth interval (:616-618), Matcher::doLineStereo

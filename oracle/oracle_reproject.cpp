@@ -193,8 +193,8 @@ void selection_walk(int M, const orc_reproj_cand* cands, const orc_reproj_grid* 
     auto it = cell.begin();
     int succees = 0;
     while (it != cell.end()) {
-      if (cands[it->idx].pt_type == 0) { it = cell.erase(it); continue; }  // TYPE_DELETED (not counted, see header)
-      ++n_trials;
+      ++n_trials;  // counted before the TYPE_DELETED test, reprojector.cpp:361-367
+      if (cands[it->idx].pt_type == 0) { it = cell.erase(it); continue; }
       out[it->idx].tried = 1;
       const bool ok = match(it->idx, it->px);
       out[it->idx].px[0] = it->px[0]; out[it->idx].px[1] = it->px[1];
@@ -213,8 +213,8 @@ void selection_walk(int M, const orc_reproj_cand* cands, const orc_reproj_grid* 
     // Reprojector::reprojectCellAll — reprojector.cpp:545-615
     summary->used_cell_all = 1;
     for (auto& cd : all) {
+      ++n_trials;  // reprojector.cpp:553-559
       if (cands[cd.idx].pt_type == 0) continue;
-      ++n_trials;
       out[cd.idx].tried = 1;
       const bool ok = match(cd.idx, cd.px);
       out[cd.idx].px[0] = cd.px[0]; out[cd.idx].px[1] = cd.px[1];

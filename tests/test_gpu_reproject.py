@@ -153,3 +153,50 @@ def test_reproject_capacity_and_grid_errors():
     with pytest.raises(HsoError):
         ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], Context.reproj_cands(s["cands"], frame_ids=kf_ids), small_grid, np.arange(4, dtype=np.int32))
     ctx.close()
+
+
+def test_selection_kernel_random_grids_incl_first_cell_third_pass(oracle):
+    """The selection kernel alone (hso_reproject_select_only) against the oracle's std::list walk on 400 random grids, every 4th one with
+    cell_order[0] holding >= 3 alignable candidates while the 3rd pass runs (the 2nd pass never visits that cell: src/reprojector.cpp:278-288).
+    tried / matched / creation order / n_matches / n_trials (TYPE_DELETED entries are counted, :361-367) must agree exactly."""
+    from test_oracle_reproject import random_selection_case
+    from hso_b200 import _capi as K
+    s = synth.make_reproject_scene(5, "icl", M=8)
+    c = s["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]))
+    rng = np.random.default_rng(77)
+    multi = 0
+    for trial in range(400):
+        cands, in_frame, cell, ok, grid, order = random_selection_case(rng, force_pass3_in_first_cell=(trial % 4 == 0))
+        M = len(in_frame)
+        io = (oracle.orc_reproj_result * M)()
+        for i in range(M):
+            io[i].in_frame, io[i].cell = int(in_frame[i]), int(cell[i])
+        osum = oracle.reproject_select(cands, ok, grid, order, io)
+        kc = (K.hso_reproj_cand * M)()
+        for i in range(M):
+            kc[i].pt_type, kc[i].pt_ftr_type = cands[i].pt_type, cands[i].pt_ftr_type
+        g = dict(cell_size=grid.cell_size, n_cols=grid.n_cols, n_rows=grid.n_rows, max_fts=grid.max_fts)
+        got, gsum = ctx.reproject_select_only(kc, in_frame, cell, ok, g, order)
+        assert (gsum.used_cell_all, gsum.n_matches, gsum.n_trials, gsum.n_in_frame) == (0, osum.n_matches, osum.n_trials, int(in_frame.sum())), trial
+        assert [got[i].tried for i in range(M)] == [io[i].tried for i in range(M)], trial
+        assert [got[i].matched for i in range(M)] == [io[i].matched for i in range(M)], trial
+        assert [got[i].order for i in range(M)] == [io[i].order for i in range(M)], trial
+        multi += sum(1 for i in range(M) if in_frame[i] and cell[i] == order[0] and io[i].matched) >= 3
+    assert multi >= 50
+    # the reprojectCellAll branch with deleted points in the list
+    for trial in range(50):
+        cands, in_frame, cell, ok, grid, order = random_selection_case(rng)
+        M = len(in_frame)
+        grid.max_fts = int(in_frame.sum())  # n_in_frame < max_fts + 50
+        io = (oracle.orc_reproj_result * M)()
+        for i in range(M):
+            io[i].in_frame, io[i].cell = int(in_frame[i]), int(cell[i])
+        osum = oracle.reproject_select(cands, ok, grid, order, io)
+        kc = (K.hso_reproj_cand * M)()
+        for i in range(M):
+            kc[i].pt_type, kc[i].pt_ftr_type = cands[i].pt_type, cands[i].pt_ftr_type
+        got, gsum = ctx.reproject_select_only(kc, in_frame, cell, ok, dict(cell_size=20, n_cols=grid.n_cols, n_rows=grid.n_rows, max_fts=grid.max_fts), order)
+        assert (gsum.used_cell_all, gsum.n_matches, gsum.n_trials) == (1, osum.n_matches, osum.n_trials), trial
+        assert [(got[i].tried, got[i].matched, got[i].order) for i in range(M)] == [(io[i].tried, io[i].matched, io[i].order) for i in range(M)], trial
+    ctx.close()

@@ -68,7 +68,7 @@ def _brute_force_selection(cands, in_frame, cell, ok, grid, cell_order):
             cells[cell[i]].append(i)
             allp.append(i)
     tried, matched, order = np.zeros(M, int), np.zeros(M, int), -np.ones(M, int)
-    st = dict(n=0, o=0)
+    st = dict(n=0, o=0, trials=0)
 
     def hit(i):
         matched[i] = 1
@@ -76,6 +76,7 @@ def _brute_force_selection(cands, in_frame, cell, ok, grid, cell_order):
         st["o"] += 1
     if len(allp) < grid.max_fts + 50:
         for i in allp:
+            st["trials"] += 1  # ++n_trials_ precedes the TYPE_DELETED test (src/reprojector.cpp:553-559)
             if cands[i].pt_type == 0:
                 continue
             tried[i] = 1
@@ -84,7 +85,7 @@ def _brute_force_selection(cands, in_frame, cell, ok, grid, cell_order):
                 st["n"] += 1
                 if st["n"] >= grid.max_fts:
                     break
-        return tried, matched, order, st["n"], 1
+        return tried, matched, order, st["n"], 1, st["trials"]
 
     def reproject_cell(lst, is_2nd, is_3rd):
         if not lst:
@@ -94,6 +95,7 @@ def _brute_force_selection(cands, in_frame, cell, ok, grid, cell_order):
         succ = 0
         while lst:
             i = lst.pop(0)
+            st["trials"] += 1  # src/reprojector.cpp:361-367
             if cands[i].pt_type == 0:
                 continue
             tried[i] = 1
@@ -123,7 +125,7 @@ def _brute_force_selection(cands, in_frame, cell, ok, grid, cell_order):
             reproject_cell(cells[cell_order[i]], True, True)
             if st["n"] >= grid.max_fts:
                 break
-    return tried, matched, order, st["n"], 0
+    return tried, matched, order, st["n"], 0, st["trials"]
 
 
 def test_selection_walk_matches_brute_force():
@@ -143,8 +145,61 @@ def test_selection_walk_matches_brute_force():
         cell_order = rng.permutation(n_cells).astype(np.int32)
         exp = _brute_force_selection(cands, [io[i].in_frame for i in range(M)], [io[i].cell for i in range(M)], ok, grid, cell_order)
         summ = O.reproject_select(cands, ok, grid, cell_order, io)
-        assert summ.used_cell_all == exp[4] and summ.n_matches == exp[3], trial
+        assert summ.used_cell_all == exp[4] and summ.n_matches == exp[3] and summ.n_trials == exp[5], trial
         assert [io[i].tried for i in range(M)] == list(exp[0]), trial
         assert [io[i].matched for i in range(M)] == list(exp[1]), trial
         assert [io[i].order for i in range(M)] == list(exp[2]), trial
         assert summ.n_matches <= max_fts and sorted(o for o in exp[2] if o >= 0) == list(range(summ.n_matches))
+
+
+def random_selection_case(rng, force_pass3_in_first_cell=False):
+    """A random grid / candidate set for the three selection passes. With force_pass3_in_first_cell the configuration the round-1 advisor found
+    (pass 3 reached, cell_order[0] holding >= 3 alignable candidates: the 2nd pass never visits that cell, so its 2nd..4th successes are all
+    taken by the 3rd pass) is constructed explicitly."""
+    n_cols, n_rows = int(rng.integers(2, 9)), int(rng.integers(2, 8))
+    nc = n_cols * n_rows
+    maxf = int(rng.integers(0, 60))
+    M = int(rng.integers(maxf + 60, maxf + 400))
+    p_ok = float(rng.choice([0.05, 0.2, 0.5, 0.9]))
+    cands = (O.orc_reproj_cand * M)()
+    in_frame = (rng.uniform(size=M) < 0.9).astype(np.int32)
+    cell = np.where(in_frame > 0, rng.integers(0, nc, M), -1).astype(np.int32)
+    ok = (rng.uniform(size=M) < p_ok).astype(np.uint8)
+    order = rng.permutation(nc).astype(np.int32)
+    for i in range(M):
+        cands[i].pt_type = int(rng.choice([0, 1, 2, 3, 4], p=[0.08, 0.12, 0.2, 0.3, 0.3]))
+        cands[i].pt_ftr_type = int(rng.integers(0, 3))
+    if force_pass3_in_first_cell:
+        maxf = M  # never reached: all three passes run to the end
+        k = int(rng.integers(3, 7))
+        idx = rng.choice(M, k, replace=False)
+        in_frame[idx], cell[idx], ok[idx] = 1, order[0], 1
+        for i in idx:
+            cands[int(i)].pt_type = int(rng.integers(1, 5))
+    if int(in_frame.sum()) < maxf + 50:  # stay in the three-pass branch
+        maxf = max(0, int(in_frame.sum()) - 50)
+    grid = O.orc_reproj_grid(20, n_cols, n_rows, maxf, 10, 0)
+    return cands, in_frame, cell, ok, grid, order
+
+
+def test_selection_walk_random_grids_incl_first_cell_third_pass():
+    """1200 random grids (every 4th one the forced cell_order[0] case): the oracle's std::list walk against the brute-force statement, all
+    flags, the creation order and both counters."""
+    rng = np.random.default_rng(2024)
+    seen_first_cell_multi = 0
+    for trial in range(1200):
+        cands, in_frame, cell, ok, grid, order = random_selection_case(rng, force_pass3_in_first_cell=(trial % 4 == 0))
+        M = len(in_frame)
+        io = (O.orc_reproj_result * M)()
+        for i in range(M):
+            io[i].in_frame, io[i].cell = int(in_frame[i]), int(cell[i])
+        exp = _brute_force_selection(cands, list(in_frame), list(cell), ok, grid, order)
+        summ = O.reproject_select(cands, ok, grid, order, io)
+        assert exp[4] == 0 and summ.used_cell_all == 0
+        assert (summ.n_matches, summ.n_trials) == (exp[3], exp[5]), trial
+        assert [io[i].tried for i in range(M)] == list(exp[0]) and [io[i].matched for i in range(M)] == list(exp[1]), trial
+        assert [io[i].order for i in range(M)] == list(exp[2]), trial
+        assert sorted(o for o in exp[2] if o >= 0) == list(range(summ.n_matches)), trial  # a permutation: no collision, nothing out of range
+        if sum(1 for i in range(M) if in_frame[i] and cell[i] == order[0] and exp[1][i]) >= 3:
+            seen_first_cell_multi += 1
+    assert seen_first_cell_multi >= 100
