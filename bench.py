@@ -516,6 +516,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-rows", action="store_true")
     ap.add_argument("--no-ic-dual", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--parity-samples", type=int, default=16, help="problems of the timed batch whose final pose is checked against the oracle")
     args = ap.parse_args()
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -618,6 +620,7 @@ def main():
         ctx._chk(lib.hso_track_level_profile(ctx.h, l, C.byref(ms), C.byref(n)))
         lvl_ms[l] = ms.value / max(n.value, 1)
     ctx._chk(lib.hso_track_set_profile(ctx.h, 0))
+    final_dev = ctx.track_collect()  # results of the last timed device-resident step (checked against the oracle below)
 
     # ---- e2e: host buffers through the C-ABI ------------------------------------------------------------------------------------
     e2e = None
@@ -668,6 +671,35 @@ def main():
         d2h = B * (C.sizeof(K.hso_track_result) + 8)  # results + {integralImage_, gradMean_}
         e2e = dict(ms=ms_e2e, steps=n_e2e_steps, iters=it_e2e, h2d=h2d, d2h=d2h)
 
+    # ---- parity of the timed batch: final poses of sampled problems against the CPU oracle (checker only, outside every timed region) ----------
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        O.load()
+        final = final_dev
+        n_chk = min(B, args.parity_samples)
+        sample = [int(round(i * (B - 1) / max(n_chk - 1, 1))) for i in range(n_chk)]
+        pyr = {}
+        worst = worst_a = worst_e2e = 0.0
+        for b in sample:
+            p = probs[b]
+            if p["base"] not in pyr:
+                pyr[p["base"]] = (O.create_pyramid(p["ref_img"], 5)[0], O.create_pyramid(p["cur_img"], 5)[0])
+            tpo = O.TrackProblem(c, pyr[p["base"]][0], pyr[p["base"]][1], p["px"], p["f"], p["dist"])
+            ro = tpo.run(p["T0"], jobs[b]["exposure_rat"], inverse_comp=args.ic)
+            Tg = np.array(final[b].T_cur_ref[:]).reshape(3, 4)
+            worst = max(worst, float(np.abs(Tg - ro["T_cur_ref"]).max()))
+            worst_a = max(worst_a, abs(float(final[b].exposure_rat) - ro["exposure_rat"]))
+            if e2e:
+                worst_e2e = max(worst_e2e, float(np.abs(np.array(res[b].T_cur_ref[:]).reshape(3, 4) - ro["T_cur_ref"]).max()))
+        tol = 2e-4
+        parity = {"n": n_chk, "tol_abs_pose_entry": tol, "max_abs_pose_diff": worst, "max_abs_exposure_diff": worst_a,
+                  "e2e_max_abs_pose_diff": worst_e2e if e2e else None, "ok": bool(worst < tol and worst_a < tol and worst_e2e < tol),
+                  "against": "oracle/liboracle_hso.so CoarseTracker::run restatement, same inputs (final pose of the timed batch's problems)"}
+        if not parity["ok"]:
+            print(f"bench.py: PARITY FAILURE against the oracle: {parity}", file=sys.stderr)
+
     # ---- reduce over ranks: max time, summed work -----------------------------------------------------------------------------------
     stat = torch.tensor([ms_total, float(iters_per_step * args.steps), float(B * args.steps), e2e["ms"] if e2e else 0.0,
                          float(e2e["iters"]) if e2e else 0.0, float(launches)], dtype=torch.float64, device=dev)
@@ -705,7 +737,7 @@ def main():
                        "batch_per_gpu": B, "patches": F, "lm_iterations_per_step_per_gpu": iters_per_step,
                        "l2": f"inputs larger than L2: {B} x (2 pyramids + feature scratch) = {B * (2 * 410000 + F * 25 * 8 + F * 40) / 1e6:.0f} MB per step vs 126 MB L2",
                        "parallelism": f"{world} independent batch(es), one per GPU, no data-path collective", "numa_binding_rank0": numa},
-            "gpu_launches": int(launches_all), "diag": diag,
+            "gpu_launches": int(launches_all), "diag": diag, "parity_checked": parity["n"] if parity else 0, "parity": parity,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": f"k_track_level (level {dom})", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,

@@ -356,6 +356,15 @@ class Context:
     def set_cluster(self, ctas=0, threads=0):
         self._chk(self.lib.hso_track_set_cluster(self.h, ctas, threads))
 
+    def set_level_shape(self, level, ctas=0, threads=0):
+        self._chk(self.lib.hso_track_set_level_shape(self.h, level, ctas, threads))
+
+    def level_shape(self, level):
+        """(ctas per problem, threads per CTA, mode, absres_smem) of the last tracker run at `level`."""
+        v = [C.c_int() for _ in range(4)]
+        self._chk(self.lib.hso_track_get_level_shape(self.h, level, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
     def synchronize(self):
         self._chk(self.lib.hso_synchronize(self.h))
 

@@ -1,6 +1,8 @@
 // C-ABI of hso_b200 (include/hso_b200.h): context, device-resident frame table, staging of flattened feature arrays,
 // kernel sequencing. Host-side only; all arithmetic of the path lives in the kernels. There is no CPU fallback.
+#if defined(__x86_64__)
 #include <immintrin.h>
+#endif
 
 #include <atomic>
 #include <cmath>
@@ -47,6 +49,42 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// Pinned staging for small records that asynchronous entry points re-write on every call: three regions used in rotation, each guarded by an
+// event recorded behind the H2D copy that reads it, so a call never overwrites records a previous call's copy has not consumed yet.
+struct PinRing {
+  static constexpr int N = 3;
+  PinBuf buf;
+  size_t slot_cap = 0;
+  cudaEvent_t ev[N] = {nullptr, nullptr, nullptr};
+  bool pending[N] = {false, false, false};
+  int next = 0, cur = 0;
+  cudaError_t acquire(size_t bytes, void** out) {
+    cudaError_t e;
+    if (bytes > slot_cap) {
+      for (int i = 0; i < N; ++i)
+        if (pending[i]) { if ((e = cudaEventSynchronize(ev[i])) != cudaSuccess) return e; pending[i] = false; }
+      const size_t want = (bytes + bytes / 4 + 255) / 256 * 256;
+      if ((e = buf.reserve(want * N)) != cudaSuccess) return e;
+      slot_cap = want;
+    }
+    cur = next;
+    next = (next + 1) % N;
+    if (!ev[cur] && (e = cudaEventCreateWithFlags(&ev[cur], cudaEventDisableTiming)) != cudaSuccess) return e;
+    if (pending[cur]) { if ((e = cudaEventSynchronize(ev[cur])) != cudaSuccess) return e; pending[cur] = false; }
+    *out = (char*)buf.p + slot_cap * cur;
+    return cudaSuccess;
+  }
+  cudaError_t commit(cudaStream_t stream) {  // call right behind the copy that reads the acquired region
+    cudaError_t e = cudaEventRecord(ev[cur], stream);
+    if (e == cudaSuccess) pending[cur] = true;
+    return e;
+  }
+  void release() {
+    for (int i = 0; i < N; ++i) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; pending[i] = false; }
+    buf.release(); slot_cap = 0;
+  }
+};
+
 struct FrameSlot {
   bool used = false;
   uint8_t* pyr = nullptr;
@@ -75,12 +113,14 @@ struct hso_ctx {
   size_t pyr_slot_bytes = 0;
   DevBuf pyr_jobs_dev, pyr_counters, resize_tab_dev, stats_table;  // stats_table: [max_frames][2] floats, one D2H per read
   PinBuf pyr_jobs_host, stats_host;
+  PinRing pyr_jobs_ring, t_jobs_ring;  // job records of the asynchronous (unsynchronised) entry points
   std::vector<ResizeTabDev> resize_tabs;
   // tracker
   hso_track_params tprm;
   int tB = 0, t_trace_cap = 0;
   int t_cluster = 0, t_threads = 0;  // 0 = auto
   int t_shape[kMaxLevels][2] = {{0}};  // per-level override {cluster, threads}
+  int t_used[kMaxLevels][5] = {{0}};   // launch shape of the last run per level: {cluster, threads, mode, absres_smem, hist_bits}
   DevBuf t_arena, t_jobs_dev, t_T0, t_a0, t_out_dev;
   PinBuf t_stage_host, t_jobs_host, t_out_host;
   std::vector<size_t> t_trace_off;  // byte offset of each job's trace in the arena
@@ -245,14 +285,23 @@ FrameSlot* get_frame(hso_ctx* ctx, hso_frame_id id) {
 int run_pyramid(hso_ctx* ctx, int B, const hso_frame_id* ids, const uint8_t* const* srcs, int src_stride, int aligned, int slot0 = 0,
                 cudaStream_t copy = nullptr) {
   const size_t need = (size_t)slot0 + B;
-  if (ctx->pyr_jobs_host.cap < sizeof(PyrJobDev) * need) CU(cudaStreamSynchronize(ctx->stream));  // before re-allocating staging
-  CU(ctx->pyr_jobs_host.reserve(sizeof(PyrJobDev) * need));
   CU(ctx->pyr_jobs_dev.reserve(sizeof(PyrJobDev) * need));
   if (ctx->pyr_counters.cap < sizeof(unsigned) * need) {
     CU(ctx->pyr_counters.reserve(sizeof(unsigned) * need));
     CU(cudaMemsetAsync(ctx->pyr_counters.p, 0, ctx->pyr_counters.cap, ctx->stream));
   }
-  PyrJobDev* jobs = (PyrJobDev*)ctx->pyr_jobs_host.p + slot0;
+  PyrJobDev* jobs;
+  if (copy) {
+    // pipelined batch: the caller reserved pyr_jobs_host for the whole batch and every chunk has its own records
+    if (ctx->pyr_jobs_host.cap < sizeof(PyrJobDev) * need) return fail(ctx, HSO_ERR_INVALID, "pipelined pyramid records not reserved");
+    jobs = (PyrJobDev*)ctx->pyr_jobs_host.p + slot0;
+  } else {
+    // asynchronous entry points (hso_frame_[re]build_batch_device return unsynchronised): the previous call's H2D may not have read its
+    // records yet, so each call writes into its own region of a small ring
+    void* region = nullptr;
+    CU(ctx->pyr_jobs_ring.acquire(sizeof(PyrJobDev) * B, &region));
+    jobs = (PyrJobDev*)region;
+  }
   for (int i = 0; i < B; ++i) {
     FrameSlot* s = get_frame(ctx, ids[i]);
     jobs[i].src = srcs[i];
@@ -264,6 +313,7 @@ int run_pyramid(hso_ctx* ctx, int B, const hso_frame_id* ids, const uint8_t* con
   PyrJobDev* jobs_dev = (PyrJobDev*)ctx->pyr_jobs_dev.p + slot0;
   CU(cudaMemcpyAsync(jobs_dev, jobs, sizeof(PyrJobDev) * B, cudaMemcpyHostToDevice, copy ? copy : ctx->stream));
   if (copy) return HSO_OK;  // the caller launches after its event wait (launch_pyramid_slots)
+  CU(ctx->pyr_jobs_ring.commit(ctx->stream));
   CU(launch_pyramid(ctx->geom, jobs_dev, B, src_stride, ctx->resize_tabs.data() /* host array; passed by value */,
                     ctx->cfg.materialize_sobel, (unsigned*)ctx->pyr_counters.p + slot0, aligned, ctx->stream, &ctx->launches));
   return HSO_OK;
@@ -382,6 +432,7 @@ void hso_destroy(hso_ctx* ctx) {
   PinBuf* pb[] = {&ctx->f_out_host, &ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
                   &ctx->a_jobs_host, &ctx->a_out_host, &ctx->in_ptrs_host, &ctx->d_stage_host, &ctx->d_out_host, &ctx->r_stage_host, &ctx->r_out_host, &ctx->p_stage_host, &ctx->p_out_host};
   for (PinBuf* b : pb) b->release();
+  ctx->pyr_jobs_ring.release(); ctx->t_jobs_ring.release();
   for (cudaEvent_t e : ctx->t_ev) if (e) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -403,6 +454,7 @@ int hso_set_stream(hso_ctx* ctx, void* s) {
 void* hso_get_stream(hso_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int hso_synchronize(hso_ctx* ctx) {
   if (!ctx) return HSO_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
   return HSO_OK;
 }
@@ -548,6 +600,7 @@ int hso_frame_build_batch_device(hso_ctx* ctx, int B, const void* const* dev_img
 int hso_frame_rebuild_batch_device(hso_ctx* ctx, int B, const void* const* dev_imgs, int W, int H, int stride, const hso_frame_id* ids) {
   if (!ctx || B <= 0 || !dev_imgs || !ids) return HSO_ERR_INVALID;
   if (W != ctx->cam.width || H != ctx->cam.height || stride < W) return fail(ctx, HSO_ERR_INVALID, "image size does not match the camera model");
+  CU(cudaSetDevice(ctx->device));
   int aligned = 1;
   for (int i = 0; i < B; ++i) {
     if (!get_frame(ctx, ids[i])) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
@@ -559,6 +612,7 @@ int hso_frame_rebuild_batch_device(hso_ctx* ctx, int B, const void* const* dev_i
 int hso_frame_stats(hso_ctx* ctx, hso_frame_id id, float* integral, float* grad_mean) {
   if (!ctx) return HSO_ERR_INVALID;
   if (!get_frame(ctx, id)) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
+  CU(cudaSetDevice(ctx->device));
   return read_stats(ctx, 1, &id, integral, grad_mean);
 }
 
@@ -574,6 +628,7 @@ int hso_frame_download_level(hso_ctx* ctx, hso_frame_id id, int level, uint8_t* 
   if (!ctx || !dst || level < 0 || level >= ctx->geom.n_levels) return HSO_ERR_INVALID;
   FrameSlot* s = get_frame(ctx, id);
   if (!s) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
+  CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(dst, s->pyr + ctx->geom.off[level], (size_t)ctx->geom.w[level] * ctx->geom.h[level], cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return HSO_OK;
@@ -584,6 +639,7 @@ int hso_frame_download_sobel(hso_ctx* ctx, hso_frame_id id, int level, int16_t* 
   FrameSlot* s = get_frame(ctx, id);
   if (!s) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
   if (!s->sobel) return fail(ctx, HSO_ERR_INVALID, "context was created without materialize_sobel");
+  CU(cudaSetDevice(ctx->device));
   size_t so = 0;
   for (int l = 0; l < level; ++l) so += (size_t)2 * ctx->geom.w[l] * ctx->geom.h[l];
   const size_t n = (size_t)ctx->geom.w[level] * ctx->geom.h[level];
@@ -629,6 +685,15 @@ int hso_set_pipeline(hso_ctx* ctx, int chunk, int streams) {
 int hso_track_set_ic_dual(hso_ctx* ctx, int enable) {
   if (!ctx) return HSO_ERR_INVALID;
   ctx->t_no_dual = enable ? 0 : 1;
+  return HSO_OK;
+}
+
+int hso_track_get_level_shape(hso_ctx* ctx, int level, int* ctas, int* threads, int* mode, int* absres_smem) {
+  if (!ctx || level < 0 || level >= kMaxLevels) return HSO_ERR_INVALID;
+  if (ctas) *ctas = ctx->t_used[level][0];
+  if (threads) *threads = ctx->t_used[level][1];
+  if (mode) *mode = ctx->t_used[level][2];
+  if (absres_smem) *absres_smem = ctx->t_used[level][3];
   return HSO_OK;
 }
 
@@ -719,10 +784,20 @@ static int track_plan(hso_ctx* ctx, const hso_track_params* prm, int B, const hs
   return HSO_OK;
 }
 
+// Non-temporal 8-byte store where the host ISA has one (x86-64); plain store elsewhere (e.g. aarch64 / Grace hosts).
 static inline void nt_store(double* p, double v) {
+#if defined(__x86_64__)
   long long bits;
   memcpy(&bits, &v, sizeof bits);
   _mm_stream_si64(reinterpret_cast<long long*>(p), bits);
+#else
+  *p = v;
+#endif
+}
+static inline void nt_fence() {
+#if defined(__x86_64__)
+  _mm_sfence();
+#endif
 }
 
 // Flatten the Feature list of job b to SoA in the pinned staging blob, keeping only features with a valid depth (dist >= 0): the
@@ -748,7 +823,7 @@ static void track_stage_one(hso_ctx* ctx, const hso_track_job* jobs, int b) {
     ++k;
   }
   hj[b].F = k;
-  _mm_sfence();
+  nt_fence();
   for (; k < Fpad; ++k) { px[k] = px[Fpad + k] = 0; xyz[k] = xyz[Fpad + k] = 0; xyz[2 * Fpad + k] = 1; }
   double* T0 = (double*)(hbase + ctx->t_geo_bytes);
   float* a0 = (float*)(T0 + 12 * B);
@@ -817,13 +892,18 @@ int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_
 
 int hso_track_restage_frames(hso_ctx* ctx, int B, const hso_frame_id* ref, const hso_frame_id* cur) {
   if (!ctx || B != ctx->tB || !ref || !cur) return HSO_ERR_INVALID;
-  TrackJobDev* hj = (TrackJobDev*)ctx->t_jobs_host.p;
+  CU(cudaSetDevice(ctx->device));
+  TrackJobDev* hj = (TrackJobDev*)ctx->t_jobs_host.p;  // the plan's host mirror; the copy below reads a snapshot of it
   for (int b = 0; b < B; ++b) {
     if (!get_frame(ctx, ref[b]) || !get_frame(ctx, cur[b])) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
     hj[b].ref_pyr = get_frame(ctx, ref[b])->pyr;
     hj[b].cur_pyr = get_frame(ctx, cur[b])->pyr;
   }
-  CU(cudaMemcpyAsync(ctx->t_jobs_dev.p, hj, sizeof(TrackJobDev) * B, cudaMemcpyHostToDevice, ctx->stream));
+  void* region = nullptr;
+  CU(ctx->t_jobs_ring.acquire(sizeof(TrackJobDev) * B, &region));
+  memcpy(region, hj, sizeof(TrackJobDev) * B);
+  CU(cudaMemcpyAsync(ctx->t_jobs_dev.p, region, sizeof(TrackJobDev) * B, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->t_jobs_ring.commit(ctx->stream));
   return HSO_OK;
 }
 
@@ -931,6 +1011,8 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
       p.absres_smem = 1;
       if (track_level_smem_bytes(p, threads) > 227 * 1024) p.absres_smem = 0;
     }
+    ctx->t_used[level][0] = cluster; ctx->t_used[level][1] = threads; ctx->t_used[level][2] = p.fast; ctx->t_used[level][3] = p.absres_smem;
+    ctx->t_used[level][4] = p.hist_bits;
     CU(launch_track_level(p, jd, B, cluster, threads, stream, &ctx->launches));
   }
   if (profile) {
@@ -943,12 +1025,14 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
 
 int hso_track_run(hso_ctx* ctx) {
   if (!ctx || ctx->tB <= 0) return HSO_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
   return track_run_range(ctx, 0, ctx->tB, ctx->t_profile != 0);
 }
 
 int hso_track_collect(hso_ctx* ctx, hso_track_result* out, hso_trace* trace, int* trace_len) {
   if (!ctx || ctx->tB <= 0 || !out) return HSO_ERR_INVALID;
   const int B = ctx->tB;
+  CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(ctx->t_out_host.p, ctx->t_out_dev.p, sizeof(hso_track_result) * B, cudaMemcpyDeviceToHost, ctx->stream));
   if (trace && ctx->t_trace_cap) {
     for (int b = 0; b < B; ++b)
@@ -1007,6 +1091,12 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   for (int b = 0; b < B; ++b) jobs[b].cur = new_ids[b];
   int rc = track_plan(ctx, prm, B, jobs.data(), 0);  // synchronises ctx->stream: nothing of a previous call is in flight below
   if (rc != HSO_OK) { release_all(); return rc; }
+  // Everything that can fail after the frames were allocated runs inside `pipeline`, so that every error path — a CUDA error in the middle of
+  // the chunk loop included — goes through the same clean-up: wait for the streams, hand the new frames back.
+  int S = 1;
+  StageTimer tm(ctx, 1);
+  std::unique_ptr<StageWorkers> workers;  // started right after the first chunk's image copy is on its way (spawning the pool takes ~0.3 ms)
+  auto pipeline = [&]() -> int {
   if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   // chunk = one wave of single-CTA problems (148 SMs); few enough chunks that the per-chunk launch overhead stays small
   const int unit = ctx->pipe_chunk > 0 ? ctx->pipe_chunk : 111;  // 3/4 of a wave of single-CTA problems: measured best with 3 streams
@@ -1021,7 +1111,7 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   while (bounds.back() < B - tail_sz) bounds.push_back(std::min(B - tail_sz, bounds.back() + chunk));
   if (ramp) { bounds.push_back(B - chunk / 3); bounds.push_back(B); }
   const int n_chunks = (int)bounds.size() - 1;
-  const int S = std::max(1, std::min(n_chunks, ctx->pipe_n_streams > 0 ? ctx->pipe_n_streams : 3));
+  S = std::max(1, std::min(n_chunks, ctx->pipe_n_streams > 0 ? ctx->pipe_n_streams : 3));
   while ((int)ctx->pipe_streams.size() < S - 1) {
     cudaStream_t st; cudaEvent_t e;
     CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -1045,9 +1135,7 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   // tuning aid (tools/e2e_breakdown.py): HSO_PIPE_DEBUG bit 0 skips the kernel launches, bit 1 the image / feature copies (bit 2: images only, bit 3: features only), to time the stages alone
   const char* dbg_env = getenv("HSO_PIPE_DEBUG");
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
-  StageTimer tm(ctx, 1);
   std::vector<const uint8_t*> srcs(B);
-  std::unique_ptr<StageWorkers> workers;  // started right after the first chunk's image copy is on its way (spawning 8 threads takes ~0.3 ms)
   for (int c = 0; c < n_chunks; ++c) {
     const int b0 = bounds[c], b1 = bounds[c + 1], n = b1 - b0;
     // images straight into the level-0 slots (one 2-D copy for equally spaced images going to consecutive slots)
@@ -1065,10 +1153,10 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
     }
     if (!workers) workers.reset(new StageWorkers(ctx, jobs.data(), B, bounds));
     rc = run_pyramid(ctx, n, new_ids + b0, srcs.data() + b0, W, 1, b0, ctx->copy_stream);
-    if (rc != HSO_OK) break;
+    if (rc != HSO_OK) return rc;
     workers->wait_chunk(c);
     rc = (dbg & (2 | 8)) ? HSO_OK : track_copy_range(ctx, b0, b1, ctx->copy_stream);
-    if (rc != HSO_OK) break;
+    if (rc != HSO_OK) return rc;
     CU(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
     cudaStream_t cs = (c % S == 0) ? ctx->stream : ctx->pipe_streams[c % S - 1];
     CU(cudaStreamWaitEvent(cs, ctx->chunk_ev[c], 0));
@@ -1076,13 +1164,22 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
     CU(launch_pyramid(ctx->geom, (const PyrJobDev*)ctx->pyr_jobs_dev.p + b0, n, W, ctx->resize_tabs.data(), ctx->cfg.materialize_sobel,
                       (unsigned*)ctx->pyr_counters.p + b0, 1, cs, &ctx->launches));
     rc = track_run_range(ctx, b0, n, false, B, cs);
-    if (rc != HSO_OK) break;
+    if (rc != HSO_OK) return rc;
   }
-  for (int k = 0; k < S - 1; ++k) {  // join the extra compute streams into the context stream
+    return HSO_OK;
+  };
+  rc = pipeline();
+  workers.reset();  // joins the flattening threads
+  for (int k = 0; k < S - 1 && k < (int)ctx->pipe_streams.size(); ++k) {  // join the extra compute streams into the context stream
     cudaEventRecord(ctx->pipe_ev[k], ctx->pipe_streams[k]);
     cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[k], 0);
   }
-  if (rc != HSO_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); release_all(); return rc; }
+  if (rc != HSO_OK) {
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
+    release_all();
+    return rc;
+  }
   rc = hso_track_collect(ctx, out, nullptr, nullptr);
   if (rc != HSO_OK) return rc;
   rc = read_stats(ctx, B, new_ids, integral, grad_mean);

@@ -57,6 +57,11 @@ class Context {
     int rc = hso_create(device, &cam, cfg, &h_);
     if (rc != HSO_OK) throw std::runtime_error("hso_create failed (" + std::to_string(rc) + "): no sm_100 device? there is no CPU fallback");
   }
+  // A context without a device: for host-only use of the data-model glue (makeDepthRef, getCloseViewObs, the wire formats) — e.g. unit tests on
+  // a machine without a GPU. Every device call through it fails with HSO_ERR_INVALID (the C-ABI rejects a null context); nothing is computed on
+  // the CPU instead.
+  struct HostOnly {};
+  Context(const hso_cam& cam, HostOnly) : cam_(cam) {}
   ~Context() { hso_destroy(h_); }
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
@@ -107,7 +112,9 @@ struct Frame {  // include/hso/frame.h (subset): the pyramid lives on the device
     if (rc == HSO_ERR_INVALID) throw std::runtime_error("Frame: provided image has not the same size as the camera model or image is not grayscale");
     ctx.check(rc);
   }
-  ~Frame() { hso_frame_release(ctx_.get(), id); }
+  // A frame without a device pyramid (host-only contexts): pose, features and statistics are the caller's to fill.
+  Frame(Context& ctx, Context::HostOnly, double timestamp) : ctx_(ctx), timestamp_(timestamp) {}
+  ~Frame() { if (id >= 0) hso_frame_release(ctx_.get(), id); }
   Frame(const Frame&) = delete;
   Frame& operator=(const Frame&) = delete;
   Context& ctx_;

@@ -160,6 +160,10 @@ int hso_track_level_profile(hso_ctx* ctx, int level, double* ms_total, uint64_t*
 int hso_track_set_cluster(hso_ctx* ctx, int ctas_per_problem, int threads_per_cta);
 /* Same, for one pyramid level only (overrides hso_track_set_cluster for that level; 0,0 restores auto). */
 int hso_track_set_level_shape(hso_ctx* ctx, int level, int ctas_per_problem, int threads_per_cta);
+/* Launch shape the last run used for `level`: CTAs per problem, threads per CTA, mode (0 = images and caches in global memory, 1 = current level
+ * + reference-patch cache in shared memory, 2 = both levels in shared memory), and whether the |r| scratch of the threshold selection sat in
+ * shared memory. The parity tests use it to prove that they exercise the shape the benchmark runs. */
+int hso_track_get_level_shape(hso_ctx* ctx, int level, int* ctas, int* threads, int* mode, int* absres_smem);
 /* Inverse-compositional mode: 1 (default) keeps both pyramid levels in shared memory and recomputes the reference samples per evaluation
  * whenever two copies of the level fit; 0 forces the cached-reference-patch path. Results are identical. */
 int hso_track_set_ic_dual(hso_ctx* ctx, int enable);

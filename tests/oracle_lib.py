@@ -169,6 +169,18 @@ class TrackProblem:
         return hu.value, ou.value, n.value
 
 
+def make_depth_ref(T_ref_w, has_point, f_host, idist, T_host_w):
+    """CoarseTracker::makeDepthRef (src/CoarseTracker.cpp:210-240): T_host_w is one 3x4 pose PER FEATURE (its point's host frame)."""
+    lib = load()
+    F = len(idist)
+    out = np.zeros(F)
+    hp = np.ascontiguousarray(has_point, np.uint8)
+    lib.orc_make_depth_ref(dp(np.ascontiguousarray(T_ref_w, np.float64).reshape(12)), F, hp.ctypes.data_as(C.POINTER(C.c_uint8)),
+                           dp(np.ascontiguousarray(f_host, np.float64)), dp(np.ascontiguousarray(idist, np.float64)),
+                           dp(np.ascontiguousarray(T_host_w, np.float64)), dp(out))
+    return out
+
+
 def track_solve(H, b, lam):
     lib = load()
     H = np.ascontiguousarray(H, np.float64).reshape(49)

@@ -118,3 +118,60 @@ def test_host_layer_wire_formats(tmp_path):
                            f"-Wl,-rpath,{libdir}"])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and out.stdout.strip() == "OK", out.stderr
+
+
+def test_host_make_depth_ref_matches_oracle(tmp_path):
+    """Row a4: hso::b200::CoarseTracker::makeDepthRef (the pointer-chasing host half of src/CoarseTracker.cpp:210-240) against the oracle's
+    orc_make_depth_ref and an independent numpy statement: 5 host keyframes with distinct non-identity poses, a non-identity reference pose,
+    features without a point, points behind the reference camera and points with z below the 1e-5 cut."""
+    import subprocess
+    import oracle_lib as O
+    from hso_b200 import _capi, synth
+    rng = np.random.default_rng(404)
+    F, K = 400, 5
+    T_ref = synth.se3_exp(np.array([0.3, -0.2, 0.1, 0.05, -0.08, 0.12]))
+    T_hosts = [synth.se3_exp(np.concatenate([rng.normal(0, 0.4, 3), rng.normal(0, 0.15, 3)])) for _ in range(K)]
+    host_of = rng.integers(0, K, F).astype(np.int32)
+    has = (rng.uniform(size=F) < 0.85).astype(np.int32)
+    ray = np.stack([rng.uniform(-0.6, 0.6, F), rng.uniform(-0.5, 0.5, F), np.ones(F)], axis=1)
+    f_host = ray / np.linalg.norm(ray, axis=1, keepdims=True)
+    idist = 1.0 / rng.uniform(0.5, 8.0, F)
+    # force the rejections: points whose position in the reference frame has z < 1e-5 (behind the camera, and just below the threshold)
+    T_r_h = [T_ref @ np.linalg.inv(T) for T in T_hosts]
+    forced = []
+    for i in range(0, 60, 3):
+        T = np.linalg.inv(T_r_h[host_of[i]])
+        z = -1.0 if i % 2 else 0.5e-5
+        p_ref = np.array([0.1, -0.05, z])
+        p_h = T[:3, :3] @ p_ref + T[:3, 3]
+        d = np.linalg.norm(p_h)
+        f_host[i], idist[i], has[i] = p_h / d, 1.0 / d, 1
+        forced.append(i)
+    blob = tmp_path / "depthref.bin"
+    with open(blob, "wb") as fh:
+        fh.write(np.array([F, K], np.int32).tobytes())
+        fh.write(np.ascontiguousarray(T_ref[:3], np.float64).tobytes())
+        fh.write(np.ascontiguousarray(np.stack([T[:3] for T in T_hosts]), np.float64).tobytes())
+        fh.write(np.ascontiguousarray(f_host, np.float64).tobytes()); fh.write(idist.astype(np.float64).tobytes())
+        fh.write(has.tobytes()); fh.write(host_of.tobytes())
+    exe = tmp_path / "host_depthref"
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "host_depthref.cpp"), "-o", str(exe), f"-L{libdir}", "-lhso_b200",
+                           f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe), str(blob)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    got = np.array([float(x) for x in out.stdout.split()])
+    exp = O.make_depth_ref(T_ref[:3], has, f_host, idist, np.stack([T_hosts[h][:3] for h in host_of]))
+    # independent numpy statement
+    ref = -np.ones(F)
+    for i in range(F):
+        if not has[i]:
+            continue
+        p = T_r_h[host_of[i]][:3, :3] @ (f_host[i] / idist[i]) + T_r_h[host_of[i]][:3, 3]
+        if p[2] >= 0.00001:
+            ref[i] = np.linalg.norm(p)
+    assert got.shape == (F,)
+    assert np.array_equal(got < 0, exp < 0) and np.array_equal(exp < 0, ref < 0)
+    assert all(got[i] == -1.0 for i in forced) and (got[has == 0] == -1.0).all() and (got >= 0).sum() > 250
+    ok = exp >= 0
+    assert np.abs(got[ok] - exp[ok]).max() < 1e-12 * np.abs(exp[ok]).max() and np.abs(ref[ok] - exp[ok]).max() < 1e-12 * np.abs(exp[ok]).max()

@@ -254,3 +254,133 @@ def test_pipelined_entry_edge_cases(oracle):
     with pytest.raises(HsoError):
         ctx.add_frames_track_batch([p["cur_img"]], [dict(full, ref=12345)])
     ctx.close()
+
+
+# ---- parity at the benchmarked launch shape and configuration (bench.py: icl 640x480, F = 3000, B = 1184 per GPU) ---------------------------
+# With B >= 148 problems in flight track_run_range gives every problem ONE CTA of 512 threads at levels 4..2 and a cluster of 2 x 512 at level 1
+# (231 KB of image + reference-patch cache do not fit one SM), the |r| scratch of the threshold selection in global memory at level 1; the
+# inverse-compositional mode keeps both levels resident (mode 2) with one CTA per problem. BENCH_SHAPE is what bench.py's batch runs;
+# hso_track_get_level_shape proves the tests run exactly that.
+BENCH_SHAPE_FWD = {4: (1, 512, 1, 1), 3: (1, 512, 1, 1), 2: (1, 512, 1, 1), 1: (2, 512, 1, 0)}
+
+
+def _bench_problem(oracle, seed, F=3000, cam="icl"):
+    import bench
+    probs = bench.build_workload(1, F, cam, seed, 0)
+    return probs[0]
+
+
+@pytest.mark.parametrize("ic", [False, True])
+def test_benchmark_shape_single_problem_trace_parity(oracle, ic):
+    """One problem of the headline configuration (icl 640x480, F = 3000) forced into the launch shape the B = 1184 batch uses; every
+    evaluation of the trace against the oracle at the same state."""
+    p, ctx, tp, job, a0 = _setup(oracle, 3000, "icl", 3000)
+    big, _ = ctx.coarse_track_batch([job] * 148, inverse_comp=ic)  # what the auto shape picks for a full wave
+    auto = {l: ctx.level_shape(l) for l in (4, 3, 2, 1)}
+    if not ic:
+        assert auto == BENCH_SHAPE_FWD, auto
+    for l in (4, 3, 2, 1):
+        ctx.set_level_shape(l, auto[l][0], auto[l][1])
+    res, traces = ctx.coarse_track_batch([job], inverse_comp=ic, trace_cap=256)
+    assert {l: ctx.level_shape(l) for l in (4, 3, 2, 1)} == auto
+    worst = _check_trace(oracle, tp, traces[0], ic, 4)
+    assert worst <= REL
+    # identical launch shape, identical data => the batched run gives the same bits for every copy of the problem
+    for b in (0, 77, 147):
+        assert np.array_equal(big[b]["T_cur_ref"], res[0]["T_cur_ref"]) and big[b]["n_iters"] == res[0]["n_iters"]
+    ro = tp.run(np.eye(4)[:3], a0, inverse_comp=ic)
+    assert np.abs(res[0]["T_cur_ref"] - ro["T_cur_ref"]).max() < 2e-4 and abs(res[0]["exposure_rat"] - ro["exposure_rat"]) < 2e-4
+    ctx.close()
+
+
+@pytest.mark.parametrize("ic", [False, True])
+def test_benchmark_batch_traces_vs_oracle(oracle, ic):
+    """A batch of 160 distinct problems built by bench.py's own generator (F = 3000, 2 % of the features without depth, perturbed initial
+    poses) in ONE launch set, auto shape: the traces of 10 sampled problems go through the per-evaluation check, every final pose is compared
+    with the oracle's own run."""
+    import bench
+    B = 160
+    probs = bench.build_workload(B, 3000, "icl", 0x450, 0)
+    c = probs[0]["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]), max_frames=2 * 12 + 4)
+    nb = len(set(p["base"] for p in probs))
+    first = {}
+    for p in probs:
+        first.setdefault(p["base"], p)
+    ids, integ, _ = ctx.upload_frames([first[k]["ref_img"] for k in range(nb)] + [first[k]["cur_img"] for k in range(nb)])
+    jobs = []
+    for p in probs:
+        k = p["base"]
+        a0 = float(np.float32(integ[nb + k]) / np.float32(integ[k]))
+        jobs.append(dict(ref=ids[k], cur=ids[nb + k], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=p["T0"], exposure_rat=a0))
+    res, traces = ctx.coarse_track_batch(jobs, inverse_comp=ic, trace_cap=96)
+    if not ic:
+        assert {l: ctx.level_shape(l) for l in (4, 3, 2, 1)} == BENCH_SHAPE_FWD
+    else:
+        assert all(ctx.level_shape(l)[0] == 1 and ctx.level_shape(l)[2] == 2 for l in (4, 3, 2, 1))
+    pyr = {}
+    for k in range(nb):
+        pyr[k] = (oracle.create_pyramid(first[k]["ref_img"], 5)[0], oracle.create_pyramid(first[k]["cur_img"], 5)[0])
+    sampled = list(range(0, B, 16))
+    worst = 0.0
+    for b in sampled:
+        p = probs[b]
+        tp = oracle.TrackProblem(c, pyr[p["base"]][0], pyr[p["base"]][1], p["px"], p["f"], p["dist"])
+        assert len(traces[b]) < 96
+        worst = max(worst, _check_trace(oracle, tp, traces[b], ic, 4))
+        ro = tp.run(p["T0"], jobs[b]["exposure_rat"], inverse_comp=ic)
+        assert np.abs(res[b]["T_cur_ref"] - ro["T_cur_ref"]).max() < 2e-4, b
+        assert abs(res[b]["exposure_rat"] - ro["exposure_rat"]) < 2e-4 and abs(res[b]["n_tracked"] - ro["n_tracked"]) <= 2
+    assert worst <= REL
+    ctx.close()
+
+
+@pytest.mark.parametrize("ic", [False, True])
+def test_pipelined_entry_vs_oracle_at_benchmark_config(oracle, ic):
+    """hso_add_frames_track_batch (the call bench.py's e2e number times) on 300 problems of the benchmark generator — three chunks on three
+    streams, device-formed exposure ratio — against the ORACLE: frame statistics, the pyramid of the last new frame, and the final pose /
+    exposure ratio / tracked count of 10 sampled problems."""
+    import bench
+    B = 300
+    probs = bench.build_workload(B, 3000, "icl", 0x450, 0)
+    c = probs[0]["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]), max_frames=B + 16)
+    nb = len(set(p["base"] for p in probs))
+    first = {}
+    for p in probs:
+        first.setdefault(p["base"], p)
+    ref_ids, ref_int, _ = ctx.upload_frames([first[k]["ref_img"] for k in range(nb)])
+    jobs = [dict(ref=ref_ids[p["base"]], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=p["T0"]) for p in probs]
+    ids, integ, gm, res = ctx.add_frames_track_batch([p["cur_img"] for p in probs], jobs, inverse_comp=ic)
+    assert ctx.level_shape(1)[:2] == ((1, 512) if ic else (2, 512))  # chunks are shaped by the whole batch (>= 148 in flight)
+    for b in list(range(0, B, 33)) + [B - 1]:
+        p = probs[b]
+        rl, _ = oracle.create_pyramid(p["ref_img"], 5)
+        cl, _ = oracle.create_pyramid(p["cur_img"], 5)
+        oi, og = oracle.frame_stats(p["cur_img"])
+        assert abs(integ[b] - oi) <= 5e-5 * oi and abs(gm[b] - og) <= 2.5e-4 * og
+        a0 = float(np.float32(integ[b]) / np.float32(ref_int[p["base"]]))  # CoarseTracker.cpp:60 on the frames' own statistics
+        tp = oracle.TrackProblem(c, rl, cl, p["px"], p["f"], p["dist"])
+        ro = tp.run(p["T0"], a0, inverse_comp=ic)
+        assert np.abs(res[b]["T_cur_ref"] - ro["T_cur_ref"]).max() < 2e-4, b
+        assert abs(res[b]["exposure_rat"] - ro["exposure_rat"]) < 2e-4 and abs(res[b]["n_tracked"] - ro["n_tracked"]) <= 2
+    cl, _ = oracle.create_pyramid(probs[B - 1]["cur_img"], 5)
+    for l in range(5):
+        assert np.array_equal(ctx.download_level(ids[B - 1], l), cl[l])
+    ctx.close()
+
+
+@pytest.mark.parametrize("cam,F,ic", [("euroc", 2000, False), ("euroc", 2000, True), ("tum_fov", 3000, False), ("tum_fov", 3000, True), ("icl", 3000, False)])
+def test_relocalisation_pyramid_to_level0_slow_path(oracle, cam, F, ic):
+    """BASELINE config 2 ("full CoarseTracker pyramid L4->L0", the reference's relocalisation settings: min_level 0, 15 iterations,
+    src/frame_handler_mono.cpp:366) at 752x480 / 920x736 / 640x480 with the headline feature counts: level 0 does not fit shared memory
+    and runs the global-memory path (mode 0). Per-evaluation parity on every level incl. the 25-pixel pattern of level 0."""
+    p, ctx, tp, job, a0 = _setup(oracle, 200 + F, cam, F)
+    res, traces = ctx.coarse_track_batch([job], inverse_comp=ic, min_level=0, n_iter=15, trace_cap=256)
+    assert ctx.level_shape(0)[2] == 0, ctx.level_shape(0)
+    assert {e.level for e in traces[0]} == {4, 3, 2, 1, 0}
+    worst = _check_trace(oracle, tp, traces[0], ic, 4)
+    assert worst <= REL
+    ro = tp.run(np.eye(4)[:3], a0, inverse_comp=ic, min_level=0, n_iter=15)
+    assert np.abs(res[0]["T_cur_ref"] - ro["T_cur_ref"]).max() < 2e-4
+    ctx.close()
