@@ -54,6 +54,7 @@ void orc_frame_stats(const uint8_t* img, const int16_t* gx, const int16_t* gy, i
 
 /* ---- a4: makeDepthRef (src/CoarseTracker.cpp:210-240) ----
  * has_point[i]==0 => -1 ; T_ref_host[i] = ref.T_f_w * host.T_f_w^-1 is formed here from the two world poses. */
+void orc_accumulator7(int n, const float* J /*7n*/, const float* w /*n*/, float* H49);
 void orc_make_depth_ref(const double T_ref_w[12], int F, const uint8_t* has_point, const double* f_host /*3F*/,
                         const double* idist /*F*/, const double* T_host_w /*12F*/, double* dist_out /*F*/);
 
@@ -153,6 +154,7 @@ typedef struct {
 typedef struct { int32_t n_in_frame, n_matches, n_trials, used_cell_all; } orc_reproj_summary;
 /* cam2world of the three camera models (src/camera.cpp:66-87,169-190,297-300); unit-norm bearing. */
 void orc_cam2world(const orc_cam* cam, double u, double v, double xyz_out[3]);
+void orc_cv_undistort_point(const float K[4] /*fx fy cx cy*/, const float D[5], float u, float v, float out[2]);
 /* warp::getWarpMatrixAffine (src/matcher.cpp:46-72); A row-major. */
 void orc_get_warp_matrix_affine(const orc_cam* cam, const double px_ref[2], const double f_ref[3], double depth_ref, const double T_cur_ref[12],
                                 int level_ref, double A_cur_ref[4]);

@@ -21,30 +21,40 @@ using namespace orc;
 
 extern "C" {
 
+// cv::undistortPoints for one CV_32FC2 point with a float camera matrix K = (fx, fy, cx, cy) and float distortion (k1, k2, p1, p2, k3), no R / P:
+// cvUndistortPointsInternal's 5 fixed-point iterations in double, float in / float out.
+void orc_cv_undistort_point(const float K[4], const float D[5], float uf, float vf, float out[2]) {
+  const double fx = (double)K[0], fy = (double)K[1], cx = (double)K[2], cy = (double)K[3];
+  double k[5];
+  for (int i = 0; i < 5; ++i) k[i] = (double)D[i];
+  const double ifx = 1. / fx, ify = 1. / fy;
+  double xx = ((double)uf - cx) * ifx, yy = ((double)vf - cy) * ify;
+  const double x0 = xx, y0 = yy;
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = xx * xx + yy * yy;
+    const double icdist = (1 + ((0 * r2 + 0) * r2 + 0) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+    if (icdist < 0) { xx = ((double)uf - cx) * ifx; yy = ((double)vf - cy) * ify; break; }
+    const double deltaX = 2 * k[2] * xx * yy + k[3] * (r2 + 2 * xx * xx);
+    const double deltaY = k[2] * (r2 + 2 * yy * yy) + 2 * k[3] * xx * yy;
+    xx = (x0 - deltaX) * icdist;
+    yy = (y0 - deltaY) * icdist;
+  }
+  out[0] = (float)xx;
+  out[1] = (float)yy;
+}
+
 // src/camera.cpp:66-87 (PinholeCamera), :169-190 (FOVCamera), :297-300 (EquidistantCamera)
 void orc_cam2world(const orc_cam* cam, double u, double v, double xyz_out[3]) {
   double x, y;
   const bool distortion = cam->model == 0 && std::fabs(cam->d[0]) > 0.0000001;  // camera.cpp:36
   if (cam->model == 0 && distortion) {
     // cv::undistortPoints(src(1x1 CV_32FC2), dst, cvK_ (float 3x3), cvD_ (float 1x5)) — no R, no P, criteria (MAX_ITER, 5)
-    const float uf = (float)u, vf = (float)v;
-    const double fx = (double)(float)cam->fx, fy = (double)(float)cam->fy, cx = (double)(float)cam->cx, cy = (double)(float)cam->cy;
-    double k[5];
-    for (int i = 0; i < 5; ++i) k[i] = (double)(float)cam->d[i];
-    const double ifx = 1. / fx, ify = 1. / fy;
-    double xx = ((double)uf - cx) * ifx, yy = ((double)vf - cy) * ify;
-    const double x0 = xx, y0 = yy;
-    for (int j = 0; j < 5; ++j) {
-      const double r2 = xx * xx + yy * yy;
-      const double icdist = (1 + ((0 * r2 + 0) * r2 + 0) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
-      if (icdist < 0) { xx = ((double)uf - cx) * ifx; yy = ((double)vf - cy) * ify; break; }
-      const double deltaX = 2 * k[2] * xx * yy + k[3] * (r2 + 2 * xx * xx);
-      const double deltaY = k[2] * (r2 + 2 * yy * yy) + 2 * k[3] * xx * yy;
-      xx = (x0 - deltaX) * icdist;
-      yy = (y0 - deltaY) * icdist;
-    }
-    x = (double)(float)xx;
-    y = (double)(float)yy;
+    const float K[4] = {(float)cam->fx, (float)cam->fy, (float)cam->cx, (float)cam->cy};
+    float D[5], out[2];
+    for (int i = 0; i < 5; ++i) D[i] = (float)cam->d[i];
+    orc_cv_undistort_point(K, D, (float)u, (float)v, out);
+    x = (double)out[0];
+    y = (double)out[1];
   } else if (cam->model == 1 && !cam->undistort) {
     const double ud = (u - cam->cx) / cam->fx, vd = (v - cam->cy) / cam->fy;
     const double dist = std::sqrt(ud * ud + vd * vd);

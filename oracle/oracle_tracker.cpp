@@ -330,6 +330,17 @@ void fill_trace(orc_trace* e, const Tracker& tr, int iter, const SE3& T, float a
 
 extern "C" {
 
+// The tiered float accumulator alone, driven like computeGS drives it (src/CoarseTracker.cpp:507-518): for pinning against the reference's own
+// Accumulator7 (oracle/_ref).
+void orc_accumulator7(int n, const float* J /*7n*/, const float* w /*n*/, float* H49) {
+  Acc7 acc;
+  acc.initialize();
+  for (int i = 0; i < n; ++i) acc.update(J[7 * i], J[7 * i + 1], J[7 * i + 2], J[7 * i + 3], J[7 * i + 4], J[7 * i + 5], J[7 * i + 6], w[i]);
+  double H[49];
+  acc.finish(H);
+  for (int k = 0; k < 49; ++k) H49[k] = (float)H[k];
+}
+
 void orc_make_depth_ref(const double T_ref_w[12], int F, const uint8_t* has_point, const double* f_host, const double* idist,
                         const double* T_host_w, double* dist_out) {
   SE3 Tref = SE3::from_rt(T_ref_w);

@@ -1,0 +1,31 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Stand-in for the Boost headers the reference includes (system dependency, absent from this image): the
+// handful of names the hot-path headers mention, mapped onto their C++17 standard-library equivalents. No arithmetic lives here.
+#pragma once
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+namespace boost {
+using std::shared_ptr;
+using std::make_shared;
+using std::function;
+using std::mutex;
+using std::unique_lock;
+using std::lock_guard;
+using std::condition_variable;
+using std::thread;
+using std::ref;
+using std::cref;
+class noncopyable {
+ protected:
+  noncopyable() = default;
+  ~noncopyable() = default;
+  noncopyable(const noncopyable&) = delete;
+  noncopyable& operator=(const noncopyable&) = delete;
+};
+template <class... A> auto bind(A&&... a) -> decltype(std::bind(std::forward<A>(a)...)) { return std::bind(std::forward<A>(a)...); }
+namespace this_thread { using std::this_thread::yield; using std::this_thread::sleep_for; }
+}  // namespace boost
+// boost/bind.hpp puts _1.._9 into the global namespace
+using namespace std::placeholders;
