@@ -165,14 +165,24 @@ def measured_peak():
 
 # ---------------------------------------------------------------------------------------------------------------------------
 def cpu_frame(O, prob, ic):
-    """The reference algorithm (oracle) for one frame of the step: pyramid + Sobel + stats of the current image, CoarseTracker::run."""
+    """The reference algorithm (oracle PORT) for one frame of the step: pyramid + Sobel + stats of the current image, CoarseTracker::run."""
     cl, _ = O.create_pyramid(prob["cur_img"], 5)
     for l in range(3):
         O.sobel5(cl[l])
     ci, _ = O.frame_stats(prob["cur_img"])
     tp = O.TrackProblem(prob["cam"], prob["_ref_levels"], cl, prob["px"], prob["f"], prob["dist"])
-    r = tp.run(prob["T0"], float(np.float32(ci) / np.float32(prob["_ref_integral"])), inverse_comp=ic, trace_cap=1)
+    r = tp.run(prob["T0"], float(np.float32(ci) / np.float32(prob["_ref_integral"])), inverse_comp=ic, trace_cap=64)
     return r["n_evals"] - 4  # evaluations minus one entry evaluation per level = LM trials
+
+
+def ref_frame(R, prob, ic):
+    """The REFERENCE ITSELF (oracle/_ref/libhso_ref.so: the reference's sources compiled unmodified) for one frame of the step: new hso::Frame
+    (pyramid, Sobel images, statistics: src/frame.cpp:45-96) then CoarseTracker::run(ref, cur) (src/CoarseTracker.cpp:51-208). The reference
+    does not report its trial count; the step's LM iterations are counted by the oracle port on the same frames outside the timed region."""
+    cur = R.Frame(prob["cam"], prob["cur_img"])
+    R.coarse_track(prob["_ref_frame"], cur, prob["T0"], inverse_comp=ic)
+    cur.close()
+    return 0
 
 
 def cpu_prepare(O, probs):
@@ -184,20 +194,43 @@ def cpu_prepare(O, probs):
         p["_ref_levels"], p["_ref_integral"] = cache[p["base"]]
 
 
-def run_cpu(probs, ic, threads):
+def run_cpu(probs, ic, threads, kind="auto"):
+    """Times the CPU implementation of the step on `probs`. kind: "reference" = the reference's own code (oracle/_ref), "port" = the oracle
+    restatement, "auto" = reference when its library is present. Returns (LM iterations, seconds, kind)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
+    import ref_lib as R
     O.load()
+    if kind == "auto":
+        kind = "reference" if R.available() else "port"
     cpu_prepare(O, probs)
+    if kind == "reference":
+        R.load()
+        # every problem gets its own reference Frame object carrying its own features (the reference keeps features inside the Frame);
+        # built outside the timed region like the resident reference frames of the GPU arm
+        for p in probs:
+            p["_ref_frame"] = R.Frame(p["cam"], p["ref_img"])
+            p["_ref_frame"].set_track_features(p["px"], p["f"], p["dist"])
+        work = lambda p: ref_frame(R, p, ic)
+    else:
+        work = lambda p: cpu_frame(O, p, ic)
     t0 = time.perf_counter()
     if threads <= 1:
-        iters = sum(cpu_frame(O, p, ic) for p in probs)
+        iters = sum(work(p) for p in probs)
     else:
         from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL inside the oracle
-            iters = sum(ex.map(lambda p: cpu_frame(O, p, ic), probs))
+        with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL inside the native code
+            iters = sum(ex.map(work, probs))
     dt = time.perf_counter() - t0
-    return iters, dt
+    if kind == "reference":
+        for p in probs:
+            p["_ref_frame"].close()
+            del p["_ref_frame"]
+        for p in probs:  # LM iterations of these frames, counted once by the port (same algorithm, same trial sequence)
+            if "_iters_port" not in p:
+                p["_iters_port"] = cpu_frame(O, p, ic)
+        iters = sum(p["_iters_port"] for p in probs)
+    return iters, dt, kind
 
 
 def reference_arm(args, rank, world):
@@ -210,9 +243,12 @@ def reference_arm(args, rank, world):
         run_cpu(probs[: max(2, cores // 4)], args.ic, cores)
     tot_it, tot_t = 0, 0.0
     steps = max(1, args.steps)  # exactly K timed steps; a step is a bounded sample (4 frames per host thread, ~0.2 s)
+    kind = "port"
     for _ in range(steps):
-        it, dt = run_cpu(probs, args.ic, cores)
+        it, dt, kind = run_cpu(probs, args.ic, cores)
         tot_it += it; tot_t += dt
+    what = ("the reference's own sources compiled unmodified (oracle/_ref/libhso_ref.so: new hso::Frame + CoarseTracker::run; cv::Sobel / cv::resize "
+            "are the shim's scalar restatements, ~6 % of a frame)" if kind == "reference" else "oracle/liboracle_hso.so (-O3 x86-64-v3)")
     v = tot_it / tot_t
     line = {"impl": "reference", "metric": "CoarseTracker LM iterations/sec @640x480, 3k patches", "value": v, "unit": "iterations/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True,
@@ -221,8 +257,8 @@ def reference_arm(args, rank, world):
             "config": {"workload": f"{args.cam} {probs[0]['cam']['width']}x{probs[0]['cam']['height']}, {args.patches} patches/frame, "
                                    f"pyramid+stats then CoarseTracker L4->L1 n_iter=50 {'inverse-compositional' if args.ic else 'forward'}",
                        "sample": f"{n} frames per step"},
-            "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} frames/step x {steps} steps, one frame per thread, oracle/liboracle_hso.so (-O3 x86-64-v3)"},
+            "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": cores, "kind": kind,
+                             "sample": f"{n} frames/step x {steps} steps, one frame per thread, {what}"},
             "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -465,7 +501,7 @@ def single_stream(args, device, torch):
             for p in use:
                 its += frame(p)
         dt = time.perf_counter() - t0
-        it_c, dt_c = run_cpu(use, ic, 1)
+        it_c, dt_c, _ = run_cpu(use, ic, 1)
         # the same frames through ONE C-ABI call per frame (hso_add_frames_track_batch, B = 1) with argument records built once, as a C++
         # caller holding long-lived Frame / Feature objects would: no Python marshalling inside the timed loop
         from hso_b200 import _capi as K
@@ -756,10 +792,14 @@ def main():
             cores = 1
             sample = build_workload(256, F, args.cam, args.seed, 0)
             run_cpu(sample[:1], args.ic, 1)
-            it, dt = run_cpu(sample, args.ic, 1)
-            line["cpu_baseline"] = {"value": it / dt, "unit": "iterations/s", "cores": cores, "kind": "port",
+            it, dt, kind = run_cpu(sample, args.ic, 1)
+            line["cpu_baseline"] = {"value": it / dt, "unit": "iterations/s", "cores": cores, "kind": kind,
                                     "sample": f"256 frames of the same workload ({it} LM iterations, {dt:.1f} s) single-threaded like the reference's "
-                                              f"tracking thread; host has {os.cpu_count()} cores", "frames_per_s": 256 / dt}
+                                              f"tracking thread, " + ("the reference's own sources compiled unmodified (oracle/_ref/libhso_ref.so)"
+                                                                      if kind == "reference" else "oracle port") + f"; host has {os.cpu_count()} cores",
+                                    "frames_per_s": 256 / dt}
+            it_p, dt_p, _ = run_cpu(sample[:64], args.ic, 1, kind="port")
+            line["cpu_baseline"]["port_value"] = it_p / dt_p  # the oracle restatement on the same host core, for comparison
         if world == 1 and not args.no_other_rows:
             # the same batch in the other Jacobian mode (the reference picks inverse-compositional unless the new frame's gradients
             # got stronger, src/frame_handler_mono.cpp:184-203), device-resident like `value`

@@ -334,8 +334,8 @@ class Matrix : public MatrixBase<Matrix<T, R, C, Opt, MR, MC>> {
   // a 1x1 matrix (inner product) converts to its coefficient, as in Eigen
   operator typename std::conditional<(R == 1 && C == 1), T, internal::no_conversion<T, R, C>>::type() const { return m_[0]; }
 
-  Index rows_() const { return r_; }
-  Index cols_() const { return c_; }
+  Index rows_() const { return R == Dynamic ? r_ : Index(R); }  // compile-time constants for fixed sizes: the loops below unroll
+  Index cols_() const { return C == Dynamic ? c_ : Index(C); }
   T get(Index i, Index j) const { return m_[idx(i, j)]; }
   T& ref(Index i, Index j) { return m_[idx(i, j)]; }
   T* data() { return &m_[0]; }
@@ -364,7 +364,7 @@ class Matrix : public MatrixBase<Matrix<T, R, C, Opt, MR, MC>> {
 
  private:
   T& vec(Index i) { return m_[i]; }
-  Index idx(Index i, Index j) const { return kRowMajor ? i * c_ + j : j * r_ + i; }
+  Index idx(Index i, Index j) const { return kRowMajor ? i * cols_() + j : j * rows_() + i; }
   template <class A, class B> void init_two(const A& a, const B& b) {
     init_zero();
     if (kFixed && R * C == 2) { m_[0] = T(a); m_[1] = T(b); }
@@ -381,11 +381,17 @@ class Matrix : public MatrixBase<Matrix<T, R, C, Opt, MR, MC>> {
     bool tr = false;
     // vectors are transposed on assignment when the orientation differs (Eigen does the same)
     if ((R == 1 && C != 1 && oc == 1 && orr != 1) || (C == 1 && R != 1 && orr == 1 && oc != 1)) { tr = true; std::swap(orr, oc); }
-    // the source may alias this matrix (e.g. x = x.transpose()): evaluate first
-    std::vector<T> tmp((size_t)(orr * oc));
-    for (Index j = 0; j < oc; ++j) for (Index i = 0; i < orr; ++i) tmp[(size_t)(j * orr + i)] = T(tr ? o.coeff(j, i) : o.coeff(i, j));
-    resize_impl(orr, oc);
-    for (Index j = 0; j < oc; ++j) for (Index i = 0; i < orr; ++i) ref(i, j) = tmp[(size_t)(j * orr + i)];
+    // the source may be a view of this matrix: evaluate it completely first (on the stack for fixed sizes, like Eigen's own temporaries)
+    if (kFixed) {
+      T tmp[kFixed ? (R * C > 0 ? R * C : 1) : 1];
+      for (Index j = 0; j < oc; ++j) for (Index i = 0; i < orr; ++i) tmp[j * orr + i] = T(tr ? o.coeff(j, i) : o.coeff(i, j));
+      for (Index j = 0; j < oc; ++j) for (Index i = 0; i < orr; ++i) ref(i, j) = tmp[j * orr + i];
+    } else {
+      std::vector<T> tmp((size_t)(orr * oc));
+      for (Index j = 0; j < oc; ++j) for (Index i = 0; i < orr; ++i) tmp[(size_t)(j * orr + i)] = T(tr ? o.coeff(j, i) : o.coeff(i, j));
+      resize_impl(orr, oc);
+      for (Index j = 0; j < oc; ++j) for (Index i = 0; i < orr; ++i) ref(i, j) = tmp[(size_t)(j * orr + i)];
+    }
   }
 };
 
@@ -402,8 +408,8 @@ class Block : public MatrixBase<Block<X, BR, BC>> {
   using Base::operator-=;
   Block(X& x, Index i0, Index j0, Index r, Index c) : x_(x), i0_(i0), j0_(j0), r_(r), c_(c) {}
   Block(const Block&) = default;
-  Index rows_() const { return r_; }
-  Index cols_() const { return c_; }
+  Index rows_() const { return BR == Dynamic ? r_ : Index(BR); }
+  Index cols_() const { return BC == Dynamic ? c_ : Index(BC); }
   Scalar get(Index i, Index j) const { return x_.get(i0_ + i, j0_ + j); }
   Scalar& ref(Index i, Index j) { return const_cast<typename std::remove_const<X>::type&>(x_).ref(i0_ + i, j0_ + j); }
   template <class O> Block& operator=(const MatrixBase<O>& o) {
