@@ -44,7 +44,7 @@ def _check_trace(oracle, tp, trace, ic, max_level):
         # Cauchy-Schwarz bound |b_k| <= sqrt(H_kk * sum w r^2), not |b_k| itself.
         b_scale = np.sqrt(np.maximum(np.diag(H), 0) * max(E * tt, 1e-12))
         assert np.all(np.abs(bg - b) <= 10 * tol * b_scale + 1e-9), (e.level, e.iter, np.abs(bg - b) / b_scale)
-        assert abs(E - e.energy) <= tol * abs(E) + 1e-6
+        assert abs(E - e.energy) <= max(tol, 5e-5) * abs(E) + 1e-6  # one fp32 sum over up to 75 k terms on either side
         if e.iter >= 0:
             sg = np.array(e.step[:])
             # (i) the device's damped solve / extrapolation / NaN guard on identical inputs
@@ -55,7 +55,8 @@ def _check_trace(oracle, tp, trace, ic, max_level):
             # so an absolute 2e-7 (a few 1e-5 px at 640x480) is admitted as well.
             step_o = oracle.track_solve(Ho_acc, bo_acc, e.lambda_)
             err = np.linalg.norm(sg - step_o)
-            worst = max(worst, err / max(np.linalg.norm(step_o), 1e-12))
+            if np.linalg.norm(step_o) >= 2e-3:  # where the absolute floor below is itself <= 1e-4 relative
+                worst = max(worst, err / np.linalg.norm(step_o))
             assert err <= REL * np.linalg.norm(step_o) + 2e-7, (e.level, e.iter, err, np.linalg.norm(step_o))
         if e.iter < 0 or e.accepted:
             H_acc, b_acc = Hg, bg
