@@ -53,7 +53,7 @@ class hso_trace(C.Structure):
 class hso_align_job(C.Structure):
     _fields_ = [("ref_level", C.c_int32), ("search_level", C.c_int32), ("type", C.c_int32), ("scale_patch", C.c_int32),
                 ("px_ref", C.c_double * 2), ("A_cur_ref", C.c_double * 4), ("grad", C.c_double * 2), ("px_cur", C.c_double * 2),
-                ("exposure_rat", C.c_float), ("pad_", C.c_float)]
+                ("exposure_rat", C.c_float), ("ncc_thresh", C.c_float)]
 
 
 class hso_align_result(C.Structure):
@@ -147,6 +147,8 @@ SYMBOLS = {
                                       _P(C.c_int32), _P(hso_reproj_result), _P(hso_reproj_summary)]),
     "hso_reproject_select_only": (C.c_int, [_vp, C.c_int, _P(hso_reproj_cand), _P(C.c_int32), _P(C.c_int32), _P(C.c_uint8), _P(hso_reproj_grid),
                                             _P(C.c_int32), _P(hso_reproj_result), _P(hso_reproj_summary)]),
+    "hso_reproject_seeds": (C.c_int, [_vp, C.c_int32, _P(C.c_double), C.c_int, _P(C.c_double), C.c_int, _P(hso_seed_obs), _P(hso_reproj_grid), _P(C.c_int32),
+                                      C.c_int, _P(hso_reproj_result), _P(hso_reproj_summary)]),
     "hso_depth_observe": (C.c_int, [_vp, C.c_int32, _P(C.c_double), C.c_int, _P(C.c_double), C.c_double, C.c_int, C.c_int, _P(hso_seed_obs),
                                     _P(hso_seed_result)]),
     "hso_pose_optimize": (C.c_int, [_vp, C.c_double, C.c_int, C.c_int, C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_int32), C.c_int,

@@ -255,6 +255,20 @@ class Context:
                                                order.ctypes.data_as(C.POINTER(C.c_int32)), out, C.byref(summ)))
         return out, summ
 
+    def reproject_seeds(self, cur, T_cur_w, T_f_w, seeds, grid, cell_order, n_matches_in=0, S=None):
+        """a13b: the seed stage of Reprojector::reprojectMap. seeds: ctypes array from seed_obs(). Returns (hso_reproj_result array, summary)."""
+        S = len(seeds) if S is None else S
+        T = np.ascontiguousarray(T_cur_w, np.float64).reshape(12)
+        Tk = np.ascontiguousarray(T_f_w, np.float64).reshape(-1)
+        g = K.hso_reproj_grid(int(grid["cell_size"]), int(grid["n_cols"]), int(grid["n_rows"]), int(grid["max_fts"]),
+                              int(grid.get("align_max_iter", 10)), 0)
+        order = np.ascontiguousarray(cell_order, np.int32)
+        out = (K.hso_reproj_result * max(S, 1))()
+        summ = K.hso_reproj_summary()
+        self._chk(self.lib.hso_reproject_seeds(self.h, int(cur), _dp(T), Tk.size // 12, _dp(Tk), S, seeds, C.byref(g),
+                                               order.ctypes.data_as(C.POINTER(C.c_int32)), int(n_matches_in), out, C.byref(summ)))
+        return out, summ
+
     def reproject_select_only(self, cands, in_frame, cell, align_ok, grid, cell_order):
         """Test hook: the selection kernel alone on given per-candidate facts. Returns (results, summary)."""
         M = len(in_frame)

@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32) k_align(const AlignKParams P
       num += p1 * p2; d1 += p1 * p1; d2 += p2 * p2;
     }
     num = warp_sum(num); d1 = warp_sum(d1); d2 = warp_sum(d2);
-    ok = ((double)num / ((double)sqrtf(d1 * d2) + 1e-12)) > (double)0.7f;
+    const float thresh = jb.ncc_thresh > 0.f ? jb.ncc_thresh : 0.7f;  // findMatchDirect 0.7 (matcher.cpp:366), findMatchSeed 0.8 (:510)
+    ok = ((double)num / ((double)sqrtf(d1 * d2) + 1e-12)) > (double)thresh;
   }
   if (ok) {
     const double dx = px_s0 - ps0, dy = px_s1 - ps1;

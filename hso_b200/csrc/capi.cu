@@ -1315,6 +1315,86 @@ int hso_reproject_match(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12]
   return HSO_OK;
 }
 
+// ---- a13b: seed stage of Reprojector::reprojectMap ---------------------------------------------------------------------------------------------
+int hso_reproject_seeds(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], int n_poses, const double* T_f_w, int S, const hso_seed_obs* seeds,
+                        const hso_reproj_grid* grid, const int32_t* cell_order, int n_matches_in, hso_reproj_result* out, hso_reproj_summary* summary) {
+  if (!ctx || !T_cur_w || !grid || !summary || S < 0 || n_poses < 0 || n_matches_in < 0) return HSO_ERR_INVALID;
+  memset(summary, 0, sizeof *summary);
+  summary->n_matches = n_matches_in;
+  const int n_cells = grid->n_cols * grid->n_rows;
+  if (grid->cell_size <= 0 || grid->n_cols <= 0 || grid->n_rows <= 0 || n_cells > 4096 || grid->max_fts < 0 || !cell_order)
+    return fail(ctx, HSO_ERR_INVALID, "bad reprojection grid (cells must be <= 4096)");
+  if ((long long)grid->n_cols * grid->cell_size < ctx->cam.width || (long long)grid->n_rows * grid->cell_size < ctx->cam.height)
+    return fail(ctx, HSO_ERR_INVALID, "reprojection grid does not cover the image");
+  if (S == 0) return HSO_OK;
+  if (!seeds || !out || !T_f_w || n_poses == 0) return HSO_ERR_INVALID;
+  if (S > 16384) return fail(ctx, HSO_ERR_CAPACITY, "more than 16384 seeds");
+  FrameSlot* fc = get_frame(ctx, cur);
+  if (!fc) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown current frame id");
+  {
+    std::vector<uint8_t> seen(n_cells, 0);
+    for (int i = 0; i < n_cells; ++i) {
+      if (cell_order[i] < 0 || cell_order[i] >= n_cells || seen[cell_order[i]]) return fail(ctx, HSO_ERR_INVALID, "cell_order is not a permutation");
+      seen[cell_order[i]] = 1;
+    }
+  }
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = (o + 127) / 128 * 128; o = r + bytes; return r; };
+  const size_t o_s = take(sizeof(hso_seed_obs) * S), o_rp = take(sizeof(void*) * S), o_T = take(sizeof(double) * 12 * n_poses),
+               o_co = take(sizeof(int32_t) * n_cells);
+  const size_t staged = o;
+  const size_t o_j = take(sizeof(AlignJobDev) * S), o_ar = take(sizeof(hso_align_result) * S), o_res = take(sizeof(hso_reproj_result) * S),
+               o_sum = take(sizeof(hso_reproj_summary));
+  CU(ctx->r_arena.reserve(o));
+  CU(ctx->r_stage_host.reserve(staged));
+  CU(ctx->r_out_host.reserve(sizeof(hso_reproj_result) * S + sizeof(hso_reproj_summary)));
+  char* h = (char*)ctx->r_stage_host.p;
+  char* d = (char*)ctx->r_arena.p;
+  memcpy(h + o_s, seeds, sizeof(hso_seed_obs) * S);
+  const uint8_t** rp = (const uint8_t**)(h + o_rp);
+  for (int i = 0; i < S; ++i) {
+    const hso_seed_obs& sd = seeds[i];
+    if (sd.ref_pose < 0 || sd.ref_pose >= n_poses) return fail(ctx, HSO_ERR_INVALID, "pose index out of range in seed");
+    FrameSlot* fr = get_frame(ctx, sd.ref_frame);
+    if (!fr) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown reference frame id in seed");
+    if (sd.level < 0 || sd.level >= ctx->geom.n_levels) return fail(ctx, HSO_ERR_INVALID, "seed level out of range");
+    if (sd.ftr_type == 1 && !fc->sobel) return fail(ctx, HSO_ERR_INVALID, "edgelet seeds need hso_cfg.materialize_sobel (checkNormal reads sobelX_/Y_)");
+    if (!(sd.sigma2 >= 0.f)) return fail(ctx, HSO_ERR_INVALID, "seed variance must be non-negative");
+    rp[i] = fr->pyr;
+  }
+  memcpy(h + o_T, T_f_w, sizeof(double) * 12 * n_poses);
+  memcpy(h + o_co, cell_order, sizeof(int32_t) * n_cells);
+  StageTimer tm(ctx, 2);
+  CU(cudaMemcpyAsync(d, h, staged, cudaMemcpyHostToDevice, ctx->stream));
+  ReprojKParams kp;
+  memset(&kp, 0, sizeof kp);
+  kp.cam = ctx->camdev;
+  memcpy(kp.T_cur_w, T_cur_w, sizeof kp.T_cur_w);
+  kp.T_f_w = (const double*)(d + o_T);
+  kp.n_poses = n_poses; kp.M = S; kp.cell_size = grid->cell_size; kp.n_cols = grid->n_cols;
+  kp.max_search_level = std::min(ctx->cfg.n_pyr_levels, ctx->geom.n_levels) - 1;
+  CU(launch_reproject_seed(kp, (const hso_seed_obs*)(d + o_s), (const uint8_t* const*)(d + o_rp), (AlignJobDev*)(d + o_j), (hso_reproj_result*)(d + o_res),
+                           ctx->stream, &ctx->launches));
+  CU(launch_align(ctx->geom, fc->pyr, fc->sobel, (const AlignJobDev*)(d + o_j), S, grid->align_max_iter, (hso_align_result*)(d + o_ar), ctx->stream,
+                  &ctx->launches));
+  SeedSelParams sp;
+  sp.S = S; sp.n_cells = n_cells; sp.max_fts = grid->max_fts; sp.n_matches_in = n_matches_in;
+  sp.n_sort = 2;
+  while (sp.n_sort < S) sp.n_sort *= 2;
+  CU(launch_seed_select(sp, (const hso_seed_obs*)(d + o_s), (const hso_align_result*)(d + o_ar), (const int32_t*)(d + o_co), (hso_reproj_result*)(d + o_res),
+                        (hso_reproj_summary*)(d + o_sum), ctx->stream, &ctx->launches));
+  char* oh = (char*)ctx->r_out_host.p;
+  CU(cudaMemcpyAsync(oh, d + o_res, sizeof(hso_reproj_result) * S, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(oh + sizeof(hso_reproj_result) * S, d + o_sum, sizeof(hso_reproj_summary), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, oh, sizeof(hso_reproj_result) * S);
+  memcpy(summary, oh + sizeof(hso_reproj_result) * S, sizeof(hso_reproj_summary));
+  tm.stop_after_sync();
+  return HSO_OK;
+}
+
 // Test hook for row N1: only the selection kernel, on caller-given per-candidate facts (what k_reproject / k_align would have produced).
 int hso_reproject_select_only(hso_ctx* ctx, int M, const hso_reproj_cand* cands, const int32_t* in_frame, const int32_t* cell, const uint8_t* align_ok,
                               const hso_reproj_grid* grid, const int32_t* cell_order, hso_reproj_result* out, hso_reproj_summary* summary) {

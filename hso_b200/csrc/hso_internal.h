@@ -134,6 +134,14 @@ struct ReprojSelParams {
 };
 cudaError_t launch_reproject(const ReprojKParams& p, const hso_reproj_cand* cands_dev, const uint8_t* const* ref_pyr_dev, AlignJobDev* jobs_dev,
                              hso_reproj_result* res_dev, cudaStream_t stream, uint64_t* launches);
+// a13b: seed stage of reprojectMap (src/reprojector.cpp:309-328,431-503,531-552 ; src/matcher.cpp:442-518)
+cudaError_t launch_reproject_seed(const ReprojKParams& p, const hso_seed_obs* seeds_dev, const uint8_t* const* ref_pyr_dev, AlignJobDev* jobs_dev,
+                                  hso_reproj_result* res_dev, cudaStream_t stream, uint64_t* launches);
+struct SeedSelParams {
+  int S, n_sort /* power of two >= S */, n_cells, max_fts, n_matches_in;
+};
+cudaError_t launch_seed_select(const SeedSelParams& p, const hso_seed_obs* seeds_dev, const hso_align_result* align_dev, const int32_t* cell_order_dev,
+                               hso_reproj_result* res_dev, hso_reproj_summary* summ_dev, cudaStream_t stream, uint64_t* launches);
 size_t reproj_select_smem(int n_sort, int n_cells);
 cudaError_t launch_reproj_select(const ReprojSelParams& p, const hso_reproj_cand* cands_dev, const hso_align_result* align_dev,
                                  const int32_t* cell_order_dev, hso_reproj_result* res_dev, hso_reproj_summary* summ_dev, cudaStream_t stream,

@@ -436,6 +436,76 @@ class Reprojector {
     }
   }
 
+  // The seed stage of reprojectMap (src/reprojector.cpp:309-328): call after reprojectMap when n_matches_ < 100 and
+  // Options::reproject_unconverged_seeds. `seeds`: the depth filter's seeds that pass the reference's own filter
+  // (sqrt(sigma2) < z_range / reproject_seed_thresh && !haveReprojected, :316), in list order. For every accepted seed a TYPE_TEMPORARY Point and
+  // a Feature are created exactly like Reprojector::reprojectorSeeds does (:438-489); the caller marks the seed haveReprojected / temp and hands
+  // the point to map_.point_candidates_.addPauseSeedPoint (the Map is the caller's). Returns the accepted seeds' indices in creation order.
+  struct SeedRef { const Feature* ftr; float mu, sigma2; };
+  std::vector<int> reprojectSeeds(FramePtr frame, const std::vector<SeedRef>& seeds, std::vector<Frame*>& keyframes, std::vector<std::unique_ptr<Point>>& new_points) {
+    const size_t S = seeds.size();
+    std::vector<hso_seed_obs> rec(S);
+    std::vector<double> T_f_w;
+    auto pose_index = [&](const Frame* f) {
+      for (size_t k = 0; k < keyframes.size(); ++k) if (keyframes[k] == f) return (int32_t)k;
+      keyframes.push_back(const_cast<Frame*>(f));
+      return (int32_t)(keyframes.size() - 1);
+    };
+    for (size_t i = 0; i < S; ++i) {
+      const Feature* ft = seeds[i].ftr;
+      hso_seed_obs& r = rec[i];
+      std::memset(&r, 0, sizeof r);
+      r.px[0] = ft->px[0]; r.px[1] = ft->px[1];
+      for (int k = 0; k < 3; ++k) r.f[k] = ft->f[k];
+      r.grad[0] = ft->grad[0]; r.grad[1] = ft->grad[1];
+      r.ref_frame = ft->frame->id; r.ref_pose = pose_index(ft->frame);
+      r.level = ft->level; r.ftr_type = ft->type;
+      r.mu = seeds[i].mu; r.sigma2 = seeds[i].sigma2;
+      r.exposure_rat = frame->m_exposure_time / ft->frame->m_exposure_time;                 // matcher.cpp:472
+    }
+    for (Frame* kf : keyframes) T_f_w.insert(T_f_w.end(), kf->T_f_w_.m, kf->T_f_w_.m + 12);
+    hso_reproj_grid g;
+    g.cell_size = grid_.cell_size; g.n_cols = grid_.grid_n_cols; g.n_rows = grid_.grid_n_rows; g.max_fts = (int32_t)max_fts_;
+    g.align_max_iter = 10; g.pad_ = 0;
+    std::vector<hso_reproj_result> res(S + 1);
+    hso_reproj_summary summ;
+    ctx_.check(hso_reproject_seeds(ctx_.get(), frame->id, frame->T_f_w_.m, (int)keyframes.size(), T_f_w.data(), (int)S, rec.data(), &g,
+                                   grid_.cell_order.data(), (int)n_matches_, res.data(), &summ));
+    const int n_new = summ.n_matches - (int)n_matches_;
+    n_matches_ = (size_t)summ.n_matches;
+    std::vector<int> by_order(n_new > 0 ? n_new : 0, -1);
+    for (size_t i = 0; i < S; ++i)
+      if (res[i].matched) {
+        if (res[i].order < 0 || res[i].order >= n_new || by_order[res[i].order] >= 0) throw std::runtime_error("hso_reproject_seeds: inconsistent creation order");
+        by_order[res[i].order] = (int)i;
+      }
+    for (int i : by_order) {
+      if (i < 0) continue;
+      const Feature* ft = seeds[i].ftr;
+      const hso_reproj_result& r = res[i];
+      // Point(xyz_world, seed.ftr): xyz_world = T_f_w^-1 * (f / mu); idist_ = mu; hostFeature_ = seed.ftr; TYPE_TEMPORARY (:444-452)
+      std::unique_ptr<Point> pt(new Point());
+      const double inv = 1.0 / seeds[i].mu;
+      const double ph[3] = {ft->f[0] * inv, ft->f[1] * inv, ft->f[2] * inv};
+      ft->frame->T_f_w_.inverse().apply(ph, pt->pos_);
+      pt->idist_ = seeds[i].mu; pt->hostFeature_ = ft; pt->type_ = Point::TYPE_TEMPORARY;
+      pt->ftr_type_ = ft->type == Feature::EDGELET ? Point::FEATURE_EDGELET : (ft->type == Feature::CORNER ? Point::FEATURE_CORNER : Point::FEATURE_GRADIENT);
+      Feature nf;
+      nf.frame = frame.get(); nf.px[0] = r.px[0]; nf.px[1] = r.px[1]; nf.level = r.search_level; nf.point = pt.get();
+      if (ft->type == Feature::EDGELET) {
+        nf.type = Feature::EDGELET;
+        const double gx = r.A_cur_ref[0] * ft->grad[0] + r.A_cur_ref[1] * ft->grad[1], gy = r.A_cur_ref[2] * ft->grad[0] + r.A_cur_ref[3] * ft->grad[1];
+        const double n = std::sqrt(gx * gx + gy * gy);
+        nf.grad[0] = gx / n; nf.grad[1] = gy / n;
+      } else {
+        nf.type = ft->type == Feature::GRADIENT ? Feature::GRADIENT : Feature::CORNER;
+      }
+      frame->fts_.push_back(nf);
+      new_points.push_back(std::move(pt));
+    }
+    return by_order;
+  }
+
  private:
   Context& ctx_;
   size_t max_fts_;

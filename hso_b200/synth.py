@@ -241,3 +241,20 @@ def make_depth_scene(seed, cam="icl", S=2000, n_kf=3, depth=4.0, gain=1.0, frac_
     focal = abs((c["fx"] + c["fy"]) * 0.5)
     return dict(cam=c, kf_imgs=kf_imgs, cur_img=cur_img, T_f_w=np.stack([T[:3] for T in T_kf]), T_cur_w=T_cur[:3], seeds=seeds,
                 px_error_angle=float(np.arctan(1.0 / (2.0 * focal)) * 2.0))
+
+
+def make_seed_reproject_scene(seed, cam="icl", S=600, max_fts=200, gain=1.0, **kw):
+    """Inputs of the seed stage of Reprojector::reprojectMap (row a13b, src/reprojector.cpp:309-328): the keyframes, active frame and seeds of
+    make_depth_scene() — depth estimates near the truth with a spread of variances, a few behind the camera — plus the reprojection grid."""
+    sc = make_depth_scene(seed, cam, S=S, gain=gain, **kw)
+    c = sc["cam"]
+    rng = np.random.default_rng(seed + 99991)
+    W, H = c["width"], c["height"]
+    cell_size = int(np.floor(np.float32(np.sqrt(np.float32(W * H) / max_fts)) * np.float32(0.6)))
+    n_cols, n_rows = int(np.ceil(W / cell_size)), int(np.ceil(H / cell_size))
+    sc["grid"] = dict(cell_size=cell_size, n_cols=n_cols, n_rows=n_rows, max_fts=max_fts, align_max_iter=10)
+    sc["cell_order"] = rng.permutation(n_cols * n_rows).astype(np.int32)
+    for i, sd in enumerate(sc["seeds"]):
+        if i % 9 == 0:  # ties in sigma2 exercise the stable sort
+            sd["sigma2"] = float(np.float32(0.004))
+    return sc

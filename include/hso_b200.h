@@ -187,7 +187,8 @@ int hso_set_pipeline(hso_ctx* ctx, int chunk, int streams);
 typedef struct {
   int32_t ref_level, search_level, type /* Feature::FeatureType: 0 corner, 1 edgelet, 2 gradient */, scale_patch;
   double px_ref[2], A_cur_ref[4], grad[2], px_cur[2];
-  float exposure_rat, pad_;
+  float exposure_rat;
+  float ncc_thresh;      /* checkNCC threshold; 0 = Matcher::findMatchDirect's 0.7 (matcher.cpp:366); findMatchSeed passes 0.8 (:510) */
 } hso_align_job;
 typedef struct {
   int32_t ok, align_converged;
@@ -286,6 +287,19 @@ typedef struct {
 /* px_error_angle: DepthFilter::px_error_angle_ = atan(px_noise / (2 focal_length)) * 2 (:360-365). align_max_iter: Matcher::Options (10). */
 int hso_depth_observe(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], int n_poses, const double* T_f_w, double px_error_angle,
                       int align_max_iter, int S, const hso_seed_obs* seeds, hso_seed_result* out);
+
+/* ---- a13b: seed reprojection — replaces the seed stage of Reprojector::reprojectMap (src/reprojector.cpp:309-328): Reprojector::reprojectorSeed
+ * (:531-552: project 1/mu * f of every unconverged-but-narrow seed into the frame, z < 0.001 and the 8-px frame test, grid cell), the per-cell
+ * ordering by Seed::sigma2 (seedComparator :346-349, std::list::sort is stable), Reprojector::reprojectorSeeds (:431-503: first seed of a cell
+ * that Matcher::findMatchSeed accepts) over grid_.cell_order until n_matches_ reaches Config::maxFts(), and the whole Matcher::findMatchSeed
+ * (src/matcher.cpp:442-518: parallax test cos < 0.5, warp matrix at depth 1/mu, search level, warpAffine, exposure scaling whenever
+ * |128 a - 128| > 30, align1D / align2D, checkNormal, checkNCC at 0.8, 20-px gate). The host keeps the seed list: it selects the seeds
+ * (sqrt(sigma2) < z_range / reproject_seed_thresh && !haveReprojected, :316), decides whether the stage runs at all (n_matches_ < 100) and
+ * creates the TYPE_TEMPORARY Points / Features from the results. Seeds use the record of row N3 (hso_seed_obs, above; exposure_rat = frame.m_exposure_time / seed frame's); results use
+ * hso_reproj_result (tried = findMatchSeed was called; matched = a Feature is created; order = position among the Features created by this
+ * stage). summary->n_matches = n_matches_ after the stage (n_matches_in + new), n_trials = findMatchSeed calls, used_cell_all = 0. ---- */
+int hso_reproject_seeds(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], int n_poses, const double* T_f_w, int S, const hso_seed_obs* seeds,
+                        const hso_reproj_grid* grid, const int32_t* cell_order, int n_matches_in, hso_reproj_result* out, hso_reproj_summary* summary);
 
 /* ---- F4: pose refinement — replaces void pose_optimizer::optimizeLevenbergMarquardt3rd(double reproj_thresh, size_t n_iter,
  * bool verbose, FramePtr&, double& scale, double& err_init, double& err_final, size_t& num_obs)

@@ -125,7 +125,7 @@ typedef struct {
   double grad[2];           /* ref feature gradient direction (edgelets) */
   double px_cur[2];         /* initial estimate, level 0 pixels */
   float exposure_rat;
-  float pad_;
+  float ncc_thresh;         /* checkNCC threshold; 0 = findMatchDirect's 0.7 (matcher.cpp:366); findMatchSeed: 0.8 (:510) */
 } orc_align_job;
 typedef struct {
   int32_t ok;               /* findMatchDirect's return value */
@@ -208,6 +208,21 @@ void orc_depth_observe(const orc_cam* cam, const double T_cur_w[12], int n_poses
                        const orc_seed_obs* seeds, int max_search_level, int align_max_iter, const uint8_t* const* const* ref_levels,
                        const uint8_t* const* cur_levels, const int* lw, const int* lh, const int16_t* const* cur_sobx, const int16_t* const* cur_soby,
                        orc_seed_result* out);
+
+/* ---- a13b: the seed stage of Reprojector::reprojectMap (src/reprojector.cpp:309-328,431-503,531-552) + Matcher::findMatchSeed
+ * (src/matcher.cpp:442-518). Seeds as orc_seed_obs, results as orc_reproj_result (see include/hso_b200.h, hso_reproject_seeds). */
+void orc_reproject_seeds(const orc_cam* cam, const double T_cur_w[12], int n_poses, const double* T_f_w, int S, const orc_seed_obs* seeds,
+                         const orc_reproj_grid* grid, const int32_t* cell_order, int n_matches_in, int max_search_level,
+                         const uint8_t* const* const* ref_levels, const uint8_t* const* cur_levels, const int* lw, const int* lh,
+                         const int16_t* const* cur_sobx, const int16_t* const* cur_soby, orc_reproj_result* out, orc_reproj_summary* summary);
+/* findMatchSeed for EVERY seed that entered a cell (what the CUDA path computes speculatively); px_after: the pixel findMatchSeed leaves. */
+void orc_reproject_seeds_speculative(const orc_cam* cam, const double T_cur_w[12], int n_poses, const double* T_f_w, int S, const orc_seed_obs* seeds,
+                                     const orc_reproj_grid* grid, int max_search_level, const uint8_t* const* const* ref_levels,
+                                     const uint8_t* const* cur_levels, const int* lw, const int* lh, const int16_t* const* cur_sobx,
+                                     const int16_t* const* cur_soby, orc_reproj_result* out, double* px_after);
+/* The walk alone (per-cell stable sort by sigma2, first accepted seed per cell, break at maxFts) with findMatchSeed's outcome supplied. */
+void orc_seed_select(int S, const orc_seed_obs* seeds, const uint8_t* match_ok, const orc_reproj_grid* grid, const int32_t* cell_order, int n_matches_in,
+                     orc_reproj_result* io, orc_reproj_summary* summary);
 
 /* ---- N4: undistortion maps (src/camera.cpp:47-54,223-265,317-363) and cv::remap INTER_LINEAR (:127-131,267-271,365-369) ---- */
 void orc_convert_maps(const float* mapx, const float* mapy, int n, int16_t* map1, uint16_t* map2);

@@ -302,7 +302,7 @@ void orc_match_direct_batch(int M, const orc_align_job* jobs, const uint8_t* con
       alignResult = orc_align2d(cur_levels[sl], lw[sl], lh[sl], lw[sl], patch_with_border_f_, patch_f_, align_max_iter, px_scaled, patchNCC);
       rs.align_converged = alignResult;
     }
-    if (alignResult) alignResult = orc_check_ncc(patch_f_, patchNCC, 0.7);
+    if (alignResult) alignResult = orc_check_ncc(patch_f_, patchNCC, jb.ncc_thresh > 0.f ? jb.ncc_thresh : 0.7);
     if (alignResult) {
       double dx = px_scaled_orig[0] - px_scaled[0], dy = px_scaled_orig[1] - px_scaled[1];
       alignResult = std::sqrt(dx * dx + dy * dy) < 20;

@@ -329,3 +329,195 @@ void orc_reproject_speculative(const orc_cam* cam, const double T_cur_w[12], int
 }
 
 }  // extern "C"
+
+// ---- a13b: seed stage of Reprojector::reprojectMap -------------------------------------------------------------------------------------------
+namespace {
+
+struct SeedCtx {
+  const orc_cam* cam;
+  SE3 T_cur_w;
+  std::vector<SE3> T_f_w;
+  const orc_seed_obs* seeds;
+  const uint8_t* const* const* ref_levels;
+  const uint8_t* const* cur_levels;
+  const int* lw; const int* lh;
+  const int16_t* const* cur_sobx; const int16_t* const* cur_soby;
+  int align_max_iter, max_search_level;
+  orc_reproj_result* out;
+};
+
+// Matcher::findMatchSeed — src/matcher.cpp:442-518
+bool find_match_seed(SeedCtx& m, int idx, double px_cur[2]) {
+  const orc_seed_obs& s = m.seeds[idx];
+  orc_reproj_result& r = m.out[idx];
+  const SE3& T_ref = m.T_f_w[s.ref_pose];
+  const SE3 T_ref_inv = T_ref.inverse();
+  const double inv_mu = 1.0 / s.mu;  // 1.0/seed.mu: float promoted to double
+  // compute parallax angle
+  const V3 seed_pos = T_ref_inv.apply(V3{inv_mu * s.f[0], inv_mu * s.f[1], inv_mu * s.f[2]});
+  V3 ref_dir = T_ref_inv.t - seed_pos;            // Frame::pos() = T_f_w_.inverse().translation()
+  { const double n = ref_dir.norm(); ref_dir = V3{ref_dir.x / n, ref_dir.y / n, ref_dir.z / n}; }  // Eigen normalize(): divides by the norm
+  V3 cur_dir = m.T_cur_w.inverse().t - seed_pos;
+  { const double n = cur_dir.norm(); cur_dir = V3{cur_dir.x / n, cur_dir.y / n, cur_dir.z / n}; }
+  const double cos_angle = ref_dir.dot(cur_dir);
+  if (cos_angle < 0.5) return false;
+  {
+    const int lv = s.level;
+    const int ox = (int)(s.px[0] / (1 << lv)), oy = (int)(s.px[1] / (1 << lv));
+    const int boundary = 4 + 2;
+    if (!(ox >= boundary && ox < m.cam->width / (1 << lv) - boundary && oy >= boundary && oy < m.cam->height / (1 << lv) - boundary)) return false;
+  }
+  const SE3 T_c_r = m.T_cur_w.mul(T_ref_inv);
+  double A[4];
+  {
+    const int halfpatch_size = 5;
+    const double depth_ref = 1. / s.mu;
+    const V3 xyz_ref{s.f[0] * depth_ref, s.f[1] * depth_ref, s.f[2] * depth_ref};
+    const int ratio = (1 << s.level);
+    double du[3], dv[3];
+    orc_cam2world(m.cam, s.px[0] + (double)(halfpatch_size * ratio), s.px[1], du);
+    orc_cam2world(m.cam, s.px[0], s.px[1] + (double)(halfpatch_size * ratio), dv);
+    const double sdu = xyz_ref.z / du[2], sdv = xyz_ref.z / dv[2];
+    const V3 xyz_du{du[0] * sdu, du[1] * sdu, du[2] * sdu}, xyz_dv{dv[0] * sdv, dv[1] * sdv, dv[2] * sdv};
+    const V3 a = T_c_r.apply(xyz_ref), b = T_c_r.apply(xyz_du), cc = T_c_r.apply(xyz_dv);
+    const double av[3] = {a.x, a.y, a.z}, bv[3] = {b.x, b.y, b.z}, cv[3] = {cc.x, cc.y, cc.z};
+    double pc[2], pu[2], pv[2];
+    orc_world2cam(m.cam, av, pc);
+    orc_world2cam(m.cam, bv, pu);
+    orc_world2cam(m.cam, cv, pv);
+    A[0] = (pu[0] - pc[0]) / halfpatch_size; A[2] = (pu[1] - pc[1]) / halfpatch_size;
+    A[1] = (pv[0] - pc[0]) / halfpatch_size; A[3] = (pv[1] - pc[1]) / halfpatch_size;
+  }
+  const int search_level = orc_get_best_search_level(A, m.max_search_level);
+  for (int k = 0; k < 4; ++k) r.A_cur_ref[k] = A[k];
+  r.search_level = search_level;
+  orc_align_job job;
+  std::memset(&job, 0, sizeof job);
+  job.ref_level = s.level; job.search_level = search_level; job.type = s.ftr_type;
+  job.scale_patch = std::fabs(s.exposure_rat * 128 - 128) > 30.0f ? 1 : 0;  // fabsf(exposure_rat*128 - 128) > LIGHT_THRESHOLD (:473), no keyframe-gap test
+  job.px_ref[0] = s.px[0]; job.px_ref[1] = s.px[1];
+  for (int k = 0; k < 4; ++k) job.A_cur_ref[k] = A[k];
+  job.grad[0] = s.grad[0]; job.grad[1] = s.grad[1];
+  job.px_cur[0] = px_cur[0]; job.px_cur[1] = px_cur[1];
+  job.exposure_rat = s.exposure_rat;
+  job.ncc_thresh = 0.8f;  // checkNCC(patch_f_, patchNCC, 0.8) (:510); the ncc_thresh argument of findMatchSeed is unused
+  orc_align_result res;
+  orc_match_direct_batch(1, &job, m.ref_levels[s.ref_frame], m.cur_levels, m.lw, m.lh, m.cur_sobx, m.cur_soby, m.align_max_iter, &res);
+  px_cur[0] = res.px_cur[0]; px_cur[1] = res.px_cur[1];
+  return res.ok != 0;
+}
+
+// Reprojector::reprojectorSeed — src/reprojector.cpp:531-552
+void reproject_seed_points(SeedCtx& m, const orc_cam* cam, const double T_cur_w[12], int n_poses, const double* T_f_w, int S, const orc_seed_obs* seeds,
+                           const orc_reproj_grid* grid, int max_search_level, const uint8_t* const* const* ref_levels, const uint8_t* const* cur_levels,
+                           const int* lw, const int* lh, const int16_t* const* cur_sobx, const int16_t* const* cur_soby, orc_reproj_result* out) {
+  m.cam = cam;
+  m.T_cur_w = SE3::from_rt(T_cur_w);
+  for (int k = 0; k < n_poses; ++k) m.T_f_w.push_back(SE3::from_rt(T_f_w + 12 * k));
+  m.seeds = seeds; m.ref_levels = ref_levels; m.cur_levels = cur_levels; m.lw = lw; m.lh = lh; m.cur_sobx = cur_sobx; m.cur_soby = cur_soby;
+  m.align_max_iter = grid->align_max_iter; m.max_search_level = max_search_level; m.out = out;
+  for (int i = 0; i < S; ++i) {
+    orc_reproj_result& r = out[i];
+    std::memset(&r, 0, sizeof r);
+    r.order = -1; r.cell = -1;
+    const orc_seed_obs& s = seeds[i];
+    const SE3 Tth = m.T_cur_w.mul(m.T_f_w[s.ref_pose].inverse());
+    const double inv_mu = 1.0 / s.mu;
+    const V3 pTarget = Tth.apply(V3{inv_mu * s.f[0], inv_mu * s.f[1], inv_mu * s.f[2]});
+    if (pTarget.z < 0.001) continue;
+    const double pt[3] = {pTarget.x, pTarget.y, pTarget.z};
+    double px[2];
+    orc_world2cam(cam, pt, px);
+    r.px[0] = px[0]; r.px[1] = px[1];
+    const int ox = (int)px[0], oy = (int)px[1];
+    if (ox >= 8 && ox < cam->width - 8 && oy >= 8 && oy < cam->height - 8) {
+      r.in_frame = 1;
+      r.cell = static_cast<int>(px[1] / grid->cell_size) * grid->n_cols + static_cast<int>(px[0] / grid->cell_size);
+    }
+  }
+}
+
+struct SeedCand { int idx; double px[2]; };
+
+// The seed loop of reprojectMap (src/reprojector.cpp:318-327) + Reprojector::reprojectorSeeds (:431-503); match plays findMatchSeed.
+template <class Match>
+void seed_walk(int S, const orc_seed_obs* seeds, const orc_reproj_grid* grid, const int32_t* cell_order, int n_matches_in, Match&& match,
+               orc_reproj_result* out, orc_reproj_summary* summary) {
+  const int n_cells = grid->n_cols * grid->n_rows;
+  std::vector<std::list<SeedCand>> cells(n_cells);
+  int n_in = 0;
+  for (int i = 0; i < S; ++i) {
+    if (!out[i].in_frame) continue;
+    ++n_in;
+    cells.at(out[i].cell).push_back(SeedCand{i, {out[i].px[0], out[i].px[1]}});
+  }
+  size_t n_matches = (size_t)n_matches_in, n_trials = 0;
+  int order = 0;
+  const size_t maxFts = (size_t)grid->max_fts;
+  auto seed_cmp = [&](const SeedCand& l, const SeedCand& r) { return seeds[l.idx].sigma2 < seeds[r.idx].sigma2; };  // seedComparator :346-349
+  auto reproject_seeds = [&](std::list<SeedCand>& sell) -> bool {
+    sell.sort(seed_cmp);
+    auto it = sell.begin();
+    while (it != sell.end()) {
+      ++n_trials;
+      out[it->idx].tried = 1;
+      const bool ok = match(it->idx, it->px);
+      out[it->idx].px[0] = it->px[0]; out[it->idx].px[1] = it->px[1];
+      if (ok) {
+        out[it->idx].matched = 1; out[it->idx].order = order++;
+        it = sell.erase(it);
+        return true;
+      }
+      ++it;
+    }
+    return false;
+  };
+  for (size_t i = 0; i < cells.size(); ++i) {
+    if (reproject_seeds(cells.at(cell_order[i]))) ++n_matches;
+    if (n_matches >= maxFts) break;
+  }
+  summary->n_in_frame = n_in;
+  summary->n_matches = (int)n_matches;
+  summary->n_trials = (int)n_trials;
+  summary->used_cell_all = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void orc_seed_select(int S, const orc_seed_obs* seeds, const uint8_t* match_ok, const orc_reproj_grid* grid, const int32_t* cell_order, int n_matches_in,
+                     orc_reproj_result* io, orc_reproj_summary* summary) {
+  for (int i = 0; i < S; ++i) { io[i].tried = 0; io[i].matched = 0; io[i].order = -1; }
+  seed_walk(S, seeds, grid, cell_order, n_matches_in, [&](int idx, double*) { return match_ok[idx] != 0; }, io, summary);
+}
+
+void orc_reproject_seeds(const orc_cam* cam, const double T_cur_w[12], int n_poses, const double* T_f_w, int S, const orc_seed_obs* seeds,
+                         const orc_reproj_grid* grid, const int32_t* cell_order, int n_matches_in, int max_search_level,
+                         const uint8_t* const* const* ref_levels, const uint8_t* const* cur_levels, const int* lw, const int* lh,
+                         const int16_t* const* cur_sobx, const int16_t* const* cur_soby, orc_reproj_result* out, orc_reproj_summary* summary) {
+  SeedCtx m;
+  reproject_seed_points(m, cam, T_cur_w, n_poses, T_f_w, S, seeds, grid, max_search_level, ref_levels, cur_levels, lw, lh, cur_sobx, cur_soby, out);
+  seed_walk(S, seeds, grid, cell_order, n_matches_in, [&](int idx, double* px) {
+    const bool ok = find_match_seed(m, idx, px);
+    out[idx].align_ok = ok ? 1 : 0;
+    return ok;
+  }, out, summary);
+}
+
+void orc_reproject_seeds_speculative(const orc_cam* cam, const double T_cur_w[12], int n_poses, const double* T_f_w, int S, const orc_seed_obs* seeds,
+                                     const orc_reproj_grid* grid, int max_search_level, const uint8_t* const* const* ref_levels,
+                                     const uint8_t* const* cur_levels, const int* lw, const int* lh, const int16_t* const* cur_sobx,
+                                     const int16_t* const* cur_soby, orc_reproj_result* out, double* px_after) {
+  SeedCtx m;
+  reproject_seed_points(m, cam, T_cur_w, n_poses, T_f_w, S, seeds, grid, max_search_level, ref_levels, cur_levels, lw, lh, cur_sobx, cur_soby, out);
+  for (int i = 0; i < S; ++i) {
+    px_after[2 * i] = out[i].px[0]; px_after[2 * i + 1] = out[i].px[1];
+    if (!out[i].in_frame) continue;
+    double px[2] = {out[i].px[0], out[i].px[1]};
+    out[i].align_ok = find_match_seed(m, i, px) ? 1 : 0;
+    px_after[2 * i] = px[0]; px_after[2 * i + 1] = px[1];
+  }
+}
+
+}  // extern "C"

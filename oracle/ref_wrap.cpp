@@ -430,6 +430,38 @@ void ref_find_match_batch(void* cur_handle, int n_kf, void* const* kf_handles, i
   }
 }
 
+// a13b with the seed record of rows N3 / a13b (orc_seed_obs): Matcher::findMatchSeed(seed, frame, px) with Seed{ftr = the feature (px, f, level,
+// type, grad) in keyframe kf_handles[ref_frame], mu}. px_io: the pixel Reprojector::reprojectorSeed computed in, the pixel findMatchSeed leaves out.
+void ref_find_match_seed_batch(void* cur_handle, int n_kf, void* const* kf_handles, int S, const orc_seed_obs* seeds, double* px_io /*2S*/,
+                               int32_t* ok_out, int32_t* search_level_out, double* A_out /*4S*/) {
+  FrameHandle* cur = (FrameHandle*)cur_handle;
+  Matcher matcher;
+  alignas(16) static unsigned char storage[sizeof(Seed)];  // findMatchSeed reads seed.ftr and seed.mu only; Seed's constructor lives in depth_filter.cpp
+  for (int i = 0; i < S; ++i) {
+    const orc_seed_obs& s = seeds[i];
+    ok_out[i] = 0; search_level_out[i] = 0;
+    for (int k = 0; k < 4; ++k) A_out[4 * i + k] = 0;
+    if (s.ref_frame < 0 || s.ref_frame >= n_kf) continue;
+    Frame* kf = ((FrameHandle*)kf_handles[s.ref_frame])->frame.get();
+    Feature obs(kf, Vector2d(s.px[0], s.px[1]), Vector3d(s.f[0], s.f[1], s.f[2]), s.level);
+    obs.type = (Feature::FeatureType)s.ftr_type;
+    obs.grad = Vector2d(s.grad[0], s.grad[1]);
+    std::memset(storage, 0, sizeof storage);
+    Seed* seed = reinterpret_cast<Seed*>(storage);
+    seed->ftr = &obs;
+    seed->mu = s.mu;
+    seed->sigma2 = s.sigma2;
+    matcher.A_cur_ref_.setZero();
+    Vector2d px(px_io[2 * i], px_io[2 * i + 1]);
+    const bool ok = matcher.findMatchSeed(*seed, *cur->frame, px);
+    px_io[2 * i] = px[0]; px_io[2 * i + 1] = px[1];
+    ok_out[i] = ok ? 1 : 0;
+    search_level_out[i] = matcher.search_level_;
+    A_out[4 * i] = matcher.A_cur_ref_(0, 0); A_out[4 * i + 1] = matcher.A_cur_ref_(0, 1);
+    A_out[4 * i + 2] = matcher.A_cur_ref_(1, 0); A_out[4 * i + 3] = matcher.A_cur_ref_(1, 1);
+  }
+}
+
 int ref_check_ncc(const float* p1, const float* p2, float thresh) {
   Matcher m;
   return m.checkNCC(const_cast<float*>(p1), const_cast<float*>(p2), thresh) ? 1 : 0;

@@ -28,7 +28,7 @@ class orc_track_params(C.Structure):
 class orc_align_job(C.Structure):
     _fields_ = [("ref_level", C.c_int32), ("search_level", C.c_int32), ("type", C.c_int32), ("scale_patch", C.c_int32),
                 ("px_ref", C.c_double * 2), ("A_cur_ref", C.c_double * 4), ("grad", C.c_double * 2), ("px_cur", C.c_double * 2),
-                ("exposure_rat", C.c_float), ("pad_", C.c_float)]
+                ("exposure_rat", C.c_float), ("ncc_thresh", C.c_float)]
 
 
 class orc_align_result(C.Structure):
@@ -460,3 +460,38 @@ def depth_observe(cam, T_cur_w, T_f_w, seeds, px_error_angle, ref_pyramids, cur_
     lib.orc_depth_observe(C.byref(cam_of(cam)), dp(T), Tk.size // 12, dp(Tk), C.c_double(px_error_angle), S, seeds, int(max_search_level),
                           int(align_max_iter), frames, curp, lw, lh, sxp, syp, out)
     return out
+
+
+# ---- a13b: seed stage of Reprojector::reprojectMap ------------------------------------------------------------------------------------
+def reproject_seeds(cam, T_cur_w, T_f_w, seeds, grid, cell_order, n_matches_in, max_search_level, ref_pyramids, cur_levels, cur_sobel):
+    """seeds: ctypes array of orc_seed_obs (ref_frame indexes ref_pyramids). Returns (results array, summary)."""
+    lib = load()
+    S = len(seeds)
+    T, Tk, frames, curp, lw, lh, sxp, syp, keep = _reproj_args(T_cur_w, T_f_w, ref_pyramids, cur_levels, cur_sobel)
+    order = np.ascontiguousarray(cell_order, np.int32)
+    out = (orc_reproj_result * max(S, 1))()
+    summ = orc_reproj_summary()
+    lib.orc_reproject_seeds(C.byref(cam_of(cam)), dp(T), Tk.size // 12, dp(Tk), S, seeds, C.byref(grid), order.ctypes.data_as(C.POINTER(C.c_int32)),
+                            int(n_matches_in), int(max_search_level), frames, curp, lw, lh, sxp, syp, out, C.byref(summ))
+    return out, summ
+
+
+def reproject_seeds_speculative(cam, T_cur_w, T_f_w, seeds, grid, max_search_level, ref_pyramids, cur_levels, cur_sobel):
+    lib = load()
+    S = len(seeds)
+    T, Tk, frames, curp, lw, lh, sxp, syp, keep = _reproj_args(T_cur_w, T_f_w, ref_pyramids, cur_levels, cur_sobel)
+    out = (orc_reproj_result * max(S, 1))()
+    px_after = np.zeros((max(S, 1), 2))
+    lib.orc_reproject_seeds_speculative(C.byref(cam_of(cam)), dp(T), Tk.size // 12, dp(Tk), S, seeds, C.byref(grid), int(max_search_level), frames, curp,
+                                        lw, lh, sxp, syp, out, dp(px_after))
+    return out, px_after
+
+
+def seed_select(seeds, match_ok, grid, cell_order, n_matches_in, io):
+    lib = load()
+    ok = np.ascontiguousarray(match_ok, np.uint8)
+    order = np.ascontiguousarray(cell_order, np.int32)
+    summ = orc_reproj_summary()
+    lib.orc_seed_select(len(seeds), seeds, ok.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(grid), order.ctypes.data_as(C.POINTER(C.c_int32)),
+                        int(n_matches_in), io, C.byref(summ))
+    return summ

@@ -281,6 +281,19 @@ def find_match_batch(cur, kfs, cands, px_init, seed_mode=False):
     return ok, px.reshape(M, 2), sl, A.reshape(M, 2, 2), hinv
 
 
+def find_match_seed_batch(cur, kfs, seeds, px_init):
+    """Matcher::findMatchSeed for every seed record (orc_seed_obs array). Returns ok, px, search_level, A."""
+    lib = load()
+    S = len(px_init)
+    px = np.ascontiguousarray(px_init, np.float64).reshape(-1).copy()
+    ok = np.zeros(S, np.int32)
+    sl = np.zeros(S, np.int32)
+    A = np.zeros(4 * S)
+    hh = (C.c_void_p * len(kfs))(*[k.h for k in kfs])
+    lib.ref_find_match_seed_batch(cur.h, len(kfs), hh, S, seeds, dp(px), ok.ctypes.data_as(C.c_void_p), sl.ctypes.data_as(C.c_void_p), dp(A))
+    return ok, px.reshape(S, 2), sl, A.reshape(S, 2, 2)
+
+
 def pose_optimize(cam, p, reproj_thresh=2.0, n_iter=12, blank=None):
     """optimizeLevenbergMarquardt3rd of the reference on a synth.make_pose_problem record."""
     lib = load()

@@ -200,3 +200,87 @@ def test_selection_kernel_random_grids_incl_first_cell_third_pass(oracle):
         assert (gsum.used_cell_all, gsum.n_matches, gsum.n_trials) == (1, osum.n_matches, osum.n_trials), trial
         assert [(got[i].tried, got[i].matched, got[i].order) for i in range(M)] == [(io[i].tried, io[i].matched, io[i].order) for i in range(M)], trial
     ctx.close()
+
+
+# ---- a13b: the seed stage of Reprojector::reprojectMap (src/reprojector.cpp:309-328) + Matcher::findMatchSeed (src/matcher.cpp:442-518) ------------
+def _seed_run(oracle, cam, seed, S, max_fts, gain, n_in=0):
+    s = synth.make_seed_reproject_scene(seed, cam, S=S, max_fts=max_fts, gain=gain)
+    c = s["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), materialize_sobel=True)
+    kf_ids, _, _ = ctx.upload_frames(s["kf_imgs"])
+    cur_id = ctx.upload_frames([s["cur_img"]])[0][0]
+    got, gsum = ctx.reproject_seeds(cur_id, s["T_cur_w"], s["T_f_w"], Context.seed_obs(s["seeds"], frame_ids=kf_ids), s["grid"], s["cell_order"], n_matches_in=n_in)
+    oc = (oracle.orc_seed_obs * S).from_buffer_copy(bytes(Context.seed_obs(s["seeds"])))
+    pyrs = [oracle.create_pyramid(im, 5)[0] for im in s["kf_imgs"]]
+    cl, _ = oracle.create_pyramid(s["cur_img"], 5)
+    sob = [oracle.sobel5(cl[l]) for l in range(3)]
+    g = oracle.orc_reproj_grid(*[s["grid"][k] for k in ("cell_size", "n_cols", "n_rows", "max_fts", "align_max_iter")], 0)
+    ctx.close()
+    return s, got, gsum, oc, g, pyrs, cl, sob
+
+
+@pytest.mark.parametrize("cam,S,max_fts,gain,n_in", [("icl", 2000, 200, 1.0, 0), ("icl", 800, 200, 1.3, 60), ("euroc", 1200, 120, 1.0, 90), ("tum_fov", 900, 200, 1.3, 0),
+                                                     ("icl", 500, 30, 1.0, 28)])
+def test_reproject_seeds_parity(oracle, cam, S, max_fts, gain, n_in):
+    """Three layers like row N1: (1) fp64 geometry of reprojectorSeed + the head of findMatchSeed, exact for the integers; (2) speculative
+    findMatchSeed outcome per seed (<= 0.5 % flips); (3) the per-cell sigma2 ordering + first-accepted-seed walk replayed by the oracle on the
+    device's own outcomes — tried / matched / order / counters exactly."""
+    s, got, gsum, oc, g, pyrs, cl, sob = _seed_run(oracle, cam, 61, S, max_fts, gain, n_in)
+    spec, px_after = oracle.reproject_seeds_speculative(s["cam"], s["T_cur_w"], s["T_f_w"], oc, g, 2, pyrs, cl, sob)
+    assert [got[i].in_frame for i in range(S)] == [spec[i].in_frame for i in range(S)]
+    assert [got[i].cell for i in range(S)] == [spec[i].cell for i in range(S)]
+    inf = [i for i in range(S) if spec[i].in_frame]
+    assert len(inf) > 0.5 * S
+    n_job = 0
+    for i in inf:
+        Ao, Ag = np.array(spec[i].A_cur_ref[:]), np.array(got[i].A_cur_ref[:])
+        if np.any(Ao != 0):
+            n_job += 1
+            assert np.allclose(Ag, Ao, rtol=1e-9, atol=1e-9) and got[i].search_level == spec[i].search_level, i
+        else:
+            assert not np.any(Ag != 0)
+    assert n_job > 0.8 * len(inf)
+    ok_g = np.array([got[i].align_ok for i in inf])
+    ok_o = np.array([spec[i].align_ok for i in inf])
+    assert 0.05 < ok_o.mean() < 0.99 and (ok_g != ok_o).mean() <= 0.005, (ok_g != ok_o).sum()
+    io = (oracle.orc_reproj_result * S)()
+    for i in range(S):
+        io[i].in_frame, io[i].cell = got[i].in_frame, got[i].cell
+    osum = oracle.seed_select(oc, np.array([got[i].align_ok for i in range(S)], np.uint8), g, s["cell_order"], n_in, io)
+    assert (gsum.n_matches, gsum.n_trials, gsum.n_in_frame, gsum.used_cell_all) == (osum.n_matches, osum.n_trials, osum.n_in_frame, 0)
+    assert [(got[i].tried, got[i].matched, got[i].order) for i in range(S)] == [(io[i].tried, io[i].matched, io[i].order) for i in range(S)]
+    assert gsum.n_matches <= max(max_fts, n_in + 1)
+    for i in inf:
+        if got[i].tried and got[i].align_ok and spec[i].align_ok:
+            assert np.hypot(got[i].px[0] - px_after[i, 0], got[i].px[1] - px_after[i, 1]) < 0.05
+        elif not got[i].tried:
+            assert abs(got[i].px[0] - spec[i].px[0]) < 1e-9 and abs(got[i].px[1] - spec[i].px[1]) < 1e-9
+
+
+def test_reproject_seeds_end_to_end_and_edges(oracle):
+    """Whole call vs whole oracle on a flip-free scene; S = 0; n_matches_in already at maxFts (the loop still visits the first cell)."""
+    for seed in range(70, 80):
+        S = 700
+        s, got, gsum, oc, g, pyrs, cl, sob = _seed_run(oracle, "icl", seed, S, 200, 1.0, 20)
+        spec, _ = oracle.reproject_seeds_speculative(s["cam"], s["T_cur_w"], s["T_f_w"], oc, g, 2, pyrs, cl, sob)
+        if any(got[i].align_ok != spec[i].align_ok for i in range(S)):
+            continue
+        exp, esum = oracle.reproject_seeds(s["cam"], s["T_cur_w"], s["T_f_w"], oc, g, s["cell_order"], 20, 2, pyrs, cl, sob)
+        assert (gsum.n_matches, gsum.n_trials, gsum.n_in_frame) == (esum.n_matches, esum.n_trials, esum.n_in_frame)
+        assert [(got[i].tried, got[i].matched, got[i].order) for i in range(S)] == [(exp[i].tried, exp[i].matched, exp[i].order) for i in range(S)]
+        break
+    else:
+        pytest.fail("no flip-free scene in 10 seeds")
+    c = s["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]), materialize_sobel=True)
+    kf_ids, _, _ = ctx.upload_frames(s["kf_imgs"])
+    cur_id = ctx.upload_frames([s["cur_img"]])[0][0]
+    arr = Context.seed_obs(s["seeds"], frame_ids=kf_ids)
+    out, summ = ctx.reproject_seeds(cur_id, s["T_cur_w"], s["T_f_w"], arr, s["grid"], s["cell_order"], n_matches_in=7, S=0)
+    assert summ.n_matches == 7 and summ.n_trials == 0
+    out, summ = ctx.reproject_seeds(cur_id, s["T_cur_w"], s["T_f_w"], arr, s["grid"], s["cell_order"], n_matches_in=200)
+    first = int(s["cell_order"][0])
+    assert all(out[i].tried == 0 for i in range(S) if out[i].cell != first) and summ.n_matches in (200, 201)
+    with pytest.raises(HsoError):
+        ctx.reproject_seeds(cur_id, s["T_cur_w"], s["T_f_w"], Context.seed_obs([dict(s["seeds"][0], ref_pose=99)], frame_ids=kf_ids), s["grid"], s["cell_order"])
+    ctx.close()

@@ -150,3 +150,39 @@ def test_find_match_direct_vs_reference(oracle, cam, M):
         k.close()
     cur.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("cam,S,gain", [("icl", 1200, 1.3), ("euroc", 800, 1.0)])
+def test_find_match_seed_vs_reference(oracle, cam, S, gain):
+    """hso_reproject_seeds' speculative per-seed outcome vs Matcher::findMatchSeed of the reference (a13b)."""
+    s = synth.make_seed_reproject_scene(43, cam, S=S, gain=gain)
+    c = s["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), materialize_sobel=True)
+    kf_ids, _, _ = ctx.upload_frames(s["kf_imgs"])
+    cur_id = ctx.upload_frames([s["cur_img"]])[0][0]
+    got, gsum = ctx.reproject_seeds(cur_id, s["T_cur_w"], s["T_f_w"], Context.seed_obs(s["seeds"], frame_ids=kf_ids), s["grid"], s["cell_order"])
+    kfs = [R.Frame(c, im, T, exposure_time=1.0, keyframe_id=1) for im, T in zip(s["kf_imgs"], s["T_f_w"])]
+    cur = R.Frame(c, s["cur_img"], s["T_cur_w"], exposure_time=gain, keyframe_id=9)
+    oc = (oracle.orc_seed_obs * S).from_buffer_copy(bytes(Context.seed_obs(s["seeds"])))
+    px0 = np.zeros((S, 2))
+    for i, sd in enumerate(s["seeds"]):
+        Tth = R.se3_mul(s["T_cur_w"], R.se3_inverse(s["T_f_w"][sd["ref_pose"]]))
+        P = Tth[:, :3] @ (np.asarray(sd["f"]) * (1.0 / float(np.float32(sd["mu"])))) + Tth[:, 3]
+        px0[i] = R.world2cam(c, P) if P[2] >= 0.001 else 0
+    ok, px, sl, A = R.find_match_seed_batch(cur, kfs, oc, px0)
+    n_job = flips = 0
+    for i in range(S):
+        if not got[i].in_frame:
+            continue
+        Ag = np.array(got[i].A_cur_ref[:]).reshape(2, 2)
+        if not np.any(Ag != 0):
+            assert ok[i] == 0
+            continue
+        n_job += 1
+        assert np.allclose(Ag, A[i], rtol=1e-7, atol=1e-7) and got[i].search_level == sl[i], i
+        flips += int(got[i].align_ok != ok[i])
+    assert n_job > 0.5 * S and flips <= 0.005 * n_job, (flips, n_job)
+    for k in kfs:
+        k.close()
+    cur.close()
+    ctx.close()

@@ -321,6 +321,99 @@ def test_a13_find_match_direct_reference_vs_restatement(cam, M, seed):
     cur.close()
 
 
+@pytest.mark.parametrize("cam,S,seed,gain", [("icl", 900, 31, 1.0), ("icl", 600, 32, 1.3), ("euroc", 600, 33, 1.0), ("tum_fov", 500, 34, 1.3)])
+def test_a13b_find_match_seed_reference_vs_restatement(cam, S, seed, gain):
+    """Matcher::findMatchSeed (src/matcher.cpp:442-518) of the reference vs the restatement for every seed Reprojector::reprojectorSeed
+    (src/reprojector.cpp:531-552) puts into the frame: return value, warp matrix, search level, final pixel."""
+    from hso_b200 import Context
+    s = synth.make_seed_reproject_scene(seed, cam, S=S, gain=gain)
+    c = s["cam"]
+    kfs = [R.Frame(c, im, T, exposure_time=1.0, keyframe_id=1) for im, T in zip(s["kf_imgs"], s["T_f_w"])]
+    cur = R.Frame(c, s["cur_img"], s["T_cur_w"], exposure_time=gain, keyframe_id=9)
+    oc = (O.orc_seed_obs * S).from_buffer_copy(bytes(Context.seed_obs(s["seeds"])))
+    pyrs = [O.create_pyramid(im, 5)[0] for im in s["kf_imgs"]]
+    cl, _ = O.create_pyramid(s["cur_img"], 5)
+    sob = [O.sobel5(cl[l]) for l in range(3)]
+    g = O.orc_reproj_grid(*[s["grid"][k] for k in ("cell_size", "n_cols", "n_rows", "max_fts", "align_max_iter")], 0)
+    spec, px_after = O.reproject_seeds_speculative(c, s["T_cur_w"], s["T_f_w"], oc, g, 2, pyrs, cl, sob)
+    px0 = np.array([[spec[i].px[0], spec[i].px[1]] for i in range(S)])
+    inf = [i for i in range(S) if spec[i].in_frame]
+    assert len(inf) > 0.5 * S
+    # the reprojection itself, through the reference's own SE3 and camera
+    for i in inf[:200]:
+        sd = s["seeds"][i]
+        Tth = R.se3_mul(s["T_cur_w"], R.se3_inverse(s["T_f_w"][sd["ref_pose"]]))
+        P = Tth[:, :3] @ (np.asarray(sd["f"]) * (1.0 / float(np.float32(sd["mu"])))) + Tth[:, 3]
+        assert np.abs(R.world2cam(c, P) - px0[i]).max() < 1e-6  # numpy 3x4 composition vs quaternion SE3
+    ok, px, sl, A = R.find_match_seed_batch(cur, kfs, oc, px0)
+    flips = n_job = 0
+    for i in inf:
+        Ao = np.array(spec[i].A_cur_ref[:]).reshape(2, 2)
+        if not np.any(Ao != 0):
+            assert ok[i] == 0  # parallax below 60 degrees' cosine or reference pixel at the border: returns before the warp
+            continue
+        n_job += 1
+        assert np.allclose(A[i], Ao, rtol=1e-9, atol=1e-9) and sl[i] == spec[i].search_level, i
+        if ok[i] != spec[i].align_ok:
+            flips += 1
+        elif ok[i]:
+            assert np.hypot(*(px[i] - px_after[i])) < 1e-3
+    assert n_job > 0.8 * len(inf) and flips <= max(1, 0.003 * n_job), (flips, n_job)
+    assert 0.08 < np.mean([spec[i].align_ok for i in inf]) < 0.99  # seeds with a wide depth interval reproject pixels off and fail
+    for k in kfs:
+        k.close()
+    cur.close()
+
+
+def _brute_force_seed_walk(sigma2, in_frame, cell, ok, n_cells, max_fts, cell_order, n_in):
+    S = len(sigma2)
+    tried, matched, order = np.zeros(S, int), np.zeros(S, int), -np.ones(S, int)
+    n, o, trials = n_in, 0, 0
+    for ci in range(n_cells):
+        members = sorted([i for i in range(S) if in_frame[i] and cell[i] == cell_order[ci]], key=lambda i: sigma2[i])  # stable, like list::sort
+        hit = False
+        for i in members:
+            trials += 1
+            tried[i] = 1
+            if ok[i]:
+                matched[i], order[i] = 1, o
+                o += 1
+                hit = True
+                break
+        if hit:
+            n += 1
+        if n >= max_fts:
+            break
+    return tried, matched, order, n, trials
+
+
+def test_a13b_seed_walk_matches_brute_force():
+    """The seed loop of reprojectMap + reprojectorSeeds (src/reprojector.cpp:318-327,431-503): the restatement's std::list walk against an
+    independent Python statement on random grids — sigma2 ties, n_matches_in at / above maxFts, empty cells."""
+    rng = np.random.default_rng(77)
+    for trial in range(300):
+        n_cols, n_rows = int(rng.integers(2, 9)), int(rng.integers(2, 8))
+        nc = n_cols * n_rows
+        S = int(rng.integers(1, 500))
+        max_fts = int(rng.integers(0, 80))
+        n_in = int(rng.integers(0, max_fts + 3))
+        seeds = (O.orc_seed_obs * S)()
+        sig = rng.choice(np.float32([0.001, 0.002, 0.004, 0.01, 0.05]), S)
+        for i in range(S):
+            seeds[i].sigma2 = float(sig[i])
+        in_frame = (rng.uniform(size=S) < 0.85).astype(np.int32)
+        cell = np.where(in_frame > 0, rng.integers(0, nc, S), -1).astype(np.int32)
+        ok = (rng.uniform(size=S) < rng.choice([0.1, 0.5, 0.9])).astype(np.uint8)
+        order = rng.permutation(nc).astype(np.int32)
+        io = (O.orc_reproj_result * S)()
+        for i in range(S):
+            io[i].in_frame, io[i].cell = int(in_frame[i]), int(cell[i])
+        summ = O.seed_select(seeds, ok, O.orc_reproj_grid(20, n_cols, n_rows, max_fts, 10, 0), order, n_in, io)
+        exp = _brute_force_seed_walk(sig, in_frame, cell, ok, nc, max_fts, order, n_in)
+        assert (summ.n_matches, summ.n_trials) == (exp[3], exp[4]), trial
+        assert [(io[i].tried, io[i].matched, io[i].order) for i in range(S)] == list(zip(exp[0], exp[1], exp[2])), trial
+
+
 # ---- a16, a17 ------------------------------------------------------------------------------------------------------------------------------
 def test_a17_robust_cost_reference_vs_restatement():
     """MADScaleEstimator::compute (src/vikit/robust_cost.cpp:67-74) = 1.4826 * nth_element(n / 2), HuberWeightFunction::value (:129-148, k = 1.345,
