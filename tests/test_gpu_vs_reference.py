@@ -80,7 +80,7 @@ def test_tracker_trace_vs_reference_functions(oracle, cam, F, ic):
 
 
 @pytest.mark.parametrize("ic", [False, True])
-@pytest.mark.parametrize("cam,F,min_level,n_iter", [("icl", 3000, 1, 50), ("icl", 500, 1, 50), ("icl", 1000, 0, 15)])
+@pytest.mark.parametrize("cam,F,min_level,n_iter", [("icl", 3000, 1, 50), ("icl", 1500, 1, 50), ("icl", 1000, 0, 15)])
 def test_tracker_full_run_vs_reference_run(cam, F, min_level, n_iter, ic):
     """hso_coarse_track vs CoarseTracker::run of the reference on the same frames (exposure ratio formed from the frames' statistics on both
     sides): final pose, exposure ratio, return value. Photoconsistent scenes only (the synthetic warp is a pinhole homography): on the
