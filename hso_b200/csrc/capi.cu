@@ -9,7 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -85,6 +87,79 @@ struct PinRing {
   }
 };
 
+// Host threads that flatten Feature lists to the device layout (track_stage_one). They live as long as the context (spawning eight threads per
+// call cost ~0.3 ms and, with one process per GPU, oversubscribed the host: 8 ranks x 8 workers on 32 cores). Size: HSO_FLATTEN_THREADS, else the
+// host's cores divided by the ranks sharing it (LOCAL_WORLD_SIZE, as torchrun exports it), capped at 8.
+class WorkerPool {
+ public:
+  typedef void (*Fn)(void* arg, int item);
+  ~WorkerPool() { stop(); }
+  int size() const { return (int)threads_.size(); }
+  void start(int n) {
+    if (!threads_.empty() || n <= 0) return;
+    for (int t = 0; t < n; ++t) threads_.emplace_back([this]() { loop(); });
+  }
+  void stop() {
+    { std::lock_guard<std::mutex> lk(m_); quit_ = true; }
+    cv_.notify_all();
+    for (auto& th : threads_) th.join();
+    threads_.clear();
+    quit_ = false;
+  }
+  // Runs fn(arg, i) for i in [0, n) on the pool, items handed out in order; returns at once. wait() blocks until all are done.
+  void submit(Fn fn, void* arg, int n) {
+    { std::lock_guard<std::mutex> lk(m_); fn_ = fn; arg_ = arg; n_ = n; next_.store(0); done_.store(0); ++gen_; }
+    cv_.notify_all();
+  }
+  void wait() {
+    // the caller helps: with no threads in the pool it simply runs everything inline
+    for (;;) {
+      const int i = next_.fetch_add(1, std::memory_order_relaxed);
+      if (i >= n_) break;
+      fn_(arg_, i);
+      done_.fetch_add(1, std::memory_order_release);
+    }
+    while (done_.load(std::memory_order_acquire) < n_) std::this_thread::yield();
+  }
+
+ private:
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&]() { return quit_ || gen_ != seen; });
+        if (quit_) return;
+        seen = gen_;
+      }
+      for (;;) {
+        const int i = next_.fetch_add(1, std::memory_order_relaxed);
+        if (i >= n_) break;
+        fn_(arg_, i);
+        done_.fetch_add(1, std::memory_order_release);
+      }
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  bool quit_ = false;
+  uint64_t gen_ = 0;
+  Fn fn_ = nullptr;
+  void* arg_ = nullptr;
+  int n_ = 0;
+  std::atomic<int> next_{0}, done_{0};
+};
+
+inline int flatten_threads_default() {
+  if (const char* e = getenv("HSO_FLATTEN_THREADS")) return std::max(0, std::min(64, atoi(e)));
+  int ranks = 1;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+  const int cores = (int)std::max(1u, std::thread::hardware_concurrency());
+  // one core stays with the rank's main thread (it issues the copies and launches)
+  return std::max(1, std::min(8, cores / ranks - 1));
+}
+
 struct FrameSlot {
   bool used = false;
   uint8_t* pyr = nullptr;
@@ -114,6 +189,7 @@ struct hso_ctx {
   DevBuf pyr_jobs_dev, pyr_counters, resize_tab_dev, stats_table;  // stats_table: [max_frames][2] floats, one D2H per read
   PinBuf pyr_jobs_host, stats_host;
   PinRing pyr_jobs_ring, t_jobs_ring;  // job records of the asynchronous (unsynchronised) entry points
+  WorkerPool pool;                     // flattening threads, started on first use
   std::vector<ResizeTabDev> resize_tabs;
   // tracker
   hso_track_params tprm;
@@ -853,31 +929,34 @@ struct StageWorkers {
   hso_ctx* ctx; const hso_track_job* jobs; int B;
   std::vector<int> bounds;    // chunk c = jobs [bounds[c], bounds[c + 1])
   std::vector<int> chunk_of;  // job -> chunk
-  std::atomic<int> next{0};
   std::vector<std::atomic<int>> done;
-  std::vector<std::thread> pool;
+  bool inline_only;
+  int inline_next = 0;
   StageWorkers(hso_ctx* c, const hso_track_job* j, int B_, const std::vector<int>& bounds_)
       : ctx(c), jobs(j), B(B_), bounds(bounds_), chunk_of(B_), done(bounds_.size() - 1) {
     for (auto& d : done) d.store(0);
     for (size_t k = 0; k + 1 < bounds.size(); ++k)
       for (int b = bounds[k]; b < bounds[k + 1]; ++b) chunk_of[b] = (int)k;
-    const int n_thr = (B >= 16) ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 0;
-    for (int t = 0; t < n_thr; ++t) pool.emplace_back([this]() { work(); });
-  }
-  void work() {
-    for (;;) {
-      const int b = next.fetch_add(1, std::memory_order_relaxed);
-      if (b >= B) return;
-      track_stage_one(ctx, jobs, b);
-      done[chunk_of[b]].fetch_add(1, std::memory_order_release);
+    inline_only = B < 16;  // a small batch is flattened by the caller's thread: waking the pool costs more than the work
+    if (!inline_only) {
+      if (ctx->pool.size() == 0) ctx->pool.start(flatten_threads_default());
+      ctx->pool.submit(&StageWorkers::item, this, B);
     }
+  }
+  static void item(void* self, int b) {
+    StageWorkers* w = (StageWorkers*)self;
+    track_stage_one(w->ctx, w->jobs, b);
+    w->done[w->chunk_of[b]].fetch_add(1, std::memory_order_release);
   }
   void wait_chunk(int c) {
     const int want = bounds[c + 1] - bounds[c];
-    if (pool.empty()) work();  // small batch: stage inline
+    if (inline_only) {
+      for (; inline_next < bounds[c + 1]; ++inline_next) item(this, inline_next);
+      return;
+    }
     while (done[c].load(std::memory_order_acquire) < want) std::this_thread::yield();
   }
-  ~StageWorkers() { for (auto& th : pool) th.join(); }
+  ~StageWorkers() { if (!inline_only) ctx->pool.wait(); }  // every job is staged (or being staged by the caller) before the records go away
 };
 
 int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_track_job* jobs, int trace_cap) {

@@ -64,6 +64,7 @@ HSO_DEV unsigned long long block_select(const unsigned long long* keys, const in
       uint32_t k;
       if (first) { k = total / 2; if (lane == 0) s->sel_n = total; }
       else k = s->sel_k;
+      __syncwarp();  // every lane has read sel_k before the lane that owns the bucket overwrites it (racecheck: read/write hazard inside the warp)
       const uint32_t excl = incl - local;
       if (total > 0 && k >= excl && k < incl) {
         uint32_t cum = excl;
