@@ -553,6 +553,7 @@ def main():
     ap.add_argument("--no-other-rows", action="store_true")
     ap.add_argument("--no-ic-dual", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--pageable-features", action="store_true", help="keep the feature arrays in pageable memory (host-side flattening path)")
     ap.add_argument("--parity-samples", type=int, default=16, help="problems of the timed batch whose final pose is checked against the oracle")
     args = ap.parse_args()
     claim_stdout()
@@ -604,10 +605,19 @@ def main():
     dev_ptrs = (C.c_void_p * B)(*[dev_cur[b].data_ptr() for b in range(B)])
     cur_ids_c = (C.c_int32 * B)(*cur_ids)
 
+    # the caller's feature arrays: one pinned blob per field for the whole batch ([B][F][2], [B][F][3], [B][F] doubles), the layout a batched
+    # caller keeps; pinned, they are DMA-copied as they are and flattened on the device (hso_track_set_direct_inputs, default auto)
+    if args.pageable_features:
+        px_all, f_all, dist_all = np.empty((B, F, 2)), np.empty((B, F, 3)), np.empty((B, F))
+    else:
+        px_all = torch.empty((B, F, 2), dtype=torch.float64).pin_memory().numpy()
+        f_all = torch.empty((B, F, 3), dtype=torch.float64).pin_memory().numpy()
+        dist_all = torch.empty((B, F), dtype=torch.float64).pin_memory().numpy()
     jobs = []
     for b, p in enumerate(probs):
+        px_all[b], f_all[b], dist_all[b] = p["px"], p["f"], p["dist"]
         a0 = float(np.float32(cur_int[b]) / np.float32(ref_int[b]))
-        jobs.append(dict(ref=ref_ids[b], cur=cur_ids[b], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=p["T0"], exposure_rat=a0))
+        jobs.append(dict(ref=ref_ids[b], cur=cur_ids[b], px=px_all[b], f=f_all[b], dist=dist_all[b], T_cur_ref=p["T0"], exposure_rat=a0))
 
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     levels = [4, 3, 2, 1]
@@ -703,7 +713,10 @@ def main():
         if ids_live is not cur_ids_c:
             C.memmove(cur_ids_c, ids_live, C.sizeof(cur_ids_c))  # later sections rebuild the frames these ids name
         nvalid = sum(int((p["dist"] >= 0).sum()) for p in probs)
-        h2d = B * W * H + sum(40 * max(32, (int((p["dist"] >= 0).sum()) + 31) // 32 * 32) for p in probs) + B * (96 + 4 + 96)
+        if args.pageable_features:  # flattened on the host: 5 doubles per feature with a depth (padded to 32 features)
+            h2d = B * W * H + sum(40 * max(32, (int((p["dist"] >= 0).sum()) + 31) // 32 * 32) for p in probs) + B * (96 + 4 + 96)
+        else:                       # direct: the caller's 6 doubles per feature as they are
+            h2d = B * W * H + 48 * B * F + B * (96 + 4 + 128)
         d2h = B * (C.sizeof(K.hso_track_result) + 8)  # results + {integralImage_, gradMean_}
         e2e = dict(ms=ms_e2e, steps=n_e2e_steps, iters=it_e2e, h2d=h2d, d2h=d2h)
 

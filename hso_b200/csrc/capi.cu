@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -202,6 +203,12 @@ struct hso_ctx {
   std::vector<size_t> t_trace_off;  // byte offset of each job's trace in the arena
   std::vector<size_t> t_goff;       // staging plan of the batch in flight (track_plan): byte offset of each job's geometry block
   size_t t_geo_bytes = 0;
+  // direct-input mode (pinned caller arrays are copied as they are and flattened on the device): -1 auto, 0 never, 1 always
+  int t_direct_mode = -1;
+  bool t_direct = false;           // decision for the batch in flight
+  DevBuf t_raw;                    // [px 2 sumF | f 3 sumF | dist sumF] doubles
+  std::vector<size_t> t_roff;      // features before job b in the raw arrays
+  size_t t_sumF = 0;
   // chunk pipeline of hso_add_frames_track_batch: H2D on its own stream, one event per chunk
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
@@ -503,7 +510,7 @@ void hso_destroy(hso_ctx* ctx) {
     if (s.sobel) cudaFree(s.sobel);
   }
   DevBuf* db[] = {&ctx->f_score, &ctx->f_rowbuf, &ctx->f_rowcount, &ctx->f_out, &ctx->f_total, &ctx->pyr_arena, &ctx->sums_arena, &ctx->stats_table, &ctx->pyr_jobs_dev, &ctx->pyr_counters, &ctx->resize_tab_dev, &ctx->t_arena, &ctx->t_jobs_dev, &ctx->t_T0, &ctx->t_a0,
-                  &ctx->t_out_dev, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->in_raw, &ctx->in_mid, &ctx->in_ptrs, &ctx->u_map1, &ctx->u_map2, &ctx->in_tab_blob, &ctx->d_arena, &ctx->r_arena, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
+                  &ctx->t_out_dev, &ctx->t_raw, &ctx->a_jobs_dev, &ctx->a_out_dev, &ctx->in_raw, &ctx->in_mid, &ctx->in_ptrs, &ctx->u_map1, &ctx->u_map2, &ctx->in_tab_blob, &ctx->d_arena, &ctx->r_arena, &ctx->p_arena, &ctx->p_jobs_dev, &ctx->p_out_dev};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ctx->f_out_host, &ctx->pyr_jobs_host, &ctx->stats_host, &ctx->t_stage_host, &ctx->t_jobs_host, &ctx->t_out_host,
                   &ctx->a_jobs_host, &ctx->a_out_host, &ctx->in_ptrs_host, &ctx->d_stage_host, &ctx->d_out_host, &ctx->r_stage_host, &ctx->r_out_host, &ctx->p_stage_host, &ctx->p_out_host};
@@ -758,6 +765,11 @@ int hso_set_pipeline(hso_ctx* ctx, int chunk, int streams) {
   ctx->pipe_chunk = chunk; ctx->pipe_n_streams = streams;
   return HSO_OK;
 }
+int hso_track_set_direct_inputs(hso_ctx* ctx, int mode) {
+  if (!ctx || mode < -1 || mode > 1) return HSO_ERR_INVALID;
+  ctx->t_direct_mode = mode;
+  return HSO_OK;
+}
 int hso_track_set_ic_dual(hso_ctx* ctx, int enable) {
   if (!ctx) return HSO_ERR_INVALID;
   ctx->t_no_dual = enable ? 0 : 1;
@@ -811,6 +823,27 @@ static int track_plan(hso_ctx* ctx, const hso_track_params* prm, int B, const hs
   }
   ctx->t_maxF = maxF;
   ctx->t_geo_bytes = arena;
+  // direct-input decision: pinned (or registered) caller arrays go to the device as they are, no host flattening pass
+  ctx->t_direct = false;
+  if (ctx->t_direct_mode != 0) {
+    bool pinned = ctx->t_direct_mode == 1;
+    if (!pinned) {
+      for (int b = 0; b < B && !pinned; ++b) {
+        if (jobs[b].n_features == 0) continue;
+        cudaPointerAttributes a0, a1, a2;
+        pinned = cudaPointerGetAttributes(&a0, jobs[b].px) == cudaSuccess && a0.type == cudaMemoryTypeHost &&
+                 cudaPointerGetAttributes(&a1, jobs[b].f) == cudaSuccess && a1.type == cudaMemoryTypeHost &&
+                 cudaPointerGetAttributes(&a2, jobs[b].dist) == cudaSuccess && a2.type == cudaMemoryTypeHost;
+        cudaGetLastError();  // an unregistered pointer is reported through the sticky-free error state on older drivers
+        break;               // the first non-empty job decides for the batch (a pageable array in a later job is still copied correctly, only slower)
+      }
+    }
+    ctx->t_direct = pinned;
+  }
+  ctx->t_roff.assign(B + 1, 0);
+  for (int b = 0; b < B; ++b) ctx->t_roff[b + 1] = ctx->t_roff[b] + (size_t)jobs[b].n_features;
+  ctx->t_sumF = ctx->t_roff[B];
+  if (ctx->t_direct) CU(ctx->t_raw.reserve(sizeof(double) * 6 * std::max<size_t>(ctx->t_sumF, 1)));
   // per-job scratch behind the geometry block
   std::vector<size_t> off_cache(B), off_gx(B), off_gy(B), off_abs(B), off_vis(B), off_state(B), off_trace(B);
   for (int b = 0; b < B; ++b) {
@@ -856,6 +889,14 @@ static int track_plan(hso_ctx* ctx, const hso_track_params* prm, int B, const hs
     d.vis = (uint8_t*)(dbase + off_vis[b]);
     d.state = (TrackState*)(dbase + off_state[b]);
     d.trace = ctx->t_trace_cap ? (hso_trace*)(dbase + off_trace[b]) : nullptr;
+    d.raw_px = d.raw_f = d.raw_dist = nullptr; d.n_raw = 0; d.pad_ = 0;
+    if (ctx->t_direct) {
+      const double* rb = (const double*)ctx->t_raw.p;
+      d.raw_px = rb + 2 * ctx->t_roff[b];
+      d.raw_f = rb + 2 * ctx->t_sumF + 3 * ctx->t_roff[b];
+      d.raw_dist = rb + 5 * ctx->t_sumF + ctx->t_roff[b];
+      d.n_raw = j.n_features;
+    }
   }
   return HSO_OK;
 }
@@ -907,6 +948,35 @@ static void track_stage_one(hso_ctx* ctx, const hso_track_job* jobs, int b) {
   a0[b] = j.exposure_rat;
 }
 
+// Direct-input mode: the caller's px / f / dist arrays of jobs [b0, b1) go to the device as they are. Arrays of consecutive jobs that are
+// adjacent in host memory (a caller that keeps a batch in one blob) travel in one copy per run.
+static int track_copy_raw(hso_ctx* ctx, const hso_track_job* jobs, int b0, int b1, cudaStream_t stream) {
+  double* rb = (double*)ctx->t_raw.p;
+  const size_t S = ctx->t_sumF;
+  const int B = ctx->tB;
+  double* T0 = (double*)((char*)ctx->t_stage_host.p + ctx->t_geo_bytes);
+  float* a0 = (float*)(T0 + 12 * B);
+  for (int b = b0; b < b1; ++b) {  // what track_stage_one records beside the geometry
+    memcpy(T0 + 12 * b, jobs[b].T_cur_ref, sizeof(double) * 12);
+    a0[b] = jobs[b].exposure_rat;
+  }
+  for (int arr = 0; arr < 3; ++arr) {
+    const size_t w = arr == 0 ? 2 : (arr == 1 ? 3 : 1);
+    double* dbase = rb + (arr == 0 ? 0 : (arr == 1 ? 2 * S : 5 * S));
+    auto ptr = [&](int b) { return arr == 0 ? jobs[b].px : (arr == 1 ? jobs[b].f : jobs[b].dist); };
+    int run0 = b0;
+    while (run0 < b1) {
+      if (jobs[run0].n_features == 0) { ++run0; continue; }
+      int run1 = run0 + 1;
+      size_t feats = (size_t)jobs[run0].n_features;
+      while (run1 < b1 && (jobs[run1].n_features == 0 || ptr(run1) == ptr(run0) + w * feats)) { feats += (size_t)jobs[run1].n_features; ++run1; }
+      CU(cudaMemcpyAsync(dbase + w * ctx->t_roff[run0], ptr(run0), sizeof(double) * w * feats, cudaMemcpyHostToDevice, stream));
+      run0 = run1;
+    }
+  }
+  return HSO_OK;
+}
+
 // H2D of the staged records of jobs [b0, b1) on `stream`.
 static int track_copy_range(hso_ctx* ctx, int b0, int b1, cudaStream_t stream) {
   const int B = ctx->tB, n = b1 - b0;
@@ -916,7 +986,7 @@ static int track_copy_range(hso_ctx* ctx, int b0, int b1, cudaStream_t stream) {
   float* a0 = (float*)(T0 + 12 * B);
   const size_t g0 = ctx->t_goff[b0], g1 = (b1 < B) ? ctx->t_goff[b1] : ctx->t_geo_bytes;
   const TrackJobDev* hj = (const TrackJobDev*)ctx->t_jobs_host.p;
-  CU(cudaMemcpyAsync(dbase + g0, hbase + g0, g1 - g0, cudaMemcpyHostToDevice, stream));
+  if (!ctx->t_direct) CU(cudaMemcpyAsync(dbase + g0, hbase + g0, g1 - g0, cudaMemcpyHostToDevice, stream));
   CU(cudaMemcpyAsync((double*)ctx->t_T0.p + 12 * b0, T0 + 12 * b0, sizeof(double) * 12 * n, cudaMemcpyHostToDevice, stream));
   CU(cudaMemcpyAsync((float*)ctx->t_a0.p + b0, a0 + b0, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
   CU(cudaMemcpyAsync((TrackJobDev*)ctx->t_jobs_dev.p + b0, hj + b0, sizeof(TrackJobDev) * n, cudaMemcpyHostToDevice, stream));
@@ -962,6 +1032,14 @@ struct StageWorkers {
 int hso_track_stage(hso_ctx* ctx, const hso_track_params* prm, int B, const hso_track_job* jobs, int trace_cap) {
   int rc = track_plan(ctx, prm, B, jobs, trace_cap);
   if (rc != HSO_OK) return rc;
+  if (ctx->t_direct) {
+    rc = track_copy_raw(ctx, jobs, 0, B, ctx->stream);
+    if (rc == HSO_OK) rc = track_copy_range(ctx, 0, B, ctx->stream);
+    if (rc != HSO_OK) return rc;
+    CU(launch_track_compact((TrackJobDev*)ctx->t_jobs_dev.p, B, ctx->stream, &ctx->launches));
+    CU(cudaStreamSynchronize(ctx->stream));  // the caller's arrays may change once this call returns
+    return HSO_OK;
+  }
   {
     StageWorkers w(ctx, jobs, B, std::vector<int>{0, B});
     w.wait_chunk(0);
@@ -978,10 +1056,14 @@ int hso_track_restage_frames(hso_ctx* ctx, int B, const hso_frame_id* ref, const
     hj[b].ref_pyr = get_frame(ctx, ref[b])->pyr;
     hj[b].cur_pyr = get_frame(ctx, cur[b])->pyr;
   }
+  // only the two pyramid pointers change: patch those 16 bytes of every device record (the rest — e.g. F, which the device wrote itself in
+  // direct-input mode — stays as it is)
+  static_assert(offsetof(TrackJobDev, ref_pyr) == 0 && offsetof(TrackJobDev, cur_pyr) == sizeof(void*), "pyramid pointers lead the record");
   void* region = nullptr;
-  CU(ctx->t_jobs_ring.acquire(sizeof(TrackJobDev) * B, &region));
-  memcpy(region, hj, sizeof(TrackJobDev) * B);
-  CU(cudaMemcpyAsync(ctx->t_jobs_dev.p, region, sizeof(TrackJobDev) * B, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->t_jobs_ring.acquire(2 * sizeof(void*) * B, &region));
+  const uint8_t** pp = (const uint8_t**)region;
+  for (int b = 0; b < B; ++b) { pp[2 * b] = hj[b].ref_pyr; pp[2 * b + 1] = hj[b].cur_pyr; }
+  CU(cudaMemcpy2DAsync(ctx->t_jobs_dev.p, sizeof(TrackJobDev), region, 2 * sizeof(void*), 2 * sizeof(void*), B, cudaMemcpyHostToDevice, ctx->stream));
   CU(ctx->t_jobs_ring.commit(ctx->stream));
   return HSO_OK;
 }
@@ -1230,16 +1312,22 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
       if (!one_copy && !(dbg & 2) && !(dbg & 4)) CU(cudaMemcpy2DAsync(s->pyr + ctx->geom.off[0], W, imgs[i], stride, W, H, cudaMemcpyHostToDevice, ctx->copy_stream));
       srcs[i] = s->pyr + ctx->geom.off[0];
     }
-    if (!workers) workers.reset(new StageWorkers(ctx, jobs.data(), B, bounds));
+    if (!ctx->t_direct && !workers) workers.reset(new StageWorkers(ctx, jobs.data(), B, bounds));
     rc = run_pyramid(ctx, n, new_ids + b0, srcs.data() + b0, W, 1, b0, ctx->copy_stream);
     if (rc != HSO_OK) return rc;
-    workers->wait_chunk(c);
+    if (ctx->t_direct) {
+      rc = (dbg & (2 | 8)) ? HSO_OK : track_copy_raw(ctx, jobs.data(), b0, b1, ctx->copy_stream);
+      if (rc != HSO_OK) return rc;
+    } else {
+      workers->wait_chunk(c);
+    }
     rc = (dbg & (2 | 8)) ? HSO_OK : track_copy_range(ctx, b0, b1, ctx->copy_stream);
     if (rc != HSO_OK) return rc;
     CU(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
     cudaStream_t cs = (c % S == 0) ? ctx->stream : ctx->pipe_streams[c % S - 1];
     CU(cudaStreamWaitEvent(cs, ctx->chunk_ev[c], 0));
     if (dbg & 1) continue;
+    if (ctx->t_direct) CU(launch_track_compact((TrackJobDev*)ctx->t_jobs_dev.p + b0, n, cs, &ctx->launches));
     CU(launch_pyramid(ctx->geom, (const PyrJobDev*)ctx->pyr_jobs_dev.p + b0, n, W, ctx->resize_tabs.data(), ctx->cfg.materialize_sobel,
                       (unsigned*)ctx->pyr_counters.p + b0, 1, cs, &ctx->launches));
     rc = track_run_range(ctx, b0, n, false, B, cs);

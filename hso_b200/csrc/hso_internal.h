@@ -81,6 +81,12 @@ struct TrackJobDev {
   hso_trace* trace;      // [trace_cap] or nullptr
   const float* ref_stats;  // device {integralImage_, gradMean_} of the two frames: the initial exposure ratio is formed on the device
   const float* cur_stats;  // when the caller passes exposure_rat < 0 (a = cur.integralImage_/ref.integralImage_, src/CoarseTracker.cpp:60)
+  // direct-input mode: the caller's own arrays as they were copied (px [n_raw][2], f [n_raw][3], dist [n_raw]); k_track_compact builds px / xyz / F
+  const double* raw_px;
+  const double* raw_f;
+  const double* raw_dist;
+  int n_raw;
+  int pad_;
 };
 
 struct TrackLevelParams {
@@ -103,6 +109,8 @@ cudaError_t launch_track_level(const TrackLevelParams& p, const TrackJobDev* job
                                uint64_t* launches);
 cudaError_t launch_track_init(const TrackJobDev* jobs_dev, const double* T0 /*[B][12]*/, const float* a0, int B, cudaStream_t stream,
                               uint64_t* launches);
+// Device-side flattening of the caller's feature arrays (direct-input mode): keeps the features with dist >= 0 in order, xyz = f * dist.
+cudaError_t launch_track_compact(TrackJobDev* jobs_dev, int B, cudaStream_t stream, uint64_t* launches);
 cudaError_t launch_track_finish(const TrackJobDev* jobs_dev, hso_track_result* out_dev, int B, cudaStream_t stream, uint64_t* launches);
 
 // ---- align --------------------------------------------------------------------------------------------------------------

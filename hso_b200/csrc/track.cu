@@ -1097,6 +1097,48 @@ __global__ void k_track_finish(const TrackJobDev* __restrict__ jobs, hso_track_r
   for (int k = 0; k < 8; ++k) o->cycles[k] = st->cycles[k];
 }
 
+// Direct-input mode: what track_stage_one does on the host (capi.cu), on the device. One CTA per job; features with a valid depth (dist >= 0)
+// are kept in order — a block-wide prefix scan per tile of 256 features — and xyz = f * dist is the same single IEEE fp64 multiplication as
+// Vector3d xyz_ref((*it_ft)->f*dist) (src/CoarseTracker.cpp:292): bit-identical to the host path.
+__global__ void __launch_bounds__(256) k_track_compact(TrackJobDev* __restrict__ jobs, int B) {
+  if ((int)blockIdx.x >= B) return;
+  const TrackJobDev job = jobs[blockIdx.x];
+  const int n = job.n_raw, Fp = job.Fpad;
+  double* px = const_cast<double*>(job.px);
+  double* xyz = const_cast<double*>(job.xyz);
+  __shared__ int s_warp[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int base = 0;
+  for (int tile = 0; tile < n; tile += 256) {
+    const int i = tile + (int)threadIdx.x;
+    double d = -1.0;
+    if (i < n) d = job.raw_dist[i];
+    const bool valid = d >= 0;  // NaN and negative distances are dropped, like if(!(d >= 0)) continue on the host
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    const int within = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; if (w < warp) before += c; total += c; }
+    if (valid) {
+      const int k = base + before + within;
+      px[k] = job.raw_px[2 * i]; px[Fp + k] = job.raw_px[2 * i + 1];
+      xyz[k] = job.raw_f[3 * i] * d; xyz[Fp + k] = job.raw_f[3 * i + 1] * d; xyz[2 * Fp + k] = job.raw_f[3 * i + 2] * d;
+    }
+    base += total;
+    __syncthreads();
+  }
+  for (int k = base + (int)threadIdx.x; k < Fp; k += 256) { px[k] = 0; px[Fp + k] = 0; xyz[k] = 0; xyz[Fp + k] = 0; xyz[2 * Fp + k] = 1; }
+  if (threadIdx.x == 0) jobs[blockIdx.x].F = base;
+}
+
+cudaError_t launch_track_compact(TrackJobDev* jobs_dev, int B, cudaStream_t stream, uint64_t* launches) {
+  k_track_compact<<<B, 256, 0, stream>>>(jobs_dev, B);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_track_init(const TrackJobDev* jobs_dev, const double* T0, const float* a0, int B, cudaStream_t stream, uint64_t* launches) {
   k_track_init<<<(B + 127) / 128, 128, 0, stream>>>(jobs_dev, T0, a0, B);
   ++*launches;

@@ -176,6 +176,11 @@ int hso_track_set_ic_dual(hso_ctx* ctx, int enable);
  * hso_coarse_track_batch on the same chunking. */
 int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B, const uint8_t* const* imgs, int W, int H, int stride,
                                const hso_track_job* jobs, hso_frame_id* new_ids, float* integral, float* grad_mean, hso_track_result* out);
+/* Where the feature arrays of a job (px, f, dist) are flattened to the device layout (features with dist >= 0 only, xyz = f * dist):
+ * -1 (default) on the device when the arrays are pinned / registered host memory — they are then DMA-copied as they are, arrays of consecutive
+ * jobs that are adjacent in memory in one copy — else by host threads into pinned staging; 0 always on the host; 1 always on the device.
+ * Both paths give bit-identical results (one IEEE fp64 multiplication per component). */
+int hso_track_set_direct_inputs(hso_ctx* ctx, int mode);
 /* Tuning knob of the call above: problems per chunk and number of compute streams the chunks rotate over (0 = default: 111, 3). */
 int hso_set_pipeline(hso_ctx* ctx, int chunk, int streams);
 

@@ -386,3 +386,53 @@ def test_relocalisation_pyramid_to_level0_slow_path(oracle, cam, F, ic):
     ro = tp.run(np.eye(4)[:3], a0, inverse_comp=ic, min_level=0, n_iter=15)
     assert np.abs(res[0]["T_cur_ref"] - ro["T_cur_ref"]).max() < 2e-4
     ctx.close()
+
+
+@pytest.mark.parametrize("ic", [False, True])
+def test_direct_input_mode_is_bit_identical_to_host_flattening(oracle, ic):
+    """Pinned caller arrays are DMA-copied as they are and flattened by k_track_compact (valid features in order, xyz = f * dist as one IEEE
+    multiplication); pageable ones are flattened by host threads. Same bits either way: two-call path and pipelined path, features without depth,
+    an empty job, NaN distances, and arrays of consecutive jobs adjacent in one blob (merged copies) as well as scattered ones."""
+    import torch
+    pairs = [synth.make_pair(300 + s, "icl", F=400 + 37 * s) for s in range(4)]
+    c = pairs[0]["cam"]
+    B = 20
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]), max_frames=3 * B + 16)
+    ref_ids, ref_int, _ = ctx.upload_frames([p["ref_img"] for p in pairs])
+    rng = np.random.default_rng(5)
+    Fs = [len(pairs[b % 4]["dist"]) for b in range(B)]
+    Fs[7] = 0  # a reference frame without features
+    tot = sum(Fs)
+    px_blob = torch.empty(tot * 2, dtype=torch.float64).pin_memory().numpy()
+    f_blob = torch.empty(tot * 3, dtype=torch.float64).pin_memory().numpy()
+    d_blob = torch.empty(tot, dtype=torch.float64).pin_memory().numpy()
+    jobs_pinned, jobs_page, o = [], [], 0
+    for b in range(B):
+        p = pairs[b % 4]
+        n = Fs[b]
+        dist = p["dist"][:n].copy()
+        if n:
+            dist[rng.uniform(size=n) < 0.1] = -1.0
+            dist[rng.integers(0, n)] = np.nan
+        px, f, d = px_blob[2 * o:2 * (o + n)].reshape(n, 2), f_blob[3 * o:3 * (o + n)].reshape(n, 3), d_blob[o:o + n]
+        px[:], f[:], d[:] = p["px"][:n], p["f"][:n], dist
+        o += n
+        T0 = synth.se3_exp(np.concatenate([rng.normal(0, 0.003, 3), rng.normal(0, 0.001, 3)]))[:3]
+        jobs_pinned.append(dict(ref=ref_ids[b % 4], px=px, f=f, dist=d, T_cur_ref=T0))
+        jobs_page.append(dict(ref=ref_ids[b % 4], px=px.copy(), f=f.copy(), dist=d.copy(), T_cur_ref=T0))
+    imgs = [pairs[b % 4]["cur_img"] for b in range(B)]
+    res = {}
+    for name, jobs, mode in (("host", jobs_page, 0), ("auto-pageable", jobs_page, -1), ("direct", jobs_pinned, -1), ("forced-direct-pageable", jobs_page, 1)):
+        ctx._chk(ctx.lib.hso_track_set_direct_inputs(ctx.h, mode))
+        ids, integ, gm, r = ctx.add_frames_track_batch(imgs, jobs, inverse_comp=ic)
+        two, _ = ctx.coarse_track_batch([dict(j, cur=ids[b], exposure_rat=-1.0) for b, j in enumerate(jobs)], inverse_comp=ic)
+        res[name] = (r, two)
+        for fid in ids:
+            ctx.release(fid)
+    base = res["host"][0]
+    for name, (r, two) in res.items():
+        for b in range(B):
+            assert np.array_equal(r[b]["T_cur_ref"], base[b]["T_cur_ref"]) and r[b]["n_iters"] == base[b]["n_iters"] and r[b]["n_tracked"] == base[b]["n_tracked"], (name, b)
+            assert np.array_equal(two[b]["T_cur_ref"], base[b]["T_cur_ref"]) and two[b]["exposure_rat"] == base[b]["exposure_rat"], (name, b)
+    assert base[7]["n_tracked"] == 0 and sum(r["n_tracked"] > 50 for r in base) >= B - 1
+    ctx.close()
