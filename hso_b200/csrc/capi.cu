@@ -1221,7 +1221,7 @@ int hso_coarse_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B, con
   for (int b = 0; b < B; ++b)
     if (jobs[b].n_features == 0) {
       memcpy(out[b].T_cur_ref, jobs[b].T_cur_ref, sizeof(double) * 12);
-      out[b].exposure_rat = jobs[b].exposure_rat;
+      if (jobs[b].exposure_rat >= 0) out[b].exposure_rat = jobs[b].exposure_rat;  // else: the ratio of the two frames' statistics, formed on the device
       out[b].n_tracked = 0;
     }
   return HSO_OK;
