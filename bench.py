@@ -347,16 +347,15 @@ def other_rows(ctx, lib, args, dev, torch, K):
     fbuf = (K.hso_corner * 65536)()
     fcnt = C.c_int()
 
-    def fast3():  # the C-ABI call itself with a caller-owned buffer (no Python list marshalling inside the timed loop)
-        n = 0
-        for l in range(3):
-            ctx._chk(lib.hso_fast_detect(ctx.h, fid[1], l, thr, 8, fbuf, 65536, C.byref(fcnt)))
-            n += fcnt.value
-        return n
+    fcnt3 = (C.c_int * 3)()
+
+    def fast3():  # the C-ABI call itself with a caller-owned buffer (no Python list marshalling inside the timed loop): levels 0..2 in one call
+        ctx._chk(lib.hso_fast_detect_levels(ctx.h, fid[1], 3, thr, 8, fbuf, 65536 // 3, fcnt3))
+        return sum(fcnt3)
     n_c = fast3()
     dt = timed(fast3, 20)
     row = {"gpu_frames_per_s_e2e": 1.0 / dt, "gpu_ms_per_frame": dt * 1e3, "corners_after_nonmax": n_c, "levels": "0..2", "threshold": thr,
-           "algorithmic_bytes_per_frame": int(W * H * (1 + 1 / 4 + 1 / 16)), "note": "hso_fast_detect x3 (one synchronous call per level) incl. D2H of the corner lists"}
+           "algorithmic_bytes_per_frame": int(W * H * (1 + 1 / 4 + 1 / 16)), "note": "hso_fast_detect_levels: levels 0..2 in one call (nine kernels back to back, one synchronisation) incl. D2H of the corner lists"}
     if O.ref_fast_available():
         lv, _ = O.create_pyramid(pair["cur_img"], 5)
         t0 = time.perf_counter()

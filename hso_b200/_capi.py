@@ -159,6 +159,8 @@ SYMBOLS = {
                                           _P(C.c_int32), _P(C.c_int32), _P(C.c_double), _P(C.c_double), _P(C.c_int8), _P(C.c_int8),
                                           _P(C.c_int8), _P(C.c_double), _P(C.c_uint8), _P(hso_pose_result)]),
     "hso_fast_detect": (C.c_int, [_vp, C.c_int32, C.c_int, C.c_int, C.c_int, _P(hso_corner), C.c_int, _P(C.c_int)]),
+    "hso_fast_detect_levels": (C.c_int, [_vp, C.c_int32, C.c_int, C.c_int, C.c_int, _P(hso_corner), C.c_int, _P(C.c_int)]),
+    "hso_stage_name": (C.c_char_p, [C.c_int]),
     "hso_stage_time_ms": (C.c_int, [_vp, C.c_int, _P(C.c_double), _P(C.c_uint64)]),
 }
 

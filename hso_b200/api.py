@@ -362,6 +362,15 @@ class Context:
             return self.fast_detect(fid, level, threshold, border, n.value)
         return [(out[i].x, out[i].y, out[i].score, out[i].shi_tomasi) for i in range(n.value)]
 
+    def fast_detect_levels(self, fid, n_levels, threshold, border=8, cap=32768):
+        """Levels 0 .. n_levels-1 in one call. Returns a list (per level) of [(x, y, score, shi_tomasi)]."""
+        out = (K.hso_corner * (cap * n_levels))()
+        cnt = (C.c_int * n_levels)()
+        self._chk(self.lib.hso_fast_detect_levels(self.h, int(fid), n_levels, int(threshold), border, out, cap, cnt))
+        if max(cnt) > cap:
+            return self.fast_detect_levels(fid, n_levels, threshold, border, max(cnt))
+        return [[(out[l * cap + i].x, out[l * cap + i].y, out[l * cap + i].score, out[l * cap + i].shi_tomasi) for i in range(cnt[l])] for l in range(n_levels)]
+
     def stage_time_ms(self, stage):
         ms, calls = C.c_double(), C.c_uint64()
         self._chk(self.lib.hso_stage_time_ms(self.h, stage, C.byref(ms), C.byref(calls)))

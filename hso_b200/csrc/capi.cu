@@ -171,6 +171,11 @@ struct FrameSlot {
 
 }  // namespace
 
+// Stage timers, named like the reference's HSO_START_TIMER sites (src/frame_handler_base.cpp:57-66) where one exists.
+enum { ST_PYRAMID = 0, ST_SPARSE_ALIGN = 1, ST_FEATURE_ALIGN = 2, ST_POSE_OPT = 3, ST_REPROJECT = 4, ST_DEPTH_FILTER = 5, ST_FEATURE_DETECT = 6, kStages = 7 };
+static const char* const kStageNames[kStages] = {"pyramid_creation", "sparse_img_align", "feature_align", "pose_optimizer", "reproject",
+                                                 "depth_filter_update", "feature_detection"};
+
 struct hso_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -242,9 +247,9 @@ struct hso_ctx {
   DevBuf a_jobs_dev, a_out_dev, p_arena, p_jobs_dev, p_out_dev;
   PinBuf a_jobs_host, a_out_host, p_stage_host, p_out_host;
   // stage timers
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double stage_ms[4] = {0, 0, 0, 0};
-  uint64_t stage_calls[4] = {0, 0, 0, 0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;  // ev2 / ev3: the alignment kernel nested inside a reprojection call
+  double stage_ms[kStages] = {0};
+  uint64_t stage_calls[kStages] = {0};
 };
 
 namespace {
@@ -426,7 +431,12 @@ struct StageTimer {
     cudaEventSynchronize(c->ev1);
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) { c->stage_ms[stage] += ms; c->stage_calls[stage]++; }
+    if (nested && cudaEventElapsedTime(&ms, c->ev2, c->ev3) == cudaSuccess) { c->stage_ms[ST_FEATURE_ALIGN] += ms; c->stage_calls[ST_FEATURE_ALIGN]++; }
   }
+  // "feature_align" runs inside "reproject" in the reference (src/reprojector.cpp:259-330): bracket the alignment kernel of a reprojection call
+  bool nested = false;
+  void align_begin() { cudaEventRecord(c->ev2, c->stream); }
+  void align_end() { cudaEventRecord(c->ev3, c->stream); nested = true; }
 };
 
 }  // namespace
@@ -473,7 +483,9 @@ int hso_create(int device, const hso_cam* cam, const hso_cfg* cfg_in, hso_ctx** 
   if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice");
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
   ctx->stream = ctx->own_stream;
-  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) return bail("cudaEventCreate");
+  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->ev2) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev3) != cudaSuccess)
+    return bail("cudaEventCreate");
   if (ctx->stats_table.reserve(sizeof(float) * 2 * ctx->cfg.max_frames) != cudaSuccess) return bail("cudaMalloc stats table");
   ctx->pyr_slot_bytes = (ctx->geom.bytes + 255) / 256 * 256;
   if (ctx->pyr_arena.reserve(ctx->pyr_slot_bytes * ctx->cfg.max_frames) != cudaSuccess) return bail("cudaMalloc pyramid arena (hso_cfg.max_frames too large?)");
@@ -519,6 +531,8 @@ void hso_destroy(hso_ctx* ctx) {
   for (cudaEvent_t e : ctx->t_ev) if (e) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+  if (ctx->ev3) cudaEventDestroy(ctx->ev3);
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
   for (cudaStream_t st : ctx->pipe_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -1453,7 +1467,7 @@ int hso_reproject_match(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12]
   }
   memcpy(h + o_T, T_f_w, sizeof(double) * 12 * n_poses);
   memcpy(h + o_co, cell_order, sizeof(int32_t) * n_cells);
-  StageTimer tm(ctx, 2);
+  StageTimer tm(ctx, ST_REPROJECT);
   CU(cudaMemcpyAsync(d, h, staged, cudaMemcpyHostToDevice, ctx->stream));
   ReprojKParams kp;
   memset(&kp, 0, sizeof kp);
@@ -1463,8 +1477,10 @@ int hso_reproject_match(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12]
   kp.n_poses = n_poses; kp.M = M; kp.cell_size = grid->cell_size; kp.n_cols = grid->n_cols; kp.max_search_level = max_search;
   CU(launch_reproject(kp, (const hso_reproj_cand*)(d + o_c), (const uint8_t* const*)(d + o_rp), (AlignJobDev*)(d + o_j),
                       (hso_reproj_result*)(d + o_res), ctx->stream, &ctx->launches));
+  tm.align_begin();
   CU(launch_align(ctx->geom, fc->pyr, fc->sobel, (const AlignJobDev*)(d + o_j), M, grid->align_max_iter, (hso_align_result*)(d + o_ar), ctx->stream,
                   &ctx->launches));
+  tm.align_end();
   ReprojSelParams sp;
   sp.M = M; sp.n_cells = n_cells; sp.max_fts = grid->max_fts;
   sp.n_sort = 2;
@@ -1533,7 +1549,7 @@ int hso_reproject_seeds(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12]
   }
   memcpy(h + o_T, T_f_w, sizeof(double) * 12 * n_poses);
   memcpy(h + o_co, cell_order, sizeof(int32_t) * n_cells);
-  StageTimer tm(ctx, 2);
+  StageTimer tm(ctx, ST_REPROJECT);
   CU(cudaMemcpyAsync(d, h, staged, cudaMemcpyHostToDevice, ctx->stream));
   ReprojKParams kp;
   memset(&kp, 0, sizeof kp);
@@ -1544,8 +1560,10 @@ int hso_reproject_seeds(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12]
   kp.max_search_level = std::min(ctx->cfg.n_pyr_levels, ctx->geom.n_levels) - 1;
   CU(launch_reproject_seed(kp, (const hso_seed_obs*)(d + o_s), (const uint8_t* const*)(d + o_rp), (AlignJobDev*)(d + o_j), (hso_reproj_result*)(d + o_res),
                            ctx->stream, &ctx->launches));
+  tm.align_begin();
   CU(launch_align(ctx->geom, fc->pyr, fc->sobel, (const AlignJobDev*)(d + o_j), S, grid->align_max_iter, (hso_align_result*)(d + o_ar), ctx->stream,
                   &ctx->launches));
+  tm.align_end();
   SeedSelParams sp;
   sp.S = S; sp.n_cells = n_cells; sp.max_fts = grid->max_fts; sp.n_matches_in = n_matches_in;
   sp.n_sort = 2;
@@ -1641,7 +1659,7 @@ int hso_depth_observe(hso_ctx* ctx, hso_frame_id cur, const double T_cur_w[12], 
     rp[i] = fr->pyr;
   }
   memcpy(h + o_T, T_f_w, sizeof(double) * 12 * n_poses);
-  StageTimer tm(ctx, 2);
+  StageTimer tm(ctx, ST_DEPTH_FILTER);
   CU(cudaMemcpyAsync(d, h, staged, cudaMemcpyHostToDevice, ctx->stream));
   DepthKParams kp;
   memset(&kp, 0, sizeof kp);
@@ -1757,6 +1775,7 @@ int hso_fast_detect(hso_ctx* ctx, hso_frame_id frame, int level, int threshold, 
   if (w < 7 || h < 7) return HSO_OK;  // fast_corner_detect_9_sse2 returns nothing (faster_corner_9_sse.cpp:246-250)
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
+  StageTimer tm(ctx, ST_FEATURE_DETECT);
   const size_t npx = (size_t)ctx->geom.w[0] * ctx->geom.h[0];
   CU(ctx->f_score.reserve(npx * sizeof(int16_t)));
   CU(ctx->f_rowbuf.reserve(npx * sizeof(uint32_t)));
@@ -1777,11 +1796,68 @@ int hso_fast_detect(hso_ctx* ctx, hso_frame_id frame, int level, int threshold, 
     memcpy(out, out_h, sizeof(hso_corner) * n);
   }
   *count = *total_h;
+  tm.stop_after_sync();
   return HSO_OK;
 }
 
+// FeatureExtractor::fastDetectMT runs the three pyramid levels on three host threads (src/feature_detection.cpp:498-514); here the nine kernels of
+// levels 0 .. n_levels-1 go out back to back and the corner lists come back with ONE synchronisation in the common case (the totals and the
+// first kSpec corners of every level travel together; a second copy fetches the rest of a level that found more).
+int hso_fast_detect_levels(hso_ctx* ctx, hso_frame_id frame, int n_levels, int threshold, int border, hso_corner* out, int cap_per_level, int* counts) {
+  if (!ctx || n_levels <= 0 || n_levels > 3 || n_levels > ctx->geom.n_levels || cap_per_level < 0 || (cap_per_level > 0 && !out) || !counts ||
+      threshold < 0 || threshold > 254)
+    return HSO_ERR_INVALID;
+  FrameSlot* f = get_frame(ctx, frame);
+  if (!f) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  StageTimer tm(ctx, ST_FEATURE_DETECT);
+  const int kSpec = std::min(cap_per_level, 4096);
+  const size_t npx = (size_t)ctx->geom.w[0] * ctx->geom.h[0];
+  CU(ctx->f_score.reserve(npx * sizeof(int16_t)));
+  CU(ctx->f_rowbuf.reserve(npx * sizeof(uint32_t)));
+  CU(ctx->f_rowcount.reserve(sizeof(int) * ctx->geom.h[0]));
+  CU(ctx->f_total.reserve(sizeof(int) * 4));
+  CU(ctx->f_out.reserve(sizeof(hso_corner) * (size_t)std::max(cap_per_level, 1) * n_levels));
+  CU(ctx->f_out_host.reserve(sizeof(hso_corner) * (size_t)std::max(cap_per_level, 1) * n_levels + 4 * sizeof(int)));
+  CU(cudaMemsetAsync(ctx->f_total.p, 0, sizeof(int) * 4, ctx->stream));
+  int* total_h = (int*)ctx->f_out_host.p;
+  hso_corner* out_h = (hso_corner*)(total_h + 4);
+  for (int l = 0; l < n_levels; ++l) {
+    const int w = ctx->geom.w[l], h = ctx->geom.h[l];
+    counts[l] = 0;
+    if (w < 7 || h < 7) continue;  // fast_corner_detect_9_sse2 returns nothing (faster_corner_9_sse.cpp:246-250)
+    CU(launch_fast(f->pyr + ctx->geom.off[l], w, h, threshold, border, (int16_t*)ctx->f_score.p, (uint32_t*)ctx->f_rowbuf.p, (int*)ctx->f_rowcount.p,
+                   (hso_corner*)ctx->f_out.p + (size_t)l * cap_per_level, cap_per_level, (int*)ctx->f_total.p + l, ctx->stream, &ctx->launches));
+    if (kSpec > 0)
+      CU(cudaMemcpyAsync(out_h + (size_t)l * cap_per_level, (hso_corner*)ctx->f_out.p + (size_t)l * cap_per_level, sizeof(hso_corner) * kSpec,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaMemcpyAsync(total_h, ctx->f_total.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  bool more = false;
+  for (int l = 0; l < n_levels; ++l) {
+    counts[l] = total_h[l];
+    const int n = std::min(total_h[l], cap_per_level);
+    if (n > kSpec) {
+      more = true;
+      CU(cudaMemcpyAsync(out_h + (size_t)l * cap_per_level + kSpec, (hso_corner*)ctx->f_out.p + (size_t)l * cap_per_level + kSpec,
+                         sizeof(hso_corner) * (n - kSpec), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  if (more) CU(cudaStreamSynchronize(ctx->stream));
+  for (int l = 0; l < n_levels; ++l) {
+    const int n = std::min(total_h[l], cap_per_level);
+    if (n > 0) memcpy(out + (size_t)l * cap_per_level, out_h + (size_t)l * cap_per_level, sizeof(hso_corner) * n);
+  }
+  tm.stop_after_sync();
+  return HSO_OK;
+}
+
+const char* hso_stage_name(int stage) { return (stage >= 0 && stage < kStages) ? kStageNames[stage] : nullptr; }
+
 int hso_stage_time_ms(hso_ctx* ctx, int stage, double* ms, uint64_t* calls) {
-  if (!ctx || stage < 0 || stage > 3) return HSO_ERR_INVALID;
+  if (!ctx || stage < 0 || stage >= kStages) return HSO_ERR_INVALID;
   if (ms) *ms = ctx->stage_ms[stage];
   if (calls) *calls = ctx->stage_calls[stage];
   return HSO_OK;

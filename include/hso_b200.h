@@ -336,10 +336,18 @@ typedef struct {
 } hso_corner;
 /* threshold = floor(minThresh_); border = 8 in the reference. count receives the number of corners found (may exceed cap: only cap are written). */
 int hso_fast_detect(hso_ctx* ctx, hso_frame_id frame, int level, int threshold, int border, hso_corner* out, int cap, int* count);
+/* Levels 0 .. n_levels-1 in one call (what FeatureExtractor::fastDetectMT does on three threads, feature_detection.cpp:498-514): out is
+ * [n_levels][cap_per_level], counts[l] the number of corners found on level l. One synchronisation when no level finds more than 4096 corners. */
+int hso_fast_detect_levels(hso_ctx* ctx, hso_frame_id frame, int n_levels, int threshold, int border, hso_corner* out, int cap_per_level, int* counts);
 
 /* ---- stage timers, named like the reference's HSO_START_TIMER sites (src/frame_handler_base.cpp:57-66) ------------------- */
-/* Accumulated device time in ms of: 0 "pyramid_creation", 1 "sparse_img_align", 2 "feature_align", 3 "pose_optimizer". */
+/* Accumulated device time in ms and number of calls of stage: 0 "pyramid_creation", 1 "sparse_img_align", 2 "feature_align" (the alignment kernel:
+ * hso_align_batch, and nested inside hso_reproject_match / hso_reproject_seeds as in src/reprojector.cpp:259-330), 3 "pose_optimizer",
+ * 4 "reproject" (whole hso_reproject_match / hso_reproject_seeds call), 5 "depth_filter_update" (hso_depth_observe; the reference logs it on
+ * the mapping thread), 6 "feature_detection" (hso_fast_detect*). "reproject_kfs" / "reproject_candidates" / "local_ba" / "tot_time" time host
+ * loops of the caller and stay there. hso_stage_name returns the name, NULL beyond the last stage. */
 int hso_stage_time_ms(hso_ctx* ctx, int stage, double* ms, uint64_t* calls);
+const char* hso_stage_name(int stage);
 
 #ifdef __cplusplus
 }

@@ -177,3 +177,14 @@ def test_host_make_depth_ref_matches_oracle(tmp_path):
     assert all(got[i] == -1.0 for i in forced) and (got[has == 0] == -1.0).all() and (got >= 0).sum() > 250
     ok = exp >= 0
     assert np.abs(got[ok] - exp[ok]).max() < 1e-12 * np.abs(exp[ok]).max() and np.abs(ref[ok] - exp[ok]).max() < 1e-12 * np.abs(exp[ok]).max()
+
+
+def test_stage_names_follow_the_reference_timers():
+    """hso_stage_name: the reference's HSO_START_TIMER names (src/frame_handler_base.cpp:57-66) for the stages that have one."""
+    from hso_b200 import _capi
+    lib = _capi.load()
+    names = [lib.hso_stage_name(i) for i in range(8)]
+    assert names[:5] == [b"pyramid_creation", b"sparse_img_align", b"feature_align", b"pose_optimizer", b"reproject"]
+    assert names[5] == b"depth_filter_update" and names[6] == b"feature_detection" and names[7] is None
+    ref = open(os.path.join(ROOT, "tests", "golden", "reference_timer_names.txt")).read().split()
+    assert all(n.decode() in ref for n in names[:5])

@@ -57,3 +57,20 @@ def test_fast_detect_small_cap_and_levels(oracle):
     lv, _ = oracle.create_pyramid(img, 5)
     assert [(x, y, s) for x, y, s, _ in ctx.fast_detect(ids[0], 4, 30)] == [(x, y, s) for x, y, s, _ in oracle.fast_detect(lv[4], 30)]
     ctx.close()
+
+
+def test_fast_detect_levels_equals_three_single_calls(oracle):
+    """hso_fast_detect_levels (levels 0..2 in one call, one synchronisation) == three hso_fast_detect calls, incl. a level with more corners than
+    the speculative first copy (4096) and a small cap."""
+    from hso_b200 import Context, make_cam, synth
+    c = synth.CAMS["icl"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]))
+    img = synth.texture(np.random.default_rng(9), c["width"], c["height"], contrast=70.0)
+    ids, _, _ = ctx.upload_frames([img])
+    for thr in (7, 25):
+        single = [ctx.fast_detect(ids[0], l, thr) for l in range(3)]
+        assert ctx.fast_detect_levels(ids[0], 3, thr) == single
+        assert ctx.fast_detect_levels(ids[0], 3, thr, cap=64) == single  # grows and retries
+        assert ctx.fast_detect_levels(ids[0], 2, thr) == single[:2]
+    assert len(ctx.fast_detect(ids[0], 0, 7)) > 4096
+    ctx.close()

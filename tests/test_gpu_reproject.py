@@ -284,3 +284,18 @@ def test_reproject_seeds_end_to_end_and_edges(oracle):
     with pytest.raises(HsoError):
         ctx.reproject_seeds(cur_id, s["T_cur_w"], s["T_f_w"], Context.seed_obs([dict(s["seeds"][0], ref_pose=99)], frame_ids=kf_ids), s["grid"], s["cell_order"])
     ctx.close()
+
+
+def test_stage_timers_of_a_reprojection_call(oracle):
+    """"reproject" times the whole call, "feature_align" the alignment kernel nested inside it (src/reprojector.cpp:96,259,330)."""
+    s = synth.make_reproject_scene(5, "icl", M=300)
+    c = s["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]), materialize_sobel=True)
+    kf_ids, _, _ = ctx.upload_frames(s["kf_imgs"])
+    cur_id = ctx.upload_frames([s["cur_img"]])[0][0]
+    ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], Context.reproj_cands(s["cands"], frame_ids=kf_ids), s["grid"], s["cell_order"])
+    ms_r, n_r = ctx.stage_time_ms(4)
+    ms_a, n_a = ctx.stage_time_ms(2)
+    ms_p, n_p = ctx.stage_time_ms(0)
+    assert n_r == 1 and n_a == 1 and n_p == 2 and 0 < ms_a < ms_r
+    ctx.close()
