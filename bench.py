@@ -34,6 +34,7 @@ from hso_b200 import synth  # noqa: E402
 BYTES_PER_PATCH_EVAL = {4: 88, 3: 132, 2: 132, 1: 200, 0: 180}
 BYTES_PER_PATCH_EVAL_IC = {4: 188, 3: 256, 2: 256, 1: 380, 0: 400}
 N_BASE = 12  # distinct synthetic scenes; problems cycle through them with different features / initial poses
+TRACK_CFG = dict(min_level=1, n_iter=50)  # set from --min-level / --n-iter; the CPU legs run the same settings
 
 
 def build_workload(B, F, cam, seed0, rank):
@@ -171,8 +172,8 @@ def cpu_frame(O, prob, ic):
         O.sobel5(cl[l])
     ci, _ = O.frame_stats(prob["cur_img"])
     tp = O.TrackProblem(prob["cam"], prob["_ref_levels"], cl, prob["px"], prob["f"], prob["dist"])
-    r = tp.run(prob["T0"], float(np.float32(ci) / np.float32(prob["_ref_integral"])), inverse_comp=ic, trace_cap=64)
-    return r["n_evals"] - 4  # evaluations minus one entry evaluation per level = LM trials
+    r = tp.run(prob["T0"], float(np.float32(ci) / np.float32(prob["_ref_integral"])), inverse_comp=ic, trace_cap=64, **TRACK_CFG)
+    return r["n_evals"] - (5 - TRACK_CFG["min_level"])  # evaluations minus one entry evaluation per level = LM trials
 
 
 def ref_frame(R, prob, ic):
@@ -180,7 +181,7 @@ def ref_frame(R, prob, ic):
     (pyramid, Sobel images, statistics: src/frame.cpp:45-96) then CoarseTracker::run(ref, cur) (src/CoarseTracker.cpp:51-208). The reference
     does not report its trial count; the step's LM iterations are counted by the oracle port on the same frames outside the timed region."""
     cur = R.Frame(prob["cam"], prob["cur_img"])
-    R.coarse_track(prob["_ref_frame"], cur, prob["T0"], inverse_comp=ic)
+    R.coarse_track(prob["_ref_frame"], cur, prob["T0"], inverse_comp=ic, **TRACK_CFG)
     cur.close()
     return 0
 
@@ -255,7 +256,7 @@ def reference_arm(args, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "frames_per_s": steps * n / tot_t,
             "config": {"workload": f"{args.cam} {probs[0]['cam']['width']}x{probs[0]['cam']['height']}, {args.patches} patches/frame, "
-                                   f"pyramid+stats then CoarseTracker L4->L1 n_iter=50 {'inverse-compositional' if args.ic else 'forward'}",
+                                   f"pyramid+stats then CoarseTracker L4->L{args.min_level} n_iter={args.n_iter} {'inverse-compositional' if args.ic else 'forward'}",
                        "sample": f"{n} frames per step"},
             "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": cores, "kind": kind,
                              "sample": f"{n} frames/step x {steps} steps, one frame per thread, {what}"},
@@ -283,6 +284,24 @@ def other_rows(ctx, lib, args, dev, torch, K):
         ctx.synchronize()
         return (time.perf_counter() - t0) / reps
 
+    peak, _src = measured_peak()
+
+    class Roof:
+        """Device time of a stage (CUDA events inside the library, hso_stage_time_ms) over a block of calls -> achieved algorithmic GB/s
+        against the measured HBM peak. These rows run one small problem per call: they are launch / latency bound, the fraction says so."""
+
+        def __init__(self, cx, stage):
+            self.cx, self.stage = cx, stage
+            self.ms0, self.n0 = cx.stage_time_ms(stage)
+
+        def done(self, bytes_per_call):
+            ms1, n1 = self.cx.stage_time_ms(self.stage)
+            calls = max(n1 - self.n0, 1)
+            dev_ms = (ms1 - self.ms0) / calls
+            ach = bytes_per_call / (dev_ms * 1e-3) / 1e9 if dev_ms > 0 else None
+            return {"bound": "hbm", "algorithmic_bytes_per_call": int(bytes_per_call), "device_ms_per_call": dev_ms, "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": (ach / peak) if ach else None, "stage": lib.hso_stage_name(self.stage).decode()}
+
     # ---- F1: pyramid + stats, 64 frames per call -------------------------------------------------------------------------------
     nb = 64
     imgs = [pair["cur_img"]] * nb
@@ -294,7 +313,9 @@ def other_rows(ctx, lib, args, dev, torch, K):
         ctx._chk(lib.hso_frame_upload_batch(ctx.h, nb, ptrs, W, H, W, ids, integ.ctypes.data_as(C.POINTER(C.c_float)), None))
         for i in range(nb):
             lib.hso_frame_release(ctx.h, ids[i])
+    rf = Roof(ctx, 0)
     dt = timed(up, 5)
+    roof_f1 = rf.done(nb * (W * H + (W * H) // 3))
     t0 = time.perf_counter()
     for _ in range(4):
         lv, _ = O.create_pyramid(pair["cur_img"], 5)
@@ -302,7 +323,7 @@ def other_rows(ctx, lib, args, dev, torch, K):
             O.sobel5(lv[l])
         O.frame_stats(pair["cur_img"])
     cpu = (time.perf_counter() - t0) / 4
-    out["frame_construction"] = {"gpu_frames_per_s_e2e": nb / dt, "cpu_frames_per_s_1core": 1.0 / cpu, "bytes_per_frame": W * H + (W * H) // 3,
+    out["frame_construction"] = {"gpu_frames_per_s_e2e": nb / dt, "cpu_frames_per_s_1core": 1.0 / cpu, "bytes_per_frame": W * H + (W * H) // 3, "roofline": roof_f1,
                                  "note": "hso_frame_upload_batch of 64 host images (H2D + k_pyr_tile + stats read-back) vs oracle pyramid+Sobel L0-L2+stats"}
     # ---- F3: 5000 candidates ------------------------------------------------------------------------------------------------------
     fid, _, _ = ctx.upload_frames([pair["ref_img"], pair["cur_img"]])
@@ -320,7 +341,9 @@ def other_rows(ctx, lib, args, dev, torch, K):
         a.exposure_rat = j["exposure_rat"]
     refs = (C.c_int32 * M)(*([fid[0]] * M))
     res = (K.hso_align_result * M)()
+    rf = Roof(ctx, 2)
     dt = timed(lambda: ctx._chk(lib.hso_align_batch(ctx.h, fid[1], M, arr, refs, 10, res)), 10)
+    roof_f3 = rf.done(M * (580 + 24))
     rl, _ = O.create_pyramid(pair["ref_img"], 5)
     cl, _ = O.create_pyramid(pair["cur_img"], 5)
     sob = [O.sobel5(cl[l]) for l in range(3)]
@@ -328,19 +351,21 @@ def other_rows(ctx, lib, args, dev, torch, K):
     O.match_direct_batch(jobs[:2000], rl, cl, sob)
     cpu = (time.perf_counter() - t0) / 2000
     out["align_batch"] = {"gpu_patches_per_s_e2e": M / dt, "cpu_patches_per_s_1core": 1.0 / cpu, "M": M, "ms_per_call": dt * 1e3,
-                          "algorithmic_bytes_per_patch": 580, "achieved_GBps": M * 580 / dt / 1e9,
+                          "algorithmic_bytes_per_patch": 580, "achieved_GBps_e2e": M * 580 / dt / 1e9, "roofline": roof_f3,
                           "note": "hso_align_batch (H2D jobs, k_align, D2H results) vs oracle match_direct_batch (python marshalling excluded from neither)"}
     # ---- F4: pose optimiser, 5000 features, 8 host frames; batch of 64 frames ----------------------------------------------------------
     probs = [synth.make_pose_problem(args.seed + 10 + i, args.cam, F=5000, K=8) for i in range(4)]
     batch = [probs[i % 4] for i in range(64)]
     pose_call, _ = ctx.pose_args(batch)  # flattened once; the timed call is hso_pose_optimize_batch itself on host buffers
+    rf = Roof(ctx, 3)
     dt = timed(pose_call, 5)
     t0 = time.perf_counter()
     trials = sum(O.pose_optimize(p)["n_trials_total"] for p in probs)
+    roof_f4 = rf.done(64 * 5000 * 72 * 2 * (trials / 4 + 2))  # 72 B per feature per pass, 2 passes per LM trial + the two scale / chi2 passes
     cpu = (time.perf_counter() - t0) / 4
     g = ctx.pose_optimize_batch(probs)
     out["pose_optimizer"] = {"gpu_frames_per_s_e2e": 64 / dt, "cpu_frames_per_s_1core": 1.0 / cpu, "features": 5000, "batch": 64,
-                             "lm_trials_per_frame": trials / 4, "gpu_trials_per_frame": sum(r["n_trials_total"] for r in g) / 4,
+                             "lm_trials_per_frame": trials / 4, "gpu_trials_per_frame": sum(r["n_trials_total"] for r in g) / 4, "roofline": roof_f4,
                              "note": "hso_pose_optimize_batch on flattened host arrays (H2D, k_pose_lm, D2H) vs oracle pose_optimize"}
     # ---- N2: FAST-9 detector on levels 0..2 of one frame (what fastDetectMT does per keyframe, feature_detection.cpp:498-514) ---------
     thr = 20
@@ -353,9 +378,11 @@ def other_rows(ctx, lib, args, dev, torch, K):
         ctx._chk(lib.hso_fast_detect_levels(ctx.h, fid[1], 3, thr, 8, fbuf, 65536 // 3, fcnt3))
         return sum(fcnt3)
     n_c = fast3()
+    rf = Roof(ctx, 6)
     dt = timed(fast3, 20)
+    roof_n2 = rf.done(int(W * H * (1 + 1 / 4 + 1 / 16)) * 3 + n_c * 12)  # image read by score + score map written / read + corners out
     row = {"gpu_frames_per_s_e2e": 1.0 / dt, "gpu_ms_per_frame": dt * 1e3, "corners_after_nonmax": n_c, "levels": "0..2", "threshold": thr,
-           "algorithmic_bytes_per_frame": int(W * H * (1 + 1 / 4 + 1 / 16)), "note": "hso_fast_detect_levels: levels 0..2 in one call (nine kernels back to back, one synchronisation) incl. D2H of the corner lists"}
+           "algorithmic_bytes_per_frame": int(W * H * (1 + 1 / 4 + 1 / 16)), "roofline": roof_n2, "note": "hso_fast_detect_levels: levels 0..2 in one call (nine kernels back to back, one synchronisation) incl. D2H of the corner lists"}
     if O.ref_fast_available():
         lv, _ = O.create_pyramid(pair["cur_img"], 5)
         t0 = time.perf_counter()
@@ -375,10 +402,12 @@ def other_rows(ctx, lib, args, dev, torch, K):
         cur_id = ctxs.upload_frames([sc["cur_img"]])[0][0]
         carr = Context.reproj_cands(sc["cands"], frame_ids=kf_ids)
         ctxs.reproject_match(cur_id, sc["T_cur_w"], sc["T_f_w"], carr, sc["grid"], sc["cell_order"])
+        rf = Roof(ctxs, 4)
         t0 = time.perf_counter()
         for _ in range(20):
             _, summ = ctxs.reproject_match(cur_id, sc["T_cur_w"], sc["T_f_w"], carr, sc["grid"], sc["cell_order"])
         dt = (time.perf_counter() - t0) / 20
+        roof_n1 = rf.done(3000 * (128 + 580 + 88))
         oc = (O.orc_reproj_cand * 3000).from_buffer_copy(bytes(Context.reproj_cands(sc["cands"])))
         pyrs = [O.create_pyramid(im, 5)[0] for im in sc["kf_imgs"]]
         cl2, _ = O.create_pyramid(sc["cur_img"], 5)
@@ -393,7 +422,7 @@ def other_rows(ctx, lib, args, dev, torch, K):
         cpu_all = time.perf_counter() - t0
         out["reproject_match"] = {"gpu_frames_per_s_e2e": 1.0 / dt, "gpu_ms_per_frame": dt * 1e3, "cpu_frames_per_s_1core": 1.0 / cpu,
                                   "cpu_ms_per_frame": cpu * 1e3, "cpu_ms_all_candidates": cpu_all * 1e3, "candidates": 3000, "max_fts": 200,
-                                  "gpu_matches": int(summ.n_matches), "gpu_trials": int(summ.n_trials), "cpu_trials": int(osum.n_trials),
+                                  "gpu_matches": int(summ.n_matches), "gpu_trials": int(summ.n_trials), "cpu_trials": int(osum.n_trials), "roofline": roof_n1,
                                   "note": "hso_reproject_match (H2D candidates, k_reproject + k_align on ALL candidates + k_reproj_select, D2H) vs the "
                                           "oracle's sequential walk, which stops at the first match per cell and so aligns only ~n_trials candidates; "
                                           "cpu_ms_all_candidates = the oracle aligning every candidate like the device does"}
@@ -414,10 +443,12 @@ def other_rows(ctx, lib, args, dev, torch, K):
             for i_ in ids_:
                 ctxi.release(i_)
         up_raw()
+        rf = Roof(ctxi, 0)
         t0 = time.perf_counter()
         for _ in range(5):
             up_raw()
         dt = (time.perf_counter() - t0) / 5
+        roof_n4 = rf.done(32 * (1280 * 1024 + 2 * cf["width"] * cf["height"] * 4 + cf["width"] * cf["height"] * 4 // 3))
         t0 = time.perf_counter()
         m1, m2 = O.init_undistort_maps(cf)
         t_maps = time.perf_counter() - t0
@@ -429,7 +460,7 @@ def other_rows(ctx, lib, args, dev, torch, K):
         cpu = (time.perf_counter() - t0) / 3
         out["raw_input"] = {"gpu_frames_per_s_e2e": 32 / dt, "gpu_ms_per_frame": dt * 1e3 / 32, "cpu_frames_per_s_1core": 1.0 / cpu, "raw": "1280x1024",
                             "frame": f"{cf['width']}x{cf['height']}", "bytes_per_frame": 1280 * 1024 + 2 * cf["width"] * cf["height"] * 4,
-                            "cpu_map_build_ms": t_maps * 1e3,
+                            "cpu_map_build_ms": t_maps * 1e3, "roofline": roof_n4,
                             "note": "hso_frame_upload_raw_batch (H2D raw + k_resize_u8 + k_remap_u8 + pyramid + stats read-back) vs the oracle's "
                                     "cv::resize + cv::remap restatement + pyramid + stats (scalar C, not OpenCV's SIMD)"}
         ctxi.close()
@@ -444,10 +475,12 @@ def other_rows(ctx, lib, args, dev, torch, K):
         cur_id = ctxd.upload_frames([sd["cur_img"]])[0][0]
         sarr = Context.seed_obs(sd["seeds"], frame_ids=kf_ids)
         ctxd.depth_observe(cur_id, sd["T_cur_w"], sd["T_f_w"], sarr, sd["px_error_angle"])
+        rf = Roof(ctxd, 5)
         t0 = time.perf_counter()
         for _ in range(20):
             gres = ctxd.depth_observe(cur_id, sd["T_cur_w"], sd["T_f_w"], sarr, sd["px_error_angle"])
         dt = (time.perf_counter() - t0) / 20
+        roof_n3 = rf.done(2000 * (48 + 64 + 60 * 81))  # seed record in / out + ~60 scan steps and KLT iterations of 81 B of level image each
         oc = (O.orc_seed_obs * 2000).from_buffer_copy(bytes(Context.seed_obs(sd["seeds"])))
         pyrs = [O.create_pyramid(im, 5)[0] for im in sd["kf_imgs"]]
         cl3, _ = O.create_pyramid(sd["cur_img"], 5)
@@ -457,79 +490,98 @@ def other_rows(ctx, lib, args, dev, torch, K):
             O.depth_observe(sd["cam"], sd["T_cur_w"], sd["T_f_w"], oc, sd["px_error_angle"], pyrs, cl3, sob3)
         cpu = (time.perf_counter() - t0) / 5
         out["depth_observe"] = {"gpu_seeds_per_s_e2e": 2000 / dt, "gpu_ms_per_frame": dt * 1e3, "cpu_seeds_per_s_1core": 2000 / cpu,
-                                "cpu_ms_per_frame": cpu * 1e3, "seeds": 2000, "updated": int(sum(gres[i].res == 1 for i in range(2000))),
+                                "cpu_ms_per_frame": cpu * 1e3, "seeds": 2000, "updated": int(sum(gres[i].res == 1 for i in range(2000))), "roofline": roof_n3,
                                 "note": "hso_depth_observe (H2D seeds, k_depth_observe, D2H results) vs the oracle's observeDepthRow on one core "
                                         "(the reference splits the seed list over 4 threads)"}
         ctxd.close()
     except Exception as e:
         out["depth_observe"] = {"error": repr(e)}
+    # ---- a13b: seed stage of reprojectMap, 2000 seeds -----------------------------------------------------------------------------------------
+    try:
+        from hso_b200 import Context, make_cam
+        ss = synth.make_seed_reproject_scene(args.seed + 50, args.cam, S=2000, max_fts=200)
+        ctxs2 = Context(make_cam(W, H, c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), device=dev.index, max_frames=8, materialize_sobel=True)
+        kf_ids, _, _ = ctxs2.upload_frames(ss["kf_imgs"])
+        cur_id = ctxs2.upload_frames([ss["cur_img"]])[0][0]
+        sarr = Context.seed_obs(ss["seeds"], frame_ids=kf_ids)
+        ctxs2.reproject_seeds(cur_id, ss["T_cur_w"], ss["T_f_w"], sarr, ss["grid"], ss["cell_order"], n_matches_in=40)
+        rf = Roof(ctxs2, 4)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            _, ssum = ctxs2.reproject_seeds(cur_id, ss["T_cur_w"], ss["T_f_w"], sarr, ss["grid"], ss["cell_order"], n_matches_in=40)
+        dt = (time.perf_counter() - t0) / 20
+        roof_s = rf.done(2000 * (96 + 580 + 88))
+        oc = (O.orc_seed_obs * 2000).from_buffer_copy(bytes(Context.seed_obs(ss["seeds"])))
+        pyrs = [O.create_pyramid(im, 5)[0] for im in ss["kf_imgs"]]
+        cl4, _ = O.create_pyramid(ss["cur_img"], 5)
+        sob4 = [O.sobel5(cl4[l]) for l in range(3)]
+        og = O.orc_reproj_grid(*[ss["grid"][k] for k in ("cell_size", "n_cols", "n_rows", "max_fts", "align_max_iter")], 0)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            _, osum = O.reproject_seeds(ss["cam"], ss["T_cur_w"], ss["T_f_w"], oc, og, ss["cell_order"], 40, 2, pyrs, cl4, sob4)
+        cpu = (time.perf_counter() - t0) / 10
+        out["reproject_seeds"] = {"gpu_ms_per_frame": dt * 1e3, "cpu_ms_per_frame": cpu * 1e3, "seeds": 2000, "gpu_matches": int(ssum.n_matches),
+                                  "gpu_trials": int(ssum.n_trials), "cpu_trials": int(osum.n_trials), "roofline": roof_s,
+                                  "note": "hso_reproject_seeds (k_reproject_seed + k_align on ALL seeds + k_seed_select) vs the oracle's sequential walk"}
+        ctxs2.close()
+    except Exception as e:
+        out["reproject_seeds"] = {"error": repr(e)}
     for f_ in fid:
         ctx.release(f_)
     return out
 
 
 def single_stream(args, device, torch):
-    """The reference's real operating point: ONE stream, ~200 features per frame (Config::maxFts), one frame at a time through the
-    synchronous C-ABI calls (upload + track), beside the single-threaded CPU oracle on the same frames."""
-    from hso_b200 import Context, make_cam
+    """The reference's real operating point: ONE stream, one frame at a time through the synchronous C-ABI — at ~200 features per frame
+    (Config::maxFts) and at the metric's 3000 patches — beside the single-threaded CPU implementation on the same frames. Per mode and patch
+    count: ms per frame through hso_add_frames_track_batch(B = 1) with argument records built once (as a C++ caller holding long-lived Frame /
+    Feature objects would), LM trials per frame, microseconds per LM trial (the latency floor of a serial trial sequence), the CPU's ms per frame
+    on one core and the ratio."""
+    from hso_b200 import Context, make_cam, _capi as K
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    probs = build_workload(8, 200, args.cam, args.seed + 99, 0)
-    c = probs[0]["cam"]
-    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), device=device, max_frames=8)
     out = {}
-    for mode, ic in (("forward", False), ("inverse-compositional", True)):
-        def frame(p):
-            ids, integ, _ = ctx.upload_frames([p["cur_img"]])
-            job = dict(ref=p["_rid"], cur=ids[0], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=p["T0"],
-                       exposure_rat=float(np.float32(integ[0]) / np.float32(p["_rint"])))
-            res, _ = ctx.coarse_track_batch([job], inverse_comp=ic)
-            ctx.release(ids[0])
-            return res[0]["n_iters"]
-        use = probs[:6]  # 6 resident reference frames + 1 current frame <= 8 slots
-        for p in use:
-            if "_rid" not in p:
-                ids, integ, _ = ctx.upload_frames([p["ref_img"]])
-                p["_rid"], p["_rint"] = ids[0], integ[0]
-        for p in use:
-            frame(p)
-        t0 = time.perf_counter()
-        its = 0
-        reps = 20
-        for _ in range(reps):
-            for p in use:
-                its += frame(p)
-        dt = time.perf_counter() - t0
-        it_c, dt_c, _ = run_cpu(use, ic, 1)
-        # the same frames through ONE C-ABI call per frame (hso_add_frames_track_batch, B = 1) with argument records built once, as a C++
-        # caller holding long-lived Frame / Feature objects would: no Python marshalling inside the timed loop
-        from hso_b200 import _capi as K
-        prm = K.hso_track_params(int(ic), 4, 1, 50)
-        recs = []
-        for p in use:
-            jarr, keep = ctx._track_jobs([dict(ref=p["_rid"], cur=0, px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=p["T0"], exposure_rat=-1.0)])
-            img = np.ascontiguousarray(p["cur_img"])
-            recs.append((jarr, keep, img, (C.c_void_p * 1)(img.ctypes.data)))
-        nid, res1 = (C.c_int32 * 1)(), (K.hso_track_result * 1)()
-        Wc, Hc = c["width"], c["height"]
+    for F in (200, args.patches):
+        probs = build_workload(6, F, args.cam, args.seed + 99, 0)
+        c = probs[0]["cam"]
+        ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), device=device, max_frames=8,
+                      max_features=max(8192, F))
+        row = {}
+        for mode, ic in (("forward", False), ("inverse-compositional", True)):
+            for p in probs:
+                if "_rid" not in p:
+                    ids, integ, _ = ctx.upload_frames([p["ref_img"]])
+                    p["_rid"], p["_rint"] = ids[0], integ[0]
+            prm = K.hso_track_params(int(ic), 4, args.min_level, args.n_iter)
+            recs = []
+            for p in probs:
+                jarr, keep = ctx._track_jobs([dict(ref=p["_rid"], cur=0, px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=p["T0"], exposure_rat=-1.0)])
+                img = np.ascontiguousarray(p["cur_img"])
+                recs.append((jarr, keep, img, (C.c_void_p * 1)(img.ctypes.data)))
+            nid, res1 = (C.c_int32 * 1)(), (K.hso_track_result * 1)()
+            Wc, Hc = c["width"], c["height"]
 
-        def frame1(r):
-            ctx._chk(ctx.lib.hso_add_frames_track_batch(ctx.h, C.byref(prm), 1, r[3], Wc, Hc, Wc, r[0], nid, None, None, res1))
-            ctx.lib.hso_frame_release(ctx.h, nid[0])
-            return res1[0].n_iters
-        for r in recs:
-            frame1(r)
-        t0 = time.perf_counter()
-        its1 = 0
-        for _ in range(reps):
+            def frame1(r):
+                ctx._chk(ctx.lib.hso_add_frames_track_batch(ctx.h, C.byref(prm), 1, r[3], Wc, Hc, Wc, r[0], nid, None, None, res1))
+                ctx.lib.hso_frame_release(ctx.h, nid[0])
+                return res1[0].n_iters
             for r in recs:
-                its1 += frame1(r)
-        dt1 = time.perf_counter() - t0
-        out[mode] = {"gpu_frames_per_s": reps * len(use) / dt, "gpu_ms_per_frame": 1e3 * dt / (reps * len(use)), "gpu_iterations_per_s": its / dt,
-                     "gpu_ms_per_frame_single_call": 1e3 * dt1 / (reps * len(use)), "gpu_frames_per_s_single_call": reps * len(use) / dt1,
-                     "single_call_iterations": its1, "two_call_iterations": its,
-                     "cpu_frames_per_s_1core": len(use) / dt_c, "cpu_ms_per_frame": 1e3 * dt_c / len(use), "features": 200}
-    ctx.close()
+                frame1(r)
+            reps = 20 if F <= 500 else 8
+            t0 = time.perf_counter()
+            its = 0
+            for _ in range(reps):
+                for r in recs:
+                    its += frame1(r)
+            dt = time.perf_counter() - t0
+            n_fr = reps * len(recs)
+            it_c, dt_c, kind = run_cpu(probs, ic, 1)
+            row[mode] = {"gpu_ms_per_frame": 1e3 * dt / n_fr, "gpu_frames_per_s": n_fr / dt, "gpu_iterations_per_s": its / dt,
+                         "lm_trials_per_frame": its / n_fr, "gpu_us_per_lm_trial": 1e6 * dt / max(its, 1),
+                         "cpu_ms_per_frame_1core": 1e3 * dt_c / len(probs), "cpu_kind": kind, "speedup_vs_1core": (dt_c / len(probs)) / (dt / n_fr)}
+        for p in probs:
+            p.pop("_rid", None)
+        ctx.close()
+        out[f"F={F}"] = row
     return out
 
 # ---------------------------------------------------------------------------------------------------------------------------
@@ -551,11 +603,14 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-rows", action="store_true")
     ap.add_argument("--no-ic-dual", action="store_true")
+    ap.add_argument("--min-level", type=int, default=1, help="lowest pyramid level (0 = the reference's relocalisation setting, with --n-iter 15)")
+    ap.add_argument("--n-iter", type=int, default=50)
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--pageable-features", action="store_true", help="keep the feature arrays in pageable memory (host-side flattening path)")
     ap.add_argument("--parity-samples", type=int, default=16, help="problems of the timed batch whose final pose is checked against the oracle")
     args = ap.parse_args()
     claim_stdout()
+    TRACK_CFG.update(min_level=args.min_level, n_iter=args.n_iter)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -619,7 +674,7 @@ def main():
         jobs.append(dict(ref=ref_ids[b], cur=cur_ids[b], px=px_all[b], f=f_all[b], dist=dist_all[b], T_cur_ref=p["T0"], exposure_rat=a0))
 
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
-    levels = [4, 3, 2, 1]
+    levels = list(range(4, args.min_level - 1, -1))
 
     def device_step():
         ctx._chk(lib.hso_frame_rebuild_batch_device(ctx.h, B, dev_ptrs, W, H, W, cur_ids_c))
@@ -631,7 +686,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM -------------------------------------------------------------------------------------
-    ctx.track_stage(jobs, inverse_comp=args.ic, max_level=4, min_level=1, n_iter=50)
+    ctx.track_stage(jobs, inverse_comp=args.ic, max_level=4, min_level=args.min_level, n_iter=args.n_iter)
     sampler = ClockSampler(local_rank)
     sampler.start()  # before the warm-up: nvidia-smi's first line takes ~0.1 s, the timed region may be shorter
     for _ in range(args.warmup):
@@ -642,8 +697,8 @@ def main():
     patch_evals = {l: sum(out[b].visible_patch_evals[l] for b in range(B)) for l in levels}
     cyc = [sum(out[b].cycles[k] for b in range(B)) for k in range(8)]
     diag = {"setup_frac_of_kernel_cycles": cyc[1] / max(cyc[0], 1), "refpatch_frac_of_kernel_cycles": cyc[3] / max(cyc[0], 1), "threshold_residuals_frac": cyc[4] / max(cyc[0], 1),
-            "median_select_frac": cyc[5] / max(cyc[0], 1), "pivoted_solves": cyc[7] & 0xFFFFFFFF, "select_fallbacks_per_problem_level": (cyc[7] >> 32) / (4 * B), "control_cycles_per_iteration": cyc[2] / max(iters_per_step + 4 * B, 1),
-            "kernel_cycles_per_problem_level": cyc[0] / (4 * B), "mad_select_frac": cyc[6] / max(cyc[0], 1), "serial_control_frac_of_kernel_cycles": cyc[2] / max(cyc[0], 1),
+            "median_select_frac": cyc[5] / max(cyc[0], 1), "pivoted_solves": cyc[7] & 0xFFFFFFFF, "select_fallbacks_per_problem_level": (cyc[7] >> 32) / (len(levels) * B), "control_cycles_per_iteration": cyc[2] / max(iters_per_step + len(levels) * B, 1),
+            "kernel_cycles_per_problem_level": cyc[0] / (len(levels) * B), "mad_select_frac": cyc[6] / max(cyc[0], 1), "serial_control_frac_of_kernel_cycles": cyc[2] / max(cyc[0], 1),
             "iters_per_problem": {"mean": iters_per_step / B, "max": max(out[b].n_iters for b in range(B)), "min": min(out[b].n_iters for b in range(B))}}
     ctx._chk(lib.hso_track_set_profile(ctx.h, 1))
     launches0 = ctx.kernel_launches()
@@ -672,7 +727,7 @@ def main():
     if not args.no_e2e:
         # the timed calls are the C-ABI entry points themselves on HOST buffers; the argument records are built once (the reference
         # caller owns long-lived Frame/Feature objects too) and only the per-step fields are refreshed
-        prm = K.hso_track_params(int(args.ic), 4, 1, 50)
+        prm = K.hso_track_params(int(args.ic), 4, args.min_level, args.n_iter)
         jarr, keep = ctx._track_jobs(jobs)
         img_ptrs = (C.c_void_p * B)(*[im.ctypes.data for im in cur_np])
         new_ids = (C.c_int32 * B)()
@@ -781,7 +836,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "frames_per_s": frames_all / (ms_total * 1e-3),
             "config": {"workload": f"{args.cam} {W}x{H}, {F} patches/frame, {B} independent frame pairs per GPU per step: pyramid+stats of the "
-                                   f"current image then CoarseTracker L4->L1 n_iter=50 {'inverse-compositional' if args.ic else 'forward'}, natural convergence",
+                                   f"current image then CoarseTracker L4->L{args.min_level} n_iter={args.n_iter} {'inverse-compositional' if args.ic else 'forward'}, natural convergence",
                        "batch_per_gpu": B, "patches": F, "lm_iterations_per_step_per_gpu": iters_per_step,
                        "l2": f"inputs larger than L2: {B} x (2 pyramids + feature scratch) = {B * (2 * 410000 + F * 25 * 8 + F * 40) / 1e6:.0f} MB per step vs 126 MB L2",
                        "parallelism": f"{world} independent batch(es), one per GPU, no data-path collective", "numa_binding_rank0": numa},
@@ -815,7 +870,7 @@ def main():
         if world == 1 and not args.no_other_rows:
             # the same batch in the other Jacobian mode (the reference picks inverse-compositional unless the new frame's gradients
             # got stronger, src/frame_handler_mono.cpp:184-203), device-resident like `value`
-            ctx.track_stage(jobs, inverse_comp=not args.ic, max_level=4, min_level=1, n_iter=50)
+            ctx.track_stage(jobs, inverse_comp=not args.ic, max_level=4, min_level=args.min_level, n_iter=args.n_iter)
             for _ in range(2):
                 device_step()
             ctx.synchronize()
