@@ -64,8 +64,61 @@ def warp_plane(img, K, T_cur_ref, depth, gain=1.0):
     return np.clip(np.rint(gain * val), 0, 255).astype(np.uint8).reshape(H, W)
 
 
+def cam2world_plane(c, u, v):
+    """Inverse of world2cam() on the unit plane z = 1 for arrays of pixels: pinhole closed form, radtan by fixed-point iteration (to
+    convergence, unlike cv::undistortPoints' five steps: this is scene generation), FOV by the tangent formula (src/camera.cpp:169-190)."""
+    u, v = np.asarray(u, float), np.asarray(v, float)
+    xd, yd = (u - c["cx"]) / c["fx"], (v - c["cy"]) / c["fy"]
+    d = c["d"]
+    if c.get("model", 0) == 0 and abs(d[0]) > 1e-7:
+        x, y = xd.copy(), yd.copy()
+        for _ in range(40):
+            r2 = x * x + y * y
+            cd = 1 + d[0] * r2 + d[1] * r2 * r2 + d[4] * r2 ** 3
+            dx = 2 * d[2] * x * y + d[3] * (r2 + 2 * x * x)
+            dy = d[2] * (r2 + 2 * y * y) + 2 * d[3] * x * y
+            x, y = (xd - dx) / cd, (yd - dy) / cd
+        return x, y
+    if c.get("model", 0) == 1 and not c.get("undistort", 0):
+        r = np.sqrt(xd * xd + yd * yd)
+        # the model reaches distorted radii below pi / (2 omega) only (image corners of a wide lens lie outside): clamp there
+        ang = np.minimum(r * d[0], 1.5)
+        fac = np.where(r > 1e-12, np.tan(ang) / (2 * np.maximum(r, 1e-300) * np.tan(d[0] / 2)), 1.0)
+        return fac * xd, fac * yd
+    return xd, yd
+
+
+def warp_plane_cam(img, c, T_cur_ref, depth, gain=1.0):
+    """warp_plane() through the camera MODEL (lens distortion on both sides): every current pixel is unprojected with cam2world, intersected
+    with the plane z = depth of the reference frame, and projected into the reference image with world2cam — photoconsistent for the radtan /
+    FOV cameras, where a pinhole homography is not."""
+    H, W = img.shape
+    R, t = T_cur_ref[:3, :3], T_cur_ref[:3, 3]
+    ys, xs = np.mgrid[0:H, 0:W]
+    x, y = cam2world_plane(c, xs.ravel().astype(float), ys.ravel().astype(float))
+    ray = np.stack([x, y, np.ones_like(x)])          # current-frame rays
+    rr = R.T @ ray                                    # X_ref = R^T (lambda ray - t)
+    rt = R.T @ t
+    lam = (depth + rt[2]) / rr[2]
+    Xr = rr * lam - rt[:, None]
+    uv = world2cam(c, Xr.T)
+    u, v = uv[:, 0], uv[:, 1]
+    u0, v0 = np.floor(u).astype(int), np.floor(v).astype(int)
+    su, sv = u - u0, v - v0
+    u0c, v0c = np.clip(u0, 0, W - 1), np.clip(v0, 0, H - 1)
+    u1c, v1c = np.clip(u0 + 1, 0, W - 1), np.clip(v0 + 1, 0, H - 1)
+    f = img.astype(np.float64)
+    val = (1 - su) * (1 - sv) * f[v0c, u0c] + su * (1 - sv) * f[v0c, u1c] + (1 - su) * sv * f[v1c, u0c] + su * sv * f[v1c, u1c]
+    return np.clip(np.rint(gain * val), 0, 255).astype(np.uint8).reshape(H, W)
+
+
+def has_lens_model(c):
+    return (c.get("model", 0) == 0 and abs(c["d"][0]) > 1e-7) or (c.get("model", 0) == 1 and not c.get("undistort", 0))
+
+
 def make_pair(seed, cam="icl", F=500, motion_scale=1.0, gain=1.05, depth=4.0, frac_no_point=0.05, border=8):
-    """One (ref, cur) problem. Returns dict(ref_img, cur_img, px (F,2), f (F,3), dist (F,), T_true (4x4), gain, cam)."""
+    """One (ref, cur) problem. Returns dict(ref_img, cur_img, px (F,2), f (F,3), dist (F,), T_true (4x4), gain, cam). For the cameras with a
+    lens model the current image and the bearings go through that model, so that T_true is the optimum there too."""
     rng = np.random.default_rng(seed)
     c = CAMS[cam] if isinstance(cam, str) else cam
     W, H = c["width"], c["height"]
@@ -73,12 +126,20 @@ def make_pair(seed, cam="icl", F=500, motion_scale=1.0, gain=1.05, depth=4.0, fr
     ref = texture(rng, W, H)
     xi = np.concatenate([rng.normal(0, 0.02, 3), rng.normal(0, 0.004, 3)]) * motion_scale
     T = se3_exp(xi)
-    cur = warp_plane(ref, K, T, depth, gain)
+    lens = has_lens_model(c)
+    cur = warp_plane_cam(ref, c, T, depth, gain) if lens else warp_plane(ref, K, T, depth, gain)
     px = np.stack([rng.uniform(border, W - border, F), rng.uniform(border, H - border, F)], axis=1)
-    ray = np.stack([(px[:, 0] - c["cx"]) / c["fx"], (px[:, 1] - c["cy"]) / c["fy"], np.ones(F)], axis=1)
+    if lens:
+        rx, ry = cam2world_plane(c, px[:, 0], px[:, 1])
+        ray = np.stack([rx, ry, np.ones(F)], axis=1)
+    else:
+        ray = np.stack([(px[:, 0] - c["cx"]) / c["fx"], (px[:, 1] - c["cy"]) / c["fy"], np.ones(F)], axis=1)
     f = ray / np.linalg.norm(ray, axis=1, keepdims=True)
     dist = depth / f[:, 2]
     dist[rng.uniform(size=F) < frac_no_point] = -1.0  # features without a point (Feature::point == NULL)
+    if lens and c.get("model", 0) == 1:  # pixels outside the FOV model's domain carry no point
+        rd = np.hypot((px[:, 0] - c["cx"]) / c["fx"], (px[:, 1] - c["cy"]) / c["fy"])
+        dist[rd * c["d"][0] > 1.45] = -1.0
     return dict(ref_img=ref, cur_img=cur, px=px, f=f, dist=dist, T_true=T, gain=gain, cam=c)
 
 
@@ -174,9 +235,9 @@ def make_reproject_scene(seed, cam="icl", M=3000, n_kf=4, max_fts=200, depth=4.0
     K = np.array([[c["fx"], 0, c["cx"]], [0, c["fy"], c["cy"]], [0, 0, 1.0]])
     base = texture(rng, W, H)
     T_kf = [np.eye(4)] + [se3_exp(np.concatenate([rng.normal(0, 0.05, 3), rng.normal(0, 0.01, 3)])) for _ in range(n_kf - 1)]
-    kf_imgs = [base] + [warp_plane(base, K, T, depth) for T in T_kf[1:]]
+    kf_imgs = [base] + [(warp_plane_cam(base, c, T, depth) if has_lens_model(c) else warp_plane(base, K, T, depth)) for T in T_kf[1:]]
     T_cur = se3_exp(np.concatenate([rng.normal(0, 0.04, 3), rng.normal(0, 0.008, 3)]))
-    cur_img = warp_plane(base, K, T_cur, depth, gain)
+    cur_img = warp_plane_cam(base, c, T_cur, depth, gain) if has_lens_model(c) else warp_plane(base, K, T_cur, depth, gain)
     # points on the plane, spread a little beyond the field of view so that some fall outside the current image
     x = rng.uniform(-1.12, 1.12, M) * depth * (W / 2) / c["fx"]
     y = rng.uniform(-1.12, 1.12, M) * depth * (H / 2) / c["fy"]
@@ -214,9 +275,9 @@ def make_depth_scene(seed, cam="icl", S=2000, n_kf=3, depth=4.0, gain=1.0, frac_
     K = np.array([[c["fx"], 0, c["cx"]], [0, c["fy"], c["cy"]], [0, 0, 1.0]])
     base = texture(rng, W, H)
     T_kf = [np.eye(4)] + [se3_exp(np.concatenate([rng.normal(0, 0.05, 3), rng.normal(0, 0.01, 3)])) for _ in range(n_kf - 1)]
-    kf_imgs = [base] + [warp_plane(base, K, T, depth) for T in T_kf[1:]]
+    kf_imgs = [base] + [(warp_plane_cam(base, c, T, depth) if has_lens_model(c) else warp_plane(base, K, T, depth)) for T in T_kf[1:]]
     T_cur = se3_exp(np.concatenate([rng.normal(0, baseline, 3) * [1, 1, 0.3], rng.normal(0, 0.01, 3)]))
-    cur_img = warp_plane(base, K, T_cur, depth, gain)
+    cur_img = warp_plane_cam(base, c, T_cur, depth, gain) if has_lens_model(c) else warp_plane(base, K, T_cur, depth, gain)
     seeds = []
     for i in range(S):
         r = int(rng.integers(0, n_kf))

@@ -80,12 +80,11 @@ def test_tracker_trace_vs_reference_functions(oracle, cam, F, ic):
 
 
 @pytest.mark.parametrize("ic", [False, True])
-@pytest.mark.parametrize("cam,F,min_level,n_iter", [("icl", 3000, 1, 50), ("icl", 1500, 1, 50), ("icl", 1000, 0, 15)])
+@pytest.mark.parametrize("cam,F,min_level,n_iter", [("icl", 3000, 1, 50), ("icl", 1500, 1, 50), ("icl", 1000, 0, 15), ("euroc", 2000, 1, 50)])
 def test_tracker_full_run_vs_reference_run(cam, F, min_level, n_iter, ic):
     """hso_coarse_track vs CoarseTracker::run of the reference on the same frames (exposure ratio formed from the frames' statistics on both
-    sides): final pose, exposure ratio, return value. Photoconsistent scenes only (the synthetic warp is a pinhole homography): on the
-    distorted cameras the optimum is shallow and two float pipelines end 1e-2 apart after an accept / reject flip — those cameras are covered
-    evaluation by evaluation in test_tracker_trace_vs_reference_functions."""
+    sides): final pose, exposure ratio, return value. (The wide FOV camera, whose image corners lie outside the lens model, is covered
+    evaluation by evaluation in test_tracker_trace_vs_reference_functions.)"""
     p, ctx, ids, integral, gm, rf, cf = _setup(500 + F + min_level, cam, F)
     job = dict(ref=ids[0], cur=ids[1], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=np.eye(4)[:3], exposure_rat=-1.0)
     res, _ = ctx.coarse_track_batch([job], inverse_comp=ic, min_level=min_level, n_iter=n_iter)
