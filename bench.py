@@ -48,10 +48,13 @@ def build_workload(B, F, cam, seed0, rank):
         c = base["cam"]
         W, H = c["width"], c["height"]
         px = np.stack([rng.uniform(8, W - 8, F), rng.uniform(8, H - 8, F)], axis=1)
-        ray = np.stack([(px[:, 0] - c["cx"]) / c["fx"], (px[:, 1] - c["cy"]) / c["fy"], np.ones(F)], axis=1)
+        rx, ry = synth.cam2world_plane(c, px[:, 0], px[:, 1])  # bearings through the camera model (Feature::f = cam2world(px))
+        ray = np.stack([rx, ry, np.ones(F)], axis=1)
         f = ray / np.linalg.norm(ray, axis=1, keepdims=True)
         dist = 4.0 / f[:, 2]
         dist[rng.uniform(size=F) < 0.02] = -1.0
+        if c.get("model", 0) == 1 and not c.get("undistort", 0):  # pixels outside the FOV model's domain carry no point
+            dist[np.hypot((px[:, 0] - c["cx"]) / c["fx"], (px[:, 1] - c["cy"]) / c["fy"]) * c["d"][0] > 1.45] = -1.0
         T0 = synth.se3_exp(np.concatenate([rng.normal(0, 0.004, 3), rng.normal(0, 0.001, 3)]))[:3]
         probs.append(dict(base=b % len(bases), ref_img=base["ref_img"], cur_img=base["cur_img"], px=px, f=f, dist=dist, T0=T0, cam=c))
     return probs
