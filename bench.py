@@ -608,6 +608,7 @@ def main():
     ap.add_argument("--no-ic-dual", action="store_true")
     ap.add_argument("--min-level", type=int, default=1, help="lowest pyramid level (0 = the reference's relocalisation setting, with --n-iter 15)")
     ap.add_argument("--n-iter", type=int, default=50)
+    ap.add_argument("--pipe", default="", help="chunk:streams of the pipelined e2e call (hso_set_pipeline; tuning)")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--pageable-features", action="store_true", help="keep the feature arrays in pageable memory (host-side flattening path)")
     ap.add_argument("--parity-samples", type=int, default=16, help="problems of the timed batch whose final pose is checked against the oracle")
@@ -644,6 +645,9 @@ def main():
         ctx.set_cluster(args.cluster, args.threads)
     if args.no_ic_dual:
         ctx._chk(lib.hso_track_set_ic_dual(ctx.h, 0))
+    if args.pipe:
+        ch, st = (int(v) for v in args.pipe.split(":"))
+        ctx._chk(lib.hso_set_pipeline(ctx.h, ch, st))
     for item in [x for x in args.shape.split(",") if x]:
         lv, cc, th = (int(v) for v in item.split(":"))
         ctx._chk(lib.hso_track_set_level_shape(ctx.h, lv, cc, th))
