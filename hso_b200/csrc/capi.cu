@@ -209,6 +209,7 @@ struct hso_ctx {
   std::vector<size_t> t_goff;       // staging plan of the batch in flight (track_plan): byte offset of each job's geometry block
   size_t t_geo_bytes = 0;
   // direct-input mode (pinned caller arrays are copied as they are and flattened on the device): -1 auto, 0 never, 1 always
+  int t_abs_global = getenv("HSO_TRACK_ABSRES_GLOBAL") ? 1 : 0;  // tuning: keep the |r| scratch of the threshold selection in global memory
   int t_direct_mode = -1;
   bool t_direct = false;           // decision for the batch in flight
   DevBuf t_raw;                    // [px 2 sumF | f 3 sumF | dist sumF] doubles
@@ -1158,14 +1159,25 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
       c_min = std::min(c_min, c_work);
     }
     int cluster = 0, threads = 0;
+    bool pair_ctas = false;
     if (prm.inverse_comp && !ctx->t_no_dual) {
       // inverse-compositional: keep BOTH levels resident and recompute the reference samples per evaluation — no F-dependent
       // cache, so one CTA per problem fits whenever two copies of the level do
       const int cc = c_min;
-      const int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
+      int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
+      // With two or more problems per SM in flight, two CTAs of 256 threads share an SM when their footprint allows it (no reference-patch
+      // cache in this mode; the |r| scratch then lives in global memory): one problem's serial control phase overlaps the other's evaluation.
+      // Measured at B = 1184, F = 3000: level 4 -12 %, level 3 -5 %, level 2 -4 % (profiles/r2m_ic_shapes.txt).
+      bool pair = false;
+      if (!f_threads && cc == 1 && shape_B >= 2 * 148 && th > 256) {
+        TrackLevelParams q = p;
+        q.fast = 2; q.cluster = 1; q.hist_bits = 11; q.absres_smem = 0;
+        q.pc = (maxF + 255) / 256 * 256;
+        if (track_level_smem_bytes(q, 256) <= 110 * 1024) { th = 256; pair = true; }
+      }
       const int kpt = (maxF + cc * th - 1) / (cc * th);
       p.fast = 2; p.pc = kpt * th; p.cluster = cc; p.hist_bits = 11;
-      if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; }
+      if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; pair_ctas = pair; }
     }
     for (int cc = c_min; cc <= 8 && !cluster; cc *= 2) {
       int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
@@ -1184,7 +1196,7 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
     }
     if (p.fast) {  // keep the |r| scratch of the threshold selection in shared memory too when it still fits
       p.absres_smem = 1;
-      if (track_level_smem_bytes(p, threads) > 227 * 1024) p.absres_smem = 0;
+      if (track_level_smem_bytes(p, threads) > 227 * 1024 || ctx->t_abs_global || pair_ctas) p.absres_smem = 0;
     }
     ctx->t_used[level][0] = cluster; ctx->t_used[level][1] = threads; ctx->t_used[level][2] = p.fast; ctx->t_used[level][3] = p.absres_smem;
     ctx->t_used[level][4] = p.hist_bits;

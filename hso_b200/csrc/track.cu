@@ -25,6 +25,9 @@
 //     every CTA then runs the (tiny, fp64) damped solve + SE3 update redundantly, so one cluster barrier per trial suffices.
 #include <cooperative_groups.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "hso_internal.h"
 
 namespace cg = cooperative_groups;
@@ -1156,6 +1159,15 @@ static cudaError_t launch_one(const TrackLevelParams& p, const TrackJobDev* jobs
   auto kern = k_track_level<PIDX, IC, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  // all of the unified L1 / shared memory as shared memory: two CTAs of a small-footprint shape (inverse-compositional dual-image mode at the
+  // coarse levels) can then share an SM
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  if (getenv("HSO_TRACK_DEBUG")) {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem);
+    fprintf(stderr, "k_track_level<%d,%d,%d> level shape: cluster %d x %d threads, %zu B smem -> %d CTA(s)/SM\n", PIDX, (int)IC, MODE, cluster, threads, smem, nb);
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * cluster), 1, 1);
   cfg.blockDim = dim3((unsigned)threads, 1, 1);
