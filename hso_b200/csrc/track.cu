@@ -256,21 +256,25 @@ HSO_DEV void win_row(const uint8_t* img, int byte_addr, uint32_t* out) {
   for (int j = 0; j < PG<PIDX>::NA; ++j) out[j] = __funnelshift_r(wv[j], wv[j + 1], sh);
 }
 
-struct TermCtx { float a, huber, cutoff, max_energy; bool top; };
+struct TermCtx { float a, huber, cutoff, max_energy; };
 
-// one residual term: Huber weight, energy, the nine moments (src/CoarseTracker.cpp:345-404 fused with computeGS :499-525)
+// one residual term: Huber weight, energy, the nine moments (src/CoarseTracker.cpp:345-404 fused with computeGS :499-525). TOP: the level is
+// m_max_level (no outlier cut-off, energy hw r^2), a launch constant turned into a template parameter.
+template <bool TOP>
 HSO_DEV void accumulate_term(const TermCtx& t, float c, float color, float gx, float gy, Moments& m, float& Ep, int& sat) {
-  const float r = color - (t.a * c + 0.f);
+  // residual = cur_color - (exposure_rat * ref + b) with b == 0 (:346): one fused multiply-add, as the reference's own build contracts it
+  const float r = fmaf(-t.a, c, color);
   const float ar = fabsf(r);
   // Huber weight hw = huber / |r| (:348) through the approximate reciprocal (1 ulp): hw only scales terms
   float rcp;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(ar));
   const float hw = ar < t.huber ? 1.f : t.huber * rcp;
   // branch-free form of :350-361: a saturated term adds max_energy and contributes nothing to H, b
-  const bool saturated = ar > t.cutoff && !t.top;
-  const float e_in = t.top ? hw * r * r : hw * r * r * (2.f - hw);
+  const bool saturated = !TOP && ar > t.cutoff;
+  const float hr2 = hw * r * r;
+  const float e_in = TOP ? hr2 : hr2 * (2.f - hw);
   Ep += saturated ? t.max_energy : e_in;
-  sat += saturated ? 1 : 0;
+  if (!TOP) sat += saturated ? 1 : 0;
   const float w = saturated ? 0.f : hw;
   const float wgx = w * gx, wgy = w * gy, wc = w * c;
   m.xx += wgx * gx; m.xy += wgx * gy; m.yy += wgy * gy;
@@ -374,7 +378,7 @@ HSO_DEV void ref_intensity_grad(const uint8_t* img, const RefPatch& r, int addr,
 
 // One residual evaluation over the calling thread's patches: computeResiduals + computeGS fused
 // (src/CoarseTracker.cpp:242-414, :499-525).
-template <int PIDX, bool IC, int MODE>
+template <int PIDX, bool IC, int MODE, bool TOP>
 HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const PatchStore& ps, const CamDev& cam, const double* Rt, float a, float huber,
                           float cutoff, int t0, int nt, Acc& acc) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
@@ -406,11 +410,11 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
         float Ep = 0.f;
         int sat = 0;
         TermCtx tc;
-        tc.a = a; tc.huber = huber; tc.cutoff = cutoff; tc.max_energy = max_energy; tc.top = L.top;
+        tc.a = a; tc.huber = huber; tc.cutoff = cutoff; tc.max_energy = max_energy;
         if (!IC) {
           // forward mode: colour and gradients of the CURRENT image from one streamed window
           window_samples<PIDX, FAST>(L.cur, p.base, L.w, p.wtl, p.wtr, p.wbl, p.wbr, [&](int n, float color, float gx, float gy) {
-            accumulate_term(tc, ps.cache[n * S + sl], color, gx, gy, m, Ep, sat);
+            accumulate_term<TOP>(tc, ps.cache[n * S + sl], color, gx, gy, m, Ep, sat);
           });
         } else if (DUAL) {
           // inverse-compositional, dual image: intensity and gradients of the REFERENCE image from one streamed window,
@@ -421,7 +425,7 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
             const uint32_t r0 = ld4<true>(L.cur, addr);
             const uint32_t r1 = ld4<true>(L.cur, addr + L.w);
             const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-            accumulate_term(tc, c, color, gx, gy, m, Ep, sat);
+            accumulate_term<TOP>(tc, c, color, gx, gy, m, Ep, sat);
           });
         } else {
 #pragma unroll
@@ -430,7 +434,7 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
             const uint32_t r0 = ld4<FAST>(L.cur, addr);
             const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
             const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-            accumulate_term(tc, ps.cache[n * S + sl], color, ps.gx[n * S + sl], ps.gy[n * S + sl], m, Ep, sat);
+            accumulate_term<TOP>(tc, ps.cache[n * S + sl], color, ps.gx[n * S + sl], ps.gy[n * S + sl], m, Ep, sat);
           }
         }
         // Jacobian rows of the patch after the term loop (keeps 12 registers free while the window is live)
@@ -996,7 +1000,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
           const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
           const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
           const float cref = DUAL ? ref_intensity<true>(ps.ref, rp, rp.base + poff, L.w) : ps.cache[n * ps.stride + sl];
-          out = fabsf(color - (a * cref + 0.f));
+          out = fabsf(fmaf(-a, cref, color));
           atomicAdd(&s.hist[lin ? lin_bin(out, 2048) : (__float_as_uint(out) >> (32 - hbits))], 1u);  // first pass of the median select, fused
         }
         absres[n * astride + (a_smem ? sl : i)] = out;
@@ -1035,7 +1039,9 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     const float a_eval = iter < 0 ? c->a_acc : c->a_try;
     Acc acc;
     acc_zero(acc);
-    eval_patches<PIDX, IC, MODE>(L, job, ps, prm.cam, c->Rt, a_eval, huber, cutoff, t0, nt, acc);
+    // the top level has its own energy and no cut-off (:350-361). m_offset_all = m_max_level - m_level + m_pattern_offset (:80) makes the top
+    // level the one and only user of pattern index m_pattern_offset = 2: a compile-time property of the instantiation
+    eval_patches<PIDX, IC, MODE, PIDX == 2>(L, job, ps, prm.cam, c->Rt, a_eval, huber, cutoff, t0, nt, acc);
     reduce_acc(acc, s, slot, csize, nwarps);
     slot ^= 1;
     ++level_evals;
