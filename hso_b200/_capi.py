@@ -142,6 +142,7 @@ SYMBOLS = {
     "hso_track_set_level_shape": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "hso_track_get_level_shape": (C.c_int, [_vp, C.c_int, _P(C.c_int), _P(C.c_int), _P(C.c_int), _P(C.c_int)]),
     "hso_track_set_ic_dual": (C.c_int, [_vp, C.c_int]),
+    "hso_track_set_stream_cache": (C.c_int, [_vp, C.c_int]),
     "hso_track_set_direct_inputs": (C.c_int, [_vp, C.c_int]),
     "hso_align_batch": (C.c_int, [_vp, C.c_int32, C.c_int, _P(hso_align_job), _P(C.c_int32), C.c_int, _P(hso_align_result)]),
     "hso_reproject_match": (C.c_int, [_vp, C.c_int32, _P(C.c_double), C.c_int, _P(C.c_double), C.c_int, _P(hso_reproj_cand), _P(hso_reproj_grid),

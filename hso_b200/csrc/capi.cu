@@ -209,6 +209,8 @@ struct hso_ctx {
   std::vector<size_t> t_goff;       // staging plan of the batch in flight (track_plan): byte offset of each job's geometry block
   size_t t_geo_bytes = 0;
   // direct-input mode (pinned caller arrays are copied as they are and flattened on the device): -1 auto, 0 never, 1 always
+  int t_force_stream = getenv("HSO_TRACK_FORCE_STREAM") ? 1 : 0;  // tuning / tests: mode 3 at every forward level where it fits
+  int t_no_stream = getenv("HSO_TRACK_NO_STREAM") ? 1 : 0;        // tuning: never use the streamed-cache mode (mode 3) of the forward tracker
   int t_abs_global = getenv("HSO_TRACK_ABSRES_GLOBAL") ? 1 : 0;  // tuning: keep the |r| scratch of the threshold selection in global memory
   int t_direct_mode = -1;
   bool t_direct = false;           // decision for the batch in flight
@@ -791,6 +793,13 @@ int hso_track_set_ic_dual(hso_ctx* ctx, int enable) {
   return HSO_OK;
 }
 
+int hso_track_set_stream_cache(hso_ctx* ctx, int mode) {
+  if (!ctx || mode < -1 || mode > 1) return HSO_ERR_INVALID;
+  ctx->t_no_stream = mode < 0 ? 1 : 0;
+  ctx->t_force_stream = mode > 0 ? 1 : 0;
+  return HSO_OK;
+}
+
 int hso_track_get_level_shape(hso_ctx* ctx, int level, int* ctas, int* threads, int* mode, int* absres_smem) {
   if (!ctx || level < 0 || level >= kMaxLevels) return HSO_ERR_INVALID;
   if (ctas) *ctas = ctx->t_used[level][0];
@@ -1182,11 +1191,22 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
     for (int cc = c_min; cc <= 8 && !cluster; cc *= 2) {
       int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
       const int kpt = (maxF + cc * th - 1) / (cc * th);
-      p.fast = 1; p.pc = kpt * th; p.cluster = cc;
+      p.pc = kpt * th; p.cluster = cc;
+      if (ctx->t_force_stream && !prm.inverse_comp) {  // tuning / tests: the streamed-cache mode wherever it fits
+        p.fast = 3; p.hist_bits = 11;
+        if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
+      }
+      p.fast = 1;
       p.hist_bits = 11;
       if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
       p.hist_bits = 8;
       if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
+      // forward mode: image resident, reference-patch cache streamed from L2 through a per-warp ring (mode 3) before the problem is split
+      // over more CTAs — a cluster costs two cluster barriers per trial, a second staged image and a second (redundant) control step
+      if (!prm.inverse_comp && !ctx->t_no_stream) {
+        p.fast = 3; p.hist_bits = 11;
+        if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
+      }
       if (f_cluster) break;  // the caller fixed the cluster size
     }
     if (!cluster) {

@@ -118,6 +118,9 @@ __host__ __device__ inline size_t smem_layout(uint32_t img_bytes, size_t cache_b
   return o;
 }
 
+// MODE 3 (streamed cache): per warp two buffers of N rows x 32 patches of reference intensities
+__host__ __device__ inline size_t ring_bytes(int N, int nwarps) { return (size_t)nwarps * 2 * N * 32 * sizeof(float); }
+
 static __host__ __device__ inline int pattern_n(int pidx) { return pidx <= 0 ? 1 : pidx == 1 ? 5 : pidx == 2 ? 9 : pidx <= 4 ? 13 : pidx == 5 ? 21 : 25; }
 
 // Shared memory of one CTA. fast: image + patch caches resident; pc = patch slots per CTA (patches-per-thread * threads).
@@ -125,7 +128,7 @@ size_t track_level_smem_bytes(const TrackLevelParams& p, int threads) {
   size_t a, b, c, d, e, f, g, h, i, j;
   const int N = pattern_n(p.max_level - p.level + 2);
   const size_t absb = (p.fast && p.absres_smem) ? (size_t)N * p.pc * sizeof(float) : 0;
-  const size_t cache = p.fast == 1 ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : 0;
+  const size_t cache = p.fast == 1 ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : p.fast == 3 ? ring_bytes(N, threads / 32) : 0;
   const uint32_t img = p.fast == 2 ? 2 * (uint32_t)align_up(p.img_bytes, 128) : (p.fast ? p.img_bytes : 0);
   return smem_layout(img, cache, absb, p.fast ? (size_t)p.pc : 0, threads / 32, p.hist_bits, p.cluster, &a, &j, &b, &c, &d, &e, &f, &g, &h, &i);
 }
@@ -331,6 +334,7 @@ struct LevelCtx {
 struct PatchStore {
   const uint8_t* ref;  // MODE 2 (dual image): the reference level in shared memory; intensities/gradients are recomputed per evaluation
   float* cache;    // reference intensities
+  float* ring;     // MODE 3: this warp's two staging buffers [2][N][32] for the cache rows streamed from global memory (L2)
   float* gx;       // inverse-compositional reference gradients
   float* gy;
   uint8_t* vis;
@@ -378,12 +382,40 @@ HSO_DEV void ref_intensity_grad(const uint8_t* img, const RefPatch& r, int addr,
 
 // One residual evaluation over the calling thread's patches: computeResiduals + computeGS fused
 // (src/CoarseTracker.cpp:242-414, :499-525).
+// MODE 3: the reference-intensity cache of a problem stays in global memory (L2 resident: it is written once per level and re-read by every
+// evaluation) and is streamed through a small per-warp ring in shared memory — cp.async (LDGSTS, 16 B per lane) fetches the N rows x 32 patches of
+// the warp's NEXT patch group while the current group is evaluated. That frees the 108-258 KB the resident cache takes, so that a level whose
+// image + cache exceed one SM (level 1 at 640x480 with 3000 patches) still runs as ONE CTA per problem: no cluster barriers, no DSMEM exchange,
+// one control step and one staged image per problem instead of two.
+HSO_DEV void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+HSO_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int KEEP>
+HSO_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory"); }
+// rows n = 0..N-1 of patches [i0, i0 + 32) -> dst[n * 32 + lane]; i0 is a multiple of 32 and the rows are 128-byte aligned (Fpad % 32 == 0)
+template <int N>
+HSO_DEV void ring_fetch(const float* gcache, int Fp, int i0, float* dst) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c0 = 0; c0 < N * 8; c0 += 32) {
+    const int c = c0 + lane;
+    if (N * 8 - c0 >= 32 || c < N * 8) cp_async16(dst + (c >> 3) * 32 + (c & 7) * 4, gcache + (size_t)(c >> 3) * Fp + i0 + (c & 7) * 4);
+  }
+}
+
 template <int PIDX, bool IC, int MODE, bool TOP>
 HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const PatchStore& ps, const CamDev& cam, const double* Rt, float a, float huber,
                           float cutoff, int t0, int nt, Acc& acc) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
-  constexpr bool FAST = MODE != 0, DUAL = MODE == 2;
+  constexpr bool FAST = MODE != 0, DUAL = MODE == 2, STREAM = MODE == 3;
+  static_assert(!STREAM || !IC, "the streamed cache exists for the forward mode only");
   const int Fp = job.Fpad, S = ps.stride;
+  const int lane = threadIdx.x & 31;
+  if (STREAM) {
+    if (t0 - lane < job.F) ring_fetch<N>(ps.cache, Fp, t0 - lane, ps.ring);
+    cp_async_commit();
+  }
   // max_energy = 2*huber*cutoff - huber^2, evaluated in double like the reference (cutoff_error is a double there)
   const float max_energy = (float)(2.0 * (double)huber * (double)cutoff - (double)(huber * huber));
   // geometry of the next patch is fetched while the current one is processed (the only global loads of the FAST path)
@@ -394,8 +426,18 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
     X = job.xyz[i]; Y = job.xyz[Fp + i]; Z = job.xyz[2 * Fp + i];
     if (DUAL) { PU = job.px[i]; PV = job.px[Fp + i]; }
   }
-  while (i < job.F) {
+  // (STREAM: the trip count is warp uniform — the ring is filled and drained by the whole warp)
+  while ((STREAM ? i - lane : i) < job.F) {
     const int in = i + nt, kn = k + 1;
+    const float* cbuf = nullptr;
+    if (STREAM) {
+      // group k+1 goes into the buffer group k-1 was read from (every lane is past it: __syncwarp at the end of the iteration)
+      if (in - lane < job.F) ring_fetch<N>(ps.cache, Fp, in - lane, ps.ring + (kn & 1) * (N * 32));
+      cp_async_commit();
+      cp_async_wait<1>();  // everything but the newest group has landed: group k
+      __syncwarp();        // ... for every lane's copies
+      cbuf = ps.ring + (k & 1) * (N * 32) + lane;
+    }
     const bool have_n = in < job.F && ps.vis[slot_of<FAST>(in, kn)] != 0;
     double Xn = 0, Yn = 0, Zn = 1, PUn = 0, PVn = 0;
     if (have_n) {
@@ -414,7 +456,7 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
         if (!IC) {
           // forward mode: colour and gradients of the CURRENT image from one streamed window
           window_samples<PIDX, FAST>(L.cur, p.base, L.w, p.wtl, p.wtr, p.wbl, p.wbr, [&](int n, float color, float gx, float gy) {
-            accumulate_term<TOP>(tc, ps.cache[n * S + sl], color, gx, gy, m, Ep, sat);
+            accumulate_term<TOP>(tc, STREAM ? cbuf[n * 32] : ps.cache[n * S + sl], color, gx, gy, m, Ep, sat);
           });
         } else if (DUAL) {
           // inverse-compositional, dual image: intensity and gradients of the REFERENCE image from one streamed window,
@@ -454,7 +496,9 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
       }
     }
     i = in; k = kn; have = have_n; X = Xn; Y = Yn; Z = Zn; PU = PUn; PV = PVn;
+    if (STREAM) __syncwarp();
   }
+  if (STREAM) cp_async_wait<0>();
 }
 
 // CTA + cluster reduction of the per-thread partial sums into s.tot[0..NRED) (identical in every CTA of the cluster).
@@ -842,7 +886,7 @@ template <int PIDX, bool IC, int MODE>
 __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams prm, const TrackJobDev* __restrict__ jobs) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
   constexpr int PAD = (PIDX == 5) ? 3 : (PIDX == 7) ? 4 : (PIDX <= 2) ? 1 : 2;
-  constexpr bool FAST = MODE != 0, DUAL = MODE == 2;
+  constexpr bool FAST = MODE != 0, DUAL = MODE == 2, STREAM = MODE == 3;
   static_assert(!DUAL || IC, "the dual-image mode exists for the inverse-compositional path only");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -857,7 +901,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   {
     size_t oc, oa, ov, ow, op, ot, oh, og, ox, om;
     const size_t abs_bytes = (FAST && prm.absres_smem) ? (size_t)N * prm.pc * sizeof(float) : 0;
-    const size_t cache_bytes = MODE == 1 ? (size_t)N * (IC ? 3 : 1) * prm.pc * sizeof(float) : 0;
+    const size_t cache_bytes = MODE == 1 ? (size_t)N * (IC ? 3 : 1) * prm.pc * sizeof(float) : STREAM ? ring_bytes(N, nwarps) : 0;
     const uint32_t img_total = DUAL ? 2 * (uint32_t)align_up(prm.img_bytes, 128) : (FAST ? prm.img_bytes : 0);
     smem_layout(img_total, cache_bytes, abs_bytes, FAST ? (size_t)prm.pc : 0, nwarps, prm.hist_bits, csize, &oc, &oa, &ov, &ow, &op, &ot, &oh, &og, &ox, &om);
     s.absres = reinterpret_cast<float*>(smem_raw + oa);
@@ -879,7 +923,10 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
 
   PatchStore ps;
   ps.ref = s.img + align_up(prm.img_bytes, 128);
-  if (FAST) {
+  ps.ring = s.cache + (threadIdx.x >> 5) * (2 * N * 32);
+  if (STREAM) {
+    ps.cache = job.ref_cache; ps.gx = nullptr; ps.gy = nullptr; ps.vis = s.vis; ps.stride = Fp;
+  } else if (FAST) {
     ps.cache = s.cache; ps.gx = s.cache + (size_t)N * prm.pc; ps.gy = s.cache + (size_t)2 * N * prm.pc; ps.vis = s.vis; ps.stride = prm.pc;
   } else {
     ps.cache = job.ref_cache; ps.gx = job.ref_gx; ps.gy = job.ref_gy; ps.vis = job.vis; ps.stride = Fp;
@@ -930,6 +977,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     int k = 0;
     for (int i = t0; i < job.F; i += nt, ++k) {
       const int sl = slot_of<FAST>(i, k);
+      const int csl = STREAM ? i : sl;  // the streamed cache is indexed by patch like the global-memory path
       const RefPatch rp = ref_patch(job.px[i], job.px[Fp + i], L.scale, L.border, L.w, L.h);
       ps.vis[sl] = rp.in ? 1 : 0;
       if (!rp.in || DUAL) continue;  // dual-image mode recomputes the reference samples in every evaluation
@@ -937,7 +985,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
       for (int n = 0; n < N; ++n) {
         const int addr = rp.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
         if (!IC) {
-          ps.cache[n * ps.stride + sl] = ref_intensity<FAST>(ref_src, rp, addr, L.w);
+          ps.cache[n * ps.stride + csl] = ref_intensity<FAST>(ref_src, rp, addr, L.w);
         } else {
           float cc, gx, gy;
           ref_intensity_grad<FAST>(ref_src, rp, addr, L.w, cc, gx, gy);
@@ -999,7 +1047,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
           const uint32_t r0 = ld4<FAST>(L.cur, addr);
           const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
           const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-          const float cref = DUAL ? ref_intensity<true>(ps.ref, rp, rp.base + poff, L.w) : ps.cache[n * ps.stride + sl];
+          const float cref = DUAL ? ref_intensity<true>(ps.ref, rp, rp.base + poff, L.w) : ps.cache[n * ps.stride + (STREAM ? i : sl)];
           out = fabsf(fmaf(-a, cref, color));
           atomicAdd(&s.hist[lin ? lin_bin(out, 2048) : (__float_as_uint(out) >> (32 - hbits))], 1u);  // first pass of the median select, fused
         }
@@ -1197,6 +1245,7 @@ static cudaError_t launch_pidx(const TrackLevelParams& p, const TrackJobDev* job
     return p.fast ? launch_one<PIDX, true, 1>(p, jobs_dev, B, cluster, threads, smem, stream)
                   : launch_one<PIDX, true, 0>(p, jobs_dev, B, cluster, threads, smem, stream);
   }
+  if (p.fast == 3) return launch_one<PIDX, false, 3>(p, jobs_dev, B, cluster, threads, smem, stream);
   return p.fast ? launch_one<PIDX, false, 1>(p, jobs_dev, B, cluster, threads, smem, stream)
                 : launch_one<PIDX, false, 0>(p, jobs_dev, B, cluster, threads, smem, stream);
 }

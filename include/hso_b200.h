@@ -161,12 +161,16 @@ int hso_track_set_cluster(hso_ctx* ctx, int ctas_per_problem, int threads_per_ct
 /* Same, for one pyramid level only (overrides hso_track_set_cluster for that level; 0,0 restores auto). */
 int hso_track_set_level_shape(hso_ctx* ctx, int level, int ctas_per_problem, int threads_per_cta);
 /* Launch shape the last run used for `level`: CTAs per problem, threads per CTA, mode (0 = images and caches in global memory, 1 = current level
- * + reference-patch cache in shared memory, 2 = both levels in shared memory), and whether the |r| scratch of the threshold selection sat in
+ * + reference-patch cache in shared memory, 2 = both levels in shared memory, 3 = current level in shared memory + streamed cache), and whether the |r| scratch of the threshold selection sat in
  * shared memory. The parity tests use it to prove that they exercise the shape the benchmark runs. */
 int hso_track_get_level_shape(hso_ctx* ctx, int level, int* ctas, int* threads, int* mode, int* absres_smem);
 /* Inverse-compositional mode: 1 (default) keeps both pyramid levels in shared memory and recomputes the reference samples per evaluation
  * whenever two copies of the level fit; 0 forces the cached-reference-patch path. Results are identical. */
 int hso_track_set_ic_dual(hso_ctx* ctx, int enable);
+/* Forward mode: where the reference-patch cache (precomputeReferencePatches, src/CoarseTracker.cpp:416-497) of a level lives. 0 (default):
+ * in shared memory when image + cache fit one CTA, else in global memory streamed through a per-warp shared-memory ring (mode 3), else split
+ * over a cluster; 1: mode 3 wherever it fits; -1: never mode 3. Results are identical for a given CTA count / thread count. */
+int hso_track_set_stream_cache(hso_ctx* ctx, int mode);
 
 /* F1 + F2 in one call for B independent streams — the front end of FrameHandlerMono::addImage (src/frame_handler_mono.cpp:92 new Frame(cam, img),
  * :190-204 CoarseTracker::run(last_frame, new_frame)). imgs[b] becomes a new device frame (id in new_ids[b], statistics in integral / grad_mean,

@@ -116,6 +116,28 @@ def test_cluster_shapes_agree(oracle, cluster, threads):
     ctx.close()
 
 
+@pytest.mark.parametrize("cam,F,cluster,threads", [("icl", 900, 1, 256), ("icl", 3000, 1, 512), ("euroc", 2000, 2, 512), ("tum_fov", 700, 1, 96)])
+def test_streamed_cache_mode_vs_oracle_and_resident_cache(oracle, cam, F, cluster, threads):
+    """Mode 3 (reference-patch cache in global memory, streamed through the per-warp ring) forced at every level: per-evaluation parity with the
+    oracle, and the same bits as the resident-cache path (mode 1) at the same launch shape — the summation order does not depend on where the
+    cache lives."""
+    p, ctx, tp, job, a0 = _setup(oracle, 41, cam, F)
+    ctx.set_cluster(cluster, threads)
+    ctx._chk(ctx.lib.hso_track_set_stream_cache(ctx.h, 1))
+    r3, t3 = ctx.coarse_track_batch([job], trace_cap=256)
+    assert all(ctx.level_shape(l)[:3] == (cluster, threads, 3) for l in (4, 3, 2, 1)), [ctx.level_shape(l) for l in (4, 3, 2, 1)]
+    assert _check_trace(oracle, tp, t3[0], False, 4) <= REL
+    ctx._chk(ctx.lib.hso_track_set_stream_cache(ctx.h, -1))
+    r1, t1 = ctx.coarse_track_batch([job], trace_cap=256)
+    if all(ctx.level_shape(l)[:3] == (cluster, threads, 1) for l in (4, 3, 2, 1)):
+        assert len(t1[0]) == len(t3[0]) and np.array_equal(r1[0]["T_cur_ref"], r3[0]["T_cur_ref"])
+        for e1, e3 in zip(t1[0], t3[0]):
+            assert np.array_equal(np.array(e1.H[:]), np.array(e3.H[:])) and np.array_equal(np.array(e1.b[:]), np.array(e3.b[:]))
+    else:
+        assert np.abs(r1[0]["T_cur_ref"] - r3[0]["T_cur_ref"]).max() < 2e-4
+    ctx.close()
+
+
 def test_ic_dual_image_and_cached_paths_agree(oracle):
     p, ctx, tp, job, a0 = _setup(oracle, 35, "icl", 900)
     r_dual, t_dual = ctx.coarse_track_batch([job], inverse_comp=True, trace_cap=256)
@@ -258,12 +280,13 @@ def test_pipelined_entry_edge_cases(oracle):
 
 
 # ---- parity at the benchmarked launch shape and configuration (bench.py: icl 640x480, F = 3000, B = 1184 per GPU) ---------------------------
-# With B >= 148 problems in flight track_run_range gives every problem ONE CTA of 512 threads at levels 4..2 and a cluster of 2 x 512 at level 1
-# (231 KB of image + reference-patch cache do not fit one SM), the |r| scratch of the threshold selection in global memory (it does not fit
+# With B >= 148 problems in flight track_run_range gives every problem ONE CTA of 512 threads at every level: mode 1 (image + reference-patch
+# cache in shared memory) at levels 4..2, mode 3 at level 1 (image resident, the 252 KB cache streamed from L2 through a per-warp ring —
+# 231 KB of image + cache per CTA needed a cluster of 2 before), the |r| scratch of the threshold selection in global memory (it does not fit
 # beside the 108-156 KB reference-patch cache of 3000 patches at any level); the
 # inverse-compositional mode keeps both levels resident (mode 2) with one CTA per problem. BENCH_SHAPE is what bench.py's batch runs;
 # hso_track_get_level_shape proves the tests run exactly that.
-BENCH_SHAPE_FWD = {4: (1, 512, 1, 0), 3: (1, 512, 1, 0), 2: (1, 512, 1, 0), 1: (2, 512, 1, 0)}
+BENCH_SHAPE_FWD = {4: (1, 512, 1, 0), 3: (1, 512, 1, 0), 2: (1, 512, 1, 0), 1: (1, 512, 3, 0)}
 
 
 def _bench_problem(oracle, seed, F=3000, cam="icl"):
@@ -354,7 +377,7 @@ def test_pipelined_entry_vs_oracle_at_benchmark_config(oracle, ic):
     ref_ids, ref_int, _ = ctx.upload_frames([first[k]["ref_img"] for k in range(nb)])
     jobs = [dict(ref=ref_ids[p["base"]], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=p["T0"]) for p in probs]
     ids, integ, gm, res = ctx.add_frames_track_batch([p["cur_img"] for p in probs], jobs, inverse_comp=ic)
-    assert ctx.level_shape(1)[:2] == ((1, 512) if ic else (2, 512))  # chunks are shaped by the whole batch (>= 148 in flight)
+    assert ctx.level_shape(1)[:3] == ((1, 512, 2) if ic else (1, 512, 3))  # chunks are shaped by the whole batch (>= 148 in flight)
     for b in list(range(0, B, 33)) + [B - 1]:
         p = probs[b]
         rl, _ = oracle.create_pyramid(p["ref_img"], 5)
