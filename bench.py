@@ -598,6 +598,7 @@ def main():
     ap.add_argument("--cam", default="icl", choices=list(synth.CAMS))
     ap.add_argument("--ic", action="store_true", help="inverse-compositional mode")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-debug", action="store_true", help="time the stages of the pipelined e2e call alone and print one traced call (stderr)")
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--shape", default="", help="per-level launch shape overrides 'level:ctas:threads,...' (tuning)")
@@ -770,6 +771,17 @@ def main():
         f1.record(stream)
         barrier()
         ms_e2e = f0.elapsed_time(f1)
+        if args.e2e_debug and rank == 0:  # tuning aid: the stages of the pipelined call alone (HSO_PIPE_DEBUG) and one traced call (HSO_PIPE_TRACE)
+            for name, flag in (("copies only", "1"), ("kernels only", "2"), ("everything", "0")):
+                os.environ["HSO_PIPE_DEBUG"] = flag
+                tt = []
+                for _ in range(6):
+                    torch.cuda.synchronize(); t0 = time.perf_counter(); e2e_step(); torch.cuda.synchronize(); tt.append(1e3 * (time.perf_counter() - t0))
+                print(f"[e2e-debug] {name}: median {np.median(tt[2:]):.2f} ms min {min(tt):.2f} ms", file=sys.stderr)
+            os.environ["HSO_PIPE_DEBUG"] = "0"
+            os.environ["HSO_PIPE_TRACE"] = "1"
+            e2e_step()
+            del os.environ["HSO_PIPE_TRACE"]
         it_e2e = n_e2e_steps * sum(res[b].n_iters for b in range(B))  # every step runs the same problems: counted once, outside the timed region
         if ids_live is not cur_ids_c:
             C.memmove(cur_ids_c, ids_live, C.sizeof(cur_ids_c))  # later sections rebuild the frames these ids name

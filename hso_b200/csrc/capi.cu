@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstddef>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -974,16 +975,21 @@ static void track_stage_one(hso_ctx* ctx, const hso_track_job* jobs, int b) {
 
 // Direct-input mode: the caller's px / f / dist arrays of jobs [b0, b1) go to the device as they are. Arrays of consecutive jobs that are
 // adjacent in host memory (a caller that keeps a batch in one blob) travel in one copy per run.
-static int track_copy_raw(hso_ctx* ctx, const hso_track_job* jobs, int b0, int b1, cudaStream_t stream) {
-  double* rb = (double*)ctx->t_raw.p;
-  const size_t S = ctx->t_sumF;
+// direct-input mode: what track_stage_one records beside the geometry (initial pose, exposure ratio) for jobs [b0, b1)
+static void track_fill_pose(hso_ctx* ctx, const hso_track_job* jobs, int b0, int b1) {
   const int B = ctx->tB;
   double* T0 = (double*)((char*)ctx->t_stage_host.p + ctx->t_geo_bytes);
   float* a0 = (float*)(T0 + 12 * B);
-  for (int b = b0; b < b1; ++b) {  // what track_stage_one records beside the geometry
+  for (int b = b0; b < b1; ++b) {
     memcpy(T0 + 12 * b, jobs[b].T_cur_ref, sizeof(double) * 12);
     a0[b] = jobs[b].exposure_rat;
   }
+}
+
+static int track_copy_raw(hso_ctx* ctx, const hso_track_job* jobs, int b0, int b1, cudaStream_t stream, bool fill_pose = true) {
+  double* rb = (double*)ctx->t_raw.p;
+  const size_t S = ctx->t_sumF;
+  if (fill_pose) track_fill_pose(ctx, jobs, b0, b1);
   for (int arr = 0; arr < 3; ++arr) {
     const size_t w = arr == 0 ? 2 : (arr == 1 ? 3 : 1);
     double* dbase = rb + (arr == 0 ? 0 : (arr == 1 ? 2 * S : 5 * S));
@@ -1287,6 +1293,12 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   if (!ctx || !prm || B <= 0 || !imgs || !jobs_in || !new_ids || !out) return HSO_ERR_INVALID;
   if (W != ctx->cam.width || H != ctx->cam.height || stride < W) return fail(ctx, HSO_ERR_INVALID, "image size does not match the camera model");
   CU(cudaSetDevice(ctx->device));
+  // tuning aid: HSO_PIPE_TRACE=1 prints host-side time stamps of the call's phases (ms since entry) to stderr
+  const bool ptrace = getenv("HSO_PIPE_TRACE") != nullptr;
+  const auto t_entry = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (ptrace) fprintf(stderr, "[pipe] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
+  };
   for (int i = 0; i < B; ++i)
     if (!imgs[i]) return fail(ctx, HSO_ERR_INVALID, "null image");
   for (int i = 0; i < B; ++i) {
@@ -1294,10 +1306,13 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
     if (rc != HSO_OK) { for (int j = 0; j < i; ++j) unuse_frame(ctx, new_ids[j]); return rc; }
   }
   auto release_all = [&]() { for (int i = 0; i < B; ++i) unuse_frame(ctx, new_ids[i]); };
+  std::vector<cudaEvent_t> tr_ev;
   std::vector<hso_track_job> jobs(jobs_in, jobs_in + B);
   for (int b = 0; b < B; ++b) jobs[b].cur = new_ids[b];
+  stamp("frames allocated");
   int rc = track_plan(ctx, prm, B, jobs.data(), 0);  // synchronises ctx->stream: nothing of a previous call is in flight below
   if (rc != HSO_OK) { release_all(); return rc; }
+  stamp("track_plan");
   // Everything that can fail after the frames were allocated runs inside `pipeline`, so that every error path — a CUDA error in the middle of
   // the chunk loop included — goes through the same clean-up: wait for the streams, hand the new frames back.
   int S = 1;
@@ -1343,6 +1358,23 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   const char* dbg_env = getenv("HSO_PIPE_DEBUG");
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   std::vector<const uint8_t*> srcs(B);
+  // direct-input mode: every small record of the batch (pyramid jobs, tracker jobs, initial poses, exposure ratios: ~300 B per problem) goes out
+  // in four copies up front instead of five per chunk — each copy costs the copy engine a few microseconds whatever its size, and the call is
+  // bound by the copy stream
+  const bool records_up_front = ctx->t_direct && !(dbg & (2 | 8));
+  if (records_up_front) {
+    for (int i = 0; i < B; ++i) srcs[i] = get_frame(ctx, new_ids[i])->pyr + ctx->geom.off[0];
+    rc = run_pyramid(ctx, B, new_ids, srcs.data(), W, 1, 0, ctx->copy_stream);
+    if (rc != HSO_OK) return rc;
+    track_fill_pose(ctx, jobs.data(), 0, B);
+    rc = track_copy_range(ctx, 0, B, ctx->copy_stream);
+    if (rc != HSO_OK) return rc;
+  }
+  if (ptrace) {  // timed events: copy end, first kernel start, last kernel end of every chunk
+    tr_ev.resize(3 * n_chunks + 1);
+    for (auto& e : tr_ev) cudaEventCreate(&e);
+    cudaEventRecord(tr_ev[3 * n_chunks], ctx->copy_stream);
+  }
   for (int c = 0; c < n_chunks; ++c) {
     const int b0 = bounds[c], b1 = bounds[c + 1], n = b1 - b0;
     // images straight into the level-0 slots (one 2-D copy for equally spaced images going to consecutive slots)
@@ -1359,29 +1391,40 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
       srcs[i] = s->pyr + ctx->geom.off[0];
     }
     if (!ctx->t_direct && !workers) workers.reset(new StageWorkers(ctx, jobs.data(), B, bounds));
-    rc = run_pyramid(ctx, n, new_ids + b0, srcs.data() + b0, W, 1, b0, ctx->copy_stream);
-    if (rc != HSO_OK) return rc;
+    if (!records_up_front) {
+      rc = run_pyramid(ctx, n, new_ids + b0, srcs.data() + b0, W, 1, b0, ctx->copy_stream);
+      if (rc != HSO_OK) return rc;
+    }
     if (ctx->t_direct) {
-      rc = (dbg & (2 | 8)) ? HSO_OK : track_copy_raw(ctx, jobs.data(), b0, b1, ctx->copy_stream);
+      rc = (dbg & (2 | 8)) ? HSO_OK : track_copy_raw(ctx, jobs.data(), b0, b1, ctx->copy_stream, !records_up_front);
       if (rc != HSO_OK) return rc;
     } else {
       workers->wait_chunk(c);
     }
-    rc = (dbg & (2 | 8)) ? HSO_OK : track_copy_range(ctx, b0, b1, ctx->copy_stream);
+    rc = ((dbg & (2 | 8)) || records_up_front) ? HSO_OK : track_copy_range(ctx, b0, b1, ctx->copy_stream);
     if (rc != HSO_OK) return rc;
     CU(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+    if (ptrace) cudaEventRecord(tr_ev[3 * c], ctx->copy_stream);
     cudaStream_t cs = (c % S == 0) ? ctx->stream : ctx->pipe_streams[c % S - 1];
     CU(cudaStreamWaitEvent(cs, ctx->chunk_ev[c], 0));
     if (dbg & 1) continue;
+    if (ptrace) cudaEventRecord(tr_ev[3 * c + 1], cs);
     if (ctx->t_direct) CU(launch_track_compact((TrackJobDev*)ctx->t_jobs_dev.p + b0, n, cs, &ctx->launches));
     CU(launch_pyramid(ctx->geom, (const PyrJobDev*)ctx->pyr_jobs_dev.p + b0, n, W, ctx->resize_tabs.data(), ctx->cfg.materialize_sobel,
                       (unsigned*)ctx->pyr_counters.p + b0, 1, cs, &ctx->launches));
+    // (measured, profiles/r2t_tail_sweep.txt: giving the last chunks latency shapes — clusters of 2/4/8 CTAs by the problems still to come — and a
+    // geometric ramp-down on streams of their own moves the end of the call by 0.15 ms of 12: the SMs are held by the older chunks' CTAs,
+    // and a problem's four level launches take >= 1.3 ms whatever its chunk size)
     rc = track_run_range(ctx, b0, n, false, B, cs);
     if (rc != HSO_OK) return rc;
+    if (ptrace) cudaEventRecord(tr_ev[3 * c + 2], cs);
+    if (ptrace && (c < 3 || c + 2 >= n_chunks)) { char nm[48]; snprintf(nm, sizeof nm, "chunk %d (%d jobs) enqueued", c, n); stamp(nm); }
   }
+    if (ptrace) { cudaStreamSynchronize(ctx->copy_stream); stamp("copy stream drained"); }
     return HSO_OK;
   };
   rc = pipeline();
+  stamp("pipeline enqueued");
   workers.reset();  // joins the flattening threads
   for (int k = 0; k < S - 1 && k < (int)ctx->pipe_streams.size(); ++k) {  // join the extra compute streams into the context stream
     cudaEventRecord(ctx->pipe_ev[k], ctx->pipe_streams[k]);
@@ -1393,10 +1436,23 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
     release_all();
     return rc;
   }
+  if (ptrace) {
+    cudaStreamSynchronize(ctx->stream);
+    stamp("kernels drained");
+    const int nc = ((int)tr_ev.size() - 1) / 3;
+    for (int c = 0; c < nc; ++c) {
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, tr_ev[3 * nc], tr_ev[3 * c]); cudaEventElapsedTime(&b, tr_ev[3 * nc], tr_ev[3 * c + 1]); cudaEventElapsedTime(&d, tr_ev[3 * nc], tr_ev[3 * c + 2]);
+      fprintf(stderr, "[pipe] chunk %2d: copy done %7.3f  kernels %7.3f .. %7.3f ms\n", c, a, b, d);
+    }
+    for (auto& e : tr_ev) cudaEventDestroy(e);
+  }
   rc = hso_track_collect(ctx, out, nullptr, nullptr);
   if (rc != HSO_OK) return rc;
+  stamp("results collected");
   rc = read_stats(ctx, B, new_ids, integral, grad_mean);
   if (rc != HSO_OK) return rc;
+  stamp("statistics read");
   tm.stop_after_sync();
   for (int b = 0; b < B; ++b)
     if (jobs[b].n_features == 0) {  // CoarseTracker::run returns 0 and leaves the pose untouched when the reference has no features (:53)

@@ -286,7 +286,9 @@ HSO_DEV void accumulate_term(const TermCtx& t, float c, float color, float gx, f
 }
 
 // Streams the window of one patch of image `img` (bilinear weights w*, integer base pixel `base`) and calls
-// f(n, Ib, dx, dy) for every pattern pixel n. Used for the current image in forward mode and for the reference image in the
+// f(n, Ib, 2 dx, 2 dy) for every pattern pixel n — the central differences WITHOUT their factor 0.5: a power-of-two factor commutes with every
+// rounding of the moment sums, so the caller applies 0.25 / 0.5 once per patch (moments_unscale) instead of two multiplications per term
+// and gets bit-identical moments. Used for the current image in forward mode and for the reference image in the
 // inverse-compositional dual-image mode.
 template <int PIDX, bool SM, class F>
 HSO_DEV void window_samples(const uint8_t* img, int base, int w, float wtl, float wtr, float wbl, float wbr, F&& f) {
@@ -313,13 +315,19 @@ HSO_DEV void window_samples(const uint8_t* img, int base, int w, float wtl, floa
       for (int n = 0; n < N; ++n) {
         if (pat_dy<PIDX>(n) + P + 1 == r - 2) {
           const int cx = pat_dx<PIDX>(n) + P + 1;
-          f(n, IbB[cx], 0.5f * (IbB[cx + 1] - IbB[cx - 1]), 0.5f * (IbC[cx] - IbA[cx]));
+          f(n, IbB[cx], IbB[cx + 1] - IbB[cx - 1], IbC[cx] - IbA[cx]);  // 2 dx, 2 dy: the caller rescales the patch's moments (exact)
         }
       }
     }
 #pragma unroll
     for (int c = 0; c < WIN; ++c) pxPrev[c] = pxCur[c];
   }
+}
+
+// moments accumulated with gradients 2 dx, 2 dy -> moments of dx, dy (exact: powers of two)
+HSO_DEV void moments_unscale(Moments& m) {
+  m.xx *= 0.25f; m.xy *= 0.25f; m.yy *= 0.25f;
+  m.cx *= 0.5f; m.cy *= 0.5f; m.rx *= 0.5f; m.ry *= 0.5f;
 }
 
 struct LevelCtx {
@@ -479,6 +487,7 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
             accumulate_term<TOP>(tc, ps.cache[n * S + sl], color, ps.gx[n * S + sl], ps.gy[n * S + sl], m, Ep, sat);
           }
         }
+        if (!IC || DUAL) moments_unscale(m);  // the streamed window delivers 2 dx, 2 dy
         // Jacobian rows of the patch after the term loop (keeps 12 registers free while the window is live)
         float A[6], B[6];
         if (!IC) {
