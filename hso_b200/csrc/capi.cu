@@ -210,6 +210,7 @@ struct hso_ctx {
   std::vector<size_t> t_goff;       // staging plan of the batch in flight (track_plan): byte offset of each job's geometry block
   size_t t_geo_bytes = 0;
   // direct-input mode (pinned caller arrays are copied as they are and flattened on the device): -1 auto, 0 never, 1 always
+  int t_no_pair = getenv("HSO_TRACK_NO_PAIR") ? 1 : 0;            // tuning: never two 256-thread CTAs per SM in forward mode
   int t_force_stream = getenv("HSO_TRACK_FORCE_STREAM") ? 1 : 0;  // tuning / tests: mode 3 at every forward level where it fits
   int t_no_stream = getenv("HSO_TRACK_NO_STREAM") ? 1 : 0;        // tuning: never use the streamed-cache mode (mode 3) of the forward tracker
   int t_abs_global = getenv("HSO_TRACK_ABSRES_GLOBAL") ? 1 : 0;  // tuning: keep the |r| scratch of the threshold selection in global memory
@@ -1193,6 +1194,17 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
       const int kpt = (maxF + cc * th - 1) / (cc * th);
       p.fast = 2; p.pc = kpt * th; p.cluster = cc; p.hist_bits = 11;
       if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; pair_ctas = pair; }
+    }
+    if (!prm.inverse_comp && !ctx->t_no_stream && !ctx->t_no_pair && !f_threads && c_min == 1 && B >= 2 * 148 && maxF > 256) {
+      // forward mode, two or more problems per SM in THIS launch (a chunk of the pipelined call has less than one per SM, and a 256-thread
+      // CTA alone on its SM is just slower): two CTAs of 256 threads share an SM when the streamed-cache mode brings their
+      // footprint under half an SM (image + 8-warp ring + histogram; the |r| scratch in global memory) — one problem's serial control step,
+      // barriers and staging latencies overlap the other's evaluation. Measured at B = 1184, F = 3000 against one 512-thread CTA with the
+      // cache resident: level 4 -7 %, level 3 -3 %, level 2 -3 % (profiles/r2w_shapes.txt); level 1 (77 KB image) does not fit twice.
+      TrackLevelParams q = p;
+      q.fast = 3; q.cluster = 1; q.hist_bits = 11; q.absres_smem = 0;
+      q.pc = (maxF + 255) / 256 * 256;
+      if (track_level_smem_bytes(q, 256) <= 110 * 1024) { p.fast = 3; p.pc = q.pc; p.cluster = 1; p.hist_bits = 11; cluster = 1; threads = 256; pair_ctas = true; }
     }
     for (int cc = c_min; cc <= 8 && !cluster; cc *= 2) {
       int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));

@@ -119,7 +119,9 @@ __host__ __device__ inline size_t smem_layout(uint32_t img_bytes, size_t cache_b
 }
 
 // MODE 3 (streamed cache): per warp two buffers of N rows x 32 patches of reference intensities
-__host__ __device__ inline size_t ring_bytes(int N, int nwarps) { return (size_t)nwarps * 2 * N * 32 * sizeof(float); }
+// behind two mbarriers per warp (padded to 128 B so that the buffers stay 128-byte aligned)
+__host__ __device__ inline size_t ring_bar_bytes(int nwarps) { return ((size_t)nwarps * 16 + 127) / 128 * 128; }
+__host__ __device__ inline size_t ring_bytes(int N, int nwarps) { return ring_bar_bytes(nwarps) + (size_t)nwarps * 2 * N * 32 * sizeof(float); }
 
 static __host__ __device__ inline int pattern_n(int pidx) { return pidx <= 0 ? 1 : pidx == 1 ? 5 : pidx == 2 ? 9 : pidx <= 4 ? 13 : pidx == 5 ? 21 : 25; }
 
@@ -342,7 +344,8 @@ struct LevelCtx {
 struct PatchStore {
   const uint8_t* ref;  // MODE 2 (dual image): the reference level in shared memory; intensities/gradients are recomputed per evaluation
   float* cache;    // reference intensities
-  float* ring;     // MODE 3: this warp's two staging buffers [2][N][32] for the cache rows streamed from global memory (L2)
+  float* ring;     // MODE 3: this warp's two staging buffers [2][N][32] for the cache blocks streamed from global memory (L2)
+  uint64_t* ring_bar;  // MODE 3: this warp's two mbarriers (one per buffer)
   float* gx;       // inverse-compositional reference gradients
   float* gy;
   uint8_t* vis;
@@ -391,39 +394,39 @@ HSO_DEV void ref_intensity_grad(const uint8_t* img, const RefPatch& r, int addr,
 // One residual evaluation over the calling thread's patches: computeResiduals + computeGS fused
 // (src/CoarseTracker.cpp:242-414, :499-525).
 // MODE 3: the reference-intensity cache of a problem stays in global memory (L2 resident: it is written once per level and re-read by every
-// evaluation) and is streamed through a small per-warp ring in shared memory — cp.async (LDGSTS, 16 B per lane) fetches the N rows x 32 patches of
-// the warp's NEXT patch group while the current group is evaluated. That frees the 108-258 KB the resident cache takes, so that a level whose
-// image + cache exceed one SM (level 1 at 640x480 with 3000 patches) still runs as ONE CTA per problem: no cluster barriers, no DSMEM exchange,
-// one control step and one staged image per problem instead of two.
-HSO_DEV void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-HSO_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int KEEP>
-HSO_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory"); }
-// rows n = 0..N-1 of patches [i0, i0 + 32) -> dst[n * 32 + lane]; i0 is a multiple of 32 and the rows are 128-byte aligned (Fpad % 32 == 0)
+// evaluation) and is streamed through a small per-warp ring in shared memory: the cache is stored GROUP-major — the N x 32 floats of 32 consecutive
+// patches are one contiguous block — so that ONE TMA bulk copy (cp.async.bulk + mbarrier, issued by lane 0) fetches the warp's NEXT patch group
+// while the current group is evaluated. That frees the 108-258 KB the resident cache takes, so that a level whose image + cache exceed one SM
+// (level 1 at 640x480 with 3000 patches) still runs as ONE CTA per problem: no cluster barriers, no DSMEM exchange, one control step and one
+// staged image per problem instead of two.
 template <int N>
-HSO_DEV void ring_fetch(const float* gcache, int Fp, int i0, float* dst) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int c0 = 0; c0 < N * 8; c0 += 32) {
-    const int c = c0 + lane;
-    if (N * 8 - c0 >= 32 || c < N * 8) cp_async16(dst + (c >> 3) * 32 + (c & 7) * 4, gcache + (size_t)(c >> 3) * Fp + i0 + (c & 7) * 4);
+HSO_DEV int ring_index(int i, int n) { return (i >> 5) * (N * 32) + n * 32 + (i & 31); }  // element (patch i, pattern pixel n) of the group-major cache
+// g: running number of the group within the launch (buffer g & 1, mbarrier phase (g >> 1) & 1); i0: first patch of the group (multiple of 32)
+template <int N>
+HSO_DEV void ring_issue(const PatchStore& ps, int i0, uint32_t g) {
+  if ((threadIdx.x & 31) == 0) {
+    uint64_t* bar = ps.ring_bar + (g & 1);
+    fence_proxy_async();  // the buffer was last read through the generic proxy (every lane is past it: __syncwarp at the end of that iteration)
+    mbar_expect_tx(bar, N * 128);
+    tma_bulk_g2s(ps.ring + (g & 1) * (N * 32), ps.cache + (size_t)(i0 >> 5) * (N * 32), N * 128, bar);
   }
+}
+template <int N>
+HSO_DEV const float* ring_wait(const PatchStore& ps, uint32_t g) {
+  mbar_wait(ps.ring_bar + (g & 1), (g >> 1) & 1);
+  return ps.ring + (g & 1) * (N * 32) + (threadIdx.x & 31);
 }
 
 template <int PIDX, bool IC, int MODE, bool TOP>
 HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const PatchStore& ps, const CamDev& cam, const double* Rt, float a, float huber,
-                          float cutoff, int t0, int nt, Acc& acc) {
+                          float cutoff, int t0, int nt, Acc& acc, uint32_t& ring_g) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
   constexpr bool FAST = MODE != 0, DUAL = MODE == 2, STREAM = MODE == 3;
   static_assert(!STREAM || !IC, "the streamed cache exists for the forward mode only");
   const int Fp = job.Fpad, S = ps.stride;
   const int lane = threadIdx.x & 31;
-  if (STREAM) {
-    if (t0 - lane < job.F) ring_fetch<N>(ps.cache, Fp, t0 - lane, ps.ring);
-    cp_async_commit();
-  }
+  uint32_t g = ring_g;
+  if (STREAM && t0 - lane < job.F) ring_issue<N>(ps, t0 - lane, g);
   // max_energy = 2*huber*cutoff - huber^2, evaluated in double like the reference (cutoff_error is a double there)
   const float max_energy = (float)(2.0 * (double)huber * (double)cutoff - (double)(huber * huber));
   // geometry of the next patch is fetched while the current one is processed (the only global loads of the FAST path)
@@ -439,12 +442,9 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
     const int in = i + nt, kn = k + 1;
     const float* cbuf = nullptr;
     if (STREAM) {
-      // group k+1 goes into the buffer group k-1 was read from (every lane is past it: __syncwarp at the end of the iteration)
-      if (in - lane < job.F) ring_fetch<N>(ps.cache, Fp, in - lane, ps.ring + (kn & 1) * (N * 32));
-      cp_async_commit();
-      cp_async_wait<1>();  // everything but the newest group has landed: group k
-      __syncwarp();        // ... for every lane's copies
-      cbuf = ps.ring + (k & 1) * (N * 32) + lane;
+      // the next group goes into the buffer the previous group was read from (every lane is past it: __syncwarp at the end of the iteration)
+      if (in - lane < job.F) ring_issue<N>(ps, in - lane, g + 1);
+      cbuf = ring_wait<N>(ps, g);
     }
     const bool have_n = in < job.F && ps.vis[slot_of<FAST>(in, kn)] != 0;
     double Xn = 0, Yn = 0, Zn = 1, PUn = 0, PVn = 0;
@@ -505,9 +505,9 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
       }
     }
     i = in; k = kn; have = have_n; X = Xn; Y = Yn; Z = Zn; PU = PUn; PV = PVn;
-    if (STREAM) __syncwarp();
+    if (STREAM) { __syncwarp(); ++g; }
   }
-  if (STREAM) cp_async_wait<0>();
+  ring_g = g;
 }
 
 // CTA + cluster reduction of the per-thread partial sums into s.tot[0..NRED) (identical in every CTA of the cluster).
@@ -932,9 +932,12 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
 
   PatchStore ps;
   ps.ref = s.img + align_up(prm.img_bytes, 128);
-  ps.ring = s.cache + (threadIdx.x >> 5) * (2 * N * 32);
+  ps.ring_bar = reinterpret_cast<uint64_t*>(s.cache) + 2 * (threadIdx.x >> 5);
+  ps.ring = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.cache) + ring_bar_bytes(nwarps)) + (threadIdx.x >> 5) * (2 * N * 32);
+  uint32_t ring_g = 0;  // groups this warp has streamed so far (MODE 3)
   if (STREAM) {
     ps.cache = job.ref_cache; ps.gx = nullptr; ps.gy = nullptr; ps.vis = s.vis; ps.stride = Fp;
+    if ((threadIdx.x & 31) == 0) { mbar_init(ps.ring_bar, 1); mbar_init(ps.ring_bar + 1, 1); mbar_fence_init(); }
   } else if (FAST) {
     ps.cache = s.cache; ps.gx = s.cache + (size_t)N * prm.pc; ps.gy = s.cache + (size_t)2 * N * prm.pc; ps.vis = s.vis; ps.stride = prm.pc;
   } else {
@@ -986,7 +989,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     int k = 0;
     for (int i = t0; i < job.F; i += nt, ++k) {
       const int sl = slot_of<FAST>(i, k);
-      const int csl = STREAM ? i : sl;  // the streamed cache is indexed by patch like the global-memory path
+
       const RefPatch rp = ref_patch(job.px[i], job.px[Fp + i], L.scale, L.border, L.w, L.h);
       ps.vis[sl] = rp.in ? 1 : 0;
       if (!rp.in || DUAL) continue;  // dual-image mode recomputes the reference samples in every evaluation
@@ -994,7 +997,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
       for (int n = 0; n < N; ++n) {
         const int addr = rp.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
         if (!IC) {
-          ps.cache[n * ps.stride + csl] = ref_intensity<FAST>(ref_src, rp, addr, L.w);
+          ps.cache[STREAM ? ring_index<N>(i, n) : n * ps.stride + sl] = ref_intensity<FAST>(ref_src, rp, addr, L.w);
         } else {
           float cc, gx, gy;
           ref_intensity_grad<FAST>(ref_src, rp, addr, L.w, cc, gx, gy);
@@ -1005,6 +1008,8 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
       }
     }
   }
+  // MODE 3: the cache just written through the generic proxy is read back by TMA bulk copies (async proxy)
+  if (STREAM) asm volatile("fence.proxy.async.global;" ::: "memory");
   __syncthreads();
   const long long clk_pre = clock64();
   if (FAST && !DUAL) {
@@ -1037,9 +1042,16 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     for (int j = threadIdx.x; j < (1 << hbits); j += blockDim.x) s.hist[j] = 0;
     __syncthreads();
     int k = 0;
-    for (int i = t0; i < job.F; i += nt, ++k) {
+    const int lane = threadIdx.x & 31;
+    if (STREAM && t0 - lane < job.F) ring_issue<N>(ps, t0 - lane, ring_g);
+    for (int i = t0; (STREAM ? i - lane : i) < job.F; i += nt, ++k) {  // (STREAM: warp-uniform trip count, the ring is filled by the whole warp)
+      const float* cbuf = nullptr;
+      if (STREAM) {
+        if (i + nt - lane < job.F) ring_issue<N>(ps, i + nt - lane, ring_g + 1);
+        cbuf = ring_wait<N>(ps, ring_g);
+      }
       const int sl = slot_of<FAST>(i, k);
-      bool ok = ps.vis[sl] != 0;
+      bool ok = (!STREAM || i < job.F) && ps.vis[sl] != 0;
       Proj p;
       RefPatch rp;
       if (ok) {
@@ -1056,12 +1068,13 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
           const uint32_t r0 = ld4<FAST>(L.cur, addr);
           const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
           const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-          const float cref = DUAL ? ref_intensity<true>(ps.ref, rp, rp.base + poff, L.w) : ps.cache[n * ps.stride + (STREAM ? i : sl)];
+          const float cref = DUAL ? ref_intensity<true>(ps.ref, rp, rp.base + poff, L.w) : STREAM ? cbuf[n * 32] : ps.cache[n * ps.stride + sl];
           out = fabsf(fmaf(-a, cref, color));
           atomicAdd(&s.hist[lin ? lin_bin(out, 2048) : (__float_as_uint(out) >> (32 - hbits))], 1u);  // first pass of the median select, fused
         }
-        absres[n * astride + (a_smem ? sl : i)] = out;
+        if (!STREAM || i < job.F) absres[n * astride + (a_smem ? sl : i)] = out;
       }
+      if (STREAM) { __syncwarp(); ++ring_g; }
     }
     clk_res = clock64();
     if (lin) select_kth<N>(job, s, absres, astride, a_smem, t0, nt, false, 0.f, csize, true);
@@ -1098,7 +1111,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     acc_zero(acc);
     // the top level has its own energy and no cut-off (:350-361). m_offset_all = m_max_level - m_level + m_pattern_offset (:80) makes the top
     // level the one and only user of pattern index m_pattern_offset = 2: a compile-time property of the instantiation
-    eval_patches<PIDX, IC, MODE, PIDX == 2>(L, job, ps, prm.cam, c->Rt, a_eval, huber, cutoff, t0, nt, acc);
+    eval_patches<PIDX, IC, MODE, PIDX == 2>(L, job, ps, prm.cam, c->Rt, a_eval, huber, cutoff, t0, nt, acc, ring_g);
     reduce_acc(acc, s, slot, csize, nwarps);
     slot ^= 1;
     ++level_evals;
