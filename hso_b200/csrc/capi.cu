@@ -877,6 +877,9 @@ static int track_plan(hso_ctx* ctx, const hso_track_params* prm, int B, const hs
     auto take = [&](size_t bytes) { size_t o = (arena + 127) / 128 * 128; arena = o + bytes; return o; };
     off_cache[b] = take(sizeof(float) * kMaxPatternN * Fpad);
     if (prm->inverse_comp) { off_gx[b] = take(sizeof(float) * kMaxPatternN * Fpad); off_gy[b] = take(sizeof(float) * kMaxPatternN * Fpad); }
+    // the streamed inverse-compositional cache (mode 3) treats the three planes as ONE group-major array of 3 N Fpad floats
+    if (prm->inverse_comp && (off_gx[b] != off_cache[b] + sizeof(float) * kMaxPatternN * Fpad || off_gy[b] != off_gx[b] + sizeof(float) * kMaxPatternN * Fpad))
+      return fail(ctx, HSO_ERR_INVALID, "tracker scratch planes are not contiguous");
     off_abs[b] = take(sizeof(float) * kMaxPatternN * Fpad);
     off_vis[b] = take(Fpad);
     off_state[b] = take(sizeof(TrackState));
@@ -1176,16 +1179,35 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
     }
     int cluster = 0, threads = 0;
     bool pair_ctas = false;
-    if (prm.inverse_comp && !ctx->t_no_dual) {
+    // Two or more problems per SM in THIS launch (a chunk of the pipelined call has less than one per SM, and a 256-thread CTA alone on its SM
+    // is just slower): two CTAs of 256 threads share an SM when their footprint is under half an SM (the |r| scratch then lives in global
+    // memory) — one problem's serial control step, barriers and staging latencies overlap the other's evaluation.
+    const bool pairs_ok = !ctx->t_no_pair && !f_threads && c_min == 1 && B >= 2 * 148 && maxF > 256;
+    if (pairs_ok && !ctx->t_no_stream) {
+      // streamed-cache mode (image + 8-warp ring + histogram). Forward, measured at B = 1184, F = 3000 against one 512-thread CTA with the cache
+      // resident: level 4 -7 %, level 3 -3 %, level 2 -3 % (profiles/r2w_shapes.txt); level 1 (77 KB image) does not fit twice.
+      TrackLevelParams q = p;
+      q.fast = 3; q.cluster = 1; q.hist_bits = 11; q.absres_smem = 0;
+      q.pc = (maxF + 255) / 256 * 256;
+      if (track_level_smem_bytes(q, 256) <= 110 * 1024) { p.fast = 3; p.pc = q.pc; p.cluster = 1; p.hist_bits = 11; cluster = 1; threads = 256; pair_ctas = true; }
+    }
+    if (!cluster && prm.inverse_comp && !ctx->t_no_stream) {
+      // inverse-compositional, cached reference intensities + gradients (what the reference precomputes, src/CoarseTracker.cpp:482-492) streamed
+      // from L2: ~48 instructions per residual term against ~73 for the dual-image mode below, which re-derives them from the reference image
+      const int cc = c_min;
+      const int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
+      const int kpt = (maxF + cc * th - 1) / (cc * th);
+      p.fast = 3; p.pc = kpt * th; p.cluster = cc; p.hist_bits = 11;
+      if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; }
+    }
+    if (!cluster && prm.inverse_comp && !ctx->t_no_dual) {
       // inverse-compositional: keep BOTH levels resident and recompute the reference samples per evaluation — no F-dependent
       // cache, so one CTA per problem fits whenever two copies of the level do
       const int cc = c_min;
       int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
-      // With two or more problems per SM in flight, two CTAs of 256 threads share an SM when their footprint allows it (no reference-patch
-      // cache in this mode; the |r| scratch then lives in global memory): one problem's serial control phase overlaps the other's evaluation.
-      // Measured at B = 1184, F = 3000: level 4 -12 %, level 3 -5 %, level 2 -4 % (profiles/r2m_ic_shapes.txt).
+      // pairs of 256-thread CTAs, measured at B = 1184, F = 3000: level 4 -12 %, level 3 -5 %, level 2 -4 % (profiles/r2m_ic_shapes.txt)
       bool pair = false;
-      if (!f_threads && cc == 1 && shape_B >= 2 * 148 && th > 256) {
+      if (pairs_ok && th > 256) {
         TrackLevelParams q = p;
         q.fast = 2; q.cluster = 1; q.hist_bits = 11; q.absres_smem = 0;
         q.pc = (maxF + 255) / 256 * 256;
@@ -1195,22 +1217,11 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
       p.fast = 2; p.pc = kpt * th; p.cluster = cc; p.hist_bits = 11;
       if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; pair_ctas = pair; }
     }
-    if (!prm.inverse_comp && !ctx->t_no_stream && !ctx->t_no_pair && !f_threads && c_min == 1 && B >= 2 * 148 && maxF > 256) {
-      // forward mode, two or more problems per SM in THIS launch (a chunk of the pipelined call has less than one per SM, and a 256-thread
-      // CTA alone on its SM is just slower): two CTAs of 256 threads share an SM when the streamed-cache mode brings their
-      // footprint under half an SM (image + 8-warp ring + histogram; the |r| scratch in global memory) — one problem's serial control step,
-      // barriers and staging latencies overlap the other's evaluation. Measured at B = 1184, F = 3000 against one 512-thread CTA with the
-      // cache resident: level 4 -7 %, level 3 -3 %, level 2 -3 % (profiles/r2w_shapes.txt); level 1 (77 KB image) does not fit twice.
-      TrackLevelParams q = p;
-      q.fast = 3; q.cluster = 1; q.hist_bits = 11; q.absres_smem = 0;
-      q.pc = (maxF + 255) / 256 * 256;
-      if (track_level_smem_bytes(q, 256) <= 110 * 1024) { p.fast = 3; p.pc = q.pc; p.cluster = 1; p.hist_bits = 11; cluster = 1; threads = 256; pair_ctas = true; }
-    }
     for (int cc = c_min; cc <= 8 && !cluster; cc *= 2) {
       int th = f_threads ? f_threads : std::min(512, std::max(64, ((maxF + cc - 1) / cc + 31) / 32 * 32));
       const int kpt = (maxF + cc * th - 1) / (cc * th);
       p.pc = kpt * th; p.cluster = cc;
-      if (ctx->t_force_stream && !prm.inverse_comp) {  // tuning / tests: the streamed-cache mode wherever it fits
+      if (ctx->t_force_stream) {  // tuning / tests: the streamed-cache mode wherever it fits
         p.fast = 3; p.hist_bits = 11;
         if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
       }
@@ -1219,9 +1230,9 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
       if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
       p.hist_bits = 8;
       if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
-      // forward mode: image resident, reference-patch cache streamed from L2 through a per-warp ring (mode 3) before the problem is split
-      // over more CTAs — a cluster costs two cluster barriers per trial, a second staged image and a second (redundant) control step
-      if (!prm.inverse_comp && !ctx->t_no_stream) {
+      // image resident, reference-patch cache streamed from L2 through a per-warp ring (mode 3) before the problem is split over more
+      // CTAs — a cluster costs two cluster barriers per trial, a second staged image and a second (redundant) control step
+      if (!ctx->t_no_stream) {
         p.fast = 3; p.hist_bits = 11;
         if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; break; }
       }

@@ -130,7 +130,7 @@ size_t track_level_smem_bytes(const TrackLevelParams& p, int threads) {
   size_t a, b, c, d, e, f, g, h, i, j;
   const int N = pattern_n(p.max_level - p.level + 2);
   const size_t absb = (p.fast && p.absres_smem) ? (size_t)N * p.pc * sizeof(float) : 0;
-  const size_t cache = p.fast == 1 ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : p.fast == 3 ? ring_bytes(N, threads / 32) : 0;
+  const size_t cache = p.fast == 1 ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : p.fast == 3 ? ring_bytes(N * (p.ic ? 3 : 1), threads / 32) : 0;
   const uint32_t img = p.fast == 2 ? 2 * (uint32_t)align_up(p.img_bytes, 128) : (p.fast ? p.img_bytes : 0);
   return smem_layout(img, cache, absb, p.fast ? (size_t)p.pc : 0, threads / 32, p.hist_bits, p.cluster, &a, &j, &b, &c, &d, &e, &f, &g, &h, &i);
 }
@@ -326,6 +326,41 @@ HSO_DEV void window_samples(const uint8_t* img, int base, int w, float wtl, floa
   }
 }
 
+// Colour-only variant: the bilinearly interpolated image at the N pattern pixels, f(n, Ib), from the (2P+2)^2 window — rows loaded once as aligned
+// words instead of two unaligned 4-byte fetches per pattern pixel (4 shared-memory loads per term at ~3.4 bank conflicts each made the
+// inverse-compositional cached path and the threshold pass LSU bound). Same expression, same operand order as ld4 + the four products (:339-342).
+template <int PIDX, bool SM, class F>
+HSO_DEV void window_colors(const uint8_t* img, int base, int w, float wtl, float wtr, float wbl, float wbr, F&& f) {
+  constexpr int P = PG<PIDX>::P, WIN = 2 * P + 2, N = PG<PIDX>::N;
+  constexpr int NW = (WIN + 6) / 4, NA = (WIN + 3) / 4;
+  const int a0 = base - P * w - P;
+  float pxPrev[WIN], pxCur[WIN];
+#pragma unroll
+  for (int r = 0; r < WIN; ++r) {
+    const int byte_addr = a0 + r * w;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(img) + (byte_addr >> 2);
+    const int sh = (byte_addr & 3) << 3;
+    uint32_t wv[NW], row[NA];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) wv[j] = SM ? wp[j] : __ldg(wp + j);
+#pragma unroll
+    for (int j = 0; j < NA; ++j) row[j] = __funnelshift_r(wv[j], wv[j + 1], sh);
+#pragma unroll
+    for (int c = 0; c < WIN; ++c) pxCur[c] = byte_to_float_k(row[c >> 2], c & 3);
+    if (r >= 1) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        if (pat_dy<PIDX>(n) + P == r - 1) {
+          const int cx = pat_dx<PIDX>(n) + P;
+          f(n, wtl * pxPrev[cx] + wtr * pxPrev[cx + 1] + wbl * pxCur[cx] + wbr * pxCur[cx + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < WIN; ++c) pxPrev[c] = pxCur[c];
+  }
+}
+
 // moments accumulated with gradients 2 dx, 2 dy -> moments of dx, dy (exact: powers of two)
 HSO_DEV void moments_unscale(Moments& m) {
   m.xx *= 0.25f; m.xy *= 0.25f; m.yy *= 0.25f;
@@ -379,17 +414,6 @@ HSO_DEV float ref_intensity(const uint8_t* img, const RefPatch& r, int addr, int
   const uint32_t r1 = ld4<SM>(img, addr + w);
   return r.wtl * b0(r0) + r.wtr * b1(r0) + r.wbl * b0(r1) + r.wbr * b1(r1);
 }
-// reference intensity + central-difference gradients of one pattern pixel, inverse-compositional mode (:482-492)
-template <bool SM>
-HSO_DEV void ref_intensity_grad(const uint8_t* img, const RefPatch& r, int addr, int w, float& c, float& gx, float& gy) {
-  const uint32_t rm = ld4<SM>(img, addr - w - 1);
-  const uint32_t r0 = ld4<SM>(img, addr - 1);
-  const uint32_t r1 = ld4<SM>(img, addr + w - 1);
-  const uint32_t r2 = ld4<SM>(img, addr + 2 * w - 1);
-  c = r.wtl * b1(r0) + r.wtr * b2(r0) + r.wbl * b1(r1) + r.wbr * b2(r1);
-  gx = 0.5f * ((r.wtl * b2(r0) + r.wtr * b3(r0) + r.wbl * b2(r1) + r.wbr * b3(r1)) - (r.wtl * b0(r0) + r.wtr * b1(r0) + r.wbl * b0(r1) + r.wbr * b1(r1)));
-  gy = 0.5f * ((r.wtl * b1(r1) + r.wtr * b2(r1) + r.wbl * b1(r2) + r.wbr * b2(r2)) - (r.wtl * b1(rm) + r.wtr * b2(rm) + r.wbl * b1(r0) + r.wbr * b2(r0)));
-}
 
 // One residual evaluation over the calling thread's patches: computeResiduals + computeGS fused
 // (src/CoarseTracker.cpp:242-414, :499-525).
@@ -422,11 +446,11 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
                           float cutoff, int t0, int nt, Acc& acc, uint32_t& ring_g) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
   constexpr bool FAST = MODE != 0, DUAL = MODE == 2, STREAM = MODE == 3;
-  static_assert(!STREAM || !IC, "the streamed cache exists for the forward mode only");
+  constexpr int NR = IC ? 3 * N : N;  // rows of a streamed cache group: intensities (+ the two gradient planes, inverse-compositional)
   const int Fp = job.Fpad, S = ps.stride;
   const int lane = threadIdx.x & 31;
   uint32_t g = ring_g;
-  if (STREAM && t0 - lane < job.F) ring_issue<N>(ps, t0 - lane, g);
+  if (STREAM && t0 - lane < job.F) ring_issue<NR>(ps, t0 - lane, g);
   // max_energy = 2*huber*cutoff - huber^2, evaluated in double like the reference (cutoff_error is a double there)
   const float max_energy = (float)(2.0 * (double)huber * (double)cutoff - (double)(huber * huber));
   // geometry of the next patch is fetched while the current one is processed (the only global loads of the FAST path)
@@ -443,8 +467,8 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
     const float* cbuf = nullptr;
     if (STREAM) {
       // the next group goes into the buffer the previous group was read from (every lane is past it: __syncwarp at the end of the iteration)
-      if (in - lane < job.F) ring_issue<N>(ps, in - lane, g + 1);
-      cbuf = ring_wait<N>(ps, g);
+      if (in - lane < job.F) ring_issue<NR>(ps, in - lane, g + 1);
+      cbuf = ring_wait<NR>(ps, g);
     }
     const bool have_n = in < job.F && ps.vis[slot_of<FAST>(in, kn)] != 0;
     double Xn = 0, Yn = 0, Zn = 1, PUn = 0, PVn = 0;
@@ -478,14 +502,11 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
             accumulate_term<TOP>(tc, c, color, gx, gy, m, Ep, sat);
           });
         } else {
-#pragma unroll
-          for (int n = 0; n < N; ++n) {
-            const int addr = p.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
-            const uint32_t r0 = ld4<FAST>(L.cur, addr);
-            const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
-            const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-            accumulate_term<TOP>(tc, ps.cache[n * S + sl], color, ps.gx[n * S + sl], ps.gy[n * S + sl], m, Ep, sat);
-          }
+          // inverse-compositional, cached reference intensities and gradients: only the current colour is sampled
+          window_colors<PIDX, FAST>(L.cur, p.base, L.w, p.wtl, p.wtr, p.wbl, p.wbr, [&](int n, float color) {
+            if (STREAM) accumulate_term<TOP>(tc, cbuf[n * 32], color, cbuf[(N + n) * 32], cbuf[(2 * N + n) * 32], m, Ep, sat);
+            else accumulate_term<TOP>(tc, ps.cache[n * S + sl], color, ps.gx[n * S + sl], ps.gy[n * S + sl], m, Ep, sat);
+          });
         }
         if (!IC || DUAL) moments_unscale(m);  // the streamed window delivers 2 dx, 2 dy
         // Jacobian rows of the patch after the term loop (keeps 12 registers free while the window is live)
@@ -896,6 +917,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
   constexpr int PAD = (PIDX == 5) ? 3 : (PIDX == 7) ? 4 : (PIDX <= 2) ? 1 : 2;
   constexpr bool FAST = MODE != 0, DUAL = MODE == 2, STREAM = MODE == 3;
+  constexpr int NR = IC ? 3 * N : N;
   static_assert(!DUAL || IC, "the dual-image mode exists for the inverse-compositional path only");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -910,7 +932,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   {
     size_t oc, oa, ov, ow, op, ot, oh, og, ox, om;
     const size_t abs_bytes = (FAST && prm.absres_smem) ? (size_t)N * prm.pc * sizeof(float) : 0;
-    const size_t cache_bytes = MODE == 1 ? (size_t)N * (IC ? 3 : 1) * prm.pc * sizeof(float) : STREAM ? ring_bytes(N, nwarps) : 0;
+    const size_t cache_bytes = MODE == 1 ? (size_t)N * (IC ? 3 : 1) * prm.pc * sizeof(float) : STREAM ? ring_bytes(NR, nwarps) : 0;
     const uint32_t img_total = DUAL ? 2 * (uint32_t)align_up(prm.img_bytes, 128) : (FAST ? prm.img_bytes : 0);
     smem_layout(img_total, cache_bytes, abs_bytes, FAST ? (size_t)prm.pc : 0, nwarps, prm.hist_bits, csize, &oc, &oa, &ov, &ow, &op, &ot, &oh, &og, &ox, &om);
     s.absres = reinterpret_cast<float*>(smem_raw + oa);
@@ -933,7 +955,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   PatchStore ps;
   ps.ref = s.img + align_up(prm.img_bytes, 128);
   ps.ring_bar = reinterpret_cast<uint64_t*>(s.cache) + 2 * (threadIdx.x >> 5);
-  ps.ring = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.cache) + ring_bar_bytes(nwarps)) + (threadIdx.x >> 5) * (2 * N * 32);
+  ps.ring = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.cache) + ring_bar_bytes(nwarps)) + (threadIdx.x >> 5) * (2 * NR * 32);
   uint32_t ring_g = 0;  // groups this warp has streamed so far (MODE 3)
   if (STREAM) {
     ps.cache = job.ref_cache; ps.gx = nullptr; ps.gy = nullptr; ps.vis = s.vis; ps.stride = Fp;
@@ -993,19 +1015,25 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
       const RefPatch rp = ref_patch(job.px[i], job.px[Fp + i], L.scale, L.border, L.w, L.h);
       ps.vis[sl] = rp.in ? 1 : 0;
       if (!rp.in || DUAL) continue;  // dual-image mode recomputes the reference samples in every evaluation
-#pragma unroll
-      for (int n = 0; n < N; ++n) {
-        const int addr = rp.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
-        if (!IC) {
-          ps.cache[STREAM ? ring_index<N>(i, n) : n * ps.stride + sl] = ref_intensity<FAST>(ref_src, rp, addr, L.w);
+      if (!IC) {
+        window_colors<PIDX, FAST>(ref_src, rp.base, L.w, rp.wtl, rp.wtr, rp.wbl, rp.wbr, [&](int n, float cc) {
+          ps.cache[STREAM ? ring_index<NR>(i, n) : n * ps.stride + sl] = cc;
+        });
+        continue;
+      }
+      // inverse-compositional: intensity and central-difference gradients of the reference image (:482-492) from one streamed window
+      window_samples<PIDX, FAST>(ref_src, rp.base, L.w, rp.wtl, rp.wtr, rp.wbl, rp.wbr, [&](int n, float cc, float gx2, float gy2) {
+        const float gx = 0.5f * gx2, gy = 0.5f * gy2;
+        if (STREAM) {
+          ps.cache[ring_index<NR>(i, n)] = cc;
+          ps.cache[ring_index<NR>(i, N + n)] = gx;
+          ps.cache[ring_index<NR>(i, 2 * N + n)] = gy;
         } else {
-          float cc, gx, gy;
-          ref_intensity_grad<FAST>(ref_src, rp, addr, L.w, cc, gx, gy);
           ps.cache[n * ps.stride + sl] = cc;
           ps.gx[n * ps.stride + sl] = gx;
           ps.gy[n * ps.stride + sl] = gy;
         }
-      }
+      });
     }
   }
   // MODE 3: the cache just written through the generic proxy is read back by TMA bulk copies (async proxy)
@@ -1043,12 +1071,12 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     __syncthreads();
     int k = 0;
     const int lane = threadIdx.x & 31;
-    if (STREAM && t0 - lane < job.F) ring_issue<N>(ps, t0 - lane, ring_g);
+    if (STREAM && t0 - lane < job.F) ring_issue<NR>(ps, t0 - lane, ring_g);
     for (int i = t0; (STREAM ? i - lane : i) < job.F; i += nt, ++k) {  // (STREAM: warp-uniform trip count, the ring is filled by the whole warp)
       const float* cbuf = nullptr;
       if (STREAM) {
-        if (i + nt - lane < job.F) ring_issue<N>(ps, i + nt - lane, ring_g + 1);
-        cbuf = ring_wait<N>(ps, ring_g);
+        if (i + nt - lane < job.F) ring_issue<NR>(ps, i + nt - lane, ring_g + 1);
+        cbuf = ring_wait<NR>(ps, ring_g);
       }
       const int sl = slot_of<FAST>(i, k);
       bool ok = (!STREAM || i < job.F) && ps.vis[sl] != 0;
@@ -1059,20 +1087,18 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
         ok = p.ok;
         if (DUAL) rp = ref_patch(job.px[i], job.px[Fp + i], L.scale, L.border, L.w, L.h);
       }
-#pragma unroll
-      for (int n = 0; n < N; ++n) {
-        float out = -1.f;
-        if (ok) {
-          const int poff = pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n);
-          const int addr = p.base + poff;
-          const uint32_t r0 = ld4<FAST>(L.cur, addr);
-          const uint32_t r1 = ld4<FAST>(L.cur, addr + L.w);
-          const float color = p.wtl * b0(r0) + p.wtr * b1(r0) + p.wbl * b0(r1) + p.wbr * b1(r1);
-          const float cref = DUAL ? ref_intensity<true>(ps.ref, rp, rp.base + poff, L.w) : STREAM ? cbuf[n * 32] : ps.cache[n * ps.stride + sl];
-          out = fabsf(fmaf(-a, cref, color));
+      if (ok) {
+        // |residual| of every pattern pixel at the level's initial state (:557-606), the current colour from the streamed window
+        window_colors<PIDX, FAST>(L.cur, p.base, L.w, p.wtl, p.wtr, p.wbl, p.wbr, [&](int n, float color) {
+          const float cref = DUAL ? ref_intensity<true>(ps.ref, rp, rp.base + pat_dy<PIDX>(n) * L.w + pat_dx<PIDX>(n), L.w)
+                                  : STREAM ? cbuf[n * 32] : ps.cache[n * ps.stride + sl];
+          const float out = fabsf(fmaf(-a, cref, color));
           atomicAdd(&s.hist[lin ? lin_bin(out, 2048) : (__float_as_uint(out) >> (32 - hbits))], 1u);  // first pass of the median select, fused
-        }
-        if (!STREAM || i < job.F) absres[n * astride + (a_smem ? sl : i)] = out;
+          absres[n * astride + (a_smem ? sl : i)] = out;
+        });
+      } else if (!STREAM || i < job.F) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) absres[n * astride + (a_smem ? sl : i)] = -1.f;
       }
       if (STREAM) { __syncwarp(); ++ring_g; }
     }
@@ -1264,6 +1290,7 @@ static cudaError_t launch_pidx(const TrackLevelParams& p, const TrackJobDev* job
                                cudaStream_t stream) {
   if (p.ic) {
     if (p.fast == 2) return launch_one<PIDX, true, 2>(p, jobs_dev, B, cluster, threads, smem, stream);
+    if (p.fast == 3) return launch_one<PIDX, true, 3>(p, jobs_dev, B, cluster, threads, smem, stream);
     return p.fast ? launch_one<PIDX, true, 1>(p, jobs_dev, B, cluster, threads, smem, stream)
                   : launch_one<PIDX, true, 0>(p, jobs_dev, B, cluster, threads, smem, stream);
   }

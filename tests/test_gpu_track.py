@@ -138,17 +138,34 @@ def test_streamed_cache_mode_vs_oracle_and_resident_cache(oracle, cam, F, cluste
     ctx.close()
 
 
-def test_ic_dual_image_and_cached_paths_agree(oracle):
+def test_ic_streamed_dual_image_and_cached_paths_agree(oracle):
+    """The three inverse-compositional paths — cached intensities + gradients streamed from L2 (mode 3, the default), both levels resident with the
+    reference samples recomputed per evaluation (mode 2), cache resident in shared memory (mode 1) — against the oracle and against each other.
+    Streamed and resident cache run the same arithmetic on the same values: identical bits at the same launch shape."""
     p, ctx, tp, job, a0 = _setup(oracle, 35, "icl", 900)
+    r_str, t_str = ctx.coarse_track_batch([job], inverse_comp=True, trace_cap=256)
+    # (level 1: a ring of 63 rows per warp does not fit beside the 77 KB image at this thread count -> mode 2 there)
+    assert all(ctx.level_shape(l)[2] == 3 for l in (4, 3, 2)) and ctx.level_shape(1)[2] in (2, 3), [ctx.level_shape(l) for l in (4, 3, 2, 1)]
+    shape = {l: ctx.level_shape(l)[:3] for l in (4, 3, 2, 1)}
+    _check_trace(oracle, tp, t_str[0], True, 4)
+    ctx._chk(ctx.lib.hso_track_set_stream_cache(ctx.h, -1))
     r_dual, t_dual = ctx.coarse_track_batch([job], inverse_comp=True, trace_cap=256)
+    assert all(ctx.level_shape(l)[2] == 2 for l in (4, 3, 2, 1))
     _check_trace(oracle, tp, t_dual[0], True, 4)
     ctx._chk(ctx.lib.hso_track_set_ic_dual(ctx.h, 0))
     r_cache, t_cache = ctx.coarse_track_batch([job], inverse_comp=True, trace_cap=256)
+    assert all(ctx.level_shape(l)[2] == 1 for l in (4, 3, 2, 1))
     _check_trace(oracle, tp, t_cache[0], True, 4)
-    e0, e1 = t_dual[0][0], t_cache[0][0]
-    assert e0.total_terms == e1.total_terms and e0.huber == e1.huber
+    e0, e1, e2 = t_dual[0][0], t_cache[0][0], t_str[0][0]
+    assert e0.total_terms == e1.total_terms == e2.total_terms and e0.huber == e1.huber == e2.huber
     assert np.allclose(np.array(e0.H[:]), np.array(e1.H[:]), rtol=1e-5, atol=1e-5 * np.abs(np.array(e0.H[:])).max())
     assert np.abs(r_dual[0]["T_cur_ref"] - r_cache[0]["T_cur_ref"]).max() < 2e-4
+    if all(ctx.level_shape(l)[:2] == shape[l][:2] and shape[l][2] == 3 for l in (4, 3, 2, 1)):
+        assert len(t_cache[0]) == len(t_str[0]) and np.array_equal(r_cache[0]["T_cur_ref"], r_str[0]["T_cur_ref"])
+        for ea, eb in zip(t_cache[0], t_str[0]):
+            assert np.array_equal(np.array(ea.H[:]), np.array(eb.H[:])) and np.array_equal(np.array(ea.b[:]), np.array(eb.b[:]))
+    else:
+        assert np.abs(r_str[0]["T_cur_ref"] - r_cache[0]["T_cur_ref"]).max() < 2e-4
     ctx.close()
 
 
@@ -286,6 +303,9 @@ def test_pipelined_entry_edge_cases(oracle):
 # is in global memory. The inverse-compositional mode keeps both levels resident (mode 2) with one CTA per problem. BENCH_SHAPE is what bench.py's
 # batch runs; hso_track_get_level_shape proves the tests run exactly that.
 BENCH_SHAPE_FWD = {4: (1, 256, 3, 0), 3: (1, 256, 3, 0), 2: (1, 256, 3, 0), 1: (1, 512, 3, 0)}
+# inverse-compositional: cached intensities + gradients streamed from L2 (mode 3) as 256-thread pairs at levels 4, 3, one 512-thread CTA at level 2
+# (two 8-warp rings + two images exceed an SM), both levels resident (mode 2) at level 1 where a 16-warp ring of 63 rows does not fit
+BENCH_SHAPE_IC = {4: (1, 256, 3), 3: (1, 256, 3), 2: (1, 512, 3), 1: (1, 512, 2)}
 
 
 def _bench_problem(oracle, seed, F=3000, cam="icl"):
@@ -301,8 +321,7 @@ def test_benchmark_shape_single_problem_trace_parity(oracle, ic):
     p, ctx, tp, job, a0 = _setup(oracle, 3000, "icl", 3000)
     res, traces = ctx.coarse_track_batch([job] * 296, inverse_comp=ic, trace_cap=128)
     auto = {l: ctx.level_shape(l) for l in (4, 3, 2, 1)}
-    if not ic:
-        assert auto == BENCH_SHAPE_FWD, auto
+    assert auto == BENCH_SHAPE_FWD if not ic else {l: auto[l][:3] for l in auto} == BENCH_SHAPE_IC, auto
     assert len(traces[0]) < 128
     worst = _check_trace(oracle, tp, traces[0], ic, 4)
     assert worst <= REL
@@ -338,7 +357,7 @@ def test_benchmark_batch_traces_vs_oracle(oracle, ic):
     if not ic:
         assert {l: ctx.level_shape(l) for l in (4, 3, 2, 1)} == BENCH_SHAPE_FWD
     else:
-        assert all(ctx.level_shape(l)[0] == 1 and ctx.level_shape(l)[2] == 2 for l in (4, 3, 2, 1))
+        assert {l: ctx.level_shape(l)[:3] for l in (4, 3, 2, 1)} == BENCH_SHAPE_IC
     pyr = {}
     for k in range(nb):
         pyr[k] = (oracle.create_pyramid(first[k]["ref_img"], 5)[0], oracle.create_pyramid(first[k]["cur_img"], 5)[0])
