@@ -210,6 +210,7 @@ struct hso_ctx {
   std::vector<size_t> t_goff;       // staging plan of the batch in flight (track_plan): byte offset of each job's geometry block
   size_t t_geo_bytes = 0;
   // direct-input mode (pinned caller arrays are copied as they are and flattened on the device): -1 auto, 0 never, 1 always
+  int t_no_ring1 = getenv("HSO_TRACK_NO_RING1") ? 1 : 0;          // tuning: never the single-buffered ring (inverse-compositional level 1)
   int t_no_pair = getenv("HSO_TRACK_NO_PAIR") ? 1 : 0;            // tuning: never two 256-thread CTAs per SM in forward mode
   int t_force_stream = getenv("HSO_TRACK_FORCE_STREAM") ? 1 : 0;  // tuning / tests: mode 3 at every forward level where it fits
   int t_no_stream = getenv("HSO_TRACK_NO_STREAM") ? 1 : 0;        // tuning: never use the streamed-cache mode (mode 3) of the forward tracker
@@ -1199,6 +1200,12 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
       const int kpt = (maxF + cc * th - 1) / (cc * th);
       p.fast = 3; p.pc = kpt * th; p.cluster = cc; p.hist_bits = 11;
       if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; }
+      else if (!ctx->t_no_ring1) {
+        // level 1 at 640x480: 16 warps x 2 buffers x 63 rows = 258 KB do not fit, one buffer per warp (129 KB) beside the 77 KB image does (mode 4):
+        // 2.28 ms against 2.96 ms for the dual-image mode at B = 1184, F = 3000
+        p.fast = 4;
+        if (track_level_smem_bytes(p, th) <= 227 * 1024) { cluster = cc; threads = th; }
+      }
     }
     if (!cluster && prm.inverse_comp && !ctx->t_no_dual) {
       // inverse-compositional: keep BOTH levels resident and recompute the reference samples per evaluation — no F-dependent

@@ -96,7 +96,8 @@ struct TrackLevelParams {
   size_t level_off;         // byte offset of this level in a pyramid buffer
   int fast;                 // 0: everything in global memory; 1: level image + reference-patch caches of the CTA in shared memory;
                             // 2: (inverse-compositional) current AND reference level in shared memory, no cache
-                            // 3: (forward) level image in shared memory, reference-patch cache in global memory (L2), streamed through a per-warp ring
+                            // 3: level image in shared memory, reference-patch cache in global memory (L2), streamed through a per-warp ring of 2 buffers
+                            // 4: (inverse-compositional) as 3 with ONE buffer per warp (half the shared memory; the other warps cover the fetch)
   int pc;                   // FAST: patch slots per CTA = patches-per-thread * threads
   int absres_smem;          // FAST: the |r| scratch of the threshold selection lives in shared memory ([N][pc] floats)
   int hist_bits;            // radix-select digit width: 11 when the histogram fits next to the caches, else 8

@@ -121,7 +121,7 @@ __host__ __device__ inline size_t smem_layout(uint32_t img_bytes, size_t cache_b
 // MODE 3 (streamed cache): per warp two buffers of N rows x 32 patches of reference intensities
 // behind two mbarriers per warp (padded to 128 B so that the buffers stay 128-byte aligned)
 __host__ __device__ inline size_t ring_bar_bytes(int nwarps) { return ((size_t)nwarps * 16 + 127) / 128 * 128; }
-__host__ __device__ inline size_t ring_bytes(int N, int nwarps) { return ring_bar_bytes(nwarps) + (size_t)nwarps * 2 * N * 32 * sizeof(float); }
+__host__ __device__ inline size_t ring_bytes(int N, int nwarps, int depth) { return ring_bar_bytes(nwarps) + (size_t)nwarps * depth * N * 32 * sizeof(float); }
 
 static __host__ __device__ inline int pattern_n(int pidx) { return pidx <= 0 ? 1 : pidx == 1 ? 5 : pidx == 2 ? 9 : pidx <= 4 ? 13 : pidx == 5 ? 21 : 25; }
 
@@ -130,7 +130,7 @@ size_t track_level_smem_bytes(const TrackLevelParams& p, int threads) {
   size_t a, b, c, d, e, f, g, h, i, j;
   const int N = pattern_n(p.max_level - p.level + 2);
   const size_t absb = (p.fast && p.absres_smem) ? (size_t)N * p.pc * sizeof(float) : 0;
-  const size_t cache = p.fast == 1 ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : p.fast == 3 ? ring_bytes(N * (p.ic ? 3 : 1), threads / 32) : 0;
+  const size_t cache = p.fast == 1 ? (size_t)N * (p.ic ? 3 : 1) * p.pc * sizeof(float) : p.fast >= 3 ? ring_bytes(N * (p.ic ? 3 : 1), threads / 32, p.fast == 4 ? 1 : 2) : 0;
   const uint32_t img = p.fast == 2 ? 2 * (uint32_t)align_up(p.img_bytes, 128) : (p.fast ? p.img_bytes : 0);
   return smem_layout(img, cache, absb, p.fast ? (size_t)p.pc : 0, threads / 32, p.hist_bits, p.cluster, &a, &j, &b, &c, &d, &e, &f, &g, &h, &i);
 }
@@ -425,32 +425,37 @@ HSO_DEV float ref_intensity(const uint8_t* img, const RefPatch& r, int addr, int
 // staged image per problem instead of two.
 template <int N>
 HSO_DEV int ring_index(int i, int n) { return (i >> 5) * (N * 32) + n * 32 + (i & 31); }  // element (patch i, pattern pixel n) of the group-major cache
-// g: running number of the group within the launch (buffer g & 1, mbarrier phase (g >> 1) & 1); i0: first patch of the group (multiple of 32)
-template <int N>
+// g: running number of the group within the launch; i0: first patch of the group (multiple of 32). Depth 2: buffer g & 1, mbarrier phase
+// (g >> 1) & 1, group g + 1 is issued before group g is waited for. Depth 1 (a ring of 3 N rows for 16 warps does not fit twice beside a 77 KB
+// image): one buffer, phase g & 1, group g + 1 is issued once every lane is done with group g — the other warps of the CTA cover the fetch.
+template <int N, int DEPTH>
 HSO_DEV void ring_issue(const PatchStore& ps, int i0, uint32_t g) {
   if ((threadIdx.x & 31) == 0) {
-    uint64_t* bar = ps.ring_bar + (g & 1);
+    const uint32_t buf = DEPTH == 2 ? (g & 1) : 0;
+    uint64_t* bar = ps.ring_bar + buf;
     fence_proxy_async();  // the buffer was last read through the generic proxy (every lane is past it: __syncwarp at the end of that iteration)
     mbar_expect_tx(bar, N * 128);
-    tma_bulk_g2s(ps.ring + (g & 1) * (N * 32), ps.cache + (size_t)(i0 >> 5) * (N * 32), N * 128, bar);
+    tma_bulk_g2s(ps.ring + buf * (N * 32), ps.cache + (size_t)(i0 >> 5) * (N * 32), N * 128, bar);
   }
 }
-template <int N>
+template <int N, int DEPTH>
 HSO_DEV const float* ring_wait(const PatchStore& ps, uint32_t g) {
-  mbar_wait(ps.ring_bar + (g & 1), (g >> 1) & 1);
-  return ps.ring + (g & 1) * (N * 32) + (threadIdx.x & 31);
+  const uint32_t buf = DEPTH == 2 ? (g & 1) : 0;
+  mbar_wait(ps.ring_bar + buf, DEPTH == 2 ? (g >> 1) & 1 : g & 1);
+  return ps.ring + buf * (N * 32) + (threadIdx.x & 31);
 }
 
 template <int PIDX, bool IC, int MODE, bool TOP>
 HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const PatchStore& ps, const CamDev& cam, const double* Rt, float a, float huber,
                           float cutoff, int t0, int nt, Acc& acc, uint32_t& ring_g) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
-  constexpr bool FAST = MODE != 0, DUAL = MODE == 2, STREAM = MODE == 3;
+  constexpr bool FAST = MODE != 0, DUAL = MODE == 2, STREAM = MODE >= 3;
   constexpr int NR = IC ? 3 * N : N;  // rows of a streamed cache group: intensities (+ the two gradient planes, inverse-compositional)
+  constexpr int RD = MODE == 4 ? 1 : 2;  // ring buffers per warp
   const int Fp = job.Fpad, S = ps.stride;
   const int lane = threadIdx.x & 31;
   uint32_t g = ring_g;
-  if (STREAM && t0 - lane < job.F) ring_issue<NR>(ps, t0 - lane, g);
+  if (STREAM && t0 - lane < job.F) ring_issue<NR, RD>(ps, t0 - lane, g);
   // max_energy = 2*huber*cutoff - huber^2, evaluated in double like the reference (cutoff_error is a double there)
   const float max_energy = (float)(2.0 * (double)huber * (double)cutoff - (double)(huber * huber));
   // geometry of the next patch is fetched while the current one is processed (the only global loads of the FAST path)
@@ -467,8 +472,8 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
     const float* cbuf = nullptr;
     if (STREAM) {
       // the next group goes into the buffer the previous group was read from (every lane is past it: __syncwarp at the end of the iteration)
-      if (in - lane < job.F) ring_issue<NR>(ps, in - lane, g + 1);
-      cbuf = ring_wait<NR>(ps, g);
+      if (RD == 2 && in - lane < job.F) ring_issue<NR, RD>(ps, in - lane, g + 1);
+      cbuf = ring_wait<NR, RD>(ps, g);
     }
     const bool have_n = in < job.F && ps.vis[slot_of<FAST>(in, kn)] != 0;
     double Xn = 0, Yn = 0, Zn = 1, PUn = 0, PVn = 0;
@@ -526,7 +531,11 @@ HSO_DEV void eval_patches(const LevelCtx& L, const TrackJobDev& job, const Patch
       }
     }
     i = in; k = kn; have = have_n; X = Xn; Y = Yn; Z = Zn; PU = PUn; PV = PVn;
-    if (STREAM) { __syncwarp(); ++g; }
+    if (STREAM) {
+      __syncwarp();
+      if (RD != 2 && i - lane < job.F) ring_issue<NR, RD>(ps, i - lane, g + 1);  // (i is already the next group's patch)
+      ++g;
+    }
   }
   ring_g = g;
 }
@@ -916,8 +925,9 @@ template <int PIDX, bool IC, int MODE>
 __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams prm, const TrackJobDev* __restrict__ jobs) {
   constexpr int N = (PIDX == 2) ? 9 : (PIDX == 3 || PIDX == 4) ? 13 : (PIDX == 5) ? 21 : 25;
   constexpr int PAD = (PIDX == 5) ? 3 : (PIDX == 7) ? 4 : (PIDX <= 2) ? 1 : 2;
-  constexpr bool FAST = MODE != 0, DUAL = MODE == 2, STREAM = MODE == 3;
+  constexpr bool FAST = MODE != 0, DUAL = MODE == 2, STREAM = MODE >= 3;
   constexpr int NR = IC ? 3 * N : N;
+  constexpr int RD = MODE == 4 ? 1 : 2;
   static_assert(!DUAL || IC, "the dual-image mode exists for the inverse-compositional path only");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -932,7 +942,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   {
     size_t oc, oa, ov, ow, op, ot, oh, og, ox, om;
     const size_t abs_bytes = (FAST && prm.absres_smem) ? (size_t)N * prm.pc * sizeof(float) : 0;
-    const size_t cache_bytes = MODE == 1 ? (size_t)N * (IC ? 3 : 1) * prm.pc * sizeof(float) : STREAM ? ring_bytes(NR, nwarps) : 0;
+    const size_t cache_bytes = MODE == 1 ? (size_t)N * (IC ? 3 : 1) * prm.pc * sizeof(float) : STREAM ? ring_bytes(NR, nwarps, RD) : 0;
     const uint32_t img_total = DUAL ? 2 * (uint32_t)align_up(prm.img_bytes, 128) : (FAST ? prm.img_bytes : 0);
     smem_layout(img_total, cache_bytes, abs_bytes, FAST ? (size_t)prm.pc : 0, nwarps, prm.hist_bits, csize, &oc, &oa, &ov, &ow, &op, &ot, &oh, &og, &ox, &om);
     s.absres = reinterpret_cast<float*>(smem_raw + oa);
@@ -955,7 +965,7 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
   PatchStore ps;
   ps.ref = s.img + align_up(prm.img_bytes, 128);
   ps.ring_bar = reinterpret_cast<uint64_t*>(s.cache) + 2 * (threadIdx.x >> 5);
-  ps.ring = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.cache) + ring_bar_bytes(nwarps)) + (threadIdx.x >> 5) * (2 * NR * 32);
+  ps.ring = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.cache) + ring_bar_bytes(nwarps)) + (threadIdx.x >> 5) * (RD * NR * 32);
   uint32_t ring_g = 0;  // groups this warp has streamed so far (MODE 3)
   if (STREAM) {
     ps.cache = job.ref_cache; ps.gx = nullptr; ps.gy = nullptr; ps.vis = s.vis; ps.stride = Fp;
@@ -1071,12 +1081,12 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
     __syncthreads();
     int k = 0;
     const int lane = threadIdx.x & 31;
-    if (STREAM && t0 - lane < job.F) ring_issue<NR>(ps, t0 - lane, ring_g);
+    if (STREAM && t0 - lane < job.F) ring_issue<NR, RD>(ps, t0 - lane, ring_g);
     for (int i = t0; (STREAM ? i - lane : i) < job.F; i += nt, ++k) {  // (STREAM: warp-uniform trip count, the ring is filled by the whole warp)
       const float* cbuf = nullptr;
       if (STREAM) {
-        if (i + nt - lane < job.F) ring_issue<NR>(ps, i + nt - lane, ring_g + 1);
-        cbuf = ring_wait<NR>(ps, ring_g);
+        if (RD == 2 && i + nt - lane < job.F) ring_issue<NR, RD>(ps, i + nt - lane, ring_g + 1);
+        cbuf = ring_wait<NR, RD>(ps, ring_g);
       }
       const int sl = slot_of<FAST>(i, k);
       bool ok = (!STREAM || i < job.F) && ps.vis[sl] != 0;
@@ -1100,7 +1110,11 @@ __global__ void __launch_bounds__(512, 1) k_track_level(const TrackLevelParams p
 #pragma unroll
         for (int n = 0; n < N; ++n) absres[n * astride + (a_smem ? sl : i)] = -1.f;
       }
-      if (STREAM) { __syncwarp(); ++ring_g; }
+      if (STREAM) {
+        __syncwarp();
+        if (RD != 2 && i + nt - lane < job.F) ring_issue<NR, RD>(ps, i + nt - lane, ring_g + 1);
+        ++ring_g;
+      }
     }
     clk_res = clock64();
     if (lin) select_kth<N>(job, s, absres, astride, a_smem, t0, nt, false, 0.f, csize, true);
@@ -1291,6 +1305,7 @@ static cudaError_t launch_pidx(const TrackLevelParams& p, const TrackJobDev* job
   if (p.ic) {
     if (p.fast == 2) return launch_one<PIDX, true, 2>(p, jobs_dev, B, cluster, threads, smem, stream);
     if (p.fast == 3) return launch_one<PIDX, true, 3>(p, jobs_dev, B, cluster, threads, smem, stream);
+    if (p.fast == 4) return launch_one<PIDX, true, 4>(p, jobs_dev, B, cluster, threads, smem, stream);
     return p.fast ? launch_one<PIDX, true, 1>(p, jobs_dev, B, cluster, threads, smem, stream)
                   : launch_one<PIDX, true, 0>(p, jobs_dev, B, cluster, threads, smem, stream);
   }

@@ -161,7 +161,8 @@ int hso_track_set_cluster(hso_ctx* ctx, int ctas_per_problem, int threads_per_ct
 /* Same, for one pyramid level only (overrides hso_track_set_cluster for that level; 0,0 restores auto). */
 int hso_track_set_level_shape(hso_ctx* ctx, int level, int ctas_per_problem, int threads_per_cta);
 /* Launch shape the last run used for `level`: CTAs per problem, threads per CTA, mode (0 = images and caches in global memory, 1 = current level
- * + reference-patch cache in shared memory, 2 = both levels in shared memory, 3 = current level in shared memory + streamed cache), and whether the |r| scratch of the threshold selection sat in
+ * + reference-patch cache in shared memory, 2 = both levels in shared memory, 3 = current level in shared memory + reference-patch cache streamed from L2 through a double-buffered
+ * per-warp ring, 4 = as 3 with a single-buffered ring), and whether the |r| scratch of the threshold selection sat in
  * shared memory. The parity tests use it to prove that they exercise the shape the benchmark runs. */
 int hso_track_get_level_shape(hso_ctx* ctx, int level, int* ctas, int* threads, int* mode, int* absres_smem);
 /* Inverse-compositional mode: 1 (default) keeps both pyramid levels in shared memory and recomputes the reference samples per evaluation
