@@ -13,4 +13,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-other-rows > gpurun_out/${tag}_ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_track_level' --launch-skip 12 -c 4 -o gpurun_out/${tag}_track \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-other-rows >> gpurun_out/${tag}_ncu_bench.log 2>&1
+# gpurun brings back at most 64 MiB: the report travels gzip-compressed (gunzip it before `ncu -i`)
+gzip -1 -f gpurun_out/${tag}_track.ncu-rep
 ls -la gpurun_out

@@ -25,9 +25,11 @@ with open(f'profiles/{tag}_track_ncu_summary.csv', 'w') as f:
             i = hdr.index(k)
             f.write(f'{k},{units[i]},' + ','.join(r[i] for r in rows[2:]) + '\n')
 i_r, i_w = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}  # ncu picks one unit per column
 l1 = rows[-1]
 n_problems = int(l1[hdr.index('launch__grid_size')]) // max(int(l1[hdr.index('launch__cluster_size')]), 1)
-json.dump({"kernel": l1[ki], "problems_per_launch": n_problems, "dram_bytes_per_problem": (float(l1[i_r]) + float(l1[i_w])) * 1e6 / n_problems,
-           "dram_bytes_per_launch": (float(l1[i_r]) + float(l1[i_w])) * 1e6, "dram_read_bytes": float(l1[i_r]) * 1e6,
-           "dram_write_bytes": float(l1[i_w]) * 1e6, "source": f"profiles/{tag}_track_ncu_summary.csv (ncu --set full, {cmd})"},
+rd, wr = float(l1[i_r]) * UNIT[units[i_r]], float(l1[i_w]) * UNIT[units[i_w]]
+json.dump({"kernel": l1[ki], "problems_per_launch": n_problems, "dram_bytes_per_problem": (rd + wr) / n_problems,
+           "dram_bytes_per_launch": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
+           "source": f"profiles/{tag}_track_ncu_summary.csv (ncu --set full, {cmd})"},
           open('profiles/track_l1_traffic.json', 'w'), indent=1)
