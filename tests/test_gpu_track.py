@@ -116,19 +116,25 @@ def test_cluster_shapes_agree(oracle, cluster, threads):
     ctx.close()
 
 
+@pytest.mark.parametrize("ic", [False, True])
 @pytest.mark.parametrize("cam,F,cluster,threads", [("icl", 900, 1, 256), ("icl", 3000, 1, 512), ("euroc", 2000, 2, 512), ("tum_fov", 700, 1, 96)])
-def test_streamed_cache_mode_vs_oracle_and_resident_cache(oracle, cam, F, cluster, threads):
+def test_streamed_cache_mode_vs_oracle_and_resident_cache(oracle, cam, F, cluster, threads, ic):
     """Mode 3 (reference-patch cache in global memory, streamed through the per-warp ring) forced at every level: per-evaluation parity with the
     oracle, and the same bits as the resident-cache path (mode 1) at the same launch shape — the summation order does not depend on where the
     cache lives."""
     p, ctx, tp, job, a0 = _setup(oracle, 41, cam, F)
     ctx.set_cluster(cluster, threads)
     ctx._chk(ctx.lib.hso_track_set_stream_cache(ctx.h, 1))
-    r3, t3 = ctx.coarse_track_batch([job], trace_cap=256)
-    assert all(ctx.level_shape(l)[:3] == (cluster, threads, 3) for l in (4, 3, 2, 1)), [ctx.level_shape(l) for l in (4, 3, 2, 1)]
-    assert _check_trace(oracle, tp, t3[0], False, 4) <= REL
+    r3, t3 = ctx.coarse_track_batch([job], inverse_comp=ic, trace_cap=256)
+    # (inverse-compositional: three planes per group; where two ring buffers per warp do not fit beside the image, one does: mode 4)
+    # (... and where not even one fits — 752x480 level 1, 16 warps — the dual-image mode runs that level)
+    shapes = [ctx.level_shape(l) for l in (4, 3, 2, 1)]
+    assert all(sh[:2] == (cluster, threads) for sh in shapes), shapes
+    assert all(sh[2] == 3 for sh in shapes[:3]) and shapes[3][2] in ((3, 4, 2) if ic else (3,)), shapes
+    assert _check_trace(oracle, tp, t3[0], ic, 4) <= REL
     ctx._chk(ctx.lib.hso_track_set_stream_cache(ctx.h, -1))
-    r1, t1 = ctx.coarse_track_batch([job], trace_cap=256)
+    ctx._chk(ctx.lib.hso_track_set_ic_dual(ctx.h, 0))
+    r1, t1 = ctx.coarse_track_batch([job], inverse_comp=ic, trace_cap=256)
     if all(ctx.level_shape(l)[:3] == (cluster, threads, 1) for l in (4, 3, 2, 1)):
         assert len(t1[0]) == len(t3[0]) and np.array_equal(r1[0]["T_cur_ref"], r3[0]["T_cur_ref"])
         for e1, e3 in zip(t1[0], t3[0]):

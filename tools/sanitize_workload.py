@@ -43,6 +43,19 @@ def main():
         ctx.set_level_shape(1, 2, 512)
         ctx.coarse_track_batch([jb] * 2)
         ctx.set_level_shape(1, 0, 0)
+        # the benchmark's launch shapes (two problems per SM): 256-thread CTA pairs with the streamed reference-patch cache (mode 3: per-warp TMA
+        # ring + mbarriers) at levels 4..2, one 512-thread CTA at level 1 in mode 3 (forward) / mode 4 (inverse-compositional, single-buffered ring)
+        for ic in (False, True):
+            ctx.coarse_track_batch([jb] * 296, inverse_comp=ic)
+            assert ctx.level_shape(4)[:3] == (1, 256, 3) and ctx.level_shape(1)[:3] == (1, 512, 4 if ic else 3), [ctx.level_shape(l) for l in (4, 3, 2, 1)]
+        # streamed cache forced at every level, single CTA and clusters (the ring in a cluster launch), both modes
+        ctx._chk(ctx.lib.hso_track_set_stream_cache(ctx.h, 1))
+        for ic in (False, True):
+            for shape in ((0, 0), (1, 256), (2, 256)):
+                ctx.set_cluster(*shape)
+                ctx.coarse_track_batch([job] * 3, inverse_comp=ic, trace_cap=64)
+        ctx.set_cluster(0, 0)
+        ctx._chk(ctx.lib.hso_track_set_stream_cache(ctx.h, 0))
         ctx._chk(ctx.lib.hso_set_pipeline(ctx.h, 4, 3))  # 10 problems -> 3 chunks on 3 streams
         ctx.add_frames_track_batch([p["cur_img"]] * 10, [dict(ref=ids[0], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=np.eye(4)[:3])] * 10)
         ctx.close()
