@@ -672,14 +672,9 @@ HSO_DEV void for_each_abs(const TrackJobDev& job, const float* absres, int astri
     float vals[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) vals[n] = p[n * astride];
+    if (!(vals[0] >= 0.f)) continue;  // a patch is in view with all of its N pattern pixels or with none (the threshold pass writes -1 to all)
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-      float v = vals[n];
-      if (v >= 0.f) {
-        if (mad) v = fabsf(v - center);
-        fn(v);
-      }
-    }
+    for (int n = 0; n < N; ++n) fn(mad ? fabsf(vals[n] - center) : vals[n]);
   }
 }
 
@@ -728,6 +723,32 @@ HSO_DEV uint32_t lin_bin(float v, int nbins) {
   return (uint32_t)(b < nbins - 1 ? b : nbins - 1);
 }
 
+// Compaction pass of select_kth: the members of linear bin `bin` go to `list`. Branch-free membership mask over the patch's N values, ONE
+// (rarely taken: a bin holds < 1 % of the values) branch per patch instead of one per value.
+template <int N>
+HSO_DEV void compact_bin(const TrackJobDev& job, const float* absres, int astride, bool a_smem, int t0, int nt, bool mad, float center, uint32_t bin,
+                         int nbins, uint32_t* list, uint32_t* list_n) {
+  int kk = 0;
+  for (int i = t0; i < job.F; i += nt, ++kk) {
+    const float* p = absres + (a_smem ? kk * (int)blockDim.x + (int)threadIdx.x : i);
+    float vals[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) vals[n] = p[n * astride];
+    if (!(vals[0] >= 0.f)) continue;
+    uint32_t hit = 0;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      if (mad) vals[n] = fabsf(vals[n] - center);
+      hit |= (lin_bin(vals[n], nbins) == bin ? 1u : 0u) << n;
+    }
+    if (hit) {
+#pragma unroll
+      for (int n = 0; n < N; ++n)
+        if ((hit >> n) & 1u) list[atomicAdd(list_n, 1u)] = __float_as_uint(vals[n]);
+    }
+  }
+}
+
 // Same result as radix_select, fewer full passes: (1) histogram over linear bins (already accumulated when `prefilled`), (2) ONE pass that
 // compacts the members of the chosen bin into a list in shared memory — the CTAs of a cluster then copy each other's lists through DSMEM so
 // that every CTA holds the whole bin, (3) radix select over that list only, CTA-local (no cluster barriers), on the key's offset from the
@@ -759,9 +780,7 @@ HSO_DEV void select_kth(const TrackJobDev& job, const Smem& s, const float* absr
   uint32_t* list = s.hist + LIST_BINS;
   if (threadIdx.x == 0) s.ctrl->list_n = 0;
   __syncthreads();
-  for_each_abs<N>(job, absres, astride, a_smem, t0, nt, mad, center, [&](float v) {
-    if (lin_bin(v, NB) == bin) list[atomicAdd(&s.ctrl->list_n, 1u)] = __float_as_uint(v);
-  });
+  compact_bin<N>(job, absres, astride, a_smem, t0, nt, mad, center, bin, NB, list, &s.ctrl->list_n);
   int ln;
   if (csize == 1) {
     __syncthreads();
