@@ -599,6 +599,7 @@ def main():
     ap.add_argument("--cam", default="icl", choices=list(synth.CAMS))
     ap.add_argument("--ic", action="store_true", help="inverse-compositional mode")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--wide-features", action="store_true", help="e2e input as px / f / dist (48 B per feature) instead of the compact xyz / px32 layout (32 B)")
     ap.add_argument("--e2e-debug", action="store_true", help="time the stages of the pipelined e2e call alone and print one traced call (stderr)")
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
@@ -681,6 +682,22 @@ def main():
         px_all[b], f_all[b], dist_all[b] = p["px"], p["f"], p["dist"]
         a0 = float(np.float32(cur_int[b]) / np.float32(ref_int[b]))
         jobs.append(dict(ref=ref_ids[b], cur=cur_ids[b], px=px_all[b], f=f_all[b], dist=dist_all[b], T_cur_ref=p["T0"], exposure_rat=a0))
+    # The e2e call's default input is the compact layout of hso_track_job (32 B per feature instead of 48; the call is bound by the host->device
+    # copies): what a caller's gather loop over ref_frame->fts_ writes — xyz = f * dist (src/CoarseTracker.cpp:292), px as float32 (exact for the
+    # tracker), features without a point left out. One pinned blob per field for the whole batch. Results are bit-identical to the wide layout
+    # (tests/test_gpu_track.py::test_compact_feature_layout_is_bit_identical); --wide-features times the 48-byte layout.
+    jobs_e2e = jobs
+    if not args.wide_features and not args.pageable_features:
+        nval = [int((p["dist"] >= 0).sum()) for p in probs]
+        offs = np.concatenate([[0], np.cumsum(nval)])
+        xyz_all = torch.empty((int(offs[-1]), 3), dtype=torch.float64).pin_memory().numpy()
+        px32_all = torch.empty((int(offs[-1]), 2), dtype=torch.float32).pin_memory().numpy()
+        jobs_e2e = []
+        for b, p in enumerate(probs):
+            xyz, px32 = Context.compact_features(p["px"], p["f"], p["dist"])
+            xyz_all[offs[b]:offs[b + 1]], px32_all[offs[b]:offs[b + 1]] = xyz, px32
+            jobs_e2e.append(dict(ref=ref_ids[b], cur=cur_ids[b], xyz=xyz_all[offs[b]:offs[b + 1]], px32=px32_all[offs[b]:offs[b + 1]], T_cur_ref=p["T0"],
+                                 exposure_rat=jobs[b]["exposure_rat"]))
 
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     levels = list(range(4, args.min_level - 1, -1))
@@ -737,7 +754,7 @@ def main():
         # the timed calls are the C-ABI entry points themselves on HOST buffers; the argument records are built once (the reference
         # caller owns long-lived Frame/Feature objects too) and only the per-step fields are refreshed
         prm = K.hso_track_params(int(args.ic), 4, args.min_level, args.n_iter)
-        jarr, keep = ctx._track_jobs(jobs)
+        jarr, keep = ctx._track_jobs(jobs_e2e)
         img_ptrs = (C.c_void_p * B)(*[im.ctypes.data for im in cur_np])
         new_ids = (C.c_int32 * B)()
         integ = np.zeros(B, np.float32)
@@ -789,8 +806,10 @@ def main():
         nvalid = sum(int((p["dist"] >= 0).sum()) for p in probs)
         if args.pageable_features:  # flattened on the host: 5 doubles per feature with a depth (padded to 32 features)
             h2d = B * W * H + sum(40 * max(32, (int((p["dist"] >= 0).sum()) + 31) // 32 * 32) for p in probs) + B * (96 + 4 + 96)
-        else:                       # direct: the caller's 6 doubles per feature as they are
+        elif args.wide_features:    # direct: the caller's 6 doubles per feature as they are
             h2d = B * W * H + 48 * B * F + B * (96 + 4 + 128)
+        else:                       # compact: 3 doubles + 2 floats per feature with a point
+            h2d = B * W * H + 32 * nvalid + B * (96 + 4 + 128)
         d2h = B * (C.sizeof(K.hso_track_result) + 8)  # results + {integralImage_, gradMean_}
         e2e = dict(ms=ms_e2e, steps=n_e2e_steps, iters=it_e2e, h2d=h2d, d2h=d2h)
 
@@ -874,7 +893,10 @@ def main():
         if e2e:
             line["e2e"] = {"value": it_e2e_all / (ms_e2e_all * 1e-3), "unit": "iterations/s", "h2d_bytes_per_step": e2e["h2d"] * world,
                            "d2h_bytes_per_step": e2e["d2h"] * world, "frames_per_s": world * B * e2e["steps"] / (ms_e2e_all * 1e-3),
-                           "ms_per_step": ms_e2e_all / e2e["steps"], "steps": e2e["steps"]}
+                           "ms_per_step": ms_e2e_all / e2e["steps"], "steps": e2e["steps"],
+                           "features": ("px/f/dist doubles, 48 B per feature, pageable (flattened by the host pool)" if args.pageable_features else
+                                        "px/f/dist doubles, 48 B per feature, pinned (copied as they are, flattened on the device)" if args.wide_features else
+                                        "compact hso_track_job layout, 32 B per feature with a point: xyz = f*dist doubles + px float32, pinned")}
         if world == 1 and not args.no_cpu_baseline:
             cores = 1
             sample = build_workload(256, F, args.cam, args.seed, 0)

@@ -34,7 +34,8 @@ class hso_track_params(C.Structure):
 class hso_track_job(C.Structure):
     _fields_ = [("ref", C.c_int32), ("cur", C.c_int32), ("n_features", C.c_int32), ("reserved", C.c_int32),
                 ("px", C.POINTER(C.c_double)), ("f", C.POINTER(C.c_double)), ("dist", C.POINTER(C.c_double)),
-                ("T_cur_ref", C.c_double * 12), ("exposure_rat", C.c_float), ("reserved2", C.c_float)]
+                ("T_cur_ref", C.c_double * 12), ("exposure_rat", C.c_float), ("reserved2", C.c_float),
+                ("xyz", C.POINTER(C.c_double)), ("px32", C.POINTER(C.c_float))]
 
 
 class hso_track_result(C.Structure):

@@ -125,18 +125,34 @@ class Context:
         self._chk(self.lib.hso_frame_release(self.h, fid))
 
     # ---- F2: CoarseTracker ----------------------------------------------------------------------------------------------------
+    @staticmethod
+    def compact_features(px, f, dist):
+        """The compact input layout of hso_track_job, as a caller's gather loop over ref_frame->fts_ forms it: features without a point / with a
+        negative distance left out, xyz = f * dist (Vector3d xyz_ref((*it_ft)->f*dist), src/CoarseTracker.cpp:292), px as float32."""
+        dist = np.asarray(dist, np.float64)
+        ok = dist >= 0
+        xyz = np.ascontiguousarray(np.asarray(f, np.float64)[ok] * dist[ok, None])
+        return xyz, np.ascontiguousarray(np.asarray(px, np.float64)[ok].astype(np.float32))
+
     def _track_jobs(self, jobs):
         B = len(jobs)
         arr = (K.hso_track_job * B)()
         keep = []
         for b, j in enumerate(jobs):
-            px = np.ascontiguousarray(j["px"], np.float64).reshape(-1)
-            f = np.ascontiguousarray(j["f"], np.float64).reshape(-1)
-            dist = np.ascontiguousarray(j["dist"], np.float64).reshape(-1)
-            keep += [px, f, dist]
             a = arr[b]
-            a.ref, a.cur, a.n_features = int(j["ref"]), int(j["cur"]), dist.shape[0]
-            a.px, a.f, a.dist = _dp(px), _dp(f), _dp(dist)
+            if "xyz" in j:  # compact layout (hso_track_job::xyz / px32, see compact_features)
+                xyz = np.ascontiguousarray(j["xyz"], np.float64).reshape(-1)
+                px32 = np.ascontiguousarray(j["px32"], np.float32).reshape(-1)
+                keep += [xyz, px32]
+                a.ref, a.cur, a.n_features = int(j["ref"]), int(j["cur"]), px32.shape[0] // 2
+                a.xyz, a.px32 = _dp(xyz), px32.ctypes.data_as(C.POINTER(C.c_float))
+            else:
+                px = np.ascontiguousarray(j["px"], np.float64).reshape(-1)
+                f = np.ascontiguousarray(j["f"], np.float64).reshape(-1)
+                dist = np.ascontiguousarray(j["dist"], np.float64).reshape(-1)
+                keep += [px, f, dist]
+                a.ref, a.cur, a.n_features = int(j["ref"]), int(j["cur"]), dist.shape[0]
+                a.px, a.f, a.dist = _dp(px), _dp(f), _dp(dist)
             T = np.ascontiguousarray(j["T_cur_ref"], np.float64).reshape(12)
             for k in range(12):
                 a.T_cur_ref[k] = T[k]

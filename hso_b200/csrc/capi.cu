@@ -217,6 +217,7 @@ struct hso_ctx {
   int t_abs_global = getenv("HSO_TRACK_ABSRES_GLOBAL") ? 1 : 0;  // tuning: keep the |r| scratch of the threshold selection in global memory
   int t_direct_mode = -1;
   bool t_direct = false;           // decision for the batch in flight
+  bool t_compact = false;          // the batch in flight uses hso_track_job::xyz / px32 (t_raw = [xyz 3 sumF doubles | px32 2 sumF floats])
   DevBuf t_raw;                    // [px 2 sumF | f 3 sumF | dist sumF] doubles
   std::vector<size_t> t_roff;      // features before job b in the raw arrays
   size_t t_sumF = 0;
@@ -835,13 +836,18 @@ static int track_plan(hso_ctx* ctx, const hso_track_params* prm, int B, const hs
   ctx->tB = B;
   ctx->t_trace_cap = trace_cap > 0 ? trace_cap : 0;
   size_t host_bytes = 0, arena = 0;
-  int maxF = 0;
+  int maxF = 0, n_layout = -1;  // feature layout of the batch: 0 wide (px / f / dist), 1 compact (xyz / px32)
   ctx->t_goff.assign(B, 0);
   for (int b = 0; b < B; ++b) {
     const hso_track_job& j = jobs[b];
     if (j.n_features < 0 || j.n_features > ctx->cfg.max_features) return fail(ctx, HSO_ERR_CAPACITY, "n_features exceeds hso_cfg.max_features");
     if (!get_frame(ctx, j.ref) || !get_frame(ctx, j.cur)) return fail(ctx, HSO_ERR_BAD_FRAME, "unknown frame id in track job");
-    if (j.n_features > 0 && (!j.px || !j.f || !j.dist)) return fail(ctx, HSO_ERR_INVALID, "null feature arrays");
+    const bool compact_b = j.xyz != nullptr && j.px32 != nullptr;
+    if (j.n_features > 0 && !compact_b && (!j.px || !j.f || !j.dist)) return fail(ctx, HSO_ERR_INVALID, "null feature arrays");
+    if (j.n_features > 0) {
+      if (n_layout < 0) n_layout = compact_b ? 1 : 0;
+      else if (n_layout != (compact_b ? 1 : 0)) return fail(ctx, HSO_ERR_INVALID, "jobs of a batch must use the same feature layout");
+    }
     maxF = std::max(maxF, j.n_features);
     const int Fpad = std::max(32, (j.n_features + 31) / 32 * 32);
     ctx->t_goff[b] = host_bytes;
@@ -852,7 +858,10 @@ static int track_plan(hso_ctx* ctx, const hso_track_params* prm, int B, const hs
   ctx->t_geo_bytes = arena;
   // direct-input decision: pinned (or registered) caller arrays go to the device as they are, no host flattening pass
   ctx->t_direct = false;
-  if (ctx->t_direct_mode != 0) {
+  ctx->t_compact = n_layout == 1;
+  if (ctx->t_compact) {
+    ctx->t_direct = true;  // the compact layout always travels as it is (a pageable array is still copied correctly, only slower)
+  } else if (ctx->t_direct_mode != 0) {
     bool pinned = ctx->t_direct_mode == 1;
     if (!pinned) {
       for (int b = 0; b < B && !pinned; ++b) {
@@ -920,7 +929,13 @@ static int track_plan(hso_ctx* ctx, const hso_track_params* prm, int B, const hs
     d.state = (TrackState*)(dbase + off_state[b]);
     d.trace = ctx->t_trace_cap ? (hso_trace*)(dbase + off_trace[b]) : nullptr;
     d.raw_px = d.raw_f = d.raw_dist = nullptr; d.n_raw = 0; d.pad_ = 0;
-    if (ctx->t_direct) {
+    d.raw_xyz = nullptr; d.raw_px32 = nullptr;
+    if (ctx->t_compact) {
+      const double* rb = (const double*)ctx->t_raw.p;  // [xyz 3 sumF doubles | px32 2 sumF floats]
+      d.raw_xyz = rb + 3 * ctx->t_roff[b];
+      d.raw_px32 = (const float*)(rb + 3 * ctx->t_sumF) + 2 * ctx->t_roff[b];
+      d.n_raw = j.n_features;
+    } else if (ctx->t_direct) {
       const double* rb = (const double*)ctx->t_raw.p;
       d.raw_px = rb + 2 * ctx->t_roff[b];
       d.raw_f = rb + 2 * ctx->t_sumF + 3 * ctx->t_roff[b];
@@ -978,8 +993,6 @@ static void track_stage_one(hso_ctx* ctx, const hso_track_job* jobs, int b) {
   a0[b] = j.exposure_rat;
 }
 
-// Direct-input mode: the caller's px / f / dist arrays of jobs [b0, b1) go to the device as they are. Arrays of consecutive jobs that are
-// adjacent in host memory (a caller that keeps a batch in one blob) travel in one copy per run.
 // direct-input mode: what track_stage_one records beside the geometry (initial pose, exposure ratio) for jobs [b0, b1)
 static void track_fill_pose(hso_ctx* ctx, const hso_track_job* jobs, int b0, int b1) {
   const int B = ctx->tB;
@@ -991,21 +1004,28 @@ static void track_fill_pose(hso_ctx* ctx, const hso_track_job* jobs, int b0, int
   }
 }
 
+// Direct-input mode: the caller's feature arrays of jobs [b0, b1) (px / f / dist, or xyz / px32 in the compact layout) go to the device as they
+// are. Arrays of consecutive jobs that are adjacent in host memory (a caller that keeps a batch in one blob) travel in one copy per run.
 static int track_copy_raw(hso_ctx* ctx, const hso_track_job* jobs, int b0, int b1, cudaStream_t stream, bool fill_pose = true) {
-  double* rb = (double*)ctx->t_raw.p;
+  char* rb = (char*)ctx->t_raw.p;
   const size_t S = ctx->t_sumF;
   if (fill_pose) track_fill_pose(ctx, jobs, b0, b1);
-  for (int arr = 0; arr < 3; ++arr) {
-    const size_t w = arr == 0 ? 2 : (arr == 1 ? 3 : 1);
-    double* dbase = rb + (arr == 0 ? 0 : (arr == 1 ? 2 * S : 5 * S));
-    auto ptr = [&](int b) { return arr == 0 ? jobs[b].px : (arr == 1 ? jobs[b].f : jobs[b].dist); };
+  const int n_arr = ctx->t_compact ? 2 : 3;
+  for (int arr = 0; arr < n_arr; ++arr) {
+    // bytes per feature and device offset of the array: wide [px 16 | f 24 | dist 8], compact [xyz 24 | px32 8]
+    const size_t w = ctx->t_compact ? (arr == 0 ? 24 : 8) : (arr == 0 ? 16 : (arr == 1 ? 24 : 8));
+    char* dbase = rb + (ctx->t_compact ? (arr == 0 ? 0 : 24 * S) : (arr == 0 ? 0 : (arr == 1 ? 16 * S : 40 * S)));
+    auto ptr = [&](int b) -> const char* {
+      if (ctx->t_compact) return arr == 0 ? (const char*)jobs[b].xyz : (const char*)jobs[b].px32;
+      return arr == 0 ? (const char*)jobs[b].px : (arr == 1 ? (const char*)jobs[b].f : (const char*)jobs[b].dist);
+    };
     int run0 = b0;
     while (run0 < b1) {
       if (jobs[run0].n_features == 0) { ++run0; continue; }
       int run1 = run0 + 1;
       size_t feats = (size_t)jobs[run0].n_features;
       while (run1 < b1 && (jobs[run1].n_features == 0 || ptr(run1) == ptr(run0) + w * feats)) { feats += (size_t)jobs[run1].n_features; ++run1; }
-      CU(cudaMemcpyAsync(dbase + w * ctx->t_roff[run0], ptr(run0), sizeof(double) * w * feats, cudaMemcpyHostToDevice, stream));
+      CU(cudaMemcpyAsync(dbase + w * ctx->t_roff[run0], ptr(run0), w * feats, cudaMemcpyHostToDevice, stream));
       run0 = run1;
     }
   }

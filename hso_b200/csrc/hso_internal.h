@@ -87,6 +87,9 @@ struct TrackJobDev {
   const double* raw_dist;
   int n_raw;
   int pad_;
+  // compact layout of the caller (hso_track_job::xyz / px32): xyz [n_raw][3] doubles, px [n_raw][2] floats; every feature is valid
+  const double* raw_xyz;
+  const float* raw_px32;
 };
 
 struct TrackLevelParams {

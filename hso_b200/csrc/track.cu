@@ -1244,6 +1244,16 @@ __global__ void __launch_bounds__(256) k_track_compact(TrackJobDev* __restrict__
   const int n = job.n_raw, Fp = job.Fpad;
   double* px = const_cast<double*>(job.px);
   double* xyz = const_cast<double*>(job.xyz);
+  if (job.raw_xyz != nullptr) {
+    // compact layout: xyz formed by the caller, px as float32 ((double)(float)px * 2^-l rounds to the same float as px * 2^-l); all valid
+    for (int i = (int)threadIdx.x; i < n; i += 256) {
+      px[i] = (double)job.raw_px32[2 * i]; px[Fp + i] = (double)job.raw_px32[2 * i + 1];
+      xyz[i] = job.raw_xyz[3 * i]; xyz[Fp + i] = job.raw_xyz[3 * i + 1]; xyz[2 * Fp + i] = job.raw_xyz[3 * i + 2];
+    }
+    for (int k = n + (int)threadIdx.x; k < Fp; k += 256) { px[k] = 0; px[Fp + k] = 0; xyz[k] = 0; xyz[Fp + k] = 0; xyz[2 * Fp + k] = 1; }
+    if (threadIdx.x == 0) jobs[blockIdx.x].F = n;
+    return;
+  }
   __shared__ int s_warp[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int base = 0;

@@ -179,17 +179,23 @@ class CoarseTracker {  // include/hso/CoarseTracker.h:134-143
   size_t run(FramePtr ref_frame, FramePtr cur_frame) {
     if (ref_frame->fts_.empty()) return 0;  // :53
     const size_t F = ref_frame->fts_.size();
-    std::vector<double> px(2 * F), f(3 * F), dist;
+    // the gather loop over the Feature list writes the compact layout of hso_track_job (32 B per feature): xyz = f * dist like :292, px as
+    // float32 (exact for the tracker, see hso_b200.h), features without a usable depth left out like the reference skips them (:290)
+    std::vector<double> xyz, dist;
+    std::vector<float> px32;
+    xyz.reserve(3 * F); px32.reserve(2 * F);
     makeDepthRef(*ref_frame, dist);
     for (size_t i = 0; i < F; ++i) {
       const Feature& ft = ref_frame->fts_[i];
-      px[2 * i] = ft.px[0]; px[2 * i + 1] = ft.px[1];
-      f[3 * i] = ft.f[0]; f[3 * i + 1] = ft.f[1]; f[3 * i + 2] = ft.f[2];
+      const double d = dist[i];
+      if (!(d >= 0)) continue;
+      px32.push_back((float)ft.px[0]); px32.push_back((float)ft.px[1]);
+      xyz.push_back(ft.f[0] * d); xyz.push_back(ft.f[1] * d); xyz.push_back(ft.f[2] * d);
     }
     hso_track_job job;
     std::memset(&job, 0, sizeof job);
-    job.ref = ref_frame->id; job.cur = cur_frame->id; job.n_features = (int32_t)F;
-    job.px = px.data(); job.f = f.data(); job.dist = dist.data();
+    job.ref = ref_frame->id; job.cur = cur_frame->id; job.n_features = (int32_t)(px32.size() / 2);
+    job.xyz = xyz.data(); job.px32 = px32.data();
     const SE3 T_cur_ref = cur_frame->T_f_w_ * ref_frame->T_f_w_.inverse();  // :63
     std::memcpy(job.T_cur_ref, T_cur_ref.m, sizeof job.T_cur_ref);
     job.exposure_rat = cur_frame->integralImage_ / ref_frame->integralImage_;  // :60
@@ -518,20 +524,25 @@ inline void addImagesAndTrack(Context& ctx, const std::vector<const uint8_t*>& i
                               std::vector<hso_frame_id>& new_ids, std::vector<hso_track_result>& results) {
   const size_t B = imgs.size();
   std::vector<hso_track_job> jobs(B);
-  std::vector<std::vector<double>> px(B), f(B), dist(B);
+  // the gather loop over the Feature list writes the compact layout directly (32 B per feature: the call is bound by the host->device copies):
+  // xyz = f * dist like src/CoarseTracker.cpp:292, px as float32 (exact, see hso_b200.h), features without a usable depth left out
+  std::vector<std::vector<double>> xyz(B), dist(B);
+  std::vector<std::vector<float>> px32(B);
   for (size_t b = 0; b < B; ++b) {
     const Frame& ref = *ref_frames[b];
     const size_t F = ref.fts_.size();
-    px[b].resize(2 * F); f[b].resize(3 * F);
+    xyz[b].reserve(3 * F); px32[b].reserve(2 * F);
     CoarseTracker::makeDepthRef(ref, dist[b]);
     for (size_t i = 0; i < F; ++i) {
-      px[b][2 * i] = ref.fts_[i].px[0]; px[b][2 * i + 1] = ref.fts_[i].px[1];
-      for (int k = 0; k < 3; ++k) f[b][3 * i + k] = ref.fts_[i].f[k];
+      const double d = dist[b][i];
+      if (!(d >= 0)) continue;
+      px32[b].push_back((float)ref.fts_[i].px[0]); px32[b].push_back((float)ref.fts_[i].px[1]);
+      for (int k = 0; k < 3; ++k) xyz[b].push_back(ref.fts_[i].f[k] * d);
     }
     hso_track_job& j = jobs[b];
     std::memset(&j, 0, sizeof j);
-    j.ref = ref.id; j.n_features = (int32_t)F;
-    j.px = px[b].data(); j.f = f[b].data(); j.dist = dist[b].data();
+    j.ref = ref.id; j.n_features = (int32_t)(px32[b].size() / 2);
+    j.xyz = xyz[b].data(); j.px32 = px32[b].data();
     std::memcpy(j.T_cur_ref, T_cur_ref_init[b].m, sizeof j.T_cur_ref);
     j.exposure_rat = -1.f;  // formed on the device from the two frames' integralImage_ (CoarseTracker.cpp:60)
   }

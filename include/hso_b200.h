@@ -110,6 +110,14 @@ typedef struct {
   double T_cur_ref[12];  /* in: cur.T_f_w * ref.T_f_w^-1 (CoarseTracker.cpp:63) */
   float exposure_rat;    /* in: cur.integralImage_/ref.integralImage_ (CoarseTracker.cpp:60); < 0: formed on the device from the two frames' statistics */
   float reserved2;
+  /* Optional compact layout, 32 B per feature instead of 48 (the end-to-end call is bound by the host->device copies): when both pointers are
+   * non-null, px / f / dist are ignored. xyz = f * dist exactly as the caller's gather loop over ref_frame->fts_ forms it — the reference's own
+   * expression, Vector3d xyz_ref((*it_ft)->f*dist), src/CoarseTracker.cpp:292 — with the features that have no point / a negative distance left out
+   * (the reference skips them in every stage, :290,433,455,557); px as float32, which is exact: the tracker only ever uses
+   * (float)(px * 2^-level) (:437-441), and a power-of-two factor commutes with the rounding to float. Results are bit-identical to the wide layout.
+   * All jobs of a batch use the same layout. */
+  const double* xyz;     /* [n_features][3] */
+  const float* px32;     /* [n_features][2] */
 } hso_track_job;
 
 typedef struct {

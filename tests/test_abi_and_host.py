@@ -48,7 +48,7 @@ def test_struct_sizes_match_header_layout():
     # sizes computed from the header's field lists (natural alignment)
     assert C.sizeof(K.hso_cam) == 16 + 4 * 8 + 5 * 8
     assert C.sizeof(K.hso_cfg) == 32
-    assert C.sizeof(K.hso_track_job) == 16 + 3 * 8 + 96 + 8
+    assert C.sizeof(K.hso_track_job) == 16 + 3 * 8 + 96 + 8 + 2 * 8  # + the compact layout's two pointers (xyz, px32)
     assert C.sizeof(K.hso_trace) == 8 + 96 + 8 + 8 * (49 + 7 + 7 + 1) + 12 + 8 + 4
     assert C.sizeof(K.hso_align_job) == C.sizeof(O.orc_align_job) == 16 + 8 * 10 + 8
     assert C.sizeof(K.hso_align_result) == C.sizeof(O.orc_align_result) == 32

@@ -39,7 +39,10 @@ def test_cpp_host_layer_matches_ctypes_path(tmp_path):
     a0 = float(np.float32(integral[1]) / np.float32(integral[0]))
     # makeDepthRef for self-hosted points: |f / idist| = dist (z > 1e-5 holds)
     dist = np.where(has == 1, np.linalg.norm(p["f"] * (1.0 / idist)[:, None], axis=1), -1.0)
-    res, _ = ctx.coarse_track_batch([dict(ref=ids[0], cur=ids[1], px=p["px"], f=p["f"], dist=dist, T_cur_ref=np.eye(4)[:3], exposure_rat=a0)])
+    # the C++ layer's gather loop writes the compact feature layout (xyz = f * dist, float32 px, features without depth left out): same here, so
+    # that both paths pick the same launch shape (it follows the feature count) and the iteration counts can be compared
+    xyz, px32 = Context.compact_features(p["px"], p["f"], dist)
+    res, _ = ctx.coarse_track_batch([dict(ref=ids[0], cur=ids[1], xyz=xyz, px32=px32, T_cur_ref=np.eye(4)[:3], exposure_rat=a0)])
     assert abs(r["integral"][0] - integral[0]) < 1e-4 and abs(r["integral"][1] - integral[1]) < 1e-4
     assert r["n_tracked"] == res[0]["n_tracked"]
     assert np.abs(np.array(r["T_track"]).reshape(3, 4) - res[0]["T_cur_ref"]).max() < 1e-9

@@ -302,6 +302,53 @@ def test_pipelined_entry_edge_cases(oracle):
     ctx.close()
 
 
+@pytest.mark.parametrize("ic", [False, True])
+def test_compact_feature_layout_is_bit_identical(oracle, ic):
+    """hso_track_job::xyz / px32 (32 B per feature: xyz = f * dist formed by the caller, px as float32, features without depth left out) against
+    the wide px / f / dist layout: the tracker only uses (float)(px * 2^-level), so float32 px is exact and every result bit must agree —
+    through hso_coarse_track_batch and through the pipelined hso_add_frames_track_batch, pinned and pageable arrays alike."""
+    pairs = [synth.make_pair(300 + s, "icl", F=500 + 37 * s) for s in range(3)]
+    c = pairs[0]["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"]), max_frames=32)
+    ctx.set_cluster(1, 256)  # the automatic launch shape follows the feature count, which differs between the layouts (features without depth)
+    rng = np.random.default_rng(5)
+    wide, compact = [], []
+    ref_ids, ref_int, _ = ctx.upload_frames([p["ref_img"] for p in pairs])
+    cur_ids, cur_int, _ = ctx.upload_frames([p["cur_img"] for p in pairs])
+    for k, p in enumerate(pairs):
+        dist = p["dist"].copy()
+        dist[rng.uniform(size=dist.shape[0]) < 0.05] = -1.0  # features without a point
+        px = p["px"] + rng.uniform(-0.3, 0.3, p["px"].shape)   # sub-pixel positions that are not float32 numbers
+        a0 = float(np.float32(cur_int[k]) / np.float32(ref_int[k]))
+        base = dict(ref=ref_ids[k], cur=cur_ids[k], T_cur_ref=np.eye(4)[:3], exposure_rat=a0)
+        wide.append(dict(base, px=px, f=p["f"], dist=dist))
+        xyz, px32 = Context.compact_features(px, p["f"], dist)
+        assert px32.dtype == np.float32 and xyz.shape[0] == int((dist >= 0).sum()) and np.abs(px32 - px[dist >= 0]).max() > 0
+        compact.append(dict(base, xyz=xyz, px32=px32))
+    rw, tw = ctx.coarse_track_batch(wide, inverse_comp=ic, trace_cap=128)
+    rc, tc = ctx.coarse_track_batch(compact, inverse_comp=ic, trace_cap=128)
+    for k in range(3):
+        assert np.array_equal(rw[k]["T_cur_ref"], rc[k]["T_cur_ref"]) and rw[k]["exposure_rat"] == rc[k]["exposure_rat"]
+        assert rw[k]["n_iters"] == rc[k]["n_iters"] and rw[k]["n_tracked"] == rc[k]["n_tracked"] and len(tw[k]) == len(tc[k])
+        for ea, eb in zip(tw[k], tc[k]):
+            assert np.array_equal(np.array(ea.H[:]), np.array(eb.H[:])) and np.array_equal(np.array(ea.b[:]), np.array(eb.b[:])) and ea.huber == eb.huber
+    strip = lambda jobs: [{k: v for k, v in j.items() if k not in ("cur", "exposure_rat")} for j in jobs]
+    imgs = [p["cur_img"] for p in pairs]
+    ids_w, _, _, pw = ctx.add_frames_track_batch(imgs, strip(wide), inverse_comp=ic)
+    ids_c, _, _, pc = ctx.add_frames_track_batch(imgs, strip(compact), inverse_comp=ic)
+    for k in range(3):
+        assert np.array_equal(pw[k]["T_cur_ref"], pc[k]["T_cur_ref"]) and pw[k]["n_iters"] == pc[k]["n_iters"]
+        assert np.array_equal(pw[k]["T_cur_ref"], rw[k]["T_cur_ref"])
+    # an empty job in a compact batch, and mixed layouts are refused
+    empty = dict(compact[0], xyz=np.zeros((0, 3)), px32=np.zeros((0, 2), np.float32), T_cur_ref=np.eye(4)[:3] * 1.0)
+    r0, _ = ctx.coarse_track_batch([compact[1], empty], inverse_comp=ic)
+    assert r0[1]["n_tracked"] == 0 and np.array_equal(r0[0]["T_cur_ref"], rc[1]["T_cur_ref"])
+    from hso_b200.api import HsoError
+    with pytest.raises(HsoError):
+        ctx.coarse_track_batch([wide[0], compact[1]], inverse_comp=ic)
+    ctx.close()
+
+
 # ---- parity at the benchmarked launch shape and configuration (bench.py: icl 640x480, F = 3000, B = 1184 per GPU) ---------------------------
 # With B >= 296 problems in flight (two per SM) track_run_range gives every problem ONE CTA at every level: at levels 4..2 a 256-thread CTA in
 # mode 3 (image resident, reference-patch cache streamed from L2 through a per-warp TMA ring), two of which share an SM; at level 1 (77 KB image)
