@@ -1210,7 +1210,11 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
       TrackLevelParams q = p;
       q.fast = 3; q.cluster = 1; q.hist_bits = 11; q.absres_smem = 0;
       q.pc = (maxF + 255) / 256 * 256;
-      if (track_level_smem_bytes(q, 256) <= 110 * 1024) { p.fast = 3; p.pc = q.pc; p.cluster = 1; p.hist_bits = 11; cluster = 1; threads = 256; pair_ctas = true; }
+      // two CTAs fit an SM when each needs at most (228 KB - 2 x 1 KB reserved) / 2 = 113 KB
+      const size_t pair_limit = (228 * 1024 - 2 * 1024) / 2;
+      if (track_level_smem_bytes(q, 256) <= pair_limit) { p.fast = 3; p.pc = q.pc; p.cluster = 1; p.hist_bits = 11; cluster = 1; threads = 256; pair_ctas = true; }
+      // (level 1 at 640x480 fits twice only with the single-buffered ring — 77 KB image + 21 KB ring + 14 KB; measured, no gain over one 512-thread
+      // CTA with the double-buffered ring: 3.94 vs 3.98 ms at B = 2368)
     }
     if (!cluster && prm.inverse_comp && !ctx->t_no_stream) {
       // inverse-compositional, cached reference intensities + gradients (what the reference precomputes, src/CoarseTracker.cpp:482-492) streamed
@@ -1238,7 +1242,7 @@ static int track_run_range(hso_ctx* ctx, int b0, int B, bool profile, int shape_
         TrackLevelParams q = p;
         q.fast = 2; q.cluster = 1; q.hist_bits = 11; q.absres_smem = 0;
         q.pc = (maxF + 255) / 256 * 256;
-        if (track_level_smem_bytes(q, 256) <= 110 * 1024) { th = 256; pair = true; }
+        if (track_level_smem_bytes(q, 256) <= (228 * 1024 - 2 * 1024) / 2) { th = 256; pair = true; }
       }
       const int kpt = (maxF + cc * th - 1) / (cc * th);
       p.fast = 2; p.pc = kpt * th; p.cluster = cc; p.hist_bits = 11;

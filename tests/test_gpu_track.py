@@ -349,6 +349,21 @@ def test_compact_feature_layout_is_bit_identical(oracle, ic):
     ctx.close()
 
 
+@pytest.mark.parametrize("ic", [False, True])
+def test_large_feature_count_throughput_shapes(oracle, ic):
+    """7000 features per frame (above the benchmark's 3000) in the throughput shapes of a 300-problem batch: the streamed-cache modes have no
+    F-dependent shared-memory footprint, so every level still runs as one CTA per problem; per-evaluation parity and the final pose against the oracle."""
+    p, ctx, tp, job, a0 = _setup(oracle, 77, "icl", 7000)
+    res, traces = ctx.coarse_track_batch([job] * 300, inverse_comp=ic, trace_cap=128)
+    shapes = {l: ctx.level_shape(l) for l in (4, 3, 2, 1)}
+    assert all(sh[0] == 1 and sh[2] in (3, 4) for sh in shapes.values()), shapes
+    assert _check_trace(oracle, tp, traces[0], ic, 4) <= REL
+    assert all(np.array_equal(res[b]["T_cur_ref"], res[0]["T_cur_ref"]) for b in (1, 150, 299))
+    ro = tp.run(np.eye(4)[:3], a0, inverse_comp=ic)
+    assert np.abs(res[0]["T_cur_ref"] - ro["T_cur_ref"]).max() < 2e-4 and abs(res[0]["n_tracked"] - ro["n_tracked"]) <= 2
+    ctx.close()
+
+
 # ---- parity at the benchmarked launch shape and configuration (bench.py: icl 640x480, F = 3000, B = 1184 per GPU) ---------------------------
 # With B >= 296 problems in flight (two per SM) track_run_range gives every problem ONE CTA at every level: at levels 4..2 a 256-thread CTA in
 # mode 3 (image resident, reference-patch cache streamed from L2 through a per-warp TMA ring), two of which share an SM; at level 1 (77 KB image)
@@ -356,9 +371,9 @@ def test_compact_feature_layout_is_bit_identical(oracle, ic):
 # is in global memory. The inverse-compositional mode keeps both levels resident (mode 2) with one CTA per problem. BENCH_SHAPE is what bench.py's
 # batch runs; hso_track_get_level_shape proves the tests run exactly that.
 BENCH_SHAPE_FWD = {4: (1, 256, 3, 0), 3: (1, 256, 3, 0), 2: (1, 256, 3, 0), 1: (1, 512, 3, 0)}
-# inverse-compositional: cached intensities + gradients streamed from L2 (mode 3) as 256-thread pairs at levels 4, 3, one 512-thread CTA at level 2
-# (two 8-warp rings + two images exceed an SM), a single-buffered ring (mode 4) at level 1 where 16 warps x 2 buffers x 63 rows do not fit
-BENCH_SHAPE_IC = {4: (1, 256, 3), 3: (1, 256, 3), 2: (1, 512, 3), 1: (1, 512, 4)}
+# inverse-compositional: cached intensities + gradients streamed from L2 (mode 3) as 256-thread pairs at levels 4..2 (level 2: 112.5 KB per CTA, two
+# just fit an SM), one 512-thread CTA with a single-buffered ring (mode 4) at level 1 where 16 warps x 2 buffers x 63 rows do not fit
+BENCH_SHAPE_IC = {4: (1, 256, 3), 3: (1, 256, 3), 2: (1, 256, 3), 1: (1, 512, 4)}
 
 
 def _bench_problem(oracle, seed, F=3000, cam="icl"):
