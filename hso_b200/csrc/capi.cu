@@ -1375,7 +1375,9 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   auto pipeline = [&]() -> int {
   if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   // chunk = one wave of single-CTA problems (148 SMs); few enough chunks that the per-chunk launch overhead stays small
-  const int unit = ctx->pipe_chunk > 0 ? ctx->pipe_chunk : 111;  // 3/4 of a wave of single-CTA problems: measured best with 3 streams
+  // one wave of single-CTA problems on four streams: measured best with this round's kernels and the compact feature layout (e2e at B = 2368:
+  // 111:3 3.28, 148:3 3.27, 111:4 3.35, 74:4 3.30, 185:3 3.32, 148:4 3.36 M it/s)
+  const int unit = ctx->pipe_chunk > 0 ? ctx->pipe_chunk : 148;
   int chunk = B <= unit ? B : unit;
   while ((B + chunk - 1) / chunk > 32) chunk += unit;
   // the first two chunks ramp up (1/3, 2/3 of a chunk): the GPU starts after a third of a chunk's flattening + copy instead of a whole one;
@@ -1387,7 +1389,7 @@ int hso_add_frames_track_batch(hso_ctx* ctx, const hso_track_params* prm, int B,
   while (bounds.back() < B - tail_sz) bounds.push_back(std::min(B - tail_sz, bounds.back() + chunk));
   if (ramp) { bounds.push_back(B - chunk / 3); bounds.push_back(B); }
   const int n_chunks = (int)bounds.size() - 1;
-  S = std::max(1, std::min(n_chunks, ctx->pipe_n_streams > 0 ? ctx->pipe_n_streams : 3));
+  S = std::max(1, std::min(n_chunks, ctx->pipe_n_streams > 0 ? ctx->pipe_n_streams : 4));
   while ((int)ctx->pipe_streams.size() < S - 1) {
     cudaStream_t st; cudaEvent_t e;
     CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
