@@ -5,23 +5,27 @@
 // level loop of run() — src/CoarseTracker.cpp:74-195,242-644 — for a batch of independent problems.
 //
 // Mapping (see DESIGN.md "k_track_level"):
-//   * lane == patch. A thread owns patches i = t, t+NT, ... for the whole launch, so the reference-intensity cache it
-//     writes in phase 1 is only ever read back by itself (no barrier), and all scratch arrays are [pattern px][patch]
+//   * lane == patch. A thread owns patches i = t, t+NT, ... for the whole launch; scratch arrays are [pattern px][patch] (or group-major, below)
 //     so that a warp's accesses are coalesced / bank-conflict free.
-//   * FAST path: the current-level image is staged once per launch into shared memory with a TMA bulk copy (cp.async.bulk +
-//     mbarrier; SASS UBLKCP) and the reference-patch cache of the CTA's patches lives in shared memory too, so a residual
-//     evaluation touches global memory only for 24 B of geometry per patch (prefetched one patch ahead). The host picks the
-//     smallest cluster size whose per-CTA share fits the 227 KB of an SM. SLOW path (level 0 / oversized problems): same code
-//     reading the image and the caches from global memory through L1/L2.
+//   * the current-level image is staged once per launch into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier; SASS UBLKCP).
+//     Where the reference-patch cache of precomputeReferencePatches lives is the MODE of the instantiation: 1 = resident in shared memory
+//     (split over a cluster when image + cache exceed an SM), 2 = inverse-compositional, both levels resident and the reference samples
+//     recomputed per evaluation, 3 / 4 = in global memory (L2 resident), group-major, streamed through a per-warp ring in shared memory by one
+//     TMA bulk copy per patch group (two buffers / one buffer per warp) — the footprint no longer depends on the feature count, so every level of the
+//     headline configuration runs as ONE CTA per problem and two 256-thread CTAs share an SM at the coarse levels; 0 = image and caches in
+//     global memory (level 0 / oversized problems). The host picks the shape per level (capi.cu, track_run_range).
+//   * a residual evaluation streams the (2P+4)^2 window of a patch once (rows as aligned words + funnel shift; interpolated image formed once per
+//     window position); where only the colour is needed (threshold pass, reference gather, cached inverse-compositional path) the (2P+2)^2 window.
 //   * the 7x7 normal equations are not accumulated term by term. Every Jacobian row of a patch has the form
 //     J = [-c, gx*A + gy*B] with A,B in R^6 constant over the patch (src/CoarseTracker.cpp:372), so per term only the nine
 //     moments  sum w*{gx^2, gx gy, gy^2, c gx, c gy, c^2, r gx, r gy, r c}  are accumulated and the 28+7 entries are
 //     expanded once per patch — mathematically identical to computeGS (src/CoarseTracker.cpp:499-525), 4x fewer FMAs.
 //   * fp32 inside a patch (as the reference), fp32 tree inside a warp, fp64 across warps / CTAs in a fixed order
 //     (run-to-run deterministic); the reference accumulates H in fp32 over all terms (MatrixAccumulator.h:65-140).
-//   * the robust thresholds (median / MAD, src/CoarseTracker.cpp:608-630) are exact order statistics obtained with a
-//     3-pass radix select on the float bit patterns — the k-th element is order independent, so they match nth_element.
-//   * cluster of C CTAs per problem: partial sums and histograms are exchanged through distributed shared memory;
+//   * the robust thresholds (median / MAD, src/CoarseTracker.cpp:608-630) are exact order statistics: a linear-bin histogram fused with the
+//     residual pass, one compaction pass of the chosen bin, a radix select over the compacted list (plain 3-pass radix select on the float bit
+//     patterns as the fallback) — the k-th element is order independent, so they match nth_element.
+//   * cluster of C CTAs per problem (small batches): partial sums and histograms are exchanged through distributed shared memory;
 //     every CTA then runs the (tiny, fp64) damped solve + SE3 update redundantly, so one cluster barrier per trial suffices.
 #include <cooperative_groups.h>
 
