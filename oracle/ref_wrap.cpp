@@ -12,6 +12,7 @@
 // cpu_baseline leg time them (kind = "reference").
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -36,6 +37,14 @@
 #include "hso_oracle.h"
 
 using namespace hso;
+
+// The three symbols of src/feature_detection.cpp (not among the compiled TUs: cv::Canny, the octree distribution) that depth_filter.cpp references, so that
+// the library links: the detector's grid bookkeeping, which observeDepthRow calls for keyframes only (:668-672), and the two calls of
+// DepthFilter::initializeSeeds (:169-170). None is reached by ref_depth_observe — the active frames of the tests are not keyframes and no seeds are
+// initialised through the filter — and each one aborts if it ever is.
+void hso::feature_detection::FeatureExtractor::setGridOccpuancy(const Vector2d&, Feature*) { std::abort(); }
+void hso::feature_detection::FeatureExtractor::setExistingFeatures(const Features&) { std::abort(); }
+void hso::feature_detection::FeatureExtractor::detect(Frame*, const float, const float, Features&, Frame*) { std::abort(); }
 
 namespace {
 
@@ -460,6 +469,48 @@ void ref_find_match_seed_batch(void* cur_handle, int n_kf, void* const* kf_handl
     A_out[4 * i] = matcher.A_cur_ref_(0, 0); A_out[4 * i + 1] = matcher.A_cur_ref_(0, 1);
     A_out[4 * i + 2] = matcher.A_cur_ref_(1, 0); A_out[4 * i + 3] = matcher.A_cur_ref_(1, 1);
   }
+}
+
+// ---- N3: DepthFilter::observeDepthRow (src/depth_filter.cpp:580-675) — the reference's own function, one seed per call so that the outcome code of
+// doLineStereo can be read off the RunningStats counters. Seeds as orc_seed_obs (Seed{ftr = the feature in keyframe kf_handles[ref_frame], mu, sigma2}),
+// results as orc_seed_result. The filter object is constructed once (its constructor starts the IndexThreadReduce workers, which stay idle); the
+// mapping thread is never started.
+void ref_depth_observe(void* cur_handle, int n_kf, void* const* kf_handles, double px_error_angle, int S, const orc_seed_obs* seeds, orc_seed_result* out) {
+  FrameHandle* cur = (FrameHandle*)cur_handle;
+  static DepthFilter* df = nullptr;
+  if (!df) df = new DepthFilter(nullptr, DepthFilter::callback_t());
+  df->px_error_angle_ = px_error_angle;
+  df->active_frame_ = cur->frame;
+  df->seeds_updating_halt_ = false;
+  for (int i = 0; i < S; ++i) {
+    const orc_seed_obs& s = seeds[i];
+    orc_seed_result& o = out[i];
+    std::memset(&o, 0, sizeof o);
+    if (s.ref_frame < 0 || s.ref_frame >= n_kf) continue;
+    Frame* kf = ((FrameHandle*)kf_handles[s.ref_frame])->frame.get();
+    Feature obs(kf, Vector2d(s.px[0], s.px[1]), Vector3d(s.f[0], s.f[1], s.f[2]), s.level);
+    obs.type = (Feature::FeatureType)s.ftr_type;
+    obs.grad = Vector2d(s.grad[0], s.grad[1]);
+    df->seeds_.clear();
+    df->seeds_.emplace_back(&obs, 1.0f, 1.0f, 1.0f);   // Seed(ftr, depth_mean, depth_min, converge_threshold): only ftr, mu, sigma2, b are read below
+    Seed& seed = df->seeds_.back();
+    seed.mu = s.mu; seed.sigma2 = s.sigma2; seed.is_update = false;
+    const float b0 = seed.b;
+    RunningStats st;
+    df->observeDepthRow(0, 1, &st);
+    o.is_update = seed.is_update ? 1 : 0;
+    o.is_valid = seed.isValid ? 1 : 0;
+    o.res = st.n_updates ? 1 : st.n_fail_lsd ? -1 : st.n_fail_triangulation ? -2 : st.n_fail_alignment ? -3 : st.n_fail_score ? -4 : (seed.b != b0 ? -5 : 0);
+    o.epl_start[0] = seed.eplStart[0]; o.epl_start[1] = seed.eplStart[1]; o.epl_end[0] = seed.eplEnd[0]; o.epl_end[1] = seed.eplEnd[1];
+    o.mu = seed.mu; o.sigma2 = seed.sigma2;
+    if (st.n_updates) {
+      o.z = (double)seed.vec_distance.back();  // 1 / mu after the update (float); the triangulated z itself is a local of observeDepthRow
+      o.px_cur[0] = seed.last_matched_px[0]; o.px_cur[1] = seed.last_matched_px[1];
+      o.search_level = seed.last_matched_level;
+    }
+    df->seeds_.clear();
+  }
+  df->active_frame_.reset();
 }
 
 int ref_check_ncc(const float* p1, const float* p2, float thresh) {

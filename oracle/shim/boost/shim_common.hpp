@@ -14,7 +14,13 @@ using std::mutex;
 using std::unique_lock;
 using std::lock_guard;
 using std::condition_variable;
-using std::thread;
+// boost::thread's cooperative interruption (DepthFilter::stopThread / updateSeedsLoop, src/depth_filter.cpp:121,244): the tests drive the
+// per-seed functions directly and never start the mapping thread, so interrupt() has nothing to do and no interruption is ever pending
+class thread : public std::thread {
+ public:
+  using std::thread::thread;
+  void interrupt() {}
+};
 using std::ref;
 using std::cref;
 class noncopyable {
@@ -25,7 +31,7 @@ class noncopyable {
   noncopyable& operator=(const noncopyable&) = delete;
 };
 template <class... A> auto bind(A&&... a) -> decltype(std::bind(std::forward<A>(a)...)) { return std::bind(std::forward<A>(a)...); }
-namespace this_thread { using std::this_thread::yield; using std::this_thread::sleep_for; }
+namespace this_thread { using std::this_thread::yield; using std::this_thread::sleep_for; inline bool interruption_requested() { return false; } }
 }  // namespace boost
 // boost/bind.hpp puts _1.._9 into the global namespace
 using namespace std::placeholders;

@@ -294,6 +294,18 @@ def find_match_seed_batch(cur, kfs, seeds, px_init):
     return ok, px.reshape(S, 2), sl, A.reshape(S, 2, 2)
 
 
+def depth_observe(cur, kfs, seeds, px_error_angle):
+    """DepthFilter::observeDepthRow (src/depth_filter.cpp:580-675) of the reference for every seed record (orc_seed_obs array), one seed per call.
+    Returns an orc_seed_result array (z = 1 / mu after the update, as the reference records it in Seed::vec_distance)."""
+    import oracle_lib as O
+    lib = load()
+    S = len(seeds)
+    out = (O.orc_seed_result * max(S, 1))()
+    hh = (C.c_void_p * len(kfs))(*[k.h for k in kfs])
+    lib.ref_depth_observe(cur.h, len(kfs), hh, C.c_double(px_error_angle), S, seeds, out)
+    return out
+
+
 def pose_optimize(cam, p, reproj_thresh=2.0, n_iter=12, blank=None):
     """optimizeLevenbergMarquardt3rd of the reference on a synth.make_pose_problem record."""
     lib = load()

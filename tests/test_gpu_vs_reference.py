@@ -186,3 +186,38 @@ def test_find_match_seed_vs_reference(oracle, cam, S, gain):
         k.close()
     cur.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("cam,S", [("icl", 2000), ("euroc", 1200), ("tum_fov", 1000)])
+def test_depth_observe_vs_reference(oracle, cam, S):
+    """hso_depth_observe vs DepthFilter::observeDepthRow of the reference itself (row N3): visibility / validity exact, the outcome of
+    Matcher::doLineStereo with <= 1 % flips, and where both succeed the epipolar end points, the search level, the matched pixel and the updated seed."""
+    s = synth.make_depth_scene(8, cam, S=S)
+    c = s["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), materialize_sobel=True)
+    kf_ids, _, _ = ctx.upload_frames(s["kf_imgs"])
+    cur_id = ctx.upload_frames([s["cur_img"]])[0][0]
+    got = ctx.depth_observe(cur_id, s["T_cur_w"], s["T_f_w"], Context.seed_obs(s["seeds"], frame_ids=kf_ids), s["px_error_angle"], S=S)
+    kfs = [R.Frame(c, im, T, exposure_time=1.0, keyframe_id=1) for im, T in zip(s["kf_imgs"], s["T_f_w"])]
+    cur = R.Frame(c, s["cur_img"], s["T_cur_w"], exposure_time=1.0, keyframe_id=9)
+    oc = (oracle.orc_seed_obs * S).from_buffer_copy(bytes(Context.seed_obs(s["seeds"])))
+    ref = R.depth_observe(cur, kfs, oc, s["px_error_angle"])
+    assert [got[i].is_update for i in range(S)] == [ref[i].is_update for i in range(S)]
+    upd = [i for i in range(S) if ref[i].is_update]
+    assert [got[i].is_valid for i in upd] == [ref[i].is_valid for i in upd]
+    flips = sum(1 for i in upd if (got[i].res == 1) != (ref[i].res == 1) or (got[i].res != 1 and got[i].res != ref[i].res))
+    assert flips <= max(1, 0.01 * len(upd)), (flips, len(upd))
+    both = [i for i in upd if got[i].res == 1 and ref[i].res == 1]
+    assert len(both) >= 30
+    for i in both:
+        assert list(got[i].epl_start) == list(ref[i].epl_start) and list(got[i].epl_end) == list(ref[i].epl_end) and got[i].search_level == ref[i].search_level
+    dpx = np.array([np.hypot(got[i].px_cur[0] - ref[i].px_cur[0], got[i].px_cur[1] - ref[i].px_cur[1]) for i in both])
+    dmu = np.array([abs(got[i].mu - ref[i].mu) / abs(ref[i].mu) for i in both])
+    dsg = np.array([abs(got[i].sigma2 - ref[i].sigma2) / ref[i].sigma2 for i in both])
+    assert np.median(dpx) < 1e-3 and np.quantile(dpx, 0.99) < 0.05
+    assert np.median(dmu) < 1e-5 and np.quantile(dmu, 0.99) < 5e-3
+    assert np.median(dsg) < 1e-4 and np.quantile(dsg, 0.99) < 5e-2
+    for k in kfs:
+        k.close()
+    cur.close()
+    ctx.close()

@@ -414,6 +414,53 @@ def test_a13b_seed_walk_matches_brute_force():
         assert [(io[i].tried, io[i].matched, io[i].order) for i in range(S)] == list(zip(exp[0], exp[1], exp[2])), trial
 
 
+# ---- N3 ------------------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cam,S,seed", [("icl", 500, 4), ("euroc", 400, 5), ("tum_fov", 400, 6)])
+def test_n3_observe_depth_row_reference_vs_restatement(cam, S, seed):
+    """DepthFilter::observeDepthRow (src/depth_filter.cpp:580-675: visibility, Matcher::doLineStereo — epipolar ZMNCC scan, KLTLimited1D/2D,
+    checkNormal / checkNCC, depthFromTriangulation — computeTau, updateSeed) of the reference itself vs the restatement, seed by seed: visibility and
+    validity flags exact, the outcome code of doLineStereo with <= 1 % flips (float ZMNCC / KLT sums at the 0.8 / 1.5x / 650 thresholds), and where
+    both succeed the epipolar end points, the search level, the matched pixel and the updated (mu, sigma2)."""
+    from hso_b200 import Context
+    s = synth.make_depth_scene(seed, cam, S=S)
+    c = s["cam"]
+    kfs = [R.Frame(c, im, T, exposure_time=1.0, keyframe_id=1) for im, T in zip(s["kf_imgs"], s["T_f_w"])]
+    cur = R.Frame(c, s["cur_img"], s["T_cur_w"], exposure_time=1.0, keyframe_id=9)
+    oc = (O.orc_seed_obs * S).from_buffer_copy(bytes(Context.seed_obs(s["seeds"])))
+    pyrs = [O.create_pyramid(im, 5)[0] for im in s["kf_imgs"]]
+    cl, _ = O.create_pyramid(s["cur_img"], 5)
+    sob = [O.sobel5(cl[l]) for l in range(3)]
+    oo = O.depth_observe(c, s["T_cur_w"], s["T_f_w"], oc, s["px_error_angle"], pyrs, cl, sob)
+    rr = R.depth_observe(cur, kfs, oc, s["px_error_angle"])
+    flips = both = 0
+    dmu, dsig, dpx = [], [], []
+    for i in range(S):
+        o, r = oo[i], rr[i]
+        assert o.is_update == r.is_update and (not o.is_update or o.is_valid == r.is_valid), i
+        if not o.is_update:
+            continue
+        if (o.res == 1) != (r.res == 1) or (o.res != 1 and o.res != r.res):
+            flips += 1
+            continue
+        if o.res != 1:
+            assert r.mu == o.mu and r.sigma2 == o.sigma2 and list(r.epl_start) == [0, 0] == list(o.epl_start)
+            continue
+        both += 1
+        assert list(o.epl_start) == list(r.epl_start) and list(o.epl_end) == list(r.epl_end) and o.search_level == r.search_level, i
+        dpx.append(np.hypot(o.px_cur[0] - r.px_cur[0], o.px_cur[1] - r.px_cur[1]))
+        dmu.append(abs(o.mu - r.mu) / abs(r.mu))
+        dsig.append(abs(o.sigma2 - r.sigma2) / r.sigma2)
+        assert abs(1.0 / o.mu - r.z) <= 1e-5 * abs(r.z)  # Seed::vec_distance.back() = 1 / mu
+    n_upd = sum(1 for i in range(S) if oo[i].is_update)
+    assert both >= 30 and flips <= max(1, 0.01 * n_upd), (flips, n_upd, both)  # (the distorted cameras match fewer seeds: 72 and 36 of 400)
+    assert np.median(dpx) < 1e-3 and np.quantile(dpx, 0.99) < 0.05, (np.median(dpx), np.max(dpx))
+    assert np.median(dmu) < 1e-5 and np.quantile(dmu, 0.99) < 5e-3, (np.median(dmu), np.max(dmu))
+    assert np.median(dsig) < 1e-4 and np.quantile(dsig, 0.99) < 5e-2, (np.median(dsig), np.max(dsig))
+    for k in kfs:
+        k.close()
+    cur.close()
+
+
 # ---- a16, a17 ------------------------------------------------------------------------------------------------------------------------------
 def test_a17_robust_cost_reference_vs_restatement():
     """MADScaleEstimator::compute (src/vikit/robust_cost.cpp:67-74) = 1.4826 * nth_element(n / 2), HuberWeightFunction::value (:129-148, k = 1.345,
