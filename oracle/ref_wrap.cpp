@@ -29,7 +29,9 @@
 #include <hso/frame.h>
 #include <hso/matcher.h>
 #include <hso/point.h>
+#include <hso/map.h>
 #include <hso/pose_optimizer.h>
+#include <hso/reprojector.h>
 #include <hso/vikit/math_utils.h>
 #include <hso/vikit/robust_cost.h>
 #include <hso/vikit/vision.h>
@@ -469,6 +471,106 @@ void ref_find_match_seed_batch(void* cur_handle, int n_kf, void* const* kf_handl
     A_out[4 * i] = matcher.A_cur_ref_(0, 0); A_out[4 * i + 1] = matcher.A_cur_ref_(0, 1);
     A_out[4 * i + 2] = matcher.A_cur_ref_(1, 0); A_out[4 * i + 3] = matcher.A_cur_ref_(1, 1);
   }
+}
+
+// ---- N1: the grid stage of Reprojector::reprojectMap through the reference's own member functions ---------------------------------------------
+// Candidates use the record of row N1 (orc_reproj_cand), rebuilt as reference Points like in ref_find_match_batch (one observation = the chosen
+// reference feature, so that Point::getCloseViewObs returns it). Per candidate, in list order, Reprojector::reprojectPoint (:504-529: projection,
+// 8-px frame test, grid cell) — where reprojectMap's enumeration loops (:121-250, host side of the boundary) call it; then the selection, i.e.
+// lines :260-303 restated verbatim below around the reference's reprojectCellAll (:545-615) / reprojectCell (:351-424: per-cell stable sort by
+// point quality, first match wins, ++n_trials_ ahead of the TYPE_DELETED test, failure counters, feature creation). The grid is the reference's
+// own (initializeGrid with Config::maxFts() = grid->max_fts; its geometry must equal *grid, else n_matches = -1), cell_order replaces the
+// std::random_shuffle. Results: in_frame / cell / px per candidate, matched + creation order + search level from the Features the walk added to the
+// frame, tried from the points' own success / failure counters.
+void ref_reproject_match(void* cur_handle, int n_kf, void* const* kf_handles, int M, const orc_reproj_cand* cands, const orc_reproj_grid* grid,
+                         const int32_t* cell_order, orc_reproj_result* out, orc_reproj_summary* summary) {
+  FrameHandle* cur = (FrameHandle*)cur_handle;
+  FramePtr frame = cur->frame;
+  std::memset(summary, 0, sizeof *summary);
+  for (int i = 0; i < M; ++i) { std::memset(&out[i], 0, sizeof out[i]); out[i].order = -1; out[i].cell = -1; }
+  Config::maxFts() = (size_t)grid->max_fts;
+  Map map;
+  Reprojector rep(frame->cam_, map);
+  if (rep.grid_.cell_size != grid->cell_size || rep.grid_.grid_n_cols != grid->n_cols || rep.grid_.grid_n_rows != grid->n_rows) { summary->n_matches = -1; return; }
+  rep.resetGrid();
+  rep.grid_.cell_order.assign(cell_order, cell_order + rep.grid_.cells.size());
+  rep.matcher_.options_.align_max_iter = grid->align_max_iter;
+  std::vector<std::unique_ptr<Feature>> feats;
+  std::vector<std::unique_ptr<Point>> pts(M);
+  std::map<Point*, int> index;
+  std::vector<std::pair<Vector2d, Point*>> allPixelToDistribute;
+  for (int i = 0; i < M; ++i) {
+    const orc_reproj_cand& c = cands[i];
+    if (c.host_pose < 0 || c.host_pose >= n_kf) continue;
+    Frame* kf_host = ((FrameHandle*)kf_handles[c.host_pose])->frame.get();
+    const Vector3d p_host(c.p_host[0], c.p_host[1], c.p_host[2]);
+    feats.emplace_back(new Feature(kf_host, Vector2d(0, 0), p_host * (1.0 / p_host.norm()), 0));
+    Feature* host = feats.back().get();
+    Feature* obs = nullptr;
+    if (c.ref_pose >= 0 && c.ref_pose < n_kf) {
+      Frame* kf_ref = ((FrameHandle*)kf_handles[c.ref_frame])->frame.get();
+      feats.emplace_back(new Feature(kf_ref, Vector2d(c.px_ref[0], c.px_ref[1]), Vector3d(c.f_ref[0], c.f_ref[1], c.f_ref[2]), c.ref_level));
+      obs = feats.back().get();
+      obs->type = (Feature::FeatureType)c.ftr_type;
+      obs->grad = Vector2d(c.grad[0], c.grad[1]);
+    }
+    Point* pt = new Point(kf_host->T_f_w_.inverse() * p_host, obs ? obs : host);
+    if (!obs) pt->obs_.clear();  // no observation in view: getCloseViewObs fails, findMatchDirect returns false (matcher.cpp:276)
+    pt->hostFeature_ = (obs && c.ref_frame == c.host_pose) ? obs : host;
+    pt->idist_ = (obs && c.ref_frame == c.host_pose) ? 1.0 / c.depth_ref : 1.0 / p_host.norm();
+    pt->type_ = (Point::PointType)c.pt_type;
+    pt->ftr_type_ = (Point::FeatureType)c.pt_ftr_type;
+    pts[i].reset(pt);
+    index[pt] = i;
+    const size_t before = allPixelToDistribute.size();
+    if (rep.reprojectPoint(frame, pt, allPixelToDistribute)) {
+      const Vector2d& px = allPixelToDistribute[before].first;
+      out[i].in_frame = 1;
+      out[i].px[0] = px[0]; out[i].px[1] = px[1];
+      out[i].cell = static_cast<int>(px[1] / rep.grid_.cell_size) * rep.grid_.grid_n_cols + static_cast<int>(px[0] / rep.grid_.cell_size);
+    }
+  }
+  summary->n_in_frame = (int32_t)allPixelToDistribute.size();
+  const size_t n_fts0 = frame->fts_.size();
+  // ---- src/reprojector.cpp:260-303 ----
+  if (allPixelToDistribute.size() < Config::maxFts() + 50) {
+    summary->used_cell_all = 1;
+    rep.reprojectCellAll(allPixelToDistribute, frame);
+  } else {
+    for (size_t i = 0; i < rep.grid_.cells.size(); ++i) {
+      if (rep.reprojectCell(*rep.grid_.cells.at(rep.grid_.cell_order[i]), frame, false, false)) ++rep.n_matches_;
+      if (rep.n_matches_ >= (size_t)Config::maxFts()) break;
+    }
+    if (rep.n_matches_ < (size_t)Config::maxFts()) {
+      for (size_t i = rep.grid_.cells.size() - 1; i > 0; --i) {
+        if (rep.reprojectCell(*rep.grid_.cells.at(rep.grid_.cell_order[i]), frame, true, false)) ++rep.n_matches_;
+        if (rep.n_matches_ >= (size_t)Config::maxFts()) break;
+      }
+    }
+    if (rep.n_matches_ < (size_t)Config::maxFts()) {
+      for (size_t i = 0; i < rep.grid_.cells.size(); ++i) {
+        rep.reprojectCell(*rep.grid_.cells.at(rep.grid_.cell_order[i]), frame, true, true);
+        if (rep.n_matches_ >= (size_t)Config::maxFts()) break;
+      }
+    }
+  }
+  summary->n_matches = (int32_t)rep.n_matches_;
+  summary->n_trials = (int32_t)rep.n_trials_;
+  int order = 0;
+  size_t k = 0;
+  for (auto it = frame->fts_.begin(); it != frame->fts_.end(); ++it, ++k) {
+    if (k < n_fts0) continue;
+    Feature* ft = *it;
+    const int i = index.at(ft->point);
+    out[i].matched = 1; out[i].tried = 1; out[i].order = order++;
+    out[i].search_level = ft->level;
+    out[i].px[0] = ft->px[0]; out[i].px[1] = ft->px[1];
+    out[i].align_ok = 1;
+  }
+  for (int i = 0; i < M; ++i)
+    if (pts[i] && (pts[i]->n_failed_reproj_ > 0 || pts[i]->n_succeeded_reproj_ > 0)) out[i].tried = 1;
+  // the features the walk created point at Points that die with this call: take them out of the frame again
+  while (frame->fts_.size() > n_fts0) { delete frame->fts_.back(); frame->fts_.pop_back(); }
 }
 
 // ---- N3: DepthFilter::observeDepthRow (src/depth_filter.cpp:580-675) — the reference's own function, one seed per call so that the outcome code of

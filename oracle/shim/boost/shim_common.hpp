@@ -33,5 +33,14 @@ class noncopyable {
 template <class... A> auto bind(A&&... a) -> decltype(std::bind(std::forward<A>(a)...)) { return std::bind(std::forward<A>(a)...); }
 namespace this_thread { using std::this_thread::yield; using std::this_thread::sleep_for; inline bool interruption_requested() { return false; } }
 }  // namespace boost
+// boost::bind expressions can be compared (boost/bind/bind.hpp: relational operators build a new bind expression); Reprojector::reprojectMap sorts
+// its close keyframes with `boost::bind(&pair::second, _1) < boost::bind(&pair::second, _2)` (src/reprojector.cpp:165). Declared in namespace std so
+// that argument-dependent lookup finds it for std::bind's result types (test infrastructure only).
+namespace std {
+template <class A, class B, typename std::enable_if<std::is_bind_expression<A>::value && std::is_bind_expression<B>::value, int>::type = 0>
+auto operator<(A a, B b) {
+  return [a, b](auto&&... args) mutable { return a(args...) < b(args...); };
+}
+}  // namespace std
 // boost/bind.hpp puts _1.._9 into the global namespace
 using namespace std::placeholders;

@@ -294,6 +294,20 @@ def find_match_seed_batch(cur, kfs, seeds, px_init):
     return ok, px.reshape(S, 2), sl, A.reshape(S, 2, 2)
 
 
+def reproject_match(cur, kfs, cands, grid, cell_order):
+    """The grid stage of Reprojector::reprojectMap through the reference's own reprojectPoint / reprojectCell / reprojectCellAll
+    (oracle/ref_wrap.cpp: ref_reproject_match). cands: orc_reproj_cand array, grid: orc_reproj_grid. Returns (orc_reproj_result array, summary)."""
+    import oracle_lib as O
+    lib = load()
+    M = len(cands)
+    out = (O.orc_reproj_result * max(M, 1))()
+    summ = O.orc_reproj_summary()
+    order = np.ascontiguousarray(cell_order, np.int32)
+    hh = (C.c_void_p * len(kfs))(*[k.h for k in kfs])
+    lib.ref_reproject_match(cur.h, len(kfs), hh, M, cands, C.byref(grid), order.ctypes.data_as(C.c_void_p), out, C.byref(summ))
+    return out, summ
+
+
 def depth_observe(cur, kfs, seeds, px_error_angle):
     """DepthFilter::observeDepthRow (src/depth_filter.cpp:580-675) of the reference for every seed record (orc_seed_obs array), one seed per call.
     Returns an orc_seed_result array (z = 1 / mu after the update, as the reference records it in Seed::vec_distance)."""

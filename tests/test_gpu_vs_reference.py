@@ -221,3 +221,39 @@ def test_depth_observe_vs_reference(oracle, cam, S):
         k.close()
     cur.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("cam,M,max_fts,seed", [("icl", 3000, 200, 21), ("euroc", 1500, 150, 23), ("icl", 180, 200, 25)])
+def test_reproject_match_vs_reference(oracle, cam, M, max_fts, seed):
+    """hso_reproject_match (k_reproject + k_align on every candidate + k_reproj_select) vs the grid stage of Reprojector::reprojectMap run through the
+    reference's own reprojectPoint / reprojectCell / reprojectCellAll (row N1): in-frame flag and cell per point exact; tried / matched flags,
+    creation order and both counters equal when no alignment outcome flips along the walk, else within the flip bound."""
+    s = synth.make_reproject_scene(seed, cam, M=M, max_fts=max_fts)
+    c = s["cam"]
+    ctx = Context(make_cam(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["d"], c.get("model", 0)), materialize_sobel=True)
+    kf_ids, _, _ = ctx.upload_frames(s["kf_imgs"])
+    cur_id = ctx.upload_frames([s["cur_img"]])[0][0]
+    got, gsum = ctx.reproject_match(cur_id, s["T_cur_w"], s["T_f_w"], Context.reproj_cands(s["cands"], frame_ids=kf_ids), s["grid"], s["cell_order"])
+    kfs = [R.Frame(c, im, T, exposure_time=1.0, keyframe_id=1) for im, T in zip(s["kf_imgs"], s["T_f_w"])]
+    cur = R.Frame(c, s["cur_img"], s["T_cur_w"], exposure_time=1.0, keyframe_id=2)
+    oc = (oracle.orc_reproj_cand * M).from_buffer_copy(bytes(Context.reproj_cands(s["cands"])))
+    g = oracle.orc_reproj_grid(*[s["grid"][k] for k in ("cell_size", "n_cols", "n_rows", "max_fts", "align_max_iter")], 0)
+    ref, rsum = R.reproject_match(cur, kfs, oc, g, s["cell_order"])
+    assert rsum.n_matches >= 0
+    assert [got[i].in_frame for i in range(M)] == [ref[i].in_frame for i in range(M)]
+    inf = [i for i in range(M) if ref[i].in_frame]
+    assert [got[i].cell for i in inf] == [ref[i].cell for i in inf]
+    assert gsum.n_in_frame == rsum.n_in_frame and gsum.used_cell_all == rsum.used_cell_all
+    same = all(got[i].tried == ref[i].tried and got[i].matched == ref[i].matched for i in range(M))
+    if same:
+        assert (gsum.n_matches, gsum.n_trials) == (rsum.n_matches, rsum.n_trials)
+        dpx = [np.hypot(got[i].px[0] - ref[i].px[0], got[i].px[1] - ref[i].px[1]) for i in range(M) if ref[i].matched]
+        assert all(got[i].order == ref[i].order and got[i].search_level == ref[i].search_level for i in range(M) if ref[i].matched)
+        assert np.median(dpx) < 2e-3 and np.max(dpx) < 0.25
+    else:
+        diff = [i for i in range(M) if got[i].tried != ref[i].tried or got[i].matched != ref[i].matched]
+        assert len(diff) <= 0.02 * max(rsum.n_trials, 1) + 2 and abs(gsum.n_matches - rsum.n_matches) <= 2, (len(diff), gsum.n_matches, rsum.n_matches)
+    for k in kfs:
+        k.close()
+    cur.close()
+    ctx.close()

@@ -414,6 +414,72 @@ def test_a13b_seed_walk_matches_brute_force():
         assert [(io[i].tried, io[i].matched, io[i].order) for i in range(S)] == list(zip(exp[0], exp[1], exp[2])), trial
 
 
+# ---- N1 ------------------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cam,M,max_fts,seed,deleted", [("icl", 3000, 200, 21, 0.0), ("icl", 1200, 120, 22, 0.06), ("euroc", 1500, 150, 23, 0.03),
+                                                         ("tum_fov", 900, 100, 24, 0.0), ("icl", 180, 200, 25, 0.05)])
+def test_n1_reproject_grid_stage_reference_vs_restatement(cam, M, max_fts, seed, deleted):
+    """The grid stage of Reprojector::reprojectMap — reprojectPoint per map point, then the selection (reprojectCellAll, or the three passes over
+    reprojectCell with its per-cell stable sort, first-match-wins walk, TYPE_DELETED handling and counters) — through the reference's OWN member
+    functions vs the restatement's whole call: in-frame flag, cell and pixel per point exact; tried / matched flags, creation order, n_matches_,
+    n_trials_ equal whenever the two sides' findMatchDirect outcomes agree on every tried candidate (a flip changes the walk behind it; flips are
+    bounded by the a13 test), and the created features' pixels / search levels."""
+    from hso_b200 import Context
+    s = synth.make_reproject_scene(seed, cam, M=M, max_fts=max_fts)
+    c = s["cam"]
+    rng = np.random.default_rng(seed)
+    for cd in s["cands"]:
+        if rng.uniform() < deleted:
+            cd["pt_type"] = 0  # Point::TYPE_DELETED
+    kfs = [R.Frame(c, im, T, exposure_time=1.0, keyframe_id=1) for im, T in zip(s["kf_imgs"], s["T_f_w"])]
+    cur = R.Frame(c, s["cur_img"], s["T_cur_w"], exposure_time=1.0, keyframe_id=2)
+    oc = (O.orc_reproj_cand * M).from_buffer_copy(bytes(Context.reproj_cands(s["cands"])))
+    g = O.orc_reproj_grid(*[s["grid"][k] for k in ("cell_size", "n_cols", "n_rows", "max_fts", "align_max_iter")], 0)
+    pyrs = [O.create_pyramid(im, 5)[0] for im in s["kf_imgs"]]
+    cl, _ = O.create_pyramid(s["cur_img"], 5)
+    sob = [O.sobel5(cl[l]) for l in range(3)]
+    oo, osum = O.reproject_match(c, s["T_cur_w"], s["T_f_w"], oc, g, s["cell_order"], 2, pyrs, cl, sob)
+    rr, rsum = R.reproject_match(cur, kfs, oc, g, s["cell_order"])
+    assert rsum.n_matches >= 0, "the reference's grid geometry differs from the scene's"
+    assert [oo[i].in_frame for i in range(M)] == [rr[i].in_frame for i in range(M)]
+    inf = [i for i in range(M) if rr[i].in_frame]
+    assert [oo[i].cell for i in inf] == [rr[i].cell for i in inf]
+    assert osum.n_in_frame == rsum.n_in_frame == len(inf) and osum.used_cell_all == rsum.used_cell_all == int(M == 180)
+    # the reprojected pixel of the points the walk never reached is reprojectPoint's; exact up to the 3x4 composition
+    for i in inf:
+        if not rr[i].tried and not oo[i].tried:
+            assert abs(oo[i].px[0] - rr[i].px[0]) < 1e-9 and abs(oo[i].px[1] - rr[i].px[1]) < 1e-9
+    same = all(oo[i].tried == rr[i].tried and oo[i].matched == rr[i].matched for i in range(M) if s["cands"][i]["pt_type"] != 0)
+    if same:
+        assert (osum.n_matches, osum.n_trials) == (rsum.n_matches, rsum.n_trials)
+        dpx = []
+        for i in range(M):
+            if rr[i].matched:
+                assert oo[i].order == rr[i].order and oo[i].search_level == rr[i].search_level
+                dpx.append(np.hypot(oo[i].px[0] - rr[i].px[0], oo[i].px[1] - rr[i].px[1]))
+        # align2D stops at an update below 0.03 px of the search level (<= 2): one more / one fewer iteration on a side moves a feature by up to
+        # 0.03 * 4 level-0 pixels; the median difference is exactly 0
+        assert np.median(dpx) < 1e-3 and np.max(dpx) < 0.25, (np.median(dpx), np.max(dpx))
+    else:
+        # an alignment outcome flipped on one side: everything before the first difference in walk order must still agree
+        diff = [i for i in range(M) if s["cands"][i]["pt_type"] != 0 and (oo[i].tried != rr[i].tried or oo[i].matched != rr[i].matched)]
+        assert len(diff) <= 0.02 * max(rsum.n_trials, 1) + 2, (len(diff), rsum.n_trials)
+        assert abs(osum.n_matches - rsum.n_matches) <= 2
+    assert rsum.n_matches <= max_fts and rsum.n_trials >= rsum.n_matches
+    test_n1_reproject_grid_stage_reference_vs_restatement.stats.append((cam, M, same, osum.n_matches, rsum.n_matches, osum.n_trials, rsum.n_trials))
+    for k in kfs:
+        k.close()
+    cur.close()
+
+
+test_n1_reproject_grid_stage_reference_vs_restatement.stats = []
+
+
+def test_n1_reference_and_restatement_walks_agreed_exactly_somewhere():
+    """At least three of the five scenes above must have gone through the exact branch (no alignment flip anywhere along the walk)."""
+    st = test_n1_reproject_grid_stage_reference_vs_restatement.stats
+    assert len(st) == 5 and sum(1 for x in st if x[2]) >= 3, st
+
+
 # ---- N3 ------------------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cam,S,seed", [("icl", 500, 4), ("euroc", 400, 5), ("tum_fov", 400, 6)])
 def test_n3_observe_depth_row_reference_vs_restatement(cam, S, seed):
