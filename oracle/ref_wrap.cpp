@@ -573,6 +573,72 @@ void ref_reproject_match(void* cur_handle, int n_kf, void* const* kf_handles, in
   while (frame->fts_.size() > n_fts0) { delete frame->fts_.back(); frame->fts_.pop_back(); }
 }
 
+// ---- a13b: the seed stage of Reprojector::reprojectMap through the reference's own member functions -------------------------------------------
+// Seeds as orc_seed_obs (Seed{ftr = the feature in keyframe kf_handles[ref_frame], mu, sigma2}). Per seed, in list order, Reprojector::reprojectorSeed
+// (:531-552) — where reprojectMap's loop over depth_filter_->seeds_ (:312-317, host side: it selects the seeds) calls it; then lines :319-327
+// restated verbatim around the reference's reprojectorSeeds (:431-503: per-cell stable sort by sigma2, first seed findMatchSeed accepts, the
+// TYPE_TEMPORARY point and the feature it creates). n_matches_in = n_matches_ when the stage starts.
+void ref_reproject_seeds(void* cur_handle, int n_kf, void* const* kf_handles, int S, const orc_seed_obs* seeds, const orc_reproj_grid* grid,
+                         const int32_t* cell_order, int n_matches_in, orc_reproj_result* out, orc_reproj_summary* summary) {
+  FrameHandle* cur = (FrameHandle*)cur_handle;
+  FramePtr frame = cur->frame;
+  std::memset(summary, 0, sizeof *summary);
+  for (int i = 0; i < S; ++i) { std::memset(&out[i], 0, sizeof out[i]); out[i].order = -1; out[i].cell = -1; }
+  Config::maxFts() = (size_t)grid->max_fts;
+  Map map;
+  Reprojector rep(frame->cam_, map);
+  if (rep.grid_.cell_size != grid->cell_size || rep.grid_.grid_n_cols != grid->n_cols || rep.grid_.grid_n_rows != grid->n_rows) { summary->n_matches = -1; return; }
+  rep.resetGrid();
+  rep.grid_.cell_order.assign(cell_order, cell_order + rep.grid_.cells.size());
+  rep.matcher_.options_.align_max_iter = grid->align_max_iter;
+  rep.n_matches_ = (size_t)n_matches_in;
+  std::vector<std::unique_ptr<Feature>> feats(S);
+  std::list<Seed> list;  // DepthFilter::seeds_
+  std::map<Feature*, int> index;
+  for (int i = 0; i < S; ++i) {
+    const orc_seed_obs& s = seeds[i];
+    if (s.ref_frame < 0 || s.ref_frame >= n_kf) continue;
+    Frame* kf = ((FrameHandle*)kf_handles[s.ref_frame])->frame.get();
+    feats[i].reset(new Feature(kf, Vector2d(s.px[0], s.px[1]), Vector3d(s.f[0], s.f[1], s.f[2]), s.level));
+    feats[i]->type = (Feature::FeatureType)s.ftr_type;
+    feats[i]->grad = Vector2d(s.grad[0], s.grad[1]);
+    list.emplace_back(feats[i].get(), 1.0f, 1.0f, 1.0f);
+    Seed& seed = list.back();
+    seed.mu = s.mu; seed.sigma2 = s.sigma2;
+    index[feats[i].get()] = i;
+    auto it = std::prev(list.end());
+    if (rep.reprojectorSeed(frame, seed, it)) {
+      out[i].in_frame = 1;
+      summary->n_in_frame++;
+      // the pixel and cell reprojectorSeed computed: the candidate it just appended
+      for (size_t k = 0; k < rep.grid_.seeds.size(); ++k)
+        if (!rep.grid_.seeds[k]->empty() && &rep.grid_.seeds[k]->back().seed == &seed) {
+          out[i].cell = (int32_t)k;
+          out[i].px[0] = rep.grid_.seeds[k]->back().px[0]; out[i].px[1] = rep.grid_.seeds[k]->back().px[1];
+        }
+    }
+  }
+  const size_t n_fts0 = frame->fts_.size();
+  // ---- src/reprojector.cpp:319-327 ----
+  for (size_t i = 0; i < rep.grid_.seeds.size(); ++i) {
+    if (rep.reprojectorSeeds(*rep.grid_.seeds.at(rep.grid_.cell_order[i]), frame)) ++rep.n_matches_;
+    if (rep.n_matches_ >= (size_t)Config::maxFts()) break;
+  }
+  summary->n_matches = (int32_t)rep.n_matches_;
+  int order = 0;
+  size_t k = 0;
+  for (auto it = frame->fts_.begin(); it != frame->fts_.end(); ++it, ++k) {
+    if (k < n_fts0) continue;
+    Feature* ft = *it;
+    const int i = index.at(ft->point->hostFeature_);
+    out[i].matched = 1; out[i].tried = 1; out[i].order = order++;
+    out[i].search_level = ft->level;
+    out[i].px[0] = ft->px[0]; out[i].px[1] = ft->px[1];
+    out[i].align_ok = 1;
+  }
+  while (frame->fts_.size() > n_fts0) { delete frame->fts_.back(); frame->fts_.pop_back(); }  // their TYPE_TEMPORARY points stay with `map` and die with it
+}
+
 // ---- N3: DepthFilter::observeDepthRow (src/depth_filter.cpp:580-675) — the reference's own function, one seed per call so that the outcome code of
 // doLineStereo can be read off the RunningStats counters. Seeds as orc_seed_obs (Seed{ftr = the feature in keyframe kf_handles[ref_frame], mu, sigma2}),
 // results as orc_seed_result. The filter object is constructed once (its constructor starts the IndexThreadReduce workers, which stay idle); the

@@ -308,6 +308,20 @@ def reproject_match(cur, kfs, cands, grid, cell_order):
     return out, summ
 
 
+def reproject_seeds(cur, kfs, seeds, grid, cell_order, n_matches_in):
+    """The seed stage of Reprojector::reprojectMap through the reference's own reprojectorSeed / reprojectorSeeds (ref_reproject_seeds).
+    Returns (orc_reproj_result array — matched / order / px / search level; tried only where matched —, summary with n_in_frame, n_matches)."""
+    import oracle_lib as O
+    lib = load()
+    S = len(seeds)
+    out = (O.orc_reproj_result * max(S, 1))()
+    summ = O.orc_reproj_summary()
+    order = np.ascontiguousarray(cell_order, np.int32)
+    hh = (C.c_void_p * len(kfs))(*[k.h for k in kfs])
+    lib.ref_reproject_seeds(cur.h, len(kfs), hh, S, seeds, C.byref(grid), order.ctypes.data_as(C.c_void_p), int(n_matches_in), out, C.byref(summ))
+    return out, summ
+
+
 def depth_observe(cur, kfs, seeds, px_error_angle):
     """DepthFilter::observeDepthRow (src/depth_filter.cpp:580-675) of the reference for every seed record (orc_seed_obs array), one seed per call.
     Returns an orc_seed_result array (z = 1 / mu after the update, as the reference records it in Seed::vec_distance)."""

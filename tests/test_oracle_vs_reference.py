@@ -414,6 +414,48 @@ def test_a13b_seed_walk_matches_brute_force():
         assert [(io[i].tried, io[i].matched, io[i].order) for i in range(S)] == list(zip(exp[0], exp[1], exp[2])), trial
 
 
+@pytest.mark.parametrize("cam,S,seed,gain,n_in", [("icl", 900, 31, 1.0, 0), ("icl", 600, 32, 1.3, 40), ("euroc", 600, 33, 1.0, 0), ("tum_fov", 500, 34, 1.3, 95)])
+def test_a13b_seed_stage_reference_vs_restatement(cam, S, seed, gain, n_in):
+    """The seed stage of Reprojector::reprojectMap (src/reprojector.cpp:309-328) through the reference's OWN reprojectorSeed / reprojectorSeeds vs
+    the restatement's whole call: in-frame flag, cell and pixel per seed; which seeds become features, in which order, and n_matches_ — equal
+    whenever no findMatchSeed outcome flips along the walk."""
+    from hso_b200 import Context
+    s = synth.make_seed_reproject_scene(seed, cam, S=S, gain=gain)
+    c = s["cam"]
+    kfs = [R.Frame(c, im, T, exposure_time=1.0, keyframe_id=1) for im, T in zip(s["kf_imgs"], s["T_f_w"])]
+    cur = R.Frame(c, s["cur_img"], s["T_cur_w"], exposure_time=gain, keyframe_id=9)
+    oc = (O.orc_seed_obs * S).from_buffer_copy(bytes(Context.seed_obs(s["seeds"])))
+    pyrs = [O.create_pyramid(im, 5)[0] for im in s["kf_imgs"]]
+    cl, _ = O.create_pyramid(s["cur_img"], 5)
+    sob = [O.sobel5(cl[l]) for l in range(3)]
+    g = O.orc_reproj_grid(*[s["grid"][k] for k in ("cell_size", "n_cols", "n_rows", "max_fts", "align_max_iter")], 0)
+    oo, osum = O.reproject_seeds(c, s["T_cur_w"], s["T_f_w"], oc, g, s["cell_order"], n_in, 2, pyrs, cl, sob)
+    rr, rsum = R.reproject_seeds(cur, kfs, oc, g, s["cell_order"], n_in)
+    assert rsum.n_matches >= 0
+    assert [oo[i].in_frame for i in range(S)] == [rr[i].in_frame for i in range(S)]
+    inf = [i for i in range(S) if rr[i].in_frame]
+    assert [oo[i].cell for i in inf] == [rr[i].cell for i in inf] and len(inf) > 0.5 * S
+    if all(oo[i].matched == rr[i].matched for i in range(S)):
+        assert osum.n_matches == rsum.n_matches and [oo[i].order for i in range(S)] == [rr[i].order for i in range(S)]
+        dpx = [np.hypot(oo[i].px[0] - rr[i].px[0], oo[i].px[1] - rr[i].px[1]) for i in range(S) if rr[i].matched]
+        assert all(oo[i].search_level == rr[i].search_level for i in range(S) if rr[i].matched)
+        assert rsum.n_matches > n_in and np.median(dpx) < 1e-3 and np.max(dpx) < 0.25
+        test_a13b_seed_stage_reference_vs_restatement.exact += 1
+    else:
+        assert sum(1 for i in range(S) if oo[i].matched != rr[i].matched) <= 4 and abs(osum.n_matches - rsum.n_matches) <= 2
+    assert rsum.n_matches <= max(s["grid"]["max_fts"], n_in)
+    for k in kfs:
+        k.close()
+    cur.close()
+
+
+test_a13b_seed_stage_reference_vs_restatement.exact = 0
+
+
+def test_a13b_seed_stage_agreed_exactly_somewhere():
+    assert test_a13b_seed_stage_reference_vs_restatement.exact >= 2
+
+
 # ---- N1 ------------------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cam,M,max_fts,seed,deleted", [("icl", 3000, 200, 21, 0.0), ("icl", 1200, 120, 22, 0.06), ("euroc", 1500, 150, 23, 0.03),
                                                          ("tum_fov", 900, 100, 24, 0.0), ("icl", 180, 200, 25, 0.05)])
