@@ -681,6 +681,12 @@ void ref_depth_observe(void* cur_handle, int n_kf, void* const* kf_handles, doub
   df->active_frame_.reset();
 }
 
+// N2: hso::shiTomasiScore (src/vikit/vision.cpp:111-151) of the reference for a list of pixels
+void ref_shi_tomasi(const uint8_t* img, int w, int h, int n, const int32_t* xy, float* out) {
+  const cv::Mat m = mat_from_u8(img, w, h);
+  for (int i = 0; i < n; ++i) out[i] = hso::shiTomasiScore(m, xy[2 * i], xy[2 * i + 1]);
+}
+
 int ref_check_ncc(const float* p1, const float* p2, float thresh) {
   Matcher m;
   return m.checkNCC(const_cast<float*>(p1), const_cast<float*>(p2), thresh) ? 1 : 0;

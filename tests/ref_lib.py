@@ -294,6 +294,16 @@ def find_match_seed_batch(cur, kfs, seeds, px_init):
     return ok, px.reshape(S, 2), sl, A.reshape(S, 2, 2)
 
 
+def shi_tomasi(img, xy):
+    """hso::shiTomasiScore (src/vikit/vision.cpp:111-151) at the pixels xy (n,2)."""
+    lib = load()
+    img = np.ascontiguousarray(img, np.uint8)
+    xy = np.ascontiguousarray(xy, np.int32)
+    out = np.zeros(len(xy), np.float32)
+    lib.ref_shi_tomasi(img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0], len(xy), xy.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def reproject_match(cur, kfs, cands, grid, cell_order):
     """The grid stage of Reprojector::reprojectMap through the reference's own reprojectPoint / reprojectCell / reprojectCellAll
     (oracle/ref_wrap.cpp: ref_reproject_match). cands: orc_reproj_cand array, grid: orc_reproj_grid. Returns (orc_reproj_result array, summary)."""

@@ -522,6 +522,20 @@ def test_n1_reference_and_restatement_walks_agreed_exactly_somewhere():
     assert len(st) == 5 and sum(1 for x in st if x[2]) >= 3, st
 
 
+# ---- N2 (the FAST detector itself: tests/test_oracle_fast.py against thirdparty/fast) --------------------------------------------------------
+def test_n2_shi_tomasi_reference_vs_restatement():
+    """hso::shiTomasiScore (src/vikit/vision.cpp:111-151) of the reference at every corner the restatement's detector keeps: the restatement's score
+    is the same float expression over the same integer sums."""
+    rng = np.random.default_rng(9)
+    for w, h in ((640, 480), (376, 240), (160, 120)):
+        img = synth.texture(rng, w, h)
+        det = O.fast_detect(img, 12, border=8)
+        assert len(det) > 20
+        ref = R.shi_tomasi(img, np.array([[x, y] for x, y, _, _ in det]))
+        got = np.array([st for _, _, _, st in det], np.float32)
+        assert np.allclose(got, ref, rtol=1e-6, atol=1e-6), np.abs(got - ref).max()
+
+
 # ---- N3 ------------------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cam,S,seed", [("icl", 500, 4), ("euroc", 400, 5), ("tum_fov", 400, 6)])
 def test_n3_observe_depth_row_reference_vs_restatement(cam, S, seed):
