@@ -56,6 +56,11 @@ def main():
                 ctx.coarse_track_batch([job] * 3, inverse_comp=ic, trace_cap=64)
         ctx.set_cluster(0, 0)
         ctx._chk(ctx.lib.hso_track_set_stream_cache(ctx.h, 0))
+        # compact feature layout (xyz + float32 px): the copy-as-it-is path and its branch of k_track_compact, both entry points
+        xyz, px32 = Context.compact_features(p["px"], p["f"], p["dist"])
+        cj = dict(ref=ids[0], cur=ids[1], xyz=xyz, px32=px32, T_cur_ref=np.eye(4)[:3], exposure_rat=a0)
+        ctx.coarse_track_batch([cj] * 3)
+        ctx.add_frames_track_batch([p["cur_img"]] * 5, [dict(ref=ids[0], xyz=xyz, px32=px32, T_cur_ref=np.eye(4)[:3])] * 5)
         ctx._chk(ctx.lib.hso_set_pipeline(ctx.h, 4, 3))  # 10 problems -> 3 chunks on 3 streams
         ctx.add_frames_track_batch([p["cur_img"]] * 10, [dict(ref=ids[0], px=p["px"], f=p["f"], dist=p["dist"], T_cur_ref=np.eye(4)[:3])] * 10)
         ctx.close()
