@@ -188,3 +188,23 @@ def test_stage_names_follow_the_reference_timers():
     assert names[5] == b"depth_filter_update" and names[6] == b"feature_detection" and names[7] is None
     ref = open(os.path.join(ROOT, "tests", "golden", "reference_timer_names.txt")).read().split()
     assert all(n.decode() in ref for n in names[:5])
+
+
+def test_compact_feature_layout_float32_px_is_exact_for_the_tracker():
+    """hso_track_job::px32: the tracker only ever uses (float)(px * 2^-level) (src/CoarseTracker.cpp:437-441); rounding px to float32 first gives the
+    same float at every level, because a power-of-two factor commutes with the rounding. xyz = f * dist is the reference's own expression (:292)."""
+    import numpy as np
+    from hso_b200 import Context
+    rng = np.random.default_rng(0)
+    px = np.stack([rng.uniform(0, 1280, 200000), rng.uniform(0, 1024, 200000)], axis=1)
+    f = rng.normal(size=(200000, 3))
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    dist = rng.uniform(0.2, 50, 200000)
+    dist[::17] = -1.0
+    xyz, px32 = Context.compact_features(px, f, dist)
+    ok = dist >= 0
+    assert px32.dtype == np.float32 and px32.shape == (int(ok.sum()), 2) and xyz.shape == (int(ok.sum()), 3)
+    assert np.array_equal(xyz, f[ok] * dist[ok, None])
+    for level in range(0, 5):
+        s = 1.0 / (1 << level)
+        assert np.array_equal((px[ok] * s).astype(np.float32), (px32.astype(np.float64) * s).astype(np.float32))
